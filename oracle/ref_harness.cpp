@@ -231,6 +231,7 @@ int ref_get_grid(void* h, int field, void* out) {
     if (field == FSIM_FIELD_RHS) {
         double* o = (double*)out;
         std::fill(o, o + nc, 0.0);
+        g.fluidCellCount = (int)g.fluidCellPositions.size();  // solveIncompressibility does this first (bridsonSolverGrid.cpp:245)
         std::vector<double> rhs = g.calculateRHS(true);
         for (size_t i = 0; i < rhs.size(); i++) {
             glm::ivec3 p = g.fluidCellPositions[i];
