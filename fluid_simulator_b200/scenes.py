@@ -124,10 +124,14 @@ def cfg4_obstacles(n, step, dt):
 
 
 def hydrostatic_types(n, ny=None, nz=None):
-    """cfg 5 (projection only): cell types with the dam block WATER, everything else AIR (borders are made
-    SOLID by the grid itself), reference order (x-major, z fastest)."""
+    """cfg 5 (projection only): cell types with the dam block WATER, the rest of the interior AIR and the border
+    shell SOLID except the open top (what the MacGrid constructor leaves behind, macGrid.cpp:15-16,75-140);
+    reference order (x-major, z fastest)."""
     ny = n if ny is None else ny
     nz = n if nz is None else nz
     t = np.full((n, ny, nz), abi.AIR, dtype=np.uint8)
+    t[0, :, :] = t[-1, :, :] = abi.SOLID
+    t[:, 0, :] = abi.SOLID
+    t[:, :, 0] = t[:, :, -1] = abi.SOLID
     t[1:n // 2, 1:ny - 1, 1:nz - 1] = abi.WATER
     return t.reshape(-1)
