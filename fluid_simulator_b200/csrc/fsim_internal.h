@@ -1,0 +1,161 @@
+// fsim_internal.h -- internal state of libfsim_b200 (not part of the ABI; see include/fsim.h).
+//
+// Device layout:
+//   grid   : fp32 SoA, one array per channel, cell (x,y,z) at (z*gy + y)*gx + x  (x fastest, z slowest so that
+//            z-slab halos are contiguous planes); u8 flags; fp64 pressure / PCG vectors.
+//   particles : fp32 SoA (px,py,pz,vx,vy,vz[,c00..c22]), kept in cell-binned order (sorted by device cell
+//            index every step); two buffer sets (ping-pong) for the reorder pass.
+// The ABI transposes to/from the reference's order (x-major, z fastest; AoS fp64 particles) on upload/download.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/fsim.h"
+
+#define FSIM_MAX_OBS 31  // 5 bits; FSIM_MAX_OBSTACLES in the ABI is 32 -> the 32nd is rejected with FSIM_ERR_INVALID
+
+// flags byte
+#define FL_TYPE_MASK 0x03  // FSIM_CELL_* (reference enum order)
+#define FL_HASPART 0x04    // >= 1 particle has ivec3(pos*cellDInv) == this cell (before obstacles/borders)
+#define FL_VALID_SHIFT 3   // 2 bits: extrapolation validity 0 (WATER), 1, 2, 3 (= invalid, the reference's 100)
+#define FL_VALID_MASK 0x18
+
+struct GridDims {
+    int gx, gy, gz;     // cells
+    int sy, sz;         // strides (sx = 1): sy = gx, sz = gx*gy
+    int64_t nc;
+    float hx, hy, hz;   // cellD
+    float ihx, ihy, ihz;  // cellDInv
+    double dhx, dhy, dhz, dihx, dihy, dihz;
+    int twoD;
+};
+
+// obstacle as the kernels see it (constant memory); integer raster bounds are computed on the host with the
+// reference's exact fp64 expressions (macGrid.cpp:232-240, 268-270)
+struct DevObstacle {
+    int kind;
+    int mn[3], mx[3];   // raster bounds: sphere inclusive [mn,mx], box half-open [mn,mx)
+    double center[3];   // pos * cellDInv
+    double r2;          // (cellDInv.x * r)^2
+    double pos[3], speed[3], size[3], r;
+    double pmin[3], pmax[3];  // getMinMaxRect(pos,size) -/+ particleR  (push-out box extents, simulator.cpp:281-283)
+};
+
+struct ParticleSet {
+    float* pos[3];
+    float* vel[3];
+    float* c[9];  // APIC matrix rows c[a][b] at c[3*a+b]; allocated lazily
+    uint32_t* id; // optional persistent ids (tests / facade)
+};
+
+struct PcgScalars {  // device-resident scalars of the solve
+    double sigma, sigma_new, sq, rmax, rhs_sumsq;
+    int iterations, done, early_out, nan_break;
+    long long fluid_cells;
+};
+
+struct MgLevel;
+
+struct fsim {
+    int device;
+    cudaStream_t stream;
+    GridDims g;
+    FsimGridDesc desc;
+    FsimGridInfo info;
+    FsimParams par;
+    FsimObstacle obs[FSIM_MAX_OBS];
+    int nobs;
+    DevObstacle* d_obs;  // device copy (global memory, one per handle so handles never share state)
+    double particle_r, zval;
+    int zconst;
+
+    // particles
+    int64_t np, cap;
+    int cur;  // which ParticleSet is current
+    ParticleSet ps[2];
+    bool have_c, track_ids;
+    uint32_t next_id;         // next persistent particle id to hand out
+    FsimParticleGfx* gfx;     // device buffer of the gfx export, [gfx_cap]
+    int64_t gfx_cap;
+    uint32_t *key, *rank;     // [cap+1] each
+    uint8_t* kill;            // [cap] sink-capture flags written by the advect kernel
+    bool kill_pending;        // kill[] holds flags the next sort must honour
+    bool sorted;  // particles are in cell-binned order consistent with cell_start
+
+    // grid
+    uint32_t *cnt, *cell_start;  // [nc], [nc+1]
+    uint32_t* scan_block;        // scan scratch
+    uint8_t* flags;
+    float *u[3], *u2[3], *wsum[3], *dens;  // u: post-P2G v / accumulators; u2: working v2
+    double *p, *rhs, *r, *s, *q, *z;       // pressure + PCG vectors (fp64)
+    float *mg_r32, *mg_z32;                // fp32 views handed to the multigrid preconditioner
+    std::vector<MgLevel*> mg;
+    PcgScalars* scal;                      // device
+    PcgScalars* scal_host;                 // pinned
+    double* partials;                      // reduction partials [3][max_blocks]
+    unsigned int* red_counter;
+    int red_blocks;
+    bool pressure_valid;
+
+    // staging
+    void* stage;
+    size_t stage_bytes;
+    void* pinned;
+    size_t pinned_bytes;
+
+    // timing
+    cudaEvent_t ev[16];
+    bool ev_valid;
+    FsimTimings timings;
+    FsimSolveInfo solve;
+    double last_step_ms;
+    int64_t launches, last_step_launches;
+    int sm_count;
+
+    // error
+    mutable std::string err;
+    int sticky;
+};
+
+int fsim_fail(const fsim* h, int code, const char* fmt, ...);
+
+#define FSIM_CUDA(h, call)                                                                            \
+    do {                                                                                              \
+        cudaError_t e__ = (call);                                                                     \
+        if (e__ != cudaSuccess) {                                                                     \
+            (h)->sticky = FSIM_ERR_CUDA;                                                              \
+            return fsim_fail((h), FSIM_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                             __FILE__, __LINE__);                                                     \
+        }                                                                                             \
+    } while (0)
+
+#define FSIM_CHECK_LAUNCH(h) FSIM_CUDA(h, cudaGetLastError())
+
+static inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---- kernels' host launchers (one per stage file) ----------------------------------------------------
+int k_upload_obstacles(fsim* h);
+int k_advect(fsim* h, double dt, bool do_advect, bool do_pushout, bool do_stop);
+int k_sort(fsim* h);  // key/count -> scan -> reorder; updates np when particles were removed
+int k_p2g(fsim* h);
+int k_classify(fsim* h, double dt);
+int k_post_p2g_only(fsim* h, double gravity_increment);
+int k_pressure_apply(fsim* h, double dt);
+int k_project(fsim* h, double dt, int* iterations);
+int k_extrapolate(fsim* h);
+int k_g2p(fsim* h);
+int k_export_gfx(fsim* h, FsimParticleGfx* dev_out);
+int k_particles_aos_to_soa(fsim* h, const double* dev_aos, int64_t first, int64_t n);
+int k_particles_soa_to_aos(fsim* h, double* dev_aos, int64_t first, int64_t n);
+int k_particles_f32_to_soa(fsim* h, const float* pos, const float* vel, const float* c, int64_t first, int64_t n);
+int k_particles_soa_to_f32(fsim* h, float* pos, float* vel, float* c, int64_t first, int64_t n);
+int k_particle_cells(fsim* h, int32_t* dev_out);
+int k_grid_download(fsim* h, int field, void* dev_out);
+int k_grid_upload(fsim* h, int field, const void* dev_in);
+int k_iota_ids(fsim* h, int64_t first, int64_t n, uint32_t base);
+int k_compact_remove(fsim* h, const int32_t* dev_sorted_ids, int64_t n);
+int mg_build(fsim* h);
+void mg_free(fsim* h);

@@ -1,0 +1,244 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the fp64 oracle on identical seeded inputs.
+
+Bars (BASELINE.json north_star): cell flags and particle->cell indices bit-exact; after one step grid velocities,
+pressure and particle velocities within 1e-5 relative L2 (fp32 device state vs fp64 oracle); long runs: divergence and
+kinetic-energy statistics within 1 %.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import cases
+from fluid_simulator_b200 import abi, scenes
+from util import diag, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5  # relative L2, stated by BASELINE.json north_star
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from fluid_simulator_b200.sim import FluidSim
+    return FluidSim
+
+
+def make_pair(gpu, sc, oracle_lib, obstacles=None, particles=None):
+    from oracle.oracle import OracleSim
+    g = gpu(sc.dims, sc.resolution, sc.two_d, sc.particle_radius)
+    o = OracleSim(sc.dims, sc.resolution, sc.two_d, sc.particle_radius)
+    parts = sc.particles if particles is None else particles
+    for s in (g, o):
+        s.set_params(sc.params)
+        s.set_obstacles(obstacles if obstacles is not None else sc.obstacles)
+        s.upload_particles(parts)
+    return g, o
+
+
+def compare_state(tag, g, o, fields, tol=TOL, particles=True, exact_flags=True):
+    res = {}
+    if particles:
+        pg, po = g.download_particles(), o.download_particles()
+        assert pg.shape == po.shape, f"{tag}: particle count {pg.shape} vs {po.shape}"
+        res["pos"] = rel_l2(pg[:, 0:3], po[:, 0:3])
+        res["vel"] = rel_l2(pg[:, 3:6], po[:, 3:6])
+        res["c"] = rel_l2(pg[:, 6:15], po[:, 6:15])
+    for f, nm in fields:
+        a, b = g.download_grid(f), o.download_grid(f)
+        if nm == "type":
+            res["type_mismatch"] = int((a != b).sum())
+        else:
+            res[nm] = rel_l2(a, b)
+    diag(test=tag, **res)
+    if exact_flags and "type_mismatch" in res:
+        assert res["type_mismatch"] == 0, f"{tag}: {res['type_mismatch']} cell flags differ"
+    for k, v in res.items():
+        if k != "type_mismatch":
+            assert v <= tol, f"{tag}: {k} rel L2 {v:.3e} > {tol}"
+    return res
+
+
+ALL = cases.GRID_FIELDS
+NO_P = [x for x in cases.GRID_FIELDS if x[1] != "pressure"]
+
+
+@pytest.mark.parametrize("transfer", [abi.PIC, abi.FLIP, abi.APIC])
+def test_stage_by_stage(gpu, oracle_lib, transfer):
+    """Every stage of simulate() with non-trivial velocities, APIC matrices and two moving obstacles."""
+    n = 16
+    sc = scenes.dam_break_3d(n, transfer, tol=1e-9)
+    obs = [abi.make_obstacle(abi.BOX, pos=(0.7 * n, 0.3 * n, 0.5 * n), size=(0.2 * n, 0.5 * n, 0.4 * n), speed=(0.5, 0.0, 0.25)),
+           abi.make_obstacle(abi.SPHERE, pos=(0.3 * n, 0.35 * n, 0.5 * n), r=0.15 * n, speed=(-1.0, 0.5, 0.0))]
+    rng = np.random.default_rng(5)
+    parts = sc.particles.copy()
+    parts[:, 3:6] = rng.normal(0, 3.0, size=(parts.shape[0], 3)).astype(np.float32)
+    parts[:, 6:15] = rng.normal(0, 0.5, size=(parts.shape[0], 9)).astype(np.float32)
+    g, o = make_pair(gpu, sc, oracle_lib, obstacles=obs, particles=parts)
+    tt = ("PIC", "FLIP", "APIC")[transfer]
+    g.stage_advect(sc.dt); o.stage_advect(sc.dt)
+    compare_state(f"stage/{tt}/advect", g, o, [], tol=2e-7)
+    g.stage_push_out(); o.stage_push_out()
+    compare_state(f"stage/{tt}/push_out", g, o, [], tol=2e-7)
+    # from here on both sides must see identical (fp32-representable) particles
+    same = g.download_particles()
+    o.upload_particles(same)
+    assert np.array_equal(g.download_particle_cells(), o.download_particle_cells())
+    g.stage_p2g(); o.stage_p2g()
+    assert np.array_equal(g.download_grid(abi.FIELD_PCOUNT), o.download_grid(abi.FIELD_PCOUNT))
+    compare_state(f"stage/{tt}/p2g_wsum", g, o, [(abi.FIELD_WSUM, "wsum"), (abi.FIELD_AVGPNUM, "avgp")], particles=False)
+    g.stage_classify(sc.dt); o.stage_classify(sc.dt)
+    compare_state(f"stage/{tt}/classify", g, o, NO_P, particles=False)
+    ig = g.stage_project(sc.dt); io = o.stage_project(sc.dt)
+    diag(test=f"stage/{tt}/project_its", gpu=ig, oracle=io, rmax=g.solve_info().residual_max)
+    compare_state(f"stage/{tt}/project", g, o, ALL + [(abi.FIELD_RHS, "rhs")], particles=False)
+    g.stage_extrapolate(); o.stage_extrapolate()
+    compare_state(f"stage/{tt}/extrapolate", g, o, NO_P, particles=False)
+    g.stage_g2p(); o.stage_g2p()
+    compare_state(f"stage/{tt}/g2p", g, o, [], particles=True)
+
+
+@pytest.mark.parametrize("name,n", [("2d", 64), ("3d_flip", 32), ("3d_apic", 32), ("3d_pic", 24)])
+def test_one_step_from_rest(gpu, oracle_lib, name, n):
+    """cfg 1 (2D 64x64, 15,376 particles) and small 3D cases: one full simulate() from identical initial conditions."""
+    if name == "2d":
+        sc = scenes.dam_break_2d(n, tol=1e-9)
+    else:
+        sc = scenes.dam_break_3d(n, {"3d_flip": abi.FLIP, "3d_apic": abi.APIC, "3d_pic": abi.PIC}[name], tol=1e-9)
+    g, o = make_pair(gpu, sc, oracle_lib)
+    assert np.array_equal(g.download_particle_cells(), o.download_particle_cells())
+    ig, io = g.step(sc.dt), o.step(sc.dt)
+    diag(test=f"one_step/{name}/its", gpu=ig, oracle=io, fluid=int(g.solve_info().fluid_cells))
+    compare_state(f"one_step/{name}", g, o, ALL)
+    assert np.array_equal(g.download_particle_cells(), o.download_particle_cells())
+
+
+def test_one_step_with_obstacles_source_sink(gpu, oracle_lib):
+    """cfg-4 style: source + sink inside the block + moving box; checks flags, spawn (same rand() stream), despawn."""
+    n = 24
+    sc = scenes.dam_break_3d(n, abi.PIC, spawning_enabled=True, despawning_enabled=True, tol=1e-9)
+    obs = scenes.cfg4_obstacles(n, 3, sc.dt)
+    obs[0].spawn_rate = 4.0e4
+    obs[1].pos[:] = (0.3 * n, 0.3 * n, 0.5 * n)
+    obs[1].r = 0.1 * n
+    g, o = make_pair(gpu, sc, oracle_lib, obstacles=obs)
+    g.srand(77); ig = g.step(sc.dt)
+    o.srand(77); io = o.step(sc.dt)
+    assert g.particle_count() == o.particle_count() != sc.n_particles
+    # particle order differs after removal (the device re-bins); compare as sets through a position sort
+    pg, po = g.download_particles(by_id=False), o.download_particles()
+    kg = np.lexsort((pg[:, 2].astype(np.float32), pg[:, 1].astype(np.float32), pg[:, 0].astype(np.float32)))
+    ko = np.lexsort((po[:, 2].astype(np.float32), po[:, 1].astype(np.float32), po[:, 0].astype(np.float32)))
+    res = dict(pos=rel_l2(pg[kg, 0:3], po[ko, 0:3]), vel=rel_l2(pg[kg, 3:6], po[ko, 3:6]))
+    diag(test="one_step/source_sink", its_gpu=ig, its_oracle=io, n=g.particle_count(), **res)
+    compare_state("one_step/source_sink/grid", g, o, ALL, particles=False)
+    assert res["pos"] < 1e-6 and res["vel"] < 1e-4
+
+
+@pytest.mark.parametrize("name", ["3d_flip_nonunit", "3d_apic_obstacles"])
+def test_golden_fixture_first_step_and_drift(gpu, name):
+    """Against the committed reference outputs (tests/golden): multi-step drift stays small (chaotic growth of the
+    fp32 rounding differences is allowed for, so this is a looser, statistical bar than the one-step test)."""
+    from fluid_simulator_b200.sim import FluidSim
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+    out = cases.run_case(FluidSim, name)
+    res = {k: rel_l2(out[k], gold[k]) for k in ("particles", "v", "v2", "pressure")}
+    res["type_mismatch"] = int((out["type"] != gold["type"]).sum())
+    diag(test=f"golden/{name}", its=out["its"].tolist(), its_ref=gold["its"].tolist(), **res)
+    assert res["particles"] < 1e-3 and res["v2"] < 5e-2
+    assert res["type_mismatch"] <= max(2, gold["type"].size // 200)
+
+
+def test_long_run_statistics_2d(gpu, oracle_lib):
+    """cfg 1, 200 steps: kinetic energy and max divergence agree with the oracle within 1 %."""
+    sc = scenes.dam_break_2d(64)
+    g, o = make_pair(gpu, sc, oracle_lib)
+    ke_g, ke_o, its_g, its_o = [], [], [], []
+    for s in range(200):
+        its_g.append(g.step(sc.dt)); its_o.append(o.step(sc.dt))
+        if s % 20 == 19:
+            pg, po = g.download_particles(), o.download_particles()
+            ke_g.append(0.5 * (pg[:, 3:6] ** 2).sum()); ke_o.append(0.5 * (po[:, 3:6] ** 2).sum())
+    ke_g, ke_o = np.array(ke_g), np.array(ke_o)
+    rel = np.abs(ke_g - ke_o) / ke_o
+    com_g, com_o = pg[:, 0:3].mean(0), po[:, 0:3].mean(0)
+    diag(test="long_run/2d", ke_rel=rel.tolist(), com_gpu=com_g.tolist(), com_oracle=com_o.tolist(),
+         its_gpu_mean=float(np.mean(its_g)), its_oracle_mean=float(np.mean(its_o)))
+    assert rel.max() < 0.01
+    assert np.abs(com_g - com_o).max() < 0.01 * 64
+    # divergence of the projected field (RHS without the drift term is -div/h): both below tolerance-scale
+    assert g.solve_info().residual_max < 1e-5
+
+
+def test_edge_cases(gpu, oracle_lib):
+    from fluid_simulator_b200.sim import FluidSim, FsimError
+    # empty particle set: a step is a no-op on an all-AIR grid (sum rhs^2 < 1e-7 => early-out, 0 iterations)
+    g = FluidSim((12.0, 10.0, 9.0), 1.0, False, 0.25)
+    g.set_params(scenes.default_params())
+    assert g.step(0.005) == 0 and g.particle_count() == 0
+    t = g.download_grid(abi.FIELD_TYPE).reshape(12, 10, 9)
+    assert (t[0] == abi.SOLID).all() and (t[:, 0] == abi.SOLID).all() and (t[1:-1, 1:, 1:-1] == abi.AIR).all()
+    # ragged grid (not a multiple of the 32x4x4 tile) + capacity growth + append/remove
+    sc = scenes.dam_break_3d(12, abi.FLIP, ny=10, nz=9, tol=1e-9)
+    g2, o2 = make_pair(gpu, sc, oracle_lib)
+    extra = sc.particles[:100].copy(); extra[:, 1] += 0.3
+    g2.append_particles(extra); o2.append_particles(extra)
+    ids = np.arange(0, 300, 3, dtype=np.int32)
+    g2.remove_particles(ids); o2.remove_particles(ids)
+    assert g2.particle_count() == o2.particle_count()
+    assert rel_l2(g2.download_particles(by_id=False), o2.download_particles()) < 1e-7  # stable compaction keeps order
+    g2.step(sc.dt); o2.step(sc.dt)
+    compare_state("edge/ragged", g2, o2, ALL, particles=False)
+    # bad arguments are reported, not swallowed
+    with pytest.raises(FsimError):
+        g2.set_obstacles([abi.make_obstacle(7, (1, 1, 1))])
+    with pytest.raises(FsimError):
+        g2.download_grid(99)
+
+
+def test_projection_only_cfg5(gpu, oracle_lib):
+    """cfg 5 recipe at 48^3: hydrostatic start, converged pressure and velocities agree with the oracle."""
+    from oracle.oracle import OracleSim
+    n = 48
+    p = scenes.default_params(pressure_enabled=False, tol=1e-9)
+    types = scenes.hydrostatic_types(n)
+    g = gpu((n, n, n), 1.0, False, 0.25)
+    o = OracleSim((n, n, n), 1.0, False, 0.25)
+    for s in (g, o):
+        s.set_params(p)
+        s.upload_grid(abi.FIELD_TYPE, types)
+        s.post_p2g_update(-39.24 * 0.005)
+    ig, io = g.stage_project(0.005), o.stage_project(0.005)
+    res = dict(pressure=rel_l2(g.download_grid(abi.FIELD_PRESSURE), o.download_grid(abi.FIELD_PRESSURE)),
+               v2=rel_l2(g.download_grid(abi.FIELD_V2), o.download_grid(abi.FIELD_V2)))
+    diag(test="cfg5/48", its_gpu=ig, its_oracle=io, **res)
+    assert res["pressure"] < TOL and res["v2"] < TOL
+
+
+def test_properties_at_scale(gpu):
+    """Size-independent properties at BASELINE's single-GPU size (cfg 2: 128^3, ~8 M particles), where the CPU oracle
+    would take minutes: partition of unity (sum of face weights = particle count per axis), particle count
+    conservation, every particle inside its binned cell, divergence below tolerance after projection."""
+    n = 128
+    sc = scenes.dam_break_3d(n, abi.FLIP)
+    g = gpu(sc.dims, sc.resolution, sc.two_d, sc.particle_radius, capacity=sc.n_particles)
+    g.set_params(sc.params)
+    g.upload_particles(sc.particles)
+    for _ in range(2):
+        its = g.step(sc.dt)
+    assert g.particle_count() == sc.n_particles
+    w = g.download_grid(abi.FIELD_WSUM)
+    for a in range(3):
+        assert abs(w[:, a].sum() - sc.n_particles) < 1e-4 * sc.n_particles
+    assert abs(g.download_grid(abi.FIELD_AVGPNUM).sum() - sc.n_particles) < 1e-4 * sc.n_particles
+    cnt = g.download_grid(abi.FIELD_PCOUNT)
+    assert cnt.sum() == sc.n_particles
+    t = g.download_grid(abi.FIELD_TYPE)
+    assert ((cnt > 0) <= (t != abi.AIR)).all()       # a cell holding particles is WATER (or SOLID), never AIR
+    info = g.solve_info()
+    diag(test="scale/128", its=its, fluid=int(info.fluid_cells), rmax=info.residual_max, stats=g.last_step_stats(),
+         timings=g.step_durations())
+    assert info.residual_max < 1e-6 and not info.early_out
