@@ -1,0 +1,295 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the Simulator hot path (BASELINE.json: 3D FLIP particle-updates/s and ms/step at
+256^3, fraction of the HBM roofline), plus the reference arm (`--impl reference`: the unmodified reference Simulator
+compiled into oracle/_ref, timed on the box's host cores).
+
+One "step" = one Simulator::simulate(dt) over the synthetic dam-break scene: advect -> bin/sort ->
+P2G -> classify -> pressure projection (PCG) -> extrapolate -> G2P.  Prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "particle_updates_per_s"
+UNIT = "particle-updates/s"
+DT = 0.005
+
+# ALGORITHMIC bytes: compulsory fp32-SoA traffic only
+B_PARTICLE = {0: 72, 1: 84, 2: 144}   # PIC / FLIP / APIC bytes per particle-update (two compulsory particle passes)
+B_CELL = 205                          # bytes per cell per step for the grid stages
+B_IT_CG = 106                         # fp64 CG core per fluid cell per iteration: SpMV R8+1 W8, p/r/s updates 3x(R8+W8) .. see DESIGN.md
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks and throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def scene_params(n, transfer, tol=1e-6):
+    from fluid_simulator_b200 import scenes
+    return scenes.default_params(transfer, max_iterations=2000, tol=tol)
+
+
+def run_reference(args):
+    """Reference arm / cpu_baseline: the unmodified reference Simulator (oracle/_ref) on the host cores, on a bounded
+    sample of the workload (same dam-break recipe on a smaller grid, so one step is seconds, not minutes)."""
+    from fluid_simulator_b200 import abi, scenes
+    from oracle import refsim
+    n = args.cpu_grid
+    kind = "reference"
+    if refsim.available():
+        sc = scenes.dam_break_3d(n, abi.FLIP)
+        sim = refsim.RefSim(sc.dims, sc.resolution, sc.two_d, sc.particle_radius)
+        cores = sim.omp_threads()
+    else:  # the compiled reference always travels with the repo; the plain-C restatement is the documented stand-in
+        from oracle.oracle import OracleSim
+        kind = "port"
+        n = min(n, 64)
+        sc = scenes.dam_break_3d(n, abi.FLIP)
+        sim = OracleSim(sc.dims, sc.resolution, sc.two_d, sc.particle_radius)
+        cores = 1
+    sim.set_params(sc.params)
+    sim.upload_particles(sc.particles)
+    for _ in range(args.cpu_warmup):
+        sim.step(DT)
+    t0 = time.perf_counter()
+    its = [sim.step(DT) for _ in range(args.cpu_steps)]
+    el = time.perf_counter() - t0
+    value = sc.n_particles * args.cpu_steps / el
+    return {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "ms_per_step": 1e3 * el / args.cpu_steps,
+            "sample": f"3D FLIP dam break {n}^3, {sc.n_particles} particles, {args.cpu_steps} steps after {args.cpu_warmup} warm-up "
+                      f"(same recipe as the GPU workload, smaller grid), PCG its {its}"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--grid", type=int, default=256, help="N of the N^3 dam-break grid (256 = BASELINE.json metric config)")
+    ap.add_argument("--transfer", default="FLIP", choices=["PIC", "FLIP", "APIC"])
+    ap.add_argument("--cpu-grid", type=int, default=96)
+    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--cpu-warmup", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        args.cpu_steps = max(1, args.steps if args.steps < 10 else 3)
+        args.cpu_warmup = min(args.warmup, 1)
+        r = run_reference(args)
+        line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.cpu_steps,
+                "warmup": args.cpu_warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": r["sample"], "parallelism": f"host cores x{r['cores']} (OpenMP)"},
+                "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+                "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from fluid_simulator_b200 import abi, scenes
+    from fluid_simulator_b200.sim import FluidSim
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    transfer = {"PIC": abi.PIC, "FLIP": abi.FLIP, "APIC": abi.APIC}[args.transfer]
+    n = args.grid
+    # weak scaling over ranks: every rank advances its own N^3 dam break (independent replicas of the workload);
+    # z-slab sharding of ONE domain with NCCL halos is the next step
+    t_gen = time.perf_counter()
+    pos = scenes.block_positions_f32(1, n // 2, 1, n - 1, 1, n - 1)
+    np_local = pos.shape[0]
+    sim = FluidSim((float(n),) * 3, 1.0, False, 0.25, capacity=np_local, device=local_rank)
+    sim.set_id_tracking(False)  # ids are test support; the hot path does not carry them
+    sim.set_params(scene_params(n, transfer))
+    sim.upload_particles_f32(pos)
+    del pos
+    t_gen = time.perf_counter() - t_gen
+
+    def barrier():
+        sim.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    its = []
+    for _ in range(args.warmup):
+        its.append(sim.step(DT))
+    # the dominant kernel class is picked from the warm-up steps and event-timed live inside the timed region
+    sim.profile_enable(sim.kernel_classes())
+    sim.profile_read(reset=True)
+    sim.step(DT)
+    prof = sim.profile_read(reset=True)
+    dominant = max(prof, key=lambda k: prof[k][0])
+    sim.profile_enable([dominant])
+
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    sim.timer_record(0)
+    t0 = time.perf_counter()
+    step_its = []
+    for _ in range(args.steps):
+        step_its.append(sim.step(DT))
+    sim.timer_record(1)
+    barrier()
+    wall = time.perf_counter() - t0
+    dev_ms = sim.timer_elapsed_ms(0, 1)
+    clocks = sampler.stop()
+    prof = sim.profile_read(reset=True)
+    sim.profile_enable([])
+    launches = sum(v[2] for v in prof.values())
+    info = sim.solve_info()
+    nf = int(info.fluid_cells)
+    timings = sim.timings()
+
+    t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms_max = float(t.item())
+    total_particles = np_local * world
+    value = total_particles * args.steps / (dev_ms_max * 1e-3)
+
+    # ---- end-to-end through the C ABI with host buffers: per step set_params + set_obstacles (H2D) + simulate + the
+    # manager's gfx export into pinned host memory (D2H 20 B/particle), what simulationThreadWorker does per iteration
+    e2e = None
+    if not args.no_e2e:
+        gfx = torch.empty((np_local, 5), dtype=torch.float32, pin_memory=True)
+        params = scene_params(n, transfer)
+        k = max(2, min(args.steps, 5))
+        sim.set_params(params); sim.set_obstacles([]); sim.step(DT); sim.export_gfx_ptr(gfx.data_ptr(), np_local)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(k):
+            sim.set_params(params)
+            sim.set_obstacles([])
+            sim.step(DT)
+            sim.export_gfx_ptr(gfx.data_ptr(), np_local)
+        barrier()
+        el = time.perf_counter() - t0
+        t = torch.tensor([el], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e = {"value": total_particles * k / float(t.item()), "unit": UNIT, "steps": k,
+               "h2d_bytes_per_step": int(__import__("ctypes").sizeof(abi.Params)),
+               "d2h_bytes_per_step": int(np_local * 20),
+               "what": "fsim_set_params + fsim_set_obstacles + fsim_step + fsim_export_gfx into pinned host memory, per step"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = peaks()
+    its_mean = float(np.mean(step_its))
+    # per-launch algorithmic bytes of the dominant kernel class
+    alg = {"spmv": nf * (8 + 8 + 8) + n ** 3 * 1, "pcg_update": nf * (8 * 3 + 8 * 3 + 8) + n ** 3 * 1, "pcg_direction": nf * 24 + n ** 3,
+           "p2g": np_local * (24 if transfer != abi.APIC else 60) + n ** 3 * (8 + 28), "g2p": np_local * (36 if transfer == abi.FLIP else 24 if transfer == abi.PIC else 60) + n ** 3 * 24,
+           "advect": np_local * 48, "bin": np_local * 20, "reorder": np_local * 56, "mg": nf * 83}
+    dom_ms, dom_n, _ = prof[dominant]
+    roofline = None
+    if dom_n > 0 and dominant in alg:
+        ach = alg[dominant] / (dom_ms / dom_n * 1e-3) / 1e9
+        roofline = {"kernel": dominant, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": None, "peak_source": peak_src, "avg_launch_ms": dom_ms / dom_n, "launches_timed": dom_n,
+                    "algorithmic_bytes_per_launch": alg[dominant], "share_of_step": dom_ms / dev_ms}
+    b_step = np_local * B_PARTICLE[transfer] + n ** 3 * B_CELL + its_mean * nf * B_IT_CG
+    step_frac = b_step / (dev_ms_max / args.steps * 1e-3) / 1e9 / peak
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"3D {args.transfer} dam break {n}^3 (SURVEY §8d cfg 3 headline variant), {np_local} particles per GPU, "
+                                   f"8 per fluid cell, dt {DT}, PCG tol 1e-6", "grid": [n, n, n], "particles_per_gpu": np_local,
+                       "fluid_cells": nf, "pcg_iterations_mean": its_mean, "parallelism": f"replicas x{world}" if world > 1 else "single GPU",
+                       "l2": "inputs larger than L2 (particle + grid state >> 126 MB), no flush needed"},
+            "wall_ms_per_step": 1e3 * wall / args.steps, "clocks": clocks, "gpu_launches": int(launches),
+            "step_hbm_frac": step_frac, "step_algorithmic_bytes": b_step,
+            "stage_us": {k: v for k, v in zip(["advect", "", "", "p2g", "classify", "project", "extrapolate", "g2p"], list(timings.last_raw_us)) if k},
+            "sort_us": timings.last_sort_us, "roofline": roofline, "e2e": e2e, "setup_s": t_gen}
+    if not args.no_cpu_baseline and world >= 1:
+        try:
+            line["cpu_baseline"] = {k: v for k, v in run_reference(args).items() if k != "ms_per_step"}
+        except Exception as ex:  # the baseline is reported, never required for the GPU number
+            line["cpu_baseline"] = {"error": str(ex)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -272,6 +272,8 @@ int fsim_create(const FsimGridDesc* desc, fsim_t** out) {
     memset(&h->timings, 0, sizeof(h->timings));
     memset(&h->solve, 0, sizeof(h->solve));
     h->launches = h->last_step_launches = 0; h->last_step_ms = 0;
+    h->prof_mask = 0;
+    memset(h->prof_ms, 0, sizeof(h->prof_ms)); memset(h->prof_n, 0, sizeof(h->prof_n)); memset(h->launch_n, 0, sizeof(h->launch_n));
 
     int rc = FSIM_OK;
     auto A = [&](int r) { if (!rc) rc = r; };
@@ -328,6 +330,8 @@ int fsim_destroy(fsim_t* h) {
     cudaFree(h->p); cudaFree(h->rhs); cudaFree(h->r); cudaFree(h->s); cudaFree(h->q); cudaFree(h->z);
     cudaFree(h->d_obs); cudaFree(h->scal); cudaFree(h->partials); cudaFree(h->red_counter);
     cudaFree(h->stage); cudaFree(h->gfx);
+    for (const ProfRec& r : h->prof_recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    for (cudaEvent_t e : h->prof_free) cudaEventDestroy(e);
     if (h->scal_host) cudaFreeHost(h->scal_host);
     for (int i = 0; i < 16; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     cudaStreamDestroy(h->stream);
@@ -671,6 +675,55 @@ int fsim_get_last_step_stats(const fsim_t* hc, double* device_ms, int64_t* kerne
     fold_timings(h);
     if (device_ms) *device_ms = h->last_step_ms;
     if (kernel_launches) *kernel_launches = h->last_step_launches;
+    return FSIM_OK;
+}
+
+static const char* const kKernelNames[K_COUNT] = {"advect", "bin", "scan", "reorder", "p2g", "classify", "finalize", "rhs",
+                                                    "pcg_init", "spmv", "pcg_update", "pcg_direction", "mg", "pressure_apply",
+                                                    "extrapolate", "g2p", "gfx", "memset"};
+
+int fsim_kernel_class_count(void) { return K_COUNT; }
+const char* fsim_kernel_class_name(int kid) { return (kid >= 0 && kid < K_COUNT) ? kKernelNames[kid] : ""; }
+
+int fsim_profile_enable(fsim_t* h, uint32_t class_mask) {
+    BIND(h);
+    h->prof_mask = class_mask;
+    return FSIM_OK;
+}
+
+int fsim_profile_read(fsim_t* h, double* total_ms, int64_t* profiled_launches, int64_t* launches, int reset) {
+    BIND(h);
+    FSIM_CUDA(h, cudaStreamSynchronize(h->stream));
+    for (const ProfRec& r : h->prof_recs) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) { h->prof_ms[r.kid] += ms; h->prof_n[r.kid]++; }
+        h->prof_free.push_back(r.e0);
+        h->prof_free.push_back(r.e1);
+    }
+    h->prof_recs.clear();
+    for (int k = 0; k < K_COUNT; k++) {
+        if (total_ms) total_ms[k] = h->prof_ms[k];
+        if (profiled_launches) profiled_launches[k] = h->prof_n[k];
+        if (launches) launches[k] = h->launch_n[k];
+    }
+    if (reset) { memset(h->prof_ms, 0, sizeof(h->prof_ms)); memset(h->prof_n, 0, sizeof(h->prof_n)); memset(h->launch_n, 0, sizeof(h->launch_n)); }
+    return FSIM_OK;
+}
+
+int fsim_timer_record(fsim_t* h, int slot) {
+    BIND(h);
+    if (slot < 0 || slot > 5) return fsim_fail(h, FSIM_ERR_INVALID, "timer slot out of range");
+    FSIM_CUDA(h, cudaEventRecord(h->ev[10 + slot], h->stream));
+    return FSIM_OK;
+}
+
+int fsim_timer_elapsed_ms(fsim_t* h, int slot_begin, int slot_end, double* ms) {
+    BIND(h);
+    if (slot_begin < 0 || slot_begin > 5 || slot_end < 0 || slot_end > 5 || !ms) return fsim_fail(h, FSIM_ERR_INVALID, "bad timer slots");
+    FSIM_CUDA(h, cudaEventSynchronize(h->ev[10 + slot_end]));
+    float f = 0.f;
+    FSIM_CUDA(h, cudaEventElapsedTime(&f, h->ev[10 + slot_begin], h->ev[10 + slot_end]));
+    *ms = f;
     return FSIM_OK;
 }
 

@@ -59,6 +59,13 @@ struct PcgScalars {  // device-resident scalars of the solve
 
 struct MgLevel;
 
+// kernel classes for launch counting and the optional per-launch CUDA-event profiling (fsim_profile_*)
+enum KernelId {
+    K_ADVECT = 0, K_BIN, K_SCAN, K_REORDER, K_P2G, K_CLASSIFY, K_FINALIZE, K_RHS, K_PCG_INIT, K_SPMV, K_UPDATE,
+    K_DIRECTION, K_MG, K_APPLY, K_EXTRAP, K_G2P, K_GFX, K_MEMSET, K_COUNT
+};
+struct ProfRec { int kid; cudaEvent_t e0, e1; };
+
 struct fsim {
     int device;
     cudaStream_t stream;
@@ -115,6 +122,14 @@ struct fsim {
     int64_t launches, last_step_launches;
     int sm_count;
 
+    // per-kernel-class statistics
+    uint32_t prof_mask;                 // classes whose launches are bracketed by CUDA events
+    std::vector<cudaEvent_t> prof_free;
+    std::vector<ProfRec> prof_recs;
+    double prof_ms[K_COUNT];
+    int64_t prof_n[K_COUNT];
+    int64_t launch_n[K_COUNT];
+
     // error
     mutable std::string err;
     int sticky;
@@ -135,6 +150,30 @@ int fsim_fail(const fsim* h, int code, const char* fmt, ...);
 #define FSIM_CHECK_LAUNCH(h) FSIM_CUDA(h, cudaGetLastError())
 
 static inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// counts the launches of a kernel class and, when that class is being profiled, brackets them with CUDA events on the
+// launching stream (bench.py reads the per-class totals for the live roofline figure)
+struct KScope {
+    fsim* h;
+    int kid;
+    cudaEvent_t e0, e1;
+    bool on;
+    static cudaEvent_t get(fsim* h) {
+        cudaEvent_t e;
+        if (!h->prof_free.empty()) { e = h->prof_free.back(); h->prof_free.pop_back(); }
+        else cudaEventCreate(&e);
+        return e;
+    }
+    KScope(fsim* h_, int kid_, int n = 1) : h(h_), kid(kid_) {
+        h->launches += n;
+        h->launch_n[kid] += n;
+        on = (h->prof_mask >> kid) & 1u;
+        if (on) { e0 = get(h); e1 = get(h); cudaEventRecord(e0, h->stream); }
+    }
+    ~KScope() {
+        if (on) { cudaEventRecord(e1, h->stream); h->prof_recs.push_back({kid, e0, e1}); }
+    }
+};
 
 // ---- kernels' host launchers (one per stage file) ----------------------------------------------------
 int k_upload_obstacles(fsim* h);

@@ -172,8 +172,7 @@ int k_g2p(fsim* h) {
         a.kb = (float)cb;
     }
     dim3 grid(div_up(g.gx, TX), div_up(g.gy, TY), div_up(g.gz, TZ));
-    g2p_kernel<<<grid, NT, 0, h->stream>>>(a);
-    h->launches++;
+    { KScope ks(h, K_G2P); g2p_kernel<<<grid, NT, 0, h->stream>>>(a); }
     FSIM_CHECK_LAUNCH(h);
     return FSIM_OK;
 }
@@ -181,9 +180,11 @@ int k_g2p(fsim* h) {
 int k_export_gfx(fsim* h, FsimParticleGfx* dev_out) {
     if (h->np == 0) return FSIM_OK;
     ParticleSet& p = h->ps[h->cur];
-    gfx_kernel<<<div_up(h->np, 256), 256, 0, h->stream>>>(h->g, p.pos[0], p.pos[1], p.pos[2], p.vel[0], p.vel[1], p.vel[2],
-                                                         h->dens, h->np, dev_out);
-    h->launches++;
+    {
+        KScope ks(h, K_GFX);
+        gfx_kernel<<<div_up(h->np, 256), 256, 0, h->stream>>>(h->g, p.pos[0], p.pos[1], p.pos[2], p.vel[0], p.vel[1], p.vel[2],
+                                                             h->dens, h->np, dev_out);
+    }
     FSIM_CHECK_LAUNCH(h);
     return FSIM_OK;
 }

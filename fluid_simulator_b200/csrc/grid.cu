@@ -255,15 +255,14 @@ __global__ void __launch_bounds__(256) grid_upload_kernel(UpArgs a) {
 
 int k_classify(fsim* h, double dt) {
     const GridDims& g = h->g;
-    classify_kernel<<<div_up(g.nc, 256), 256, 0, h->stream>>>(g, h->cnt, h->d_obs, h->nobs, h->par.top_solid, h->flags);
+    { KScope ks(h, K_CLASSIFY); classify_kernel<<<div_up(g.nc, 256), 256, 0, h->stream>>>(g, h->cnt, h->d_obs, h->nobs, h->par.top_solid, h->flags); }
     FinalizeArgs a;
     a.g = g; a.flags = h->flags;
     for (int ax = 0; ax < 3; ax++) { a.u[ax] = h->u[ax]; a.u2[ax] = h->u2[ax]; a.wsum[ax] = h->wsum[ax]; }
     a.obs = h->d_obs; a.nobs = h->nobs; a.top_solid = h->par.top_solid; a.post_only = 0;
     // config.gravity is a float, dt a double: gravityEnabled ? gravity * dt : 0 (simulator.cpp:85)
     a.gdt = h->par.gravity_enabled ? (float)((double)h->par.gravity * dt) : 0.f;
-    finalize_kernel<<<div_up(g.nc, 256), 256, 0, h->stream>>>(a);
-    h->launches += 2;
+    { KScope ks(h, K_FINALIZE); finalize_kernel<<<div_up(g.nc, 256), 256, 0, h->stream>>>(a); }
     FSIM_CHECK_LAUNCH(h);
     return FSIM_OK;
 }
@@ -276,8 +275,7 @@ int k_post_p2g_only(fsim* h, double gravity_increment) {
     for (int ax = 0; ax < 3; ax++) { a.u[ax] = h->u[ax]; a.u2[ax] = h->u2[ax]; a.wsum[ax] = h->wsum[ax]; }
     a.obs = h->d_obs; a.nobs = 0; a.top_solid = h->par.top_solid; a.post_only = 1;
     a.gdt = (float)gravity_increment;
-    finalize_kernel<<<div_up(g.nc, 256), 256, 0, h->stream>>>(a);
-    h->launches++;
+    { KScope ks(h, K_FINALIZE); finalize_kernel<<<div_up(g.nc, 256), 256, 0, h->stream>>>(a); }
     FSIM_CHECK_LAUNCH(h);
     return FSIM_OK;
 }
@@ -288,8 +286,7 @@ int k_pressure_apply(fsim* h, double dt) {
     a.g = g; a.flags = h->flags; a.p = h->p;
     for (int ax = 0; ax < 3; ax++) a.u2[ax] = h->u2[ax];
     a.scale = dt / (h->par.fluid_density * h->info.cell_d[0]);
-    pressure_apply_kernel<<<div_up(g.nc, 256), 256, 0, h->stream>>>(a);
-    h->launches++;
+    { KScope ks(h, K_APPLY); pressure_apply_kernel<<<div_up(g.nc, 256), 256, 0, h->stream>>>(a); }
     FSIM_CHECK_LAUNCH(h);
     return FSIM_OK;
 }
@@ -301,8 +298,8 @@ int k_extrapolate(fsim* h) {
     for (int ax = 0; ax < 3; ax++) a.u2[ax] = h->u2[ax];
     for (int it = 0; it < 2; it++) {
         a.it = it;
+        KScope ks(h, K_EXTRAP);
         extrapolate_kernel<<<div_up(g.nc, 256), 256, 0, h->stream>>>(a);
-        h->launches++;
     }
     FSIM_CHECK_LAUNCH(h);
     return FSIM_OK;

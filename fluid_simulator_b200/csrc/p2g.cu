@@ -172,11 +172,14 @@ __global__ void __launch_bounds__(NTHREADS) p2g_kernel(P2GArgs a) {
 int k_p2g(fsim* h) {
     const GridDims& g = h->g;
     // MacGrid::resetGridValues (macGrid.cpp:221-229): v, v2, weights, avgPNum = 0 (type is rewritten by classify)
-    for (int a = 0; a < 3; a++) {
-        FSIM_CUDA(h, cudaMemsetAsync(h->u[a], 0, sizeof(float) * g.nc, h->stream));
-        FSIM_CUDA(h, cudaMemsetAsync(h->wsum[a], 0, sizeof(float) * g.nc, h->stream));
+    {
+        KScope ks(h, K_MEMSET, 7);
+        for (int a = 0; a < 3; a++) {
+            FSIM_CUDA(h, cudaMemsetAsync(h->u[a], 0, sizeof(float) * g.nc, h->stream));
+            FSIM_CUDA(h, cudaMemsetAsync(h->wsum[a], 0, sizeof(float) * g.nc, h->stream));
+        }
+        FSIM_CUDA(h, cudaMemsetAsync(h->dens, 0, sizeof(float) * g.nc, h->stream));
     }
-    FSIM_CUDA(h, cudaMemsetAsync(h->dens, 0, sizeof(float) * g.nc, h->stream));
     if (h->np == 0) return FSIM_OK;
     P2GArgs a;
     a.g = g;
@@ -189,8 +192,7 @@ int k_p2g(fsim* h) {
     a.dens = h->dens;
     a.apic = (h->par.transfer_type == FSIM_TRANSFER_APIC) && h->have_c;
     dim3 grid(div_up(g.gx, TX), div_up(g.gy, TY), div_up(g.gz, TZ));
-    p2g_kernel<<<grid, NTHREADS, 0, h->stream>>>(a);
-    h->launches++;
+    { KScope ks(h, K_P2G); p2g_kernel<<<grid, NTHREADS, 0, h->stream>>>(a); }
     FSIM_CHECK_LAUNCH(h);
     return FSIM_OK;
 }

@@ -392,10 +392,12 @@ SoA soa_of(fsim* h, int set) {
 
 int exclusive_scan(fsim* h, const uint32_t* in, int64_t n, uint32_t* out /* n+1 */) {
     const int nb = div_up(n, SCAN_TILE);
-    scan_reduce_kernel<<<nb, SCAN_THREADS, 0, h->stream>>>(in, n, h->scan_block);
-    scan_blocks_kernel<<<1, SCAN_THREADS, 0, h->stream>>>(h->scan_block, nb, out + n);
-    scan_apply_kernel<<<nb, SCAN_THREADS, 0, h->stream>>>(in, n, h->scan_block, out);
-    h->launches += 3;
+    {
+        KScope ks(h, K_SCAN, 3);
+        scan_reduce_kernel<<<nb, SCAN_THREADS, 0, h->stream>>>(in, n, h->scan_block);
+        scan_blocks_kernel<<<1, SCAN_THREADS, 0, h->stream>>>(h->scan_block, nb, out + n);
+        scan_apply_kernel<<<nb, SCAN_THREADS, 0, h->stream>>>(in, n, h->scan_block, out);
+    }
     FSIM_CHECK_LAUNCH(h);
     return FSIM_OK;
 }
@@ -433,8 +435,7 @@ int k_advect(fsim* h, double dt, bool do_advect, bool do_pushout, bool do_stop) 
     a.do_advect = do_advect; a.do_pushout = do_pushout; a.do_stop = do_stop;
     a.obs = h->d_obs;
     a.kill = h->kill;
-    advect_kernel<<<div_up(h->np, 256), 256, 0, h->stream>>>(a);
-    h->launches++;
+    { KScope ks(h, K_ADVECT); advect_kernel<<<div_up(h->np, 256), 256, 0, h->stream>>>(a); }
     FSIM_CHECK_LAUNCH(h);
     h->sorted = false;
     if (do_advect && h->par.despawning_enabled) h->kill_pending = true;
@@ -443,20 +444,19 @@ int k_advect(fsim* h, double dt, bool do_advect, bool do_pushout, bool do_stop) 
 
 int k_sort(fsim* h) {
     const GridDims& g = h->g;
-    FSIM_CUDA(h, cudaMemsetAsync(h->cnt, 0, sizeof(uint32_t) * g.nc, h->stream));
+    { KScope ks(h, K_MEMSET); FSIM_CUDA(h, cudaMemsetAsync(h->cnt, 0, sizeof(uint32_t) * g.nc, h->stream)); }
     if (h->np > 0) {
         ParticleSet& p = h->ps[h->cur];
+        KScope ks(h, K_BIN);
         bin_kernel<<<div_up(h->np, 256), 256, 0, h->stream>>>(g, p.pos[0], p.pos[1], p.pos[2],
                                                               h->kill_pending ? h->kill : nullptr, h->np, h->cnt, h->key, h->rank);
-        h->launches++;
-        FSIM_CHECK_LAUNCH(h);
     }
+    FSIM_CHECK_LAUNCH(h);
     int rc = exclusive_scan(h, h->cnt, g.nc, h->cell_start);
     if (rc) return rc;
     if (h->np > 0) {
         ReorderArgs a = reorder_args(h);
-        reorder_kernel<<<div_up(h->np, 256), 256, 0, h->stream>>>(a);
-        h->launches++;
+        { KScope ks(h, K_REORDER); reorder_kernel<<<div_up(h->np, 256), 256, 0, h->stream>>>(a); }
         FSIM_CHECK_LAUNCH(h);
         h->cur ^= 1;
     }

@@ -286,36 +286,36 @@ int k_project(fsim* h, double dt, int* iterations) {
     const int nb = h->red_blocks;
     const bool use_mg = mg_enabled(h);
 
-    rhs_kernel<<<nb, PT, 0, h->stream>>>(a);
-    h->launches++;
+    { KScope ks(h, K_RHS); rhs_kernel<<<nb, PT, 0, h->stream>>>(a); }
     if (use_mg) {
         int rc = mg_build(h);
         if (rc) return rc;
         rc = mg_apply(h);
         if (rc) return rc;
+        KScope ks(h, K_PCG_INIT);
         start_kernel<<<nb, PT, 0, h->stream>>>(a);
     } else {
+        KScope ks(h, K_PCG_INIT);
         jacobi_init_kernel<<<nb, PT, 0, h->stream>>>(a);
     }
-    h->launches++;
     FSIM_CHECK_LAUNCH(h);
 
     const int poll = use_mg ? 2 : 16;
     int done = 0;
     for (int it = 0; it < a.max_it && !done; it++) {
         a.it = it;
-        spmv_kernel<<<nb, PT, 0, h->stream>>>(a);
+        { KScope ks(h, K_SPMV); spmv_kernel<<<nb, PT, 0, h->stream>>>(a); }
         if (use_mg) {
-            update_kernel<false><<<nb, PT, 0, h->stream>>>(a);
+            { KScope ks(h, K_UPDATE); update_kernel<false><<<nb, PT, 0, h->stream>>>(a); }
             int rc = mg_apply(h);
             if (rc) return rc;
+            KScope ks(h, K_UPDATE);
             dot_zr_kernel<<<nb, PT, 0, h->stream>>>(a);
-            h->launches++;
         } else {
+            KScope ks(h, K_UPDATE);
             update_kernel<true><<<nb, PT, 0, h->stream>>>(a);
         }
-        direction_kernel<<<nb, PT, 0, h->stream>>>(a);
-        h->launches += 3;
+        { KScope ks(h, K_DIRECTION); direction_kernel<<<nb, PT, 0, h->stream>>>(a); }
         if ((it + 1) % poll == 0 || it + 1 == a.max_it) {
             FSIM_CUDA(h, cudaMemcpyAsync(h->scal_host, h->scal, sizeof(PcgScalars), cudaMemcpyDeviceToHost, h->stream));
             FSIM_CUDA(h, cudaStreamSynchronize(h->stream));

@@ -53,6 +53,25 @@ def block_particles(x0, x1, y0, y1, z0, z1, seed=SEED, two_d_z=None, jitter=0.1,
     return out
 
 
+def block_positions_f32(x0, x1, y0, y1, z0, z1, seed=SEED, jitter=0.1, chunk_x=8):
+    """Same particles as block_particles (3D), but only the fp32 positions, built in x-chunks so that the 65 M-particle
+    256^3 scene never materialises an fp64 AoS copy."""
+    out = np.empty(((x1 - x0) * (y1 - y0) * (z1 - z0) * 8, 3), dtype=np.float32)
+    sub = np.array([[i, j, k] for i in (0.25, 0.75) for j in (0.25, 0.75) for k in (0.25, 0.75)])
+    per_x = (y1 - y0) * (z1 - z0) * 8
+    for xa in range(x0, x1, chunk_x):
+        xb = min(x1, xa + chunk_x)
+        cx, cy, cz = np.meshgrid(np.arange(xa, xb), np.arange(y0, y1), np.arange(z0, z1), indexing="ij")
+        cells = np.stack([cx.ravel(), cy.ravel(), cz.ravel()], axis=1).astype(np.float64)
+        pos = (cells[:, None, :] + sub[None, :, :]).reshape(-1, 3)
+        first = (xa - x0) * per_x
+        ids = np.arange(pos.shape[0], dtype=np.uint64) + np.uint64(first)
+        for a in range(3):
+            pos[:, a] += (uniform01(seed, ids, a) * 2.0 - 1.0) * jitter
+        out[first:first + pos.shape[0]] = pos.astype(np.float32)
+    return out
+
+
 @dataclass
 class Scene:
     name: str

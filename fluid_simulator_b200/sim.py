@@ -78,6 +78,12 @@ def load_library():
         "fsim_get_solve_info": (i32, [vp, P(abi.SolveInfo)]),
         "fsim_get_last_step_stats": (i32, [vp, P(dbl), P(i64)]),
         "fsim_synchronize": (i32, [vp]),
+        "fsim_kernel_class_count": (i32, []),
+        "fsim_kernel_class_name": (C.c_char_p, [i32]),
+        "fsim_profile_enable": (i32, [vp, C.c_uint32]),
+        "fsim_profile_read": (i32, [vp, vp, vp, vp, i32]),
+        "fsim_timer_record": (i32, [vp, i32]),
+        "fsim_timer_elapsed_ms": (i32, [vp, i32, i32, P(dbl)]),
     }
     for name, (res, args) in sigs.items():
         f = getattr(L, name)
@@ -270,6 +276,34 @@ class FluidSim:
     def synchronize(self): self._ck(self.L.fsim_synchronize(self.h))
 
     def set_id_tracking(self, on): self._ck(self.L.fsim_set_id_tracking(self.h, int(on)))
+
+    # --- measurement support ----------------------------------------------------------------------
+    def kernel_classes(self):
+        return [self.L.fsim_kernel_class_name(k).decode() for k in range(self.L.fsim_kernel_class_count())]
+
+    def profile_enable(self, names):
+        """Brackets every launch of the named kernel classes with CUDA events on the launching stream."""
+        classes = self.kernel_classes()
+        mask = 0
+        for nm in names:
+            mask |= 1 << classes.index(nm)
+        self._ck(self.L.fsim_profile_enable(self.h, mask))
+
+    def profile_read(self, reset=True):
+        """{class: (event-timed ms, event-timed launches, all launches)} since the last reset."""
+        classes = self.kernel_classes()
+        ms = np.zeros(len(classes), dtype=np.float64)
+        pn = np.zeros(len(classes), dtype=np.int64)
+        ln = np.zeros(len(classes), dtype=np.int64)
+        self._ck(self.L.fsim_profile_read(self.h, ms.ctypes.data, pn.ctypes.data, ln.ctypes.data, int(reset)))
+        return {c: (float(ms[i]), int(pn[i]), int(ln[i])) for i, c in enumerate(classes)}
+
+    def timer_record(self, slot): self._ck(self.L.fsim_timer_record(self.h, slot))
+
+    def timer_elapsed_ms(self, a, b):
+        ms = C.c_double()
+        self._ck(self.L.fsim_timer_elapsed_ms(self.h, a, b, C.byref(ms)))
+        return float(ms.value)
 
     def srand(self, seed):
         """Seeds libc rand(), which spawnParticles draws from (util/random.h:13-15)."""

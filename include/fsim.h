@@ -229,6 +229,14 @@ FSIM_API int fsim_get_step_durations(const fsim_t* h, FsimTimings* out);
 FSIM_API int fsim_get_solve_info(const fsim_t* h, FsimSolveInfo* out);
 /* device time of the whole last fsim_step in ms, and the number of kernels it launched */
 FSIM_API int fsim_get_last_step_stats(const fsim_t* h, double* device_ms, int64_t* kernel_launches);
+/* measurement support (bench.py): kernel classes, per-class launch counts, optional CUDA-event bracketing of every
+ * launch of the classes in class_mask (on the launching stream), and six timer slots recorded on that same stream */
+FSIM_API int fsim_kernel_class_count(void);
+FSIM_API const char* fsim_kernel_class_name(int kernel_class);
+FSIM_API int fsim_profile_enable(fsim_t* h, uint32_t class_mask);
+FSIM_API int fsim_profile_read(fsim_t* h, double* total_ms, int64_t* profiled_launches, int64_t* launches, int reset);
+FSIM_API int fsim_timer_record(fsim_t* h, int slot);
+FSIM_API int fsim_timer_elapsed_ms(fsim_t* h, int slot_begin, int slot_end, double* ms);
 /* blocks until all queued device work of this handle is complete */
 FSIM_API int fsim_synchronize(fsim_t* h);
 
