@@ -273,6 +273,8 @@ int fsim_create(const FsimGridDesc* desc, fsim_t** out) {
     memset(&h->solve, 0, sizeof(h->solve));
     h->launches = h->last_step_launches = 0; h->last_step_ms = 0;
     h->prof_mask = 0;
+    h->mg_z32 = nullptr; h->mg_inv_scale = 1.0;
+    { const char* e = getenv("FSIM_PRECOND"); h->use_mg = !(e && strcmp(e, "jacobi") == 0); }
     memset(h->prof_ms, 0, sizeof(h->prof_ms)); memset(h->prof_n, 0, sizeof(h->prof_n)); memset(h->launch_n, 0, sizeof(h->launch_n));
 
     int rc = FSIM_OK;

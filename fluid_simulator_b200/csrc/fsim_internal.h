@@ -98,7 +98,9 @@ struct fsim {
     uint8_t* flags;
     float *u[3], *u2[3], *wsum[3], *dens;  // u: post-P2G v / accumulators; u2: working v2
     double *p, *rhs, *r, *s, *q, *z;       // pressure + PCG vectors (fp64)
-    float *mg_r32, *mg_z32;                // fp32 views handed to the multigrid preconditioner
+    float* mg_z32;                         // result of the last multigrid cycle (fp32, 0 outside WATER)
+    bool use_mg;                           // multigrid (default) or diagonal preconditioner (FSIM_PRECOND=jacobi)
+    double mg_inv_scale;                   // 1 / (dt / (rho h^2)): the hierarchy works on the integer-weight Laplacian
     std::vector<MgLevel*> mg;
     PcgScalars* scal;                      // device
     PcgScalars* scal_host;                 // pinned

@@ -27,6 +27,7 @@ struct PcgArgs {
     const float* u2[3];
     const float* dens;
     double *p, *rhs, *r, *s, *q, *z;
+    const float* z32;  // multigrid result (fp32) when the multigrid preconditioner is active, else nullptr
     PcgScalars* sc;
     double* partials;  // [3][gridDim.x]
     unsigned int* counter;
@@ -161,7 +162,7 @@ __global__ void __launch_bounds__(PT) start_kernel(PcgArgs a) {
     if (a.sc->done) return;
     double acc[1] = {0.0};
     for (int64_t c = (int64_t)blockIdx.x * PT + threadIdx.x; c < a.g.nc; c += (int64_t)gridDim.x * PT) {
-        const double z = a.z[c];
+        const double z = (double)a.z32[c];
         a.s[c] = z;
         acc[0] += z * a.r[c];
     }
@@ -241,7 +242,7 @@ __global__ void __launch_bounds__(PT) dot_zr_kernel(PcgArgs a) {
     if (a.sc->done) return;
     double acc[1] = {0.0};
     for (int64_t c = (int64_t)blockIdx.x * PT + threadIdx.x; c < a.g.nc; c += (int64_t)gridDim.x * PT)
-        acc[0] += a.z[c] * a.r[c];
+        acc[0] += (double)a.z32[c] * a.r[c];
     double out[1];
     if (grid_reduce<1, 0>(acc, a.partials, a.counter, out)) a.sc->sigma_new = out[0];
 }
@@ -252,7 +253,7 @@ __global__ void __launch_bounds__(PT) direction_kernel(PcgArgs a) {
     const double beta = a.sc->sigma_new / a.sc->sigma;
     for (int64_t c = (int64_t)blockIdx.x * PT + threadIdx.x; c < a.g.nc; c += (int64_t)gridDim.x * PT) {
         if (type_of(a.flags, c) != FSIM_CELL_WATER) continue;
-        a.s[c] = a.s[c] * beta + a.z[c];
+        a.s[c] = a.s[c] * beta + (a.z32 ? (double)a.z32[c] : a.z[c]);
     }
     // the last block to finish publishes sigma = sigma' (every block has read both scalars before arriving)
     __shared__ bool last;
@@ -283,6 +284,8 @@ int k_project(fsim* h, double dt, int* iterations) {
     a.pressure_enabled = h->par.pressure_enabled;
     a.max_it = h->par.max_iterations;
     a.it = 0;
+    a.z32 = nullptr;
+    h->mg_inv_scale = 1.0 / a.scale;
     const int nb = h->red_blocks;
     const bool use_mg = mg_enabled(h);
 
@@ -292,6 +295,7 @@ int k_project(fsim* h, double dt, int* iterations) {
         if (rc) return rc;
         rc = mg_apply(h);
         if (rc) return rc;
+        a.z32 = h->mg_z32;
         KScope ks(h, K_PCG_INIT);
         start_kernel<<<nb, PT, 0, h->stream>>>(a);
     } else {
@@ -300,7 +304,7 @@ int k_project(fsim* h, double dt, int* iterations) {
     }
     FSIM_CHECK_LAUNCH(h);
 
-    const int poll = use_mg ? 2 : 16;
+    const int poll = use_mg ? 1 : 16;
     int done = 0;
     for (int it = 0; it < a.max_it && !done; it++) {
         a.it = it;
@@ -309,6 +313,7 @@ int k_project(fsim* h, double dt, int* iterations) {
             { KScope ks(h, K_UPDATE); update_kernel<false><<<nb, PT, 0, h->stream>>>(a); }
             int rc = mg_apply(h);
             if (rc) return rc;
+            a.z32 = h->mg_z32;
             KScope ks(h, K_UPDATE);
             dot_zr_kernel<<<nb, PT, 0, h->stream>>>(a);
         } else {

@@ -39,14 +39,15 @@ def make_pair(gpu, sc, oracle_lib, obstacles=None, particles=None):
     return g, o
 
 
-def compare_state(tag, g, o, fields, tol=TOL, particles=True, exact_flags=True):
+def compare_state(tag, g, o, fields, tol=TOL, particles=True, exact_flags=True, apic=False):
     res = {}
     if particles:
         pg, po = g.download_particles(), o.download_particles()
         assert pg.shape == po.shape, f"{tag}: particle count {pg.shape} vs {po.shape}"
         res["pos"] = rel_l2(pg[:, 0:3], po[:, 0:3])
         res["vel"] = rel_l2(pg[:, 3:6], po[:, 3:6])
-        res["c"] = rel_l2(pg[:, 6:15], po[:, 6:15])
+        if apic:  # the device stores the affine matrices only while transferType == APIC
+            res["c"] = rel_l2(pg[:, 6:15], po[:, 6:15])
     for f, nm in fields:
         a, b = g.download_grid(f), o.download_grid(f)
         if nm == "type":
@@ -80,16 +81,18 @@ def test_stage_by_stage(gpu, oracle_lib, transfer):
     g, o = make_pair(gpu, sc, oracle_lib, obstacles=obs, particles=parts)
     tt = ("PIC", "FLIP", "APIC")[transfer]
     g.stage_advect(sc.dt); o.stage_advect(sc.dt)
-    compare_state(f"stage/{tt}/advect", g, o, [], tol=2e-7)
+    apic = transfer == abi.APIC
+    compare_state(f"stage/{tt}/advect", g, o, [], tol=2e-7, apic=apic)
     g.stage_push_out(); o.stage_push_out()
-    compare_state(f"stage/{tt}/push_out", g, o, [], tol=2e-7)
+    compare_state(f"stage/{tt}/push_out", g, o, [], tol=2e-7, apic=apic)
     # from here on both sides must see identical (fp32-representable) particles
     same = g.download_particles()
     o.upload_particles(same)
     assert np.array_equal(g.download_particle_cells(), o.download_particle_cells())
     g.stage_p2g(); o.stage_p2g()
     assert np.array_equal(g.download_grid(abi.FIELD_PCOUNT), o.download_grid(abi.FIELD_PCOUNT))
-    compare_state(f"stage/{tt}/p2g_wsum", g, o, [(abi.FIELD_WSUM, "wsum"), (abi.FIELD_AVGPNUM, "avgp")], particles=False)
+    # (avgPNum is accumulated by the device inside P2G but by the reference in the classify stage: compared below)
+    compare_state(f"stage/{tt}/p2g_wsum", g, o, [(abi.FIELD_WSUM, "wsum")], particles=False)
     g.stage_classify(sc.dt); o.stage_classify(sc.dt)
     compare_state(f"stage/{tt}/classify", g, o, NO_P, particles=False)
     ig = g.stage_project(sc.dt); io = o.stage_project(sc.dt)
@@ -98,7 +101,7 @@ def test_stage_by_stage(gpu, oracle_lib, transfer):
     g.stage_extrapolate(); o.stage_extrapolate()
     compare_state(f"stage/{tt}/extrapolate", g, o, NO_P, particles=False)
     g.stage_g2p(); o.stage_g2p()
-    compare_state(f"stage/{tt}/g2p", g, o, [], particles=True)
+    compare_state(f"stage/{tt}/g2p", g, o, [], particles=True, apic=apic)
 
 
 @pytest.mark.parametrize("name,n", [("2d", 64), ("3d_flip", 32), ("3d_apic", 32), ("3d_pic", 24)])
@@ -112,7 +115,7 @@ def test_one_step_from_rest(gpu, oracle_lib, name, n):
     assert np.array_equal(g.download_particle_cells(), o.download_particle_cells())
     ig, io = g.step(sc.dt), o.step(sc.dt)
     diag(test=f"one_step/{name}/its", gpu=ig, oracle=io, fluid=int(g.solve_info().fluid_cells))
-    compare_state(f"one_step/{name}", g, o, ALL)
+    compare_state(f"one_step/{name}", g, o, ALL, apic=(name == "3d_apic"))
     assert np.array_equal(g.download_particle_cells(), o.download_particle_cells())
 
 
