@@ -282,13 +282,14 @@ int fsim_create(const FsimGridDesc* desc, fsim_t** out) {
     A(dev_alloc(h, &h->cnt, g.nc));
     A(dev_alloc(h, &h->cell_start, g.nc + 1));
     A(dev_alloc(h, &h->flags, g.nc));
+    A(dev_alloc(h, &h->code, g.nc + 8));
     for (int a = 0; a < 3; a++) { A(dev_alloc(h, &h->u[a], g.nc)); A(dev_alloc(h, &h->u2[a], g.nc)); A(dev_alloc(h, &h->wsum[a], g.nc)); }
     A(dev_alloc(h, &h->dens, g.nc));
     A(dev_alloc(h, &h->p, g.nc)); A(dev_alloc(h, &h->rhs, g.nc)); A(dev_alloc(h, &h->r, g.nc));
     A(dev_alloc(h, &h->s, g.nc)); A(dev_alloc(h, &h->q, g.nc)); A(dev_alloc(h, &h->z, g.nc));
     A(dev_alloc(h, &h->d_obs, FSIM_MAX_OBS));
     A(dev_alloc(h, &h->scal, 1));
-    h->red_blocks = h->sm_count * 4;
+    h->red_blocks = (int)(g.nc / 256 + 2);  // one partial per 256-thread block of the widest solver launch
     A(dev_alloc(h, &h->partials, (size_t)3 * h->red_blocks));
     A(dev_alloc(h, &h->red_counter, 1));
     const int64_t cap0 = desc->particle_capacity > 0 ? desc->particle_capacity : 0;
@@ -326,7 +327,7 @@ int fsim_destroy(fsim_t* h) {
     free_particle_set(h->ps[0]);
     free_particle_set(h->ps[1]);
     cudaFree(h->key); cudaFree(h->rank); cudaFree(h->kill);
-    cudaFree(h->cnt); cudaFree(h->cell_start); cudaFree(h->scan_block); cudaFree(h->flags);
+    cudaFree(h->cnt); cudaFree(h->cell_start); cudaFree(h->scan_block); cudaFree(h->flags); cudaFree(h->code);
     for (int a = 0; a < 3; a++) { cudaFree(h->u[a]); cudaFree(h->u2[a]); cudaFree(h->wsum[a]); }
     cudaFree(h->dens);
     cudaFree(h->p); cudaFree(h->rhs); cudaFree(h->r); cudaFree(h->s); cudaFree(h->q); cudaFree(h->z);

@@ -23,6 +23,10 @@
 #define FL_VALID_SHIFT 3   // 2 bits: extrapolation validity 0 (WATER), 1, 2, 3 (= invalid, the reference's 100)
 #define FL_VALID_MASK 0x18
 
+// 16-bit stencil code of a cell, computed once per pressure solve (pcg.cu rhs_kernel): bits 0-5 WATER neighbours
+// (-x,+x,-y,+y,-z,+z), bits 6-8 number of non-solid neighbours, bit 15 the cell itself is WATER; 0 otherwise
+#define CODE_ACTIVE 0x8000u
+
 struct GridDims {
     int gx, gy, gz;     // cells
     int sy, sz;         // strides (sx = 1): sy = gx, sz = gx*gy
@@ -96,6 +100,7 @@ struct fsim {
     uint32_t *cnt, *cell_start;  // [nc], [nc+1]
     uint32_t* scan_block;        // scan scratch
     uint8_t* flags;
+    uint16_t* code;                        // stencil codes of the current solve
     float *u[3], *u2[3], *wsum[3], *dens;  // u: post-P2G v / accumulators; u2: working v2
     double *p, *rhs, *r, *s, *q, *z;       // pressure + PCG vectors (fp64)
     float* mg_z32;                         // result of the last multigrid cycle (fp32, 0 outside WATER)

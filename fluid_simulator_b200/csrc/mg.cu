@@ -38,7 +38,8 @@ constexpr int COARSE_MAX = 1024;     // the coarsest level fits one CTA
 struct Lv {  // kernel view of a level
     int gx, gy, gz, sy, sz;
     const float *wx, *wy, *wz, *diag;
-    const uint8_t* flags;  // level 0 only
+    const uint8_t* flags;   // level 0 only (hierarchy build)
+    const uint16_t* code;   // level 0 only: stencil codes (fsim_internal.h CODE_ACTIVE)
 };
 
 __device__ __forceinline__ bool cell_of(const Lv& L, int& x, int& y, int& z, int64_t& c) {
@@ -54,17 +55,16 @@ __device__ __forceinline__ bool cell_of(const Lv& L, int& x, int& y, int& z, int
 template <bool FINE>
 __device__ __forceinline__ float row(const Lv& L, int64_t c, const float* __restrict__ x, float* offsum) {
     if (FINE) {
-        const int64_t nb[6] = {c - 1, c + 1, c - L.sy, c + L.sy, c - L.sz, c + L.sz};
-        int ns = 0;
+        const unsigned cd = L.code[c];
         float s = 0.f;
-#pragma unroll
-        for (int k = 0; k < 6; k++) {
-            const int t = L.flags[nb[k]] & FL_TYPE_MASK;
-            ns += (t != FSIM_CELL_SOLID);
-            if (t == FSIM_CELL_WATER) s += x[nb[k]];
-        }
+        if (cd & 1u) s += x[c - 1];
+        if (cd & 2u) s += x[c + 1];
+        if (cd & 4u) s += x[c - L.sy];
+        if (cd & 8u) s += x[c + L.sy];
+        if (cd & 16u) s += x[c - L.sz];
+        if (cd & 32u) s += x[c + L.sz];
         *offsum = s;
-        return (float)ns;
+        return (float)((cd >> 6) & 7u);
     } else {
         *offsum = L.wx[c] * x[c + 1] + L.wx[c - 1] * x[c - 1] + L.wy[c] * x[c + L.sy] + L.wy[c - L.sy] * x[c - L.sy] +
                   L.wz[c] * x[c + L.sz] + L.wz[c - L.sz] * x[c - L.sz];
@@ -74,7 +74,7 @@ __device__ __forceinline__ float row(const Lv& L, int64_t c, const float* __rest
 
 template <bool FINE>
 __device__ __forceinline__ bool active(const Lv& L, int64_t c) {
-    return FINE ? ((L.flags[c] & FL_TYPE_MASK) == FSIM_CELL_WATER) : (L.diag[c] > 0.f);
+    return FINE ? ((L.code[c] & CODE_ACTIVE) != 0) : (L.diag[c] > 0.f);
 }
 
 // first sweep from a zero guess: x = omega * b / diag.  FINE also converts the fp64 CG residual: b = r / scale.
@@ -87,17 +87,7 @@ __global__ void __launch_bounds__(256) mg_first_kernel(Lv L, const double* __res
     if (active<FINE>(L, c)) {
         float bb;
         if (FINE) { bb = (float)(r64[c] * inv_scale); b[c] = bb; } else bb = b[c];
-        float dummy;
-        float d;
-        if (FINE) {
-            // diagonal only: count non-solid neighbours
-            const int64_t nb[6] = {c - 1, c + 1, c - L.sy, c + L.sy, c - L.sz, c + L.sz};
-            int ns = 0;
-#pragma unroll
-            for (int k = 0; k < 6; k++) ns += ((L.flags[nb[k]] & FL_TYPE_MASK) != FSIM_CELL_SOLID);
-            d = (float)ns;
-            (void)dummy;
-        } else d = L.diag[c];
+        const float d = FINE ? (float)((L.code[c] >> 6) & 7u) : L.diag[c];
         v = d > 0.f ? OMEGA * bb / d : 0.f;
     } else if (FINE) b[c] = 0.f;
     xout[c] = v;
@@ -158,16 +148,14 @@ __global__ void __launch_bounds__(256) mg_prolong_jacobi_kernel(Lv L, Lv C, cons
         };
         float d, off = 0.f;
         if (FINE) {
-            const int64_t nb[6] = {c - 1, c + 1, c - L.sy, c + L.sy, c - L.sz, c + L.sz};
-            const int dx[6] = {-1, 1, 0, 0, 0, 0}, dy[6] = {0, 0, -1, 1, 0, 0}, dz[6] = {0, 0, 0, 0, -1, 1};
-            int ns = 0;
-#pragma unroll
-            for (int k = 0; k < 6; k++) {
-                const int t = L.flags[nb[k]] & FL_TYPE_MASK;
-                ns += (t != FSIM_CELL_SOLID);
-                if (t == FSIM_CELL_WATER) off += xc(x + dx[k], y + dy[k], z + dz[k], nb[k]);
-            }
-            d = (float)ns;
+            const unsigned cd = L.code[c];
+            if (cd & 1u) off += xc(x - 1, y, z, c - 1);
+            if (cd & 2u) off += xc(x + 1, y, z, c + 1);
+            if (cd & 4u) off += xc(x, y - 1, z, c - L.sy);
+            if (cd & 8u) off += xc(x, y + 1, z, c + L.sy);
+            if (cd & 16u) off += xc(x, y, z - 1, c - L.sz);
+            if (cd & 32u) off += xc(x, y, z + 1, c + L.sz);
+            d = (float)((cd >> 6) & 7u);
         } else {
             d = L.diag[c];
             const float w0 = L.wx[c - 1], w1 = L.wx[c], w2 = L.wy[c - L.sy], w3 = L.wy[c], w4 = L.wz[c - L.sz], w5 = L.wz[c];
@@ -182,6 +170,156 @@ __global__ void __launch_bounds__(256) mg_prolong_jacobi_kernel(Lv L, Lv C, cons
         v = d > 0.f ? xi + OMEGA * (b[c] - (d * xi - off)) / d : 0.f;
     }
     xout[c] = v;
+}
+
+// ---- level-0 kernels, four consecutive x cells per thread (gx % 4 == 0): 16-byte loads of the iterate, 8-byte loads of
+// the codes; the x neighbours of the inner cells come from registers, only the two outer ones are extra loads ----------
+struct F4 { float v[4]; };
+__device__ __forceinline__ F4 ld4(const float* p) { const float4 t = *reinterpret_cast<const float4*>(p); F4 r; r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w; return r; }
+__device__ __forceinline__ void st4(float* p, const F4& r) { *reinterpret_cast<float4*>(p) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]); }
+__device__ __forceinline__ F4 zero4() { F4 r; r.v[0] = r.v[1] = r.v[2] = r.v[3] = 0.f; return r; }
+
+struct Stencil4 {  // the 7-point neighbourhood of four consecutive cells
+    F4 c, ym, yp, zm, zp;
+    float xl, xr;
+};
+// off-diagonal sum of cell i (0..3) of the group
+__device__ __forceinline__ float off4(const Stencil4& s, int i, unsigned cd) {
+    float o = 0.f;
+    if (cd & 1u) o += i == 0 ? s.xl : s.c.v[i - 1];
+    if (cd & 2u) o += i == 3 ? s.xr : s.c.v[i + 1];
+    if (cd & 4u) o += s.ym.v[i];
+    if (cd & 8u) o += s.yp.v[i];
+    if (cd & 16u) o += s.zm.v[i];
+    if (cd & 32u) o += s.zp.v[i];
+    return o;
+}
+__device__ __forceinline__ bool group_of(const Lv& L, int64_t& c, unsigned cd[4]) {
+    const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y, z = blockIdx.z * blockDim.z + threadIdx.z;
+    if (x >= L.gx || y >= L.gy || z >= L.gz) return false;
+    c = ((int64_t)z * L.gy + y) * L.gx + x;
+    const ushort4 t = *reinterpret_cast<const ushort4*>(L.code + c);
+    cd[0] = t.x; cd[1] = t.y; cd[2] = t.z; cd[3] = t.w;
+    return true;
+}
+__device__ __forceinline__ Stencil4 load_stencil4(const Lv& L, const float* __restrict__ x, int64_t c, const unsigned cd[4]) {
+    Stencil4 s;
+    const unsigned any = cd[0] | cd[1] | cd[2] | cd[3];
+    s.c = ld4(x + c);
+    s.ym = (any & 4u) ? ld4(x + c - L.sy) : zero4();
+    s.yp = (any & 8u) ? ld4(x + c + L.sy) : zero4();
+    s.zm = (any & 16u) ? ld4(x + c - L.sz) : zero4();
+    s.zp = (any & 32u) ? ld4(x + c + L.sz) : zero4();
+    s.xl = (cd[0] & 1u) ? x[c - 1] : 0.f;
+    s.xr = (cd[3] & 2u) ? x[c + 4] : 0.f;
+    return s;
+}
+
+__global__ void __launch_bounds__(256) mg_first4_kernel(Lv L, const double* __restrict__ r64, double inv_scale, float* __restrict__ b,
+                                                        float* __restrict__ xout) {
+    int64_t c; unsigned cd[4];
+    if (!group_of(L, c, cd)) return;
+    F4 bb = zero4(), xo = zero4();
+    if ((cd[0] | cd[1] | cd[2] | cd[3]) & CODE_ACTIVE) {
+        const double2 r0 = *reinterpret_cast<const double2*>(r64 + c), r1 = *reinterpret_cast<const double2*>(r64 + c + 2);
+        const double rr[4] = {r0.x, r0.y, r1.x, r1.y};
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            if (cd[i] & CODE_ACTIVE) {
+                bb.v[i] = (float)(rr[i] * inv_scale);
+                const float d = (float)((cd[i] >> 6) & 7u);
+                xo.v[i] = d > 0.f ? OMEGA * bb.v[i] / d : 0.f;
+            }
+    }
+    st4(b + c, bb);
+    st4(xout + c, xo);
+}
+
+__global__ void __launch_bounds__(256) mg_jacobi4_kernel(Lv L, const float* __restrict__ b, const float* __restrict__ xin,
+                                                         float* __restrict__ xout) {
+    int64_t c; unsigned cd[4];
+    if (!group_of(L, c, cd)) return;
+    F4 xo = zero4();
+    if ((cd[0] | cd[1] | cd[2] | cd[3]) & CODE_ACTIVE) {
+        const Stencil4 s = load_stencil4(L, xin, c, cd);
+        const F4 bb = ld4(b + c);
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            if (cd[i] & CODE_ACTIVE) {
+                const float d = (float)((cd[i] >> 6) & 7u);
+                const float xi = s.c.v[i];
+                xo.v[i] = d > 0.f ? xi + OMEGA * (bb.v[i] - (d * xi - off4(s, i, cd[i]))) / d : 0.f;
+            }
+    }
+    st4(xout + c, xo);
+}
+
+// one thread = two coarse cells in x = a 4x2x2 block of fine cells
+__global__ void __launch_bounds__(256) mg_restrict4_kernel(Lv L, Lv C, const float* __restrict__ b, const float* __restrict__ xf,
+                                                           float* __restrict__ bc) {
+    const int X = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
+    const int Y = blockIdx.y * blockDim.y + threadIdx.y, Z = blockIdx.z * blockDim.z + threadIdx.z;
+    if (X >= C.gx || Y >= C.gy || Z >= C.gz) return;
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 2; k++)
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const int y = 2 * Y + j, z = 2 * Z + k;
+            if (y >= L.gy || z >= L.gz) continue;
+            const int64_t c = ((int64_t)z * L.gy + y) * L.gx + 2 * X;
+            const ushort4 t = *reinterpret_cast<const ushort4*>(L.code + c);
+            const unsigned cd[4] = {t.x, t.y, t.z, t.w};
+            if (!((cd[0] | cd[1] | cd[2] | cd[3]) & CODE_ACTIVE)) continue;
+            const Stencil4 s = load_stencil4(L, xf, c, cd);
+            const F4 bb = ld4(b + c);
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                if (cd[i] & CODE_ACTIVE) {
+                    const float d = (float)((cd[i] >> 6) & 7u);
+                    const float res = bb.v[i] - (d * s.c.v[i] - off4(s, i, cd[i]));
+                    if (i < 2) s0 += res; else s1 += res;
+                }
+        }
+    *reinterpret_cast<float2*>(bc + ((int64_t)Z * C.gy + Y) * C.gx + X) = make_float2(s0, s1);
+}
+
+__global__ void __launch_bounds__(256) mg_prolong_jacobi4_kernel(Lv L, Lv C, const float* __restrict__ b, const float* __restrict__ xin,
+                                                                 const float* __restrict__ ec, float* __restrict__ xout) {
+    int64_t c; unsigned cd[4];
+    if (!group_of(L, c, cd)) return;
+    F4 xo = zero4();
+    const unsigned any = cd[0] | cd[1] | cd[2] | cd[3];
+    if (any & CODE_ACTIVE) {
+        const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+        const int y = blockIdx.y * blockDim.y + threadIdx.y, z = blockIdx.z * blockDim.z + threadIdx.z;
+        Stencil4 s = load_stencil4(L, xin, c, cd);
+        // coarse corrections: the group's parents are (X0, X0+1) in row (y>>1, z>>1); neighbours use their own rows
+        const int X0 = x >> 1;
+        auto prow = [&](int yy, int zz) -> const float* { return ec + ((int64_t)(zz >> 1) * C.gy + (yy >> 1)) * C.gx; };
+        auto add2 = [&](F4& v, const float* row) {
+            const float2 e = *reinterpret_cast<const float2*>(row + X0);
+            v.v[0] += OVER * e.x; v.v[1] += OVER * e.x; v.v[2] += OVER * e.y; v.v[3] += OVER * e.y;
+        };
+        const float* r0 = prow(y, z);
+        add2(s.c, r0);
+        if (any & 4u) add2(s.ym, prow(y - 1, z));
+        if (any & 8u) add2(s.yp, prow(y + 1, z));
+        if (any & 16u) add2(s.zm, prow(y, z - 1));
+        if (any & 32u) add2(s.zp, prow(y, z + 1));
+        if (cd[0] & 1u) s.xl += OVER * r0[X0 - 1];
+        if (cd[3] & 2u) s.xr += OVER * r0[X0 + 2];
+        const F4 bb = ld4(b + c);
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            if (cd[i] & CODE_ACTIVE) {
+                const float d = (float)((cd[i] >> 6) & 7u);
+                const float xi = s.c.v[i];
+                xo.v[i] = d > 0.f ? xi + OMEGA * (bb.v[i] - (d * xi - off4(s, i, cd[i]))) / d : 0.f;
+            }
+    }
+    st4(xout + c, xo);
 }
 
 // Galerkin operator of level 1 from the cell flags: face weight = # WATER-WATER fine connections across the coarse
@@ -281,6 +419,7 @@ Lv view(const fsim* h, const MgLevel* m, int level) {
     v.gx = m->gx; v.gy = m->gy; v.gz = m->gz; v.sy = m->sy; v.sz = m->sz;
     v.wx = m->wx; v.wy = m->wy; v.wz = m->wz; v.diag = m->diag;
     v.flags = level == 0 ? h->flags : nullptr;
+    v.code = level == 0 ? h->code : nullptr;
     return v;
 }
 
@@ -308,6 +447,9 @@ int cycle(fsim* h, int l, bool zero_guess, float** result) {
     const dim3 blk(32, 4, 2);
     const Lv L = view(h, m, l);
     const bool fine = l == 0;
+    const bool v4 = fine && (m->gx % 4 == 0);  // float4 path; then the coarse gx is even (float2 stores / loads)
+    const dim3 blk4(32, 4, 2);
+    const dim3 grd4(div_up(m->gx, 4 * 32), div_up(m->gy, 4), div_up(m->gz, 2));
     if (l == (int)h->mg.size() - 1) {  // coarsest
         KScope ks(h, K_MG);
         mg_coarse_kernel<<<1, COARSE_MAX, 0, h->stream>>>(L, m->b, m->xa, m->xa, zero_guess ? 1 : 0, COARSE_SWEEPS);
@@ -322,10 +464,12 @@ int cycle(fsim* h, int l, bool zero_guess, float** result) {
         KScope ks(h, K_MG, PRE);
         for (int s = 0; s < PRE; s++) {
             if (s == 0 && zero_guess) {
-                if (fine) mg_first_kernel<true><<<grid_of(m, blk), blk, 0, h->stream>>>(L, h->r, inv_scale, m->b, cur);
+                if (v4) mg_first4_kernel<<<grd4, blk4, 0, h->stream>>>(L, h->r, inv_scale, m->b, cur);
+                else if (fine) mg_first_kernel<true><<<grid_of(m, blk), blk, 0, h->stream>>>(L, h->r, inv_scale, m->b, cur);
                 else mg_first_kernel<false><<<grid_of(m, blk), blk, 0, h->stream>>>(L, nullptr, 0.0, m->b, cur);
             } else {
-                if (fine) mg_jacobi_kernel<true><<<grid_of(m, blk), blk, 0, h->stream>>>(L, m->b, cur, oth);
+                if (v4) mg_jacobi4_kernel<<<grd4, blk4, 0, h->stream>>>(L, m->b, cur, oth);
+                else if (fine) mg_jacobi_kernel<true><<<grid_of(m, blk), blk, 0, h->stream>>>(L, m->b, cur, oth);
                 else mg_jacobi_kernel<false><<<grid_of(m, blk), blk, 0, h->stream>>>(L, m->b, cur, oth);
                 float* t = cur; cur = oth; oth = t;
             }
@@ -333,7 +477,8 @@ int cycle(fsim* h, int l, bool zero_guess, float** result) {
     }
     {
         KScope ks(h, K_MG);
-        if (fine) mg_restrict_kernel<true><<<grid_of(mc, blk), blk, 0, h->stream>>>(L, C, m->b, cur, mc->b);
+        if (v4) mg_restrict4_kernel<<<dim3(div_up(mc->gx, 2 * 32), div_up(mc->gy, 4), div_up(mc->gz, 2)), blk4, 0, h->stream>>>(L, C, m->b, cur, mc->b);
+        else if (fine) mg_restrict_kernel<true><<<grid_of(mc, blk), blk, 0, h->stream>>>(L, C, m->b, cur, mc->b);
         else mg_restrict_kernel<false><<<grid_of(mc, blk), blk, 0, h->stream>>>(L, C, m->b, cur, mc->b);
     }
     float* ec = nullptr;
@@ -347,11 +492,13 @@ int cycle(fsim* h, int l, bool zero_guess, float** result) {
     }
     {
         KScope ks(h, K_MG, POST);
-        if (fine) mg_prolong_jacobi_kernel<true><<<grid_of(m, blk), blk, 0, h->stream>>>(L, C, m->b, cur, mc->xa, oth);
+        if (v4) mg_prolong_jacobi4_kernel<<<grd4, blk4, 0, h->stream>>>(L, C, m->b, cur, mc->xa, oth);
+        else if (fine) mg_prolong_jacobi_kernel<true><<<grid_of(m, blk), blk, 0, h->stream>>>(L, C, m->b, cur, mc->xa, oth);
         else mg_prolong_jacobi_kernel<false><<<grid_of(m, blk), blk, 0, h->stream>>>(L, C, m->b, cur, mc->xa, oth);
         { float* t = cur; cur = oth; oth = t; }
         for (int s = 1; s < POST; s++) {
-            if (fine) mg_jacobi_kernel<true><<<grid_of(m, blk), blk, 0, h->stream>>>(L, m->b, cur, oth);
+            if (v4) mg_jacobi4_kernel<<<grd4, blk4, 0, h->stream>>>(L, m->b, cur, oth);
+            else if (fine) mg_jacobi_kernel<true><<<grid_of(m, blk), blk, 0, h->stream>>>(L, m->b, cur, oth);
             else mg_jacobi_kernel<false><<<grid_of(m, blk), blk, 0, h->stream>>>(L, m->b, cur, oth);
             float* t = cur; cur = oth; oth = t;
         }

@@ -2,16 +2,17 @@
 //
 // Same linear system and stopping rule as the reference (RHS :79-89, 7-point matrix :40-77, early-out when
 // sum(rhs^2) < 1e-7 :254-258, stop when ||r||_inf < residualTolerance :276-281, NaN guard :271), but
-//   * matrix-free: coefficients are recomputed from the 1-byte cell flags inside the SpMV, the reference's
-//     compacted fluid-cell list / AMatrixRow array / cell.id indirection do not exist;
-//   * the sequential MIC(0) preconditioner (:91-163) is replaced by a parallel one (multigrid V-cycle, mg.cu;
-//     or diagonal scaling) -- equivalence is on the converged pressure field;
+//   * matrix-free: the row of a cell is a 16-bit code (6-bit WATER-neighbour mask + #non-solid neighbours) computed
+//     once per solve from the cell flags; the reference's compacted fluid-cell list / AMatrixRow array / cell.id
+//     indirection do not exist;
+//   * the sequential MIC(0) preconditioner (:91-163) is replaced by a parallel one (multigrid cycle, mg.cu; or diagonal
+//     scaling with FSIM_PRECOND=jacobi) -- equivalence is on the converged pressure field;
 //   * CG vectors (p, r, s, q) are fp64: with |p| ~ 1e4 and a 1e-6 absolute tolerance an fp32 recurrence stalls
 //     (SURVEY.md §7 "hard parts"); the preconditioner works in fp32;
-//   * SpMV is fused with the s.q reduction, the x/r update with ||r||_inf and (diagonal case) z.r; reductions are
-//     two-level (warp shuffle -> block -> fixed-order last-block sum) => deterministic, no fp64 atomics;
-//   * all scalars (sigma, alpha, beta, done flag, iteration count) stay on the device; the host only polls the
-//     done flag every few iterations.
+//   * SpMV is fused with the s.q reduction, the x/r update with ||r||_inf and (diagonal case) z.r; every thread owns two
+//     consecutive cells (16-byte loads of the fp64 vectors); reductions are warp shuffle -> block -> fixed-order
+//     last-block sum => deterministic, no fp64 atomics;
+//   * all scalars (sigma, alpha, beta, done flag, iteration count) stay on the device; the host only polls the done flag.
 #include "fsim_internal.h"
 
 int mg_apply(fsim* h);  // z = M^-1 r   (mg.cu)
@@ -19,11 +20,13 @@ bool mg_enabled(const fsim* h);
 
 namespace {
 
-constexpr int PT = 256;  // threads per block of the persistent solver kernels
+constexpr int PT = 256;  // threads per block
+constexpr int CV = 2;    // cells per thread in the vector kernels
 
 struct PcgArgs {
     GridDims g;
     const uint8_t* flags;
+    uint16_t* code;
     const float* u2[3];
     const float* dens;
     double *p, *rhs, *r, *s, *q, *z;
@@ -47,8 +50,8 @@ __device__ __forceinline__ double warp_max(double v) {
     return v;
 }
 
-// block-level reduction of up to 3 values (sum, sum, max); returns true in exactly one block (the last to arrive),
-// whose thread 0 then holds the grid-wide totals in out[].
+// block reduction of NS sums followed by NM maxima; the last block to arrive folds all per-block partials in a fixed
+// order (bitwise reproducible) and its thread 0 returns true with the grid-wide totals in out[].
 template <int NS, int NM>
 __device__ __forceinline__ bool grid_reduce(double* vals, double* partials, unsigned int* counter, double* out) {
     __shared__ double sh[NS + NM][PT / 32];
@@ -74,52 +77,62 @@ __device__ __forceinline__ bool grid_reduce(double* vals, double* partials, unsi
     __syncthreads();
     if (!last) return false;
     __threadfence();
-    // fixed-order final sum by one warp => bitwise reproducible
-    if (w == 0) {
+    double tot[NS + NM];
+#pragma unroll
+    for (int k = 0; k < NS + NM; k++) {
+        double v = 0.0;
+        for (unsigned i = threadIdx.x; i < gridDim.x; i += PT) {
+            const double x = __ldcg(partials + (size_t)k * gridDim.x + i);
+            v = k < NS ? v + x : fmax(v, x);
+        }
+        tot[k] = k < NS ? warp_sum(v) : warp_max(v);
+    }
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < NS + NM; k++) sh[k][w] = tot[k];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
 #pragma unroll
         for (int k = 0; k < NS + NM; k++) {
-            double v = k < NS ? 0.0 : 0.0;
-            for (unsigned i = lane; i < gridDim.x; i += 32) {
-                const double x = ((volatile double*)partials)[(size_t)k * gridDim.x + i];
-                v = k < NS ? v + x : fmax(v, x);
-            }
-            v = k < NS ? warp_sum(v) : warp_max(v);
-            if (lane == 0) out[k] = v;
+            double v = sh[k][0];
+            for (int i = 1; i < PT / 32; i++) v = k < NS ? v + sh[k][i] : fmax(v, sh[k][i]);
+            out[k] = v;
         }
+        return true;
     }
-    return threadIdx.x == 0;
+    return false;
 }
 
-__device__ __forceinline__ int type_of(const uint8_t* flags, int64_t c) { return flags[c] & FL_TYPE_MASK; }
+// stencil code of a cell (calculateAMatrix, bridsonSolverGrid.cpp:40-77): bits 0-5 WATER neighbours (-x,+x,-y,+y,-z,+z),
+// bits 6-8 number of non-solid neighbours (the diagonal / scale), bit 15 the cell itself is WATER.  0 for other cells.
+__device__ __forceinline__ int code_ns(unsigned c) { return (c >> 6) & 7; }
 
-// diagonal / neighbour structure of row c (calculateAMatrix, bridsonSolverGrid.cpp:40-77): returns #non-solid nbrs and a
-// 6-bit mask of WATER neighbours (-x,+x,-y,+y,-z,+z).  WATER cells are always interior, so no bounds checks.
-__device__ __forceinline__ int row_structure(const PcgArgs& a, int64_t c, unsigned* water) {
-    const int64_t nb[6] = {c - 1, c + 1, c - a.g.sy, c + a.g.sy, c - a.g.sz, c + a.g.sz};
-    int nonsolid = 0;
-    unsigned wm = 0;
-#pragma unroll
-    for (int k = 0; k < 6; k++) {
-        const int t = type_of(a.flags, nb[k]);
-        nonsolid += (t != FSIM_CELL_SOLID);
-        wm |= (t == FSIM_CELL_WATER) ? (1u << k) : 0u;
-    }
-    *water = wm;
-    return nonsolid;
-}
-
-// calculateRHS (:79-89) + p = 0, r = rhs + sum(rhs^2) (:254-258)
+// calculateRHS (:79-89) + p = 0, r = rhs + sum(rhs^2) (:254-258) + stencil codes; one thread per cell
 __global__ void __launch_bounds__(PT) rhs_kernel(PcgArgs a) {
     double acc[2] = {0.0, 0.0};
-    for (int64_t c = (int64_t)blockIdx.x * PT + threadIdx.x; c < a.g.nc; c += (int64_t)gridDim.x * PT) {
+    const int64_t c = (int64_t)blockIdx.x * PT + threadIdx.x;
+    if (c < a.g.nc) {
         double rhs = 0.0;
-        if (type_of(a.flags, c) == FSIM_CELL_WATER) {
+        unsigned code = 0;
+        if ((a.flags[c] & FL_TYPE_MASK) == FSIM_CELL_WATER) {  // WATER cells are interior: all six neighbours exist
+            const int64_t nb[6] = {c - 1, c + 1, c - a.g.sy, c + a.g.sy, c - a.g.sz, c + a.g.sz};
+            unsigned wm = 0, ns = 0;
+#pragma unroll
+            for (int k = 0; k < 6; k++) {
+                const int t = a.flags[nb[k]] & FL_TYPE_MASK;
+                ns += (t != FSIM_CELL_SOLID);
+                wm |= (t == FSIM_CELL_WATER) ? (1u << k) : 0u;
+            }
+            code = CODE_ACTIVE | (ns << 6) | wm;
             const double div = ((double)a.u2[0][c] + (double)a.u2[1][c] + (double)a.u2[2][c]) - (double)a.u2[0][c - 1] -
                                (double)a.u2[1][c - a.g.sy] - (double)a.u2[2][c - a.g.sz];
             rhs = -a.inv_h * div + (a.pressure_enabled ? ((double)a.dens[c] - a.avg_pressure) * a.pressure_k : 0.0);
-            acc[0] += rhs * rhs;
-            acc[1] += 1.0;
+            acc[0] = rhs * rhs;
+            acc[1] = 1.0;
         }
+        a.code[c] = (uint16_t)code;
         a.rhs[c] = rhs;
         a.r[c] = rhs;
         a.p[c] = 0.0;
@@ -137,58 +150,98 @@ __global__ void __launch_bounds__(PT) rhs_kernel(PcgArgs a) {
     }
 }
 
-// diagonal preconditioner: z = r / A_ii ; s = z ; sigma = z.r   (first application, :262-265)
-__global__ void __launch_bounds__(PT) jacobi_init_kernel(PcgArgs a) {
-    if (a.sc->done) return;
-    double acc[1] = {0.0};
-    for (int64_t c = (int64_t)blockIdx.x * PT + threadIdx.x; c < a.g.nc; c += (int64_t)gridDim.x * PT) {
-        double z = 0.0;
-        if (type_of(a.flags, c) == FSIM_CELL_WATER) {
-            unsigned wm;
-            const int ns = row_structure(a, c, &wm);
-            const double r = a.r[c];
-            z = ns > 0 ? r / (a.scale * ns) : r;
-            acc[0] += z * r;
-        }
-        a.z[c] = z;
-        a.s[c] = z;
-    }
-    double out[1];
-    if (grid_reduce<1, 0>(acc, a.partials, a.counter, out)) a.sc->sigma = out[0];
+__device__ __forceinline__ double jacobi_z(const PcgArgs& a, unsigned code, double r) {
+    const int ns = code_ns(code);
+    return ns > 0 ? r / (a.scale * ns) : r;
 }
 
-// generic first application: s = z ; sigma = z.r  (z supplied by the multigrid preconditioner)
+// first preconditioner application (:262-265): s = z ; sigma = z.r, with z = r / A_ii (diagonal) or the multigrid result
+template <bool JACOBI>
 __global__ void __launch_bounds__(PT) start_kernel(PcgArgs a) {
     if (a.sc->done) return;
     double acc[1] = {0.0};
-    for (int64_t c = (int64_t)blockIdx.x * PT + threadIdx.x; c < a.g.nc; c += (int64_t)gridDim.x * PT) {
-        const double z = (double)a.z32[c];
+    const int64_t c0 = ((int64_t)blockIdx.x * PT + threadIdx.x) * CV;
+#pragma unroll
+    for (int k = 0; k < CV; k++) {
+        const int64_t c = c0 + k;
+        if (c >= a.g.nc) break;
+        const unsigned code = a.code[c];
+        double z = 0.0;
+        if (code & CODE_ACTIVE) {
+            const double r = a.r[c];
+            z = JACOBI ? jacobi_z(a, code, r) : (double)a.z32[c];
+            acc[0] += z * r;
+        }
+        if (JACOBI) a.z[c] = z;
         a.s[c] = z;
-        acc[0] += z * a.r[c];
     }
     double out[1];
     if (grid_reduce<1, 0>(acc, a.partials, a.counter, out)) a.sc->sigma = out[0];
 }
 
-// q = A s fused with s.q  (applyAMatrix :165-198 + dotProduct :200-214)
+// q = A s fused with s.q  (applyAMatrix :165-198 + dotProduct :200-214); VEC: 16-byte loads, two cells per thread
+template <bool VEC>
 __global__ void __launch_bounds__(PT) spmv_kernel(PcgArgs a) {
     if (a.sc->done) return;
     double acc[1] = {0.0};
-    for (int64_t c = (int64_t)blockIdx.x * PT + threadIdx.x; c < a.g.nc; c += (int64_t)gridDim.x * PT) {
-        if (type_of(a.flags, c) != FSIM_CELL_WATER) continue;
-        unsigned wm;
-        const int ns = row_structure(a, c, &wm);
-        const double sc = a.s[c];
-        double nsum = 0.0;
-        if (wm & 1u) nsum += a.s[c - 1];
-        if (wm & 2u) nsum += a.s[c + 1];
-        if (wm & 4u) nsum += a.s[c - a.g.sy];
-        if (wm & 8u) nsum += a.s[c + a.g.sy];
-        if (wm & 16u) nsum += a.s[c - a.g.sz];
-        if (wm & 32u) nsum += a.s[c + a.g.sz];
-        const double q = a.scale * ((double)ns * sc - nsum);
-        a.q[c] = q;
-        acc[0] += sc * q;
+    const int64_t c = ((int64_t)blockIdx.x * PT + threadIdx.x) * CV;
+    const int64_t sy = a.g.sy, sz = a.g.sz;
+    if (VEC) {
+        if (c < a.g.nc) {  // nc is even in this path
+            const ushort2 cd = *reinterpret_cast<const ushort2*>(a.code + c);
+            const unsigned c0 = cd.x, c1 = cd.y;
+            if ((c0 | c1) & CODE_ACTIVE) {
+                const double2 sc = *reinterpret_cast<const double2*>(a.s + c);
+                const unsigned any = c0 | c1;
+                double2 ym = {0, 0}, yp = {0, 0}, zm = {0, 0}, zp = {0, 0};
+                if (any & 4u) ym = *reinterpret_cast<const double2*>(a.s + c - sy);
+                if (any & 8u) yp = *reinterpret_cast<const double2*>(a.s + c + sy);
+                if (any & 16u) zm = *reinterpret_cast<const double2*>(a.s + c - sz);
+                if (any & 32u) zp = *reinterpret_cast<const double2*>(a.s + c + sz);
+                const double xl = (c0 & 1u) ? a.s[c - 1] : 0.0, xr = (c1 & 2u) ? a.s[c + 2] : 0.0;
+                double2 q = {0, 0};
+                if (c0 & CODE_ACTIVE) {
+                    double n = xl;
+                    if (c0 & 2u) n += sc.y;
+                    if (c0 & 4u) n += ym.x;
+                    if (c0 & 8u) n += yp.x;
+                    if (c0 & 16u) n += zm.x;
+                    if (c0 & 32u) n += zp.x;
+                    q.x = a.scale * ((double)code_ns(c0) * sc.x - n);
+                    acc[0] += sc.x * q.x;
+                }
+                if (c1 & CODE_ACTIVE) {
+                    double n = xr;
+                    if (c1 & 1u) n += sc.x;
+                    if (c1 & 4u) n += ym.y;
+                    if (c1 & 8u) n += yp.y;
+                    if (c1 & 16u) n += zm.y;
+                    if (c1 & 32u) n += zp.y;
+                    q.y = a.scale * ((double)code_ns(c1) * sc.y - n);
+                    acc[0] += sc.y * q.y;
+                }
+                *reinterpret_cast<double2*>(a.q + c) = q;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < CV; k++) {
+            const int64_t cc = c + k;
+            if (cc >= a.g.nc) break;
+            const unsigned cd = a.code[cc];
+            if (!(cd & CODE_ACTIVE)) continue;
+            const double sc = a.s[cc];
+            double n = 0.0;
+            if (cd & 1u) n += a.s[cc - 1];
+            if (cd & 2u) n += a.s[cc + 1];
+            if (cd & 4u) n += a.s[cc - sy];
+            if (cd & 8u) n += a.s[cc + sy];
+            if (cd & 16u) n += a.s[cc - sz];
+            if (cd & 32u) n += a.s[cc + sz];
+            const double q = a.scale * ((double)code_ns(cd) * sc - n);
+            a.q[cc] = q;
+            acc[0] += sc * q;
+        }
     }
     double out[1];
     if (grid_reduce<1, 0>(acc, a.partials, a.counter, out)) a.sc->sq = out[0];
@@ -201,17 +254,20 @@ __global__ void __launch_bounds__(PT) update_kernel(PcgArgs a) {
     const double alpha = a.sc->sigma / a.sc->sq;
     const bool bad = alpha != alpha;  // NaN => the reference breaks before touching p (:271-272)
     double acc[2] = {0.0, 0.0};      // [0] = z.r (sum), [1] = max |r|
+    const int64_t c0 = ((int64_t)blockIdx.x * PT + threadIdx.x) * CV;
     if (!bad) {
-        for (int64_t c = (int64_t)blockIdx.x * PT + threadIdx.x; c < a.g.nc; c += (int64_t)gridDim.x * PT) {
-            if (type_of(a.flags, c) != FSIM_CELL_WATER) continue;
+#pragma unroll
+        for (int k = 0; k < CV; k++) {
+            const int64_t c = c0 + k;
+            if (c >= a.g.nc) break;
+            const unsigned code = a.code[c];
+            if (!(code & CODE_ACTIVE)) continue;
             a.p[c] += alpha * a.s[c];
             const double r = a.r[c] - alpha * a.q[c];
             a.r[c] = r;
             acc[1] = fmax(acc[1], fabs(r));
             if (JACOBI) {
-                unsigned wm;
-                const int ns = row_structure(a, c, &wm);
-                const double z = ns > 0 ? r / (a.scale * ns) : r;
+                const double z = jacobi_z(a, code, r);
                 a.z[c] = z;
                 acc[0] += z * r;
             }
@@ -230,7 +286,7 @@ __global__ void __launch_bounds__(PT) update_kernel(PcgArgs a) {
                 a.sc->done = 1;
                 a.sc->iterations = a.it;
             } else if (a.it + 1 >= a.max_it) {
-                a.sc->done = 2;  // iteration cap; the direction update below is skipped like the loop exit would
+                a.sc->done = 2;  // iteration cap; the direction update is skipped like the loop exit would
                 a.sc->iterations = a.max_it;
             }
         }
@@ -241,29 +297,32 @@ __global__ void __launch_bounds__(PT) update_kernel(PcgArgs a) {
 __global__ void __launch_bounds__(PT) dot_zr_kernel(PcgArgs a) {
     if (a.sc->done) return;
     double acc[1] = {0.0};
-    for (int64_t c = (int64_t)blockIdx.x * PT + threadIdx.x; c < a.g.nc; c += (int64_t)gridDim.x * PT)
-        acc[0] += (double)a.z32[c] * a.r[c];
+    const int64_t c0 = ((int64_t)blockIdx.x * PT + threadIdx.x) * CV;
+#pragma unroll
+    for (int k = 0; k < CV; k++) {
+        const int64_t c = c0 + k;
+        if (c >= a.g.nc) break;
+        if (a.code[c] & CODE_ACTIVE) acc[0] += (double)a.z32[c] * a.r[c];
+    }
     double out[1];
     if (grid_reduce<1, 0>(acc, a.partials, a.counter, out)) a.sc->sigma_new = out[0];
 }
 
-// beta = sigma'/sigma ; s = z + beta s ; sigma = sigma'   (:284-289)
+// beta = sigma'/sigma ; s = z + beta s   (:284-289); sigma <- sigma' is published by sigma_kernel afterwards
 __global__ void __launch_bounds__(PT) direction_kernel(PcgArgs a) {
     if (a.sc->done) return;
     const double beta = a.sc->sigma_new / a.sc->sigma;
-    for (int64_t c = (int64_t)blockIdx.x * PT + threadIdx.x; c < a.g.nc; c += (int64_t)gridDim.x * PT) {
-        if (type_of(a.flags, c) != FSIM_CELL_WATER) continue;
+    const int64_t c0 = ((int64_t)blockIdx.x * PT + threadIdx.x) * CV;
+#pragma unroll
+    for (int k = 0; k < CV; k++) {
+        const int64_t c = c0 + k;
+        if (c >= a.g.nc) break;
+        if (!(a.code[c] & CODE_ACTIVE)) continue;
         a.s[c] = a.s[c] * beta + (a.z32 ? (double)a.z32[c] : a.z[c]);
     }
-    // the last block to finish publishes sigma = sigma' (every block has read both scalars before arriving)
-    __shared__ bool last;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        last = atomicInc(a.counter, gridDim.x - 1) == gridDim.x - 1;
-    }
-    __syncthreads();
-    if (last && threadIdx.x == 0) a.sc->sigma = a.sc->sigma_new;
+}
+__global__ void sigma_kernel(PcgScalars* sc) {
+    if (!sc->done) sc->sigma = sc->sigma_new;
 }
 
 }  // namespace
@@ -271,7 +330,7 @@ __global__ void __launch_bounds__(PT) direction_kernel(PcgArgs a) {
 int k_project(fsim* h, double dt, int* iterations) {
     const GridDims& g = h->g;
     PcgArgs a;
-    a.g = g; a.flags = h->flags;
+    a.g = g; a.flags = h->flags; a.code = h->code;
     for (int ax = 0; ax < 3; ax++) a.u2[ax] = h->u2[ax];
     a.dens = h->dens;
     a.p = h->p; a.rhs = h->rhs; a.r = h->r; a.s = h->s; a.q = h->q; a.z = h->z;
@@ -286,10 +345,12 @@ int k_project(fsim* h, double dt, int* iterations) {
     a.it = 0;
     a.z32 = nullptr;
     h->mg_inv_scale = 1.0 / a.scale;
-    const int nb = h->red_blocks;
+    const int nb1 = div_up(g.nc, PT);        // one cell per thread
+    const int nbv = div_up(g.nc, PT * CV);   // CV cells per thread
+    const bool vec = (g.gx % 2 == 0) && (g.nc % 2 == 0);
     const bool use_mg = mg_enabled(h);
 
-    { KScope ks(h, K_RHS); rhs_kernel<<<nb, PT, 0, h->stream>>>(a); }
+    { KScope ks(h, K_RHS); rhs_kernel<<<nb1, PT, 0, h->stream>>>(a); }
     if (use_mg) {
         int rc = mg_build(h);
         if (rc) return rc;
@@ -297,10 +358,10 @@ int k_project(fsim* h, double dt, int* iterations) {
         if (rc) return rc;
         a.z32 = h->mg_z32;
         KScope ks(h, K_PCG_INIT);
-        start_kernel<<<nb, PT, 0, h->stream>>>(a);
+        start_kernel<false><<<nbv, PT, 0, h->stream>>>(a);
     } else {
         KScope ks(h, K_PCG_INIT);
-        jacobi_init_kernel<<<nb, PT, 0, h->stream>>>(a);
+        start_kernel<true><<<nbv, PT, 0, h->stream>>>(a);
     }
     FSIM_CHECK_LAUNCH(h);
 
@@ -308,19 +369,27 @@ int k_project(fsim* h, double dt, int* iterations) {
     int done = 0;
     for (int it = 0; it < a.max_it && !done; it++) {
         a.it = it;
-        { KScope ks(h, K_SPMV); spmv_kernel<<<nb, PT, 0, h->stream>>>(a); }
+        {
+            KScope ks(h, K_SPMV);
+            if (vec) spmv_kernel<true><<<nbv, PT, 0, h->stream>>>(a);
+            else spmv_kernel<false><<<nbv, PT, 0, h->stream>>>(a);
+        }
         if (use_mg) {
-            { KScope ks(h, K_UPDATE); update_kernel<false><<<nb, PT, 0, h->stream>>>(a); }
+            { KScope ks(h, K_UPDATE); update_kernel<false><<<nbv, PT, 0, h->stream>>>(a); }
             int rc = mg_apply(h);
             if (rc) return rc;
             a.z32 = h->mg_z32;
             KScope ks(h, K_UPDATE);
-            dot_zr_kernel<<<nb, PT, 0, h->stream>>>(a);
+            dot_zr_kernel<<<nbv, PT, 0, h->stream>>>(a);
         } else {
             KScope ks(h, K_UPDATE);
-            update_kernel<true><<<nb, PT, 0, h->stream>>>(a);
+            update_kernel<true><<<nbv, PT, 0, h->stream>>>(a);
         }
-        { KScope ks(h, K_DIRECTION); direction_kernel<<<nb, PT, 0, h->stream>>>(a); }
+        {
+            KScope ks(h, K_DIRECTION, 2);
+            direction_kernel<<<nbv, PT, 0, h->stream>>>(a);
+            sigma_kernel<<<1, 1, 0, h->stream>>>(h->scal);
+        }
         if ((it + 1) % poll == 0 || it + 1 == a.max_it) {
             FSIM_CUDA(h, cudaMemcpyAsync(h->scal_host, h->scal, sizeof(PcgScalars), cudaMemcpyDeviceToHost, h->stream));
             FSIM_CUDA(h, cudaStreamSynchronize(h->stream));
