@@ -274,6 +274,10 @@ int fsim_create(const FsimGridDesc* desc, fsim_t** out) {
     h->launches = h->last_step_launches = 0; h->last_step_ms = 0;
     h->prof_mask = 0;
     h->mg_z32 = nullptr; h->mg_inv_scale = 1.0;
+    h->pcg_graph = nullptr; h->pcg_graph_launches = 0; memset(h->pcg_graph_class, 0, sizeof(h->pcg_graph_class));
+    { const char* e = getenv("FSIM_NO_GRAPH"); h->use_graph = !(e && e[0] == '1'); }
+    { const char* e = getenv("FSIM_NO_WARM_START"); h->warm_start = !(e && e[0] == '1'); }
+    h->status_host = nullptr; h->status_dev = nullptr;
     { const char* e = getenv("FSIM_PRECOND"); h->use_mg = !(e && strcmp(e, "jacobi") == 0); }
     memset(h->prof_ms, 0, sizeof(h->prof_ms)); memset(h->prof_n, 0, sizeof(h->prof_n)); memset(h->launch_n, 0, sizeof(h->launch_n));
 
@@ -300,6 +304,10 @@ int fsim_create(const FsimGridDesc* desc, fsim_t** out) {
     if (!rc && cudaMalloc(&h->stage, h->stage_bytes) != cudaSuccess) rc = fsim_fail(h, FSIM_ERR_CUDA, "staging alloc failed");
     h->scal_host = nullptr;
     if (!rc && cudaMallocHost((void**)&h->scal_host, sizeof(PcgScalars)) != cudaSuccess) rc = fsim_fail(h, FSIM_ERR_CUDA, "pinned alloc failed");
+    if (!rc && (cudaHostAlloc((void**)&h->status_host, sizeof(PcgHostStatus), cudaHostAllocMapped) != cudaSuccess ||
+                cudaHostGetDevicePointer((void**)&h->status_dev, (void*)h->status_host, 0) != cudaSuccess))
+        rc = fsim_fail(h, FSIM_ERR_CUDA, "mapped status alloc failed");
+    if (!rc) { h->status_host->done = 0; h->status_host->it_done = 0; }
     for (int i = 0; i < 16 && !rc; i++)
         if (cudaEventCreate(&h->ev[i]) != cudaSuccess) rc = fsim_fail(h, FSIM_ERR_CUDA, "event create failed");
     if (!rc && cap0 > 0) rc = ensure_capacity(h, cap0);
@@ -336,6 +344,8 @@ int fsim_destroy(fsim_t* h) {
     for (const ProfRec& r : h->prof_recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     for (cudaEvent_t e : h->prof_free) cudaEventDestroy(e);
     if (h->scal_host) cudaFreeHost(h->scal_host);
+    if (h->status_host) cudaFreeHost((void*)h->status_host);
+    if (h->pcg_graph) cudaGraphExecDestroy(h->pcg_graph);
     for (int i = 0; i < 16; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     cudaStreamDestroy(h->stream);
     delete h;
@@ -682,7 +692,7 @@ int fsim_get_last_step_stats(const fsim_t* hc, double* device_ms, int64_t* kerne
 }
 
 static const char* const kKernelNames[K_COUNT] = {"advect", "bin", "scan", "reorder", "p2g", "classify", "finalize", "rhs",
-                                                    "pcg_init", "spmv", "pcg_update", "pcg_direction", "mg", "pressure_apply",
+                                                    "pcg_init", "spmv", "pcg_update", "pcg_direction", "mg", "mg_level1", "mg_coarse", "pressure_apply",
                                                     "extrapolate", "g2p", "gfx", "memset"};
 
 int fsim_kernel_class_count(void) { return K_COUNT; }

@@ -55,10 +55,17 @@ struct ParticleSet {
     uint32_t* id; // optional persistent ids (tests / facade)
 };
 
-struct PcgScalars {  // device-resident scalars of the solve
-    double sigma, sigma_new, sq, rmax, rhs_sumsq;
+struct PcgScalars {  // device-resident scalars of the solve (kernels read their parameters here so that the captured
+                     // CUDA graph of one PCG iteration never has to be re-instantiated)
+    double sigma, sigma_new, sq, rmax, rhs_sumsq, r0max;
+    double scale, inv_scale, tol;   // dt/(rho h^2), its inverse, residualTolerance
+    int max_it, it;                 // iteration cap, index of the iteration in flight
     int iterations, done, early_out, nan_break;
     long long fluid_cells;
+};
+struct PcgHostStatus {  // pinned, device-mapped: written by the device, polled by the host without a stream sync
+    volatile int done;
+    volatile int it_done;
 };
 
 struct MgLevel;
@@ -66,7 +73,7 @@ struct MgLevel;
 // kernel classes for launch counting and the optional per-launch CUDA-event profiling (fsim_profile_*)
 enum KernelId {
     K_ADVECT = 0, K_BIN, K_SCAN, K_REORDER, K_P2G, K_CLASSIFY, K_FINALIZE, K_RHS, K_PCG_INIT, K_SPMV, K_UPDATE,
-    K_DIRECTION, K_MG, K_APPLY, K_EXTRAP, K_G2P, K_GFX, K_MEMSET, K_COUNT
+    K_DIRECTION, K_MG, K_MG1, K_MG2, K_APPLY, K_EXTRAP, K_G2P, K_GFX, K_MEMSET, K_COUNT
 };
 struct ProfRec { int kid; cudaEvent_t e0, e1; };
 
@@ -109,6 +116,12 @@ struct fsim {
     std::vector<MgLevel*> mg;
     PcgScalars* scal;                      // device
     PcgScalars* scal_host;                 // pinned
+    PcgHostStatus* status_host;            // pinned + mapped
+    PcgHostStatus* status_dev;             // device alias of status_host
+    cudaGraphExec_t pcg_graph;             // one PCG iteration (SpMV, update, multigrid cycle, dot, direction)
+    int pcg_graph_launches;                // kernels per graph launch
+    int pcg_graph_class[K_COUNT];          // ... per kernel class
+    bool use_graph, warm_start;
     double* partials;                      // reduction partials [3][max_blocks]
     unsigned int* red_counter;
     int red_blocks;

@@ -79,9 +79,11 @@ __device__ __forceinline__ bool active(const Lv& L, int64_t c) {
 
 // first sweep from a zero guess: x = omega * b / diag.  FINE also converts the fp64 CG residual: b = r / scale.
 template <bool FINE>
-__global__ void __launch_bounds__(256) mg_first_kernel(Lv L, const double* __restrict__ r64, double inv_scale, float* __restrict__ b,
-                                                        float* __restrict__ xout) {
+__global__ void __launch_bounds__(256) mg_first_kernel(Lv L, const double* __restrict__ r64, const PcgScalars* __restrict__ sc,
+                                                        float* __restrict__ b, float* __restrict__ xout) {
     int x, y, z; int64_t c;
+    if (sc->done) return;
+    const double inv_scale = sc->inv_scale;
     if (!cell_of(L, x, y, z, c)) return;
     float v = 0.f;
     if (active<FINE>(L, c)) {
@@ -95,8 +97,9 @@ __global__ void __launch_bounds__(256) mg_first_kernel(Lv L, const double* __res
 
 // damped Jacobi sweep: xout = xin + omega * (b - A xin) / diag
 template <bool FINE>
-__global__ void __launch_bounds__(256) mg_jacobi_kernel(Lv L, const float* __restrict__ b, const float* __restrict__ xin,
+__global__ void __launch_bounds__(256) mg_jacobi_kernel(Lv L, const PcgScalars* __restrict__ sc, const float* __restrict__ b, const float* __restrict__ xin,
                                                          float* __restrict__ xout) {
+    if (sc->done) return;
     int x, y, z; int64_t c;
     if (!cell_of(L, x, y, z, c)) return;
     float v = 0.f;
@@ -109,10 +112,37 @@ __global__ void __launch_bounds__(256) mg_jacobi_kernel(Lv L, const float* __res
     xout[c] = v;
 }
 
+// two pre-smoothing sweeps from a zero guess in one pass (coarse levels): x1 = omega b / d needs no neighbours, so
+// x2 = x1 + omega (b - A x1) / d only reads b and d at the 7 stencil points
+__global__ void __launch_bounds__(256) mg_pre2_kernel(Lv L, const PcgScalars* __restrict__ sc, const float* __restrict__ b,
+                                                      float* __restrict__ xout) {
+    if (sc->done) return;
+    int x, y, z; int64_t c;
+    if (!cell_of(L, x, y, z, c)) return;
+    const float d = L.diag[c];
+    float v = 0.f;
+    if (d > 0.f) {
+        auto x1 = [&](int64_t cn) -> float { const float dn = L.diag[cn]; return dn > 0.f ? OMEGA * b[cn] / dn : 0.f; };
+        const float w0 = L.wx[c - 1], w1 = L.wx[c], w2 = L.wy[c - L.sy], w3 = L.wy[c], w4 = L.wz[c - L.sz], w5 = L.wz[c];
+        float off = 0.f;
+        if (w0 > 0.f) off += w0 * x1(c - 1);
+        if (w1 > 0.f) off += w1 * x1(c + 1);
+        if (w2 > 0.f) off += w2 * x1(c - L.sy);
+        if (w3 > 0.f) off += w3 * x1(c + L.sy);
+        if (w4 > 0.f) off += w4 * x1(c - L.sz);
+        if (w5 > 0.f) off += w5 * x1(c + L.sz);
+        const float bb = b[c];
+        const float xi = OMEGA * bb / d;
+        v = xi + OMEGA * (bb - (d * xi - off)) / d;
+    }
+    xout[c] = v;
+}
+
 // coarse right-hand side: b_c(I) = sum over the 2x2x2 children of (b - A x)   (restriction = P^T)
 template <bool FINE>
-__global__ void __launch_bounds__(256) mg_restrict_kernel(Lv L, Lv C, const float* __restrict__ b, const float* __restrict__ xf,
+__global__ void __launch_bounds__(256) mg_restrict_kernel(Lv L, Lv C, const PcgScalars* __restrict__ sc, const float* __restrict__ b, const float* __restrict__ xf,
                                                            float* __restrict__ bc) {
+    if (sc->done) return;
     int X, Y, Z; int64_t cc;
     if (!cell_of(C, X, Y, Z, cc)) return;
     float s = 0.f;
@@ -136,8 +166,9 @@ __global__ void __launch_bounds__(256) mg_restrict_kernel(Lv L, Lv C, const floa
 // prolongation + over-corrected update fused with the first post-smoothing sweep:
 //   xc = xin + OVER * e_c[parent] ;  xout = xc + omega * (b - A xc) / diag
 template <bool FINE>
-__global__ void __launch_bounds__(256) mg_prolong_jacobi_kernel(Lv L, Lv C, const float* __restrict__ b, const float* __restrict__ xin,
+__global__ void __launch_bounds__(256) mg_prolong_jacobi_kernel(Lv L, Lv C, const PcgScalars* __restrict__ sc, const float* __restrict__ b, const float* __restrict__ xin,
                                                                  const float* __restrict__ ec, float* __restrict__ xout) {
+    if (sc->done) return;
     int x, y, z; int64_t c;
     if (!cell_of(L, x, y, z, c)) return;
     float v = 0.f;
@@ -216,9 +247,11 @@ __device__ __forceinline__ Stencil4 load_stencil4(const Lv& L, const float* __re
     return s;
 }
 
-__global__ void __launch_bounds__(256) mg_first4_kernel(Lv L, const double* __restrict__ r64, double inv_scale, float* __restrict__ b,
-                                                        float* __restrict__ xout) {
+__global__ void __launch_bounds__(256) mg_first4_kernel(Lv L, const double* __restrict__ r64, const PcgScalars* __restrict__ sc,
+                                                        float* __restrict__ b, float* __restrict__ xout) {
     int64_t c; unsigned cd[4];
+    if (sc->done) return;
+    const double inv_scale = sc->inv_scale;
     if (!group_of(L, c, cd)) return;
     F4 bb = zero4(), xo = zero4();
     if ((cd[0] | cd[1] | cd[2] | cd[3]) & CODE_ACTIVE) {
@@ -236,8 +269,9 @@ __global__ void __launch_bounds__(256) mg_first4_kernel(Lv L, const double* __re
     st4(xout + c, xo);
 }
 
-__global__ void __launch_bounds__(256) mg_jacobi4_kernel(Lv L, const float* __restrict__ b, const float* __restrict__ xin,
+__global__ void __launch_bounds__(256) mg_jacobi4_kernel(Lv L, const PcgScalars* __restrict__ sc, const float* __restrict__ b, const float* __restrict__ xin,
                                                          float* __restrict__ xout) {
+    if (sc->done) return;
     int64_t c; unsigned cd[4];
     if (!group_of(L, c, cd)) return;
     F4 xo = zero4();
@@ -256,8 +290,9 @@ __global__ void __launch_bounds__(256) mg_jacobi4_kernel(Lv L, const float* __re
 }
 
 // one thread = two coarse cells in x = a 4x2x2 block of fine cells
-__global__ void __launch_bounds__(256) mg_restrict4_kernel(Lv L, Lv C, const float* __restrict__ b, const float* __restrict__ xf,
+__global__ void __launch_bounds__(256) mg_restrict4_kernel(Lv L, Lv C, const PcgScalars* __restrict__ sc, const float* __restrict__ b, const float* __restrict__ xf,
                                                            float* __restrict__ bc) {
+    if (sc->done) return;
     const int X = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
     const int Y = blockIdx.y * blockDim.y + threadIdx.y, Z = blockIdx.z * blockDim.z + threadIdx.z;
     if (X >= C.gx || Y >= C.gy || Z >= C.gz) return;
@@ -285,8 +320,9 @@ __global__ void __launch_bounds__(256) mg_restrict4_kernel(Lv L, Lv C, const flo
     *reinterpret_cast<float2*>(bc + ((int64_t)Z * C.gy + Y) * C.gx + X) = make_float2(s0, s1);
 }
 
-__global__ void __launch_bounds__(256) mg_prolong_jacobi4_kernel(Lv L, Lv C, const float* __restrict__ b, const float* __restrict__ xin,
+__global__ void __launch_bounds__(256) mg_prolong_jacobi4_kernel(Lv L, Lv C, const PcgScalars* __restrict__ sc, const float* __restrict__ b, const float* __restrict__ xin,
                                                                  const float* __restrict__ ec, float* __restrict__ xout) {
+    if (sc->done) return;
     int64_t c; unsigned cd[4];
     if (!group_of(L, c, cd)) return;
     F4 xo = zero4();
@@ -379,9 +415,11 @@ __global__ void __launch_bounds__(256) mg_buildn_kernel(Lv L, Lv C, float* __res
 }
 
 // coarsest level: COARSE_SWEEPS damped Jacobi sweeps inside one CTA (one thread per cell, iterate in shared memory)
-__global__ void __launch_bounds__(COARSE_MAX) mg_coarse_kernel(Lv L, const float* __restrict__ b, const float* __restrict__ xin,
-                                                                float* __restrict__ xout, int zero_guess, int sweeps) {
+__global__ void __launch_bounds__(COARSE_MAX) mg_coarse_kernel(Lv L, const PcgScalars* __restrict__ sc, const float* __restrict__ b,
+                                                                const float* __restrict__ xin, float* __restrict__ xout, int zero_guess,
+                                                                int sweeps) {
     __shared__ float xs[2][COARSE_MAX];
+    if (sc->done) return;
     const int c = threadIdx.x;
     const int nc = L.gx * L.gy * L.gz;
     const bool in = c < nc;
@@ -446,40 +484,44 @@ int cycle(fsim* h, int l, bool zero_guess, float** result) {
     MgLevel* m = h->mg[l];
     const dim3 blk(32, 4, 2);
     const Lv L = view(h, m, l);
+    const PcgScalars* sc = h->scal;
     const bool fine = l == 0;
+    const int kid = l == 0 ? K_MG : (l == 1 ? K_MG1 : K_MG2);
     const bool v4 = fine && (m->gx % 4 == 0);  // float4 path; then the coarse gx is even (float2 stores / loads)
     const dim3 blk4(32, 4, 2);
     const dim3 grd4(div_up(m->gx, 4 * 32), div_up(m->gy, 4), div_up(m->gz, 2));
     if (l == (int)h->mg.size() - 1) {  // coarsest
-        KScope ks(h, K_MG);
-        mg_coarse_kernel<<<1, COARSE_MAX, 0, h->stream>>>(L, m->b, m->xa, m->xa, zero_guess ? 1 : 0, COARSE_SWEEPS);
+        KScope ks(h, K_MG2);
+        mg_coarse_kernel<<<1, COARSE_MAX, 0, h->stream>>>(L, sc, m->b, m->xa, m->xa, zero_guess ? 1 : 0, COARSE_SWEEPS);
         *result = m->xa;
         return FSIM_OK;
     }
     MgLevel* mc = h->mg[l + 1];
     const Lv C = view(h, mc, l + 1);
     float *cur = m->xa, *oth = m->xb;
-    const double inv_scale = h->mg_inv_scale;
-    {
-        KScope ks(h, K_MG, PRE);
+    if (!fine && zero_guess && PRE == 2) {
+        KScope ks(h, kid);
+        mg_pre2_kernel<<<grid_of(m, blk), blk, 0, h->stream>>>(L, sc, m->b, cur);
+    } else {
+        KScope ks(h, kid, PRE);
         for (int s = 0; s < PRE; s++) {
             if (s == 0 && zero_guess) {
-                if (v4) mg_first4_kernel<<<grd4, blk4, 0, h->stream>>>(L, h->r, inv_scale, m->b, cur);
-                else if (fine) mg_first_kernel<true><<<grid_of(m, blk), blk, 0, h->stream>>>(L, h->r, inv_scale, m->b, cur);
-                else mg_first_kernel<false><<<grid_of(m, blk), blk, 0, h->stream>>>(L, nullptr, 0.0, m->b, cur);
+                if (v4) mg_first4_kernel<<<grd4, blk4, 0, h->stream>>>(L, h->r, sc, m->b, cur);
+                else if (fine) mg_first_kernel<true><<<grid_of(m, blk), blk, 0, h->stream>>>(L, h->r, sc, m->b, cur);
+                else mg_first_kernel<false><<<grid_of(m, blk), blk, 0, h->stream>>>(L, nullptr, sc, m->b, cur);
             } else {
-                if (v4) mg_jacobi4_kernel<<<grd4, blk4, 0, h->stream>>>(L, m->b, cur, oth);
-                else if (fine) mg_jacobi_kernel<true><<<grid_of(m, blk), blk, 0, h->stream>>>(L, m->b, cur, oth);
-                else mg_jacobi_kernel<false><<<grid_of(m, blk), blk, 0, h->stream>>>(L, m->b, cur, oth);
+                if (v4) mg_jacobi4_kernel<<<grd4, blk4, 0, h->stream>>>(L, sc, m->b, cur, oth);
+                else if (fine) mg_jacobi_kernel<true><<<grid_of(m, blk), blk, 0, h->stream>>>(L, sc, m->b, cur, oth);
+                else mg_jacobi_kernel<false><<<grid_of(m, blk), blk, 0, h->stream>>>(L, sc, m->b, cur, oth);
                 float* t = cur; cur = oth; oth = t;
             }
         }
     }
     {
-        KScope ks(h, K_MG);
-        if (v4) mg_restrict4_kernel<<<dim3(div_up(mc->gx, 2 * 32), div_up(mc->gy, 4), div_up(mc->gz, 2)), blk4, 0, h->stream>>>(L, C, m->b, cur, mc->b);
-        else if (fine) mg_restrict_kernel<true><<<grid_of(mc, blk), blk, 0, h->stream>>>(L, C, m->b, cur, mc->b);
-        else mg_restrict_kernel<false><<<grid_of(mc, blk), blk, 0, h->stream>>>(L, C, m->b, cur, mc->b);
+        KScope ks(h, kid);
+        if (v4) mg_restrict4_kernel<<<dim3(div_up(mc->gx, 2 * 32), div_up(mc->gy, 4), div_up(mc->gz, 2)), blk4, 0, h->stream>>>(L, C, sc, m->b, cur, mc->b);
+        else if (fine) mg_restrict_kernel<true><<<grid_of(mc, blk), blk, 0, h->stream>>>(L, C, sc, m->b, cur, mc->b);
+        else mg_restrict_kernel<false><<<grid_of(mc, blk), blk, 0, h->stream>>>(L, C, sc, m->b, cur, mc->b);
     }
     float* ec = nullptr;
     const int visits = (l + 1 <= W_LEVELS && l + 1 < (int)h->mg.size() - 1) ? 2 : 1;
@@ -491,15 +533,15 @@ int cycle(fsim* h, int l, bool zero_guess, float** result) {
         }
     }
     {
-        KScope ks(h, K_MG, POST);
-        if (v4) mg_prolong_jacobi4_kernel<<<grd4, blk4, 0, h->stream>>>(L, C, m->b, cur, mc->xa, oth);
-        else if (fine) mg_prolong_jacobi_kernel<true><<<grid_of(m, blk), blk, 0, h->stream>>>(L, C, m->b, cur, mc->xa, oth);
-        else mg_prolong_jacobi_kernel<false><<<grid_of(m, blk), blk, 0, h->stream>>>(L, C, m->b, cur, mc->xa, oth);
+        KScope ks(h, kid, POST);
+        if (v4) mg_prolong_jacobi4_kernel<<<grd4, blk4, 0, h->stream>>>(L, C, sc, m->b, cur, mc->xa, oth);
+        else if (fine) mg_prolong_jacobi_kernel<true><<<grid_of(m, blk), blk, 0, h->stream>>>(L, C, sc, m->b, cur, mc->xa, oth);
+        else mg_prolong_jacobi_kernel<false><<<grid_of(m, blk), blk, 0, h->stream>>>(L, C, sc, m->b, cur, mc->xa, oth);
         { float* t = cur; cur = oth; oth = t; }
         for (int s = 1; s < POST; s++) {
-            if (v4) mg_jacobi4_kernel<<<grd4, blk4, 0, h->stream>>>(L, m->b, cur, oth);
-            else if (fine) mg_jacobi_kernel<true><<<grid_of(m, blk), blk, 0, h->stream>>>(L, m->b, cur, oth);
-            else mg_jacobi_kernel<false><<<grid_of(m, blk), blk, 0, h->stream>>>(L, m->b, cur, oth);
+            if (v4) mg_jacobi4_kernel<<<grd4, blk4, 0, h->stream>>>(L, sc, m->b, cur, oth);
+            else if (fine) mg_jacobi_kernel<true><<<grid_of(m, blk), blk, 0, h->stream>>>(L, sc, m->b, cur, oth);
+            else mg_jacobi_kernel<false><<<grid_of(m, blk), blk, 0, h->stream>>>(L, sc, m->b, cur, oth);
             float* t = cur; cur = oth; oth = t;
         }
     }

@@ -34,9 +34,10 @@ struct PcgArgs {
     PcgScalars* sc;
     double* partials;  // [3][gridDim.x]
     unsigned int* counter;
-    double inv_h, scale;  // 1/h ; dt/(rho h^2)
-    double avg_pressure, pressure_k, tol;
-    int pressure_enabled, max_it, it;
+    PcgHostStatus* status;  // host-mapped progress flags
+    double inv_h;           // 1/h
+    double avg_pressure, pressure_k;
+    int pressure_enabled, warm;
 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -134,8 +135,8 @@ __global__ void __launch_bounds__(PT) rhs_kernel(PcgArgs a) {
         }
         a.code[c] = (uint16_t)code;
         a.rhs[c] = rhs;
-        a.r[c] = rhs;
-        a.p[c] = 0.0;
+        if (!a.warm) { a.r[c] = rhs; a.p[c] = 0.0; }
+        else if (!(code & CODE_ACTIVE)) a.p[c] = 0.0;  // warm start keeps last step's pressure on WATER cells only
     }
     double out[2];
     if (grid_reduce<2, 0>(acc, a.partials, a.counter, out)) {
@@ -147,12 +148,53 @@ __global__ void __launch_bounds__(PT) rhs_kernel(PcgArgs a) {
         a.sc->nan_break = 0;
         a.sc->rmax = 0.0;
         a.sc->sigma = 0.0;
+        a.sc->it = 0;
+        a.status->done = a.sc->done;
+        a.status->it_done = 0;
+        __threadfence_system();
     }
 }
 
-__device__ __forceinline__ double jacobi_z(const PcgArgs& a, unsigned code, double r) {
+// warm start: r = rhs - A p for the pressure kept from the previous step; also max |r| (already converged => done)
+__global__ void __launch_bounds__(PT) residual_kernel(PcgArgs a) {
+    if (a.sc->done) return;
+    double acc[1] = {0.0};
+    const double scale = a.sc->scale;
+    const int64_t c0 = ((int64_t)blockIdx.x * PT + threadIdx.x) * CV;
+#pragma unroll
+    for (int k = 0; k < CV; k++) {
+        const int64_t c = c0 + k;
+        if (c >= a.g.nc) break;
+        const unsigned cd = a.code[c];
+        double r = 0.0;
+        if (cd & CODE_ACTIVE) {
+            double n = 0.0;
+            if (cd & 1u) n += a.p[c - 1];
+            if (cd & 2u) n += a.p[c + 1];
+            if (cd & 4u) n += a.p[c - a.g.sy];
+            if (cd & 8u) n += a.p[c + a.g.sy];
+            if (cd & 16u) n += a.p[c - a.g.sz];
+            if (cd & 32u) n += a.p[c + a.g.sz];
+            r = a.rhs[c] - scale * ((double)code_ns(cd) * a.p[c] - n);
+            acc[0] = fmax(acc[0], fabs(r));
+        }
+        a.r[c] = r;
+    }
+    double out[1];
+    if (grid_reduce<0, 1>(acc, a.partials, a.counter, out)) {
+        a.sc->r0max = out[0];
+        if (out[0] < a.sc->tol) {  // last step's pressure already satisfies the tolerance
+            a.sc->done = 1;
+            a.sc->rmax = out[0];
+            a.status->done = 1;
+            __threadfence_system();
+        }
+    }
+}
+
+__device__ __forceinline__ double jacobi_z(double scale, unsigned code, double r) {
     const int ns = code_ns(code);
-    return ns > 0 ? r / (a.scale * ns) : r;
+    return ns > 0 ? r / (scale * ns) : r;
 }
 
 // first preconditioner application (:262-265): s = z ; sigma = z.r, with z = r / A_ii (diagonal) or the multigrid result
@@ -169,7 +211,7 @@ __global__ void __launch_bounds__(PT) start_kernel(PcgArgs a) {
         double z = 0.0;
         if (code & CODE_ACTIVE) {
             const double r = a.r[c];
-            z = JACOBI ? jacobi_z(a, code, r) : (double)a.z32[c];
+            z = JACOBI ? jacobi_z(a.sc->scale, code, r) : (double)a.z32[c];
             acc[0] += z * r;
         }
         if (JACOBI) a.z[c] = z;
@@ -186,6 +228,7 @@ __global__ void __launch_bounds__(PT) spmv_kernel(PcgArgs a) {
     double acc[1] = {0.0};
     const int64_t c = ((int64_t)blockIdx.x * PT + threadIdx.x) * CV;
     const int64_t sy = a.g.sy, sz = a.g.sz;
+    const double scale = a.sc->scale;
     if (VEC) {
         if (c < a.g.nc) {  // nc is even in this path
             const ushort2 cd = *reinterpret_cast<const ushort2*>(a.code + c);
@@ -207,7 +250,7 @@ __global__ void __launch_bounds__(PT) spmv_kernel(PcgArgs a) {
                     if (c0 & 8u) n += yp.x;
                     if (c0 & 16u) n += zm.x;
                     if (c0 & 32u) n += zp.x;
-                    q.x = a.scale * ((double)code_ns(c0) * sc.x - n);
+                    q.x = scale * ((double)code_ns(c0) * sc.x - n);
                     acc[0] += sc.x * q.x;
                 }
                 if (c1 & CODE_ACTIVE) {
@@ -217,7 +260,7 @@ __global__ void __launch_bounds__(PT) spmv_kernel(PcgArgs a) {
                     if (c1 & 8u) n += yp.y;
                     if (c1 & 16u) n += zm.y;
                     if (c1 & 32u) n += zp.y;
-                    q.y = a.scale * ((double)code_ns(c1) * sc.y - n);
+                    q.y = scale * ((double)code_ns(c1) * sc.y - n);
                     acc[0] += sc.y * q.y;
                 }
                 *reinterpret_cast<double2*>(a.q + c) = q;
@@ -238,7 +281,7 @@ __global__ void __launch_bounds__(PT) spmv_kernel(PcgArgs a) {
             if (cd & 8u) n += a.s[cc + sy];
             if (cd & 16u) n += a.s[cc - sz];
             if (cd & 32u) n += a.s[cc + sz];
-            const double q = a.scale * ((double)code_ns(cd) * sc - n);
+            const double q = scale * ((double)code_ns(cd) * sc - n);
             a.q[cc] = q;
             acc[0] += sc * q;
         }
@@ -253,6 +296,7 @@ __global__ void __launch_bounds__(PT) update_kernel(PcgArgs a) {
     if (a.sc->done) return;
     const double alpha = a.sc->sigma / a.sc->sq;
     const bool bad = alpha != alpha;  // NaN => the reference breaks before touching p (:271-272)
+    const double scale = a.sc->scale;
     double acc[2] = {0.0, 0.0};      // [0] = z.r (sum), [1] = max |r|
     const int64_t c0 = ((int64_t)blockIdx.x * PT + threadIdx.x) * CV;
     if (!bad) {
@@ -267,7 +311,7 @@ __global__ void __launch_bounds__(PT) update_kernel(PcgArgs a) {
             a.r[c] = r;
             acc[1] = fmax(acc[1], fabs(r));
             if (JACOBI) {
-                const double z = jacobi_z(a, code, r);
+                const double z = jacobi_z(scale, code, r);
                 a.z[c] = z;
                 acc[0] += z * r;
             }
@@ -275,21 +319,23 @@ __global__ void __launch_bounds__(PT) update_kernel(PcgArgs a) {
     }
     double out[2];
     if (grid_reduce<1, 1>(acc, a.partials, a.counter, out)) {
+        const int it = a.sc->it;
         if (bad) {
             a.sc->nan_break = 1;
             a.sc->done = 1;
-            a.sc->iterations = a.it;
+            a.sc->iterations = it;
         } else {
             a.sc->rmax = out[1];
             a.sc->sigma_new = out[0];
-            if (out[1] < a.tol) {  // converged inside iteration `it` => the reference returns it (:280-281, 292)
+            if (out[1] < a.sc->tol) {  // converged inside iteration `it` => the reference returns it (:280-281, 292)
                 a.sc->done = 1;
-                a.sc->iterations = a.it;
-            } else if (a.it + 1 >= a.max_it) {
+                a.sc->iterations = it;
+            } else if (it + 1 >= a.sc->max_it) {
                 a.sc->done = 2;  // iteration cap; the direction update is skipped like the loop exit would
-                a.sc->iterations = a.max_it;
+                a.sc->iterations = a.sc->max_it;
             }
         }
+        if (a.sc->done) { a.status->done = a.sc->done; __threadfence_system(); }
     }
 }
 
@@ -321,11 +367,42 @@ __global__ void __launch_bounds__(PT) direction_kernel(PcgArgs a) {
         a.s[c] = a.s[c] * beta + (a.z32 ? (double)a.z32[c] : a.z[c]);
     }
 }
-__global__ void sigma_kernel(PcgScalars* sc) {
-    if (!sc->done) sc->sigma = sc->sigma_new;
+// closes iteration `it`: sigma <- sigma', it <- it + 1, progress published to the host-mapped status word
+__global__ void sigma_kernel(PcgScalars* sc, PcgHostStatus* status) {
+    if (sc->done) return;
+    sc->sigma = sc->sigma_new;
+    sc->it = sc->it + 1;
+    status->it_done = sc->it;
+    __threadfence_system();
 }
 
 }  // namespace
+
+// one PCG iteration: SpMV -> update -> (multigrid cycle -> z.r | fused diagonal) -> direction -> close
+static int enqueue_iteration(fsim* h, const PcgArgs& a, bool vec, bool use_mg, int nbv) {
+    {
+        KScope ks(h, K_SPMV);
+        if (vec) spmv_kernel<true><<<nbv, PT, 0, h->stream>>>(a);
+        else spmv_kernel<false><<<nbv, PT, 0, h->stream>>>(a);
+    }
+    if (use_mg) {
+        { KScope ks(h, K_UPDATE); update_kernel<false><<<nbv, PT, 0, h->stream>>>(a); }
+        int rc = mg_apply(h);
+        if (rc) return rc;
+        if (a.z32 != h->mg_z32) return fsim_fail(h, FSIM_ERR_INVALID, "multigrid result buffer moved between cycles");
+        KScope ks(h, K_UPDATE);
+        dot_zr_kernel<<<nbv, PT, 0, h->stream>>>(a);
+    } else {
+        KScope ks(h, K_UPDATE);
+        update_kernel<true><<<nbv, PT, 0, h->stream>>>(a);
+    }
+    {
+        KScope ks(h, K_DIRECTION, 2);
+        direction_kernel<<<nbv, PT, 0, h->stream>>>(a);
+        sigma_kernel<<<1, 1, 0, h->stream>>>(h->scal, h->status_dev);
+    }
+    return FSIM_OK;
+}
 
 int k_project(fsim* h, double dt, int* iterations) {
     const GridDims& g = h->g;
@@ -335,22 +412,32 @@ int k_project(fsim* h, double dt, int* iterations) {
     a.dens = h->dens;
     a.p = h->p; a.rhs = h->rhs; a.r = h->r; a.s = h->s; a.q = h->q; a.z = h->z;
     a.sc = h->scal; a.partials = h->partials; a.counter = h->red_counter;
+    a.status = h->status_dev;
     const double hcell = h->info.cell_d[0];
     a.inv_h = 1.0 / hcell;
-    a.scale = dt / (h->par.fluid_density * hcell * hcell);
     a.avg_pressure = h->par.average_pressure; a.pressure_k = h->par.pressure_k;
-    a.tol = h->par.residual_tolerance;
     a.pressure_enabled = h->par.pressure_enabled;
-    a.max_it = h->par.max_iterations;
-    a.it = 0;
+    a.warm = h->warm_start && h->pressure_valid;
     a.z32 = nullptr;
-    h->mg_inv_scale = 1.0 / a.scale;
     const int nb1 = div_up(g.nc, PT);        // one cell per thread
     const int nbv = div_up(g.nc, PT * CV);   // CV cells per thread
     const bool vec = (g.gx % 2 == 0) && (g.nc % 2 == 0);
     const bool use_mg = mg_enabled(h);
+    const int max_it = h->par.max_iterations;
+
+    // solve parameters live on the device: the captured iteration graph stays valid when dt / tolerance change
+    PcgScalars* sh = h->scal_host;
+    memset(sh, 0, sizeof(*sh));
+    sh->scale = dt / (h->par.fluid_density * hcell * hcell);
+    sh->inv_scale = 1.0 / sh->scale;
+    sh->tol = h->par.residual_tolerance;
+    sh->max_it = max_it;
+    h->status_host->done = 0;
+    h->status_host->it_done = 0;
+    FSIM_CUDA(h, cudaMemcpyAsync(h->scal, sh, sizeof(PcgScalars), cudaMemcpyHostToDevice, h->stream));
 
     { KScope ks(h, K_RHS); rhs_kernel<<<nb1, PT, 0, h->stream>>>(a); }
+    if (a.warm) { KScope ks(h, K_RHS); residual_kernel<<<nbv, PT, 0, h->stream>>>(a); }
     if (use_mg) {
         int rc = mg_build(h);
         if (rc) return rc;
@@ -365,42 +452,44 @@ int k_project(fsim* h, double dt, int* iterations) {
     }
     FSIM_CHECK_LAUNCH(h);
 
-    const int poll = use_mg ? 1 : 16;
-    int done = 0;
-    for (int it = 0; it < a.max_it && !done; it++) {
-        a.it = it;
-        {
-            KScope ks(h, K_SPMV);
-            if (vec) spmv_kernel<true><<<nbv, PT, 0, h->stream>>>(a);
-            else spmv_kernel<false><<<nbv, PT, 0, h->stream>>>(a);
-        }
-        if (use_mg) {
-            { KScope ks(h, K_UPDATE); update_kernel<false><<<nbv, PT, 0, h->stream>>>(a); }
-            int rc = mg_apply(h);
-            if (rc) return rc;
-            a.z32 = h->mg_z32;
-            KScope ks(h, K_UPDATE);
-            dot_zr_kernel<<<nbv, PT, 0, h->stream>>>(a);
+    const bool graph = h->use_graph && h->prof_mask == 0;
+    if (graph && !h->pcg_graph) {  // capture one iteration once; every argument is a fixed device pointer
+        cudaGraph_t gr = nullptr;
+        const int64_t l0 = h->launches;
+        int64_t c0[K_COUNT];
+        memcpy(c0, h->launch_n, sizeof(c0));
+        FSIM_CUDA(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        int rc = enqueue_iteration(h, a, vec, use_mg, nbv);
+        cudaError_t e = cudaStreamEndCapture(h->stream, &gr);
+        if (rc) return rc;
+        if (e != cudaSuccess) return fsim_fail(h, FSIM_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+        FSIM_CUDA(h, cudaGraphInstantiate(&h->pcg_graph, gr, 0));
+        cudaGraphDestroy(gr);
+        h->pcg_graph_launches = (int)(h->launches - l0);
+        for (int k = 0; k < K_COUNT; k++) { h->pcg_graph_class[k] = (int)(h->launch_n[k] - c0[k]); h->launch_n[k] = c0[k]; }
+        h->launches = l0;  // capture does not execute
+    }
+    // the host never blocks on the stream inside the loop: it polls the host-mapped status word and keeps at most
+    // two iterations in flight; kernels of an iteration enqueued after convergence see done != 0 and exit immediately
+    for (int it = 0; it < max_it; it++) {
+        if (h->status_host->done) break;
+        if (graph) {
+            FSIM_CUDA(h, cudaGraphLaunch(h->pcg_graph, h->stream));
+            h->launches += h->pcg_graph_launches;
+            for (int k = 0; k < K_COUNT; k++) h->launch_n[k] += h->pcg_graph_class[k];
         } else {
-            KScope ks(h, K_UPDATE);
-            update_kernel<true><<<nbv, PT, 0, h->stream>>>(a);
+            int rc = enqueue_iteration(h, a, vec, use_mg, nbv);
+            if (rc) return rc;
         }
-        {
-            KScope ks(h, K_DIRECTION, 2);
-            direction_kernel<<<nbv, PT, 0, h->stream>>>(a);
-            sigma_kernel<<<1, 1, 0, h->stream>>>(h->scal);
-        }
-        if ((it + 1) % poll == 0 || it + 1 == a.max_it) {
-            FSIM_CUDA(h, cudaMemcpyAsync(h->scal_host, h->scal, sizeof(PcgScalars), cudaMemcpyDeviceToHost, h->stream));
-            FSIM_CUDA(h, cudaStreamSynchronize(h->stream));
-            done = h->scal_host->done;
+        while (!h->status_host->done && it + 1 - h->status_host->it_done > 1) {
+            if (cudaStreamQuery(h->stream) != cudaErrorNotReady) break;  // drained (or failed): flags are final
         }
     }
     FSIM_CHECK_LAUNCH(h);
     FSIM_CUDA(h, cudaMemcpyAsync(h->scal_host, h->scal, sizeof(PcgScalars), cudaMemcpyDeviceToHost, h->stream));
     FSIM_CUDA(h, cudaStreamSynchronize(h->stream));
     const PcgScalars& s = *h->scal_host;
-    h->solve.iterations = s.early_out ? 0 : (s.done ? s.iterations : a.max_it);
+    h->solve.iterations = s.early_out ? 0 : (s.done ? s.iterations : max_it);
     h->solve.early_out = s.early_out;
     h->solve.rhs_sumsq = s.rhs_sumsq;
     h->solve.residual_max = s.rmax;
