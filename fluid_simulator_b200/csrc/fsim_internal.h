@@ -114,6 +114,7 @@ struct fsim {
     bool use_mg;                           // multigrid (default) or diagonal preconditioner (FSIM_PRECOND=jacobi)
     double mg_inv_scale;                   // 1 / (dt / (rho h^2)): the hierarchy works on the integer-weight Laplacian
     std::vector<MgLevel*> mg;
+    int mg_tail_first;                     // levels >= this run inside the single-cluster tail kernel
     PcgScalars* scal;                      // device
     PcgScalars* scal_host;                 // pinned
     PcgHostStatus* status_host;            // pinned + mapped

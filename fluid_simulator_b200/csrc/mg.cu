@@ -15,7 +15,11 @@
 //    MIC(0) needs 80, independent of the grid size.
 //  * fp32 throughout (it only has to be an approximate inverse); the CG recurrence around it is fp64 (pcg.cu).
 // Every kernel is a one-thread-per-cell 7-point stencil, x fastest => coalesced, HBM/L2-bound.
+#include <cooperative_groups.h>
+
 #include "fsim_internal.h"
+
+namespace cg = cooperative_groups;
 
 struct MgLevel {
     int gx, gy, gz, sy, sz;
@@ -31,7 +35,7 @@ namespace {
 constexpr float OMEGA = 0.8f;
 constexpr float OVER = 1.8f;
 constexpr int PRE = 2, POST = 2;
-constexpr int W_LEVELS = 2;          // levels 1..W_LEVELS are visited twice
+constexpr int W_FIRST = 2, W_LAST = 2; // levels W_FIRST..W_LAST are visited twice per visit of their parent
 constexpr int COARSE_SWEEPS = 30;
 constexpr int COARSE_MAX = 1024;     // the coarsest level fits one CTA
 
@@ -452,6 +456,163 @@ __global__ void __launch_bounds__(COARSE_MAX) mg_coarse_kernel(Lv L, const PcgSc
     if (in) xout[c] = xs[cur][c];
 }
 
+// ---- the small end of the hierarchy in ONE launch -----------------------------------------------------------------
+// Levels with <= TAIL_MAX_CELLS cells are latency-bound (a separate launch per sweep costs more than the sweep), so one
+// thread-block cluster runs their whole V(2,2) sub-cycle: all CTAs stride over the cells of a level, phases are separated
+// by cluster barriers (release/acquire at cluster scope; data is exchanged through global memory, i.e. L2), and the
+// coarsest level is iterated by CTA 0 in shared memory.
+constexpr int TAIL_MAX_CELLS = 40000;
+constexpr int TAIL_MAX_LEVELS = 8;
+constexpr int TAIL_CLUSTER = 8;
+constexpr int TAIL_THREADS = 1024;
+
+struct TailLevel { Lv L; float *xa, *xb, *b; };
+struct TailArgs {
+    int n;
+    TailLevel lv[TAIL_MAX_LEVELS];
+    const PcgScalars* sc;
+    int zero_guess;
+};
+
+__device__ __forceinline__ float t_row(const Lv& L, int c, const float* x, float* offsum) {
+    *offsum = L.wx[c] * x[c + 1] + L.wx[c - 1] * x[c - 1] + L.wy[c] * x[c + L.sy] + L.wy[c - L.sy] * x[c - L.sy] +
+              L.wz[c] * x[c + L.sz] + L.wz[c - L.sz] * x[c - L.sz];
+    return L.diag[c];
+}
+__device__ void t_jacobi(const Lv& L, const float* b, const float* xin, float* xout, int t0, int nt) {
+    const int nc = L.gx * L.gy * L.gz;
+    for (int c = t0; c < nc; c += nt) {
+        float off;
+        const float d = t_row(L, c, xin, &off);
+        const float xi = xin[c];
+        xout[c] = d > 0.f ? xi + OMEGA * (b[c] - (d * xi - off)) / d : 0.f;
+    }
+}
+__device__ void t_pre2(const Lv& L, const float* b, float* xout, int t0, int nt) {
+    const int nc = L.gx * L.gy * L.gz;
+    for (int c = t0; c < nc; c += nt) {
+        const float d = L.diag[c];
+        float v = 0.f;
+        if (d > 0.f) {
+            const int nb[6] = {c - 1, c + 1, c - L.sy, c + L.sy, c - L.sz, c + L.sz};
+            const float w[6] = {L.wx[c - 1], L.wx[c], L.wy[c - L.sy], L.wy[c], L.wz[c - L.sz], L.wz[c]};
+            float off = 0.f;
+#pragma unroll
+            for (int k = 0; k < 6; k++)
+                if (w[k] > 0.f) { const float dn = L.diag[nb[k]]; if (dn > 0.f) off += w[k] * OMEGA * b[nb[k]] / dn; }
+            const float bb = b[c], xi = OMEGA * bb / d;
+            v = xi + OMEGA * (bb - (d * xi - off)) / d;
+        }
+        xout[c] = v;
+    }
+}
+__device__ void t_restrict(const Lv& L, const Lv& C, const float* b, const float* xf, float* bc, int t0, int nt) {
+    const int ncc = C.gx * C.gy * C.gz;
+    for (int cc = t0; cc < ncc; cc += nt) {
+        const int X = cc % C.gx, Y = (cc / C.gx) % C.gy, Z = cc / (C.gx * C.gy);
+        float s = 0.f;
+        for (int k = 0; k < 2; k++)
+            for (int j = 0; j < 2; j++)
+                for (int i = 0; i < 2; i++) {
+                    const int x = 2 * X + i, y = 2 * Y + j, z = 2 * Z + k;
+                    if (x >= L.gx || y >= L.gy || z >= L.gz) continue;
+                    const int c = (z * L.gy + y) * L.gx + x;
+                    float off;
+                    const float d = t_row(L, c, xf, &off);
+                    if (d > 0.f) s += b[c] - (d * xf[c] - off);
+                }
+        bc[cc] = s;
+    }
+}
+__device__ void t_prolong_jacobi(const Lv& L, const Lv& C, const float* b, const float* xin, const float* ec, float* xout, int t0, int nt) {
+    const int nc = L.gx * L.gy * L.gz;
+    for (int c = t0; c < nc; c += nt) {
+        const float d = L.diag[c];
+        float v = 0.f;
+        if (d > 0.f) {
+            const int x = c % L.gx, y = (c / L.gx) % L.gy, z = c / (L.gx * L.gy);
+            auto xc = [&](int xx, int yy, int zz, int cn) -> float {
+                return xin[cn] + OVER * ec[((zz >> 1) * C.gy + (yy >> 1)) * C.gx + (xx >> 1)];
+            };
+            const float w0 = L.wx[c - 1], w1 = L.wx[c], w2 = L.wy[c - L.sy], w3 = L.wy[c], w4 = L.wz[c - L.sz], w5 = L.wz[c];
+            float off = 0.f;
+            if (w0 > 0.f) off += w0 * xc(x - 1, y, z, c - 1);
+            if (w1 > 0.f) off += w1 * xc(x + 1, y, z, c + 1);
+            if (w2 > 0.f) off += w2 * xc(x, y - 1, z, c - L.sy);
+            if (w3 > 0.f) off += w3 * xc(x, y + 1, z, c + L.sy);
+            if (w4 > 0.f) off += w4 * xc(x, y, z - 1, c - L.sz);
+            if (w5 > 0.f) off += w5 * xc(x, y, z + 1, c + L.sz);
+            const float xi = xc(x, y, z, c);
+            v = xi + OMEGA * (b[c] - (d * xi - off)) / d;
+        }
+        xout[c] = v;
+    }
+}
+
+__global__ void __launch_bounds__(TAIL_THREADS, 1) mg_tail_kernel(TailArgs a) {
+    __shared__ float xs[2][COARSE_MAX];
+    if (a.sc->done) return;  // uniform over the cluster
+    cg::cluster_group cluster = cg::this_cluster();
+    const int t0 = (int)cluster.block_rank() * TAIL_THREADS + threadIdx.x;
+    const int nt = (int)cluster.num_blocks() * TAIL_THREADS;
+    // down
+    for (int i = 0; i + 1 < a.n; i++) {
+        const TailLevel& T = a.lv[i];
+        if (i == 0 && !a.zero_guess) {
+            t_jacobi(T.L, T.b, T.xa, T.xb, t0, nt); cluster.sync();
+            t_jacobi(T.L, T.b, T.xb, T.xa, t0, nt); cluster.sync();
+        } else {
+            t_pre2(T.L, T.b, T.xa, t0, nt); cluster.sync();
+        }
+        t_restrict(T.L, a.lv[i + 1].L, T.b, T.xa, a.lv[i + 1].b, t0, nt); cluster.sync();
+    }
+    // coarsest level: CTA 0, damped Jacobi in shared memory (zero guess unless it is the only level of a revisit)
+    {
+        const TailLevel& T = a.lv[a.n - 1];
+        const Lv& L = T.L;
+        if (cluster.block_rank() == 0) {
+            const int c = threadIdx.x;
+            const int nc = L.gx * L.gy * L.gz;
+            const bool in = c < nc;
+            float d = 0.f, w[6] = {0, 0, 0, 0, 0, 0}, bb = 0.f;
+            int nb[6] = {0, 0, 0, 0, 0, 0};
+            if (in) {
+                d = L.diag[c];
+                bb = T.b[c];
+                w[0] = L.wx[c - 1]; w[1] = L.wx[c]; w[2] = L.wy[c - L.sy]; w[3] = L.wy[c]; w[4] = L.wz[c - L.sz]; w[5] = L.wz[c];
+                nb[0] = c - 1; nb[1] = c + 1; nb[2] = c - L.sy; nb[3] = c + L.sy; nb[4] = c - L.sz; nb[5] = c + L.sz;
+#pragma unroll
+                for (int k = 0; k < 6; k++)
+                    if (!(w[k] > 0.f) || nb[k] < 0 || nb[k] >= nc) { w[k] = 0.f; nb[k] = c; }
+            }
+            xs[0][c] = (in && a.n == 1 && !a.zero_guess) ? T.xa[c] : 0.f;
+            __syncthreads();
+            int cur = 0;
+            for (int s = 0; s < COARSE_SWEEPS; s++) {
+                float v = 0.f;
+                if (in && d > 0.f) {
+                    const float* xv = xs[cur];
+                    const float off = w[0] * xv[nb[0]] + w[1] * xv[nb[1]] + w[2] * xv[nb[2]] + w[3] * xv[nb[3]] + w[4] * xv[nb[4]] + w[5] * xv[nb[5]];
+                    const float xi = xv[c];
+                    v = xi + OMEGA * (bb - (d * xi - off)) / d;
+                }
+                xs[cur ^ 1][c] = v;
+                __syncthreads();
+                cur ^= 1;
+            }
+            if (in) T.xa[c] = xs[cur][c];
+        }
+        cluster.sync();
+    }
+    // up
+    for (int i = a.n - 2; i >= 0; i--) {
+        const TailLevel& T = a.lv[i];
+        t_prolong_jacobi(T.L, a.lv[i + 1].L, T.b, T.xa, a.lv[i + 1].xa, T.xb, t0, nt); cluster.sync();
+        t_jacobi(T.L, T.b, T.xb, T.xa, t0, nt);
+        if (i > 0) cluster.sync();
+    }
+}
+
 Lv view(const fsim* h, const MgLevel* m, int level) {
     Lv v;
     v.gx = m->gx; v.gy = m->gy; v.gz = m->gz; v.sy = m->sy; v.sz = m->sz;
@@ -490,9 +651,26 @@ int cycle(fsim* h, int l, bool zero_guess, float** result) {
     const bool v4 = fine && (m->gx % 4 == 0);  // float4 path; then the coarse gx is even (float2 stores / loads)
     const dim3 blk4(32, 4, 2);
     const dim3 grd4(div_up(m->gx, 4 * 32), div_up(m->gy, 4), div_up(m->gz, 2));
-    if (l == (int)h->mg.size() - 1) {  // coarsest
+    if (l == h->mg_tail_first) {  // this level and everything below it: one cluster launch
+        TailArgs ta;
+        ta.n = (int)h->mg.size() - l;
+        for (int i = 0; i < ta.n; i++) {
+            MgLevel* t = h->mg[l + i];
+            ta.lv[i].L = view(h, t, l + i);
+            ta.lv[i].xa = t->xa; ta.lv[i].xb = t->xb; ta.lv[i].b = t->b;
+        }
+        ta.sc = sc;
+        ta.zero_guess = zero_guess ? 1 : 0;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(TAIL_CLUSTER);
+        cfg.blockDim = dim3(TAIL_THREADS);
+        cfg.stream = h->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = TAIL_CLUSTER; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
         KScope ks(h, K_MG2);
-        mg_coarse_kernel<<<1, COARSE_MAX, 0, h->stream>>>(L, sc, m->b, m->xa, m->xa, zero_guess ? 1 : 0, COARSE_SWEEPS);
+        FSIM_CUDA(h, cudaLaunchKernelEx(&cfg, mg_tail_kernel, ta));
         *result = m->xa;
         return FSIM_OK;
     }
@@ -524,7 +702,7 @@ int cycle(fsim* h, int l, bool zero_guess, float** result) {
         else mg_restrict_kernel<false><<<grid_of(mc, blk), blk, 0, h->stream>>>(L, C, sc, m->b, cur, mc->b);
     }
     float* ec = nullptr;
-    const int visits = (l + 1 <= W_LEVELS && l + 1 < (int)h->mg.size() - 1) ? 2 : 1;
+    const int visits = (l + 1 >= W_FIRST && l + 1 <= W_LAST && l + 1 < (int)h->mg.size() - 1) ? 2 : 1;
     for (int v = 0; v < visits; v++) {
         int rc = cycle(h, l + 1, v == 0, &ec);
         if (rc) return rc;
@@ -575,6 +753,11 @@ int mg_build(fsim* h) {
             if (l > 0 && m->nc <= COARSE_MAX) break;
             gx = (gx + 1) / 2; gy = (gy + 1) / 2; gz = (gz + 1) / 2;
         }
+        // first level (>= 1) that is small enough for the single-cluster tail kernel
+        const int nl = (int)h->mg.size();
+        h->mg_tail_first = nl - 1;
+        for (int l = 1; l < nl; l++)
+            if (h->mg[l]->nc <= TAIL_MAX_CELLS && nl - l <= TAIL_MAX_LEVELS) { h->mg_tail_first = l; break; }
     }
     for (size_t l = 1; l < h->mg.size(); l++) {
         MgLevel *f = h->mg[l - 1], *c = h->mg[l];

@@ -20,8 +20,9 @@ bool mg_enabled(const fsim* h);
 
 namespace {
 
-constexpr int PT = 256;  // threads per block
-constexpr int CV = 2;    // cells per thread in the vector kernels
+constexpr int PT = 256;     // threads per block
+constexpr int CV = 2;       // consecutive cells per thread and trip (16-byte fp64 loads)
+constexpr int CHUNK = 8192; // cells per block of the reducing kernels: few partials => short fixed-order final sum
 
 struct PcgArgs {
     GridDims g;
@@ -106,6 +107,12 @@ __device__ __forceinline__ bool grid_reduce(double* vals, double* partials, unsi
     return false;
 }
 
+// iteration space of the chunked kernels: block b owns cells [b*CHUNK, (b+1)*CHUNK), a thread visits CV cells per trip
+#define FOR_CHUNK(c0, nc)                                                                                      \
+    for (int64_t c0 = (int64_t)blockIdx.x * CHUNK + (int64_t)threadIdx.x * CV,                                  \
+                 cend__ = min((int64_t)(blockIdx.x + 1) * CHUNK, (int64_t)(nc));                                \
+         c0 < cend__; c0 += PT * CV)
+
 // stencil code of a cell (calculateAMatrix, bridsonSolverGrid.cpp:40-77): bits 0-5 WATER neighbours (-x,+x,-y,+y,-z,+z),
 // bits 6-8 number of non-solid neighbours (the diagonal / scale), bit 15 the cell itself is WATER.  0 for other cells.
 __device__ __forceinline__ int code_ns(unsigned c) { return (c >> 6) & 7; }
@@ -160,7 +167,7 @@ __global__ void __launch_bounds__(PT) residual_kernel(PcgArgs a) {
     if (a.sc->done) return;
     double acc[1] = {0.0};
     const double scale = a.sc->scale;
-    const int64_t c0 = ((int64_t)blockIdx.x * PT + threadIdx.x) * CV;
+    FOR_CHUNK(c0, a.g.nc)
 #pragma unroll
     for (int k = 0; k < CV; k++) {
         const int64_t c = c0 + k;
@@ -202,7 +209,7 @@ template <bool JACOBI>
 __global__ void __launch_bounds__(PT) start_kernel(PcgArgs a) {
     if (a.sc->done) return;
     double acc[1] = {0.0};
-    const int64_t c0 = ((int64_t)blockIdx.x * PT + threadIdx.x) * CV;
+    FOR_CHUNK(c0, a.g.nc)
 #pragma unroll
     for (int k = 0; k < CV; k++) {
         const int64_t c = c0 + k;
@@ -226,11 +233,11 @@ template <bool VEC>
 __global__ void __launch_bounds__(PT) spmv_kernel(PcgArgs a) {
     if (a.sc->done) return;
     double acc[1] = {0.0};
-    const int64_t c = ((int64_t)blockIdx.x * PT + threadIdx.x) * CV;
     const int64_t sy = a.g.sy, sz = a.g.sz;
     const double scale = a.sc->scale;
+    FOR_CHUNK(c, a.g.nc)
     if (VEC) {
-        if (c < a.g.nc) {  // nc is even in this path
+        {  // nc is even in this path
             const ushort2 cd = *reinterpret_cast<const ushort2*>(a.code + c);
             const unsigned c0 = cd.x, c1 = cd.y;
             if ((c0 | c1) & CODE_ACTIVE) {
@@ -298,8 +305,8 @@ __global__ void __launch_bounds__(PT) update_kernel(PcgArgs a) {
     const bool bad = alpha != alpha;  // NaN => the reference breaks before touching p (:271-272)
     const double scale = a.sc->scale;
     double acc[2] = {0.0, 0.0};      // [0] = z.r (sum), [1] = max |r|
-    const int64_t c0 = ((int64_t)blockIdx.x * PT + threadIdx.x) * CV;
     if (!bad) {
+        FOR_CHUNK(c0, a.g.nc)
 #pragma unroll
         for (int k = 0; k < CV; k++) {
             const int64_t c = c0 + k;
@@ -343,7 +350,7 @@ __global__ void __launch_bounds__(PT) update_kernel(PcgArgs a) {
 __global__ void __launch_bounds__(PT) dot_zr_kernel(PcgArgs a) {
     if (a.sc->done) return;
     double acc[1] = {0.0};
-    const int64_t c0 = ((int64_t)blockIdx.x * PT + threadIdx.x) * CV;
+    FOR_CHUNK(c0, a.g.nc)
 #pragma unroll
     for (int k = 0; k < CV; k++) {
         const int64_t c = c0 + k;
@@ -358,7 +365,7 @@ __global__ void __launch_bounds__(PT) dot_zr_kernel(PcgArgs a) {
 __global__ void __launch_bounds__(PT) direction_kernel(PcgArgs a) {
     if (a.sc->done) return;
     const double beta = a.sc->sigma_new / a.sc->sigma;
-    const int64_t c0 = ((int64_t)blockIdx.x * PT + threadIdx.x) * CV;
+    FOR_CHUNK(c0, a.g.nc)
 #pragma unroll
     for (int k = 0; k < CV; k++) {
         const int64_t c = c0 + k;
@@ -420,7 +427,7 @@ int k_project(fsim* h, double dt, int* iterations) {
     a.warm = h->warm_start && h->pressure_valid;
     a.z32 = nullptr;
     const int nb1 = div_up(g.nc, PT);        // one cell per thread
-    const int nbv = div_up(g.nc, PT * CV);   // CV cells per thread
+    const int nbv = div_up(g.nc, CHUNK);     // chunked kernels
     const bool vec = (g.gx % 2 == 0) && (g.nc % 2 == 0);
     const bool use_mg = mg_enabled(h);
     const int max_it = h->par.max_iterations;

@@ -191,3 +191,33 @@ def sweep2(n, kind="dam", min_cells=600):
                   dict(over=2.0, wlevels=2), dict(coarse_sweeps=100, wlevels=2)]:
         cfg = dict(base); cfg.update(extra)
         t0 = time.time(); x, it = pcg(A, b, lambda r: vcycle2(levels, 0, r, cfg), 1e-6); print(extra, "its", it, "%.1fs" % (time.time() - t0))
+
+def vcycle3(levels, l, b, cfg):
+    """cycle with a per-level visit multiplier cfg['visits'][l] (how often level l is visited per visit of level l-1)"""
+    L = levels[l]; om = cfg["omega"]
+    if l == len(levels) - 1:
+        return smooth(L, np.zeros_like(b), b, "jacobi", cfg["coarse_sweeps"], omega=om)
+    pre = cfg.get("pre_l", {}).get(l, cfg["pre"]); post = cfg.get("post_l", {}).get(l, cfg["post"])
+    x = smooth(L, np.zeros_like(b), b, "jacobi", pre, omega=om)
+    rc = L["P"].T @ (b - L["A"] @ x)
+    ec = np.zeros(levels[l + 1]["A"].shape[0])
+    for v in range(cfg["visits"].get(l + 1, 1) if l + 1 < len(levels) - 1 else 1):
+        ec = ec + vcycle3(levels, l + 1, rc - levels[l + 1]["A"] @ ec, cfg)
+    x = x + cfg["over"] * (L["P"] @ ec)
+    return smooth(L, x, b, "jacobi", post, omega=om)
+
+def sweep3(n, kind="dam"):
+    t = build(n, kind); A, idx = assemble(t); A = A * 0.005
+    gdt = -39.24 * 0.005
+    vy = np.zeros(t.shape); up = np.roll(t, -1, axis=1)
+    vy[(t != SOLID) & (up != SOLID)] = gdt
+    b = -(vy - np.roll(vy, 1, axis=1))[t == WATER]
+    b = b + np.random.default_rng(0).normal(0, 1.0, b.shape)
+    levels = hierarchy(t, A, idx, min_cells=600)
+    print(n, kind, "levels", [L["A"].shape[0] for L in levels])
+    base = dict(pre=2, post=2, over=1.8, omega=0.8, coarse_sweeps=30)
+    for extra in [dict(visits={1: 2, 2: 2}), dict(visits={2: 2}), dict(visits={2: 3}), dict(visits={2: 2, 3: 2}), dict(visits={2: 4}),
+                  dict(visits={1: 2}), dict(visits={3: 2}), dict(visits={2: 2}, pre_l={1: 3}, post_l={1: 3}),
+                  dict(visits={2: 2}, pre_l={2: 4, 3: 4}, post_l={2: 4, 3: 4}), dict(visits={}, pre_l={1: 4, 2: 8, 3: 8}, post_l={1: 4, 2: 8, 3: 8})]:
+        cfg = dict(base); cfg.update(extra)
+        t0 = time.time(); x, it = pcg(A, b, lambda r: vcycle3(levels, 0, r, cfg), 1e-6); print(extra, "its", it, "%.1fs" % (time.time() - t0))
