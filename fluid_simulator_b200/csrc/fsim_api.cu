@@ -379,6 +379,13 @@ int fsim_set_obstacles(fsim_t* h, const FsimObstacle* obs, int n) {
     return k_upload_obstacles(h);
 }
 
+int fsim_set_particle_radius(fsim_t* h, double r) {
+    BIND(h);
+    if (!(r > 0)) return fsim_fail(h, FSIM_ERR_INVALID, "particle radius must be > 0");
+    h->particle_r = r;
+    return k_upload_obstacles(h);  // push-out box extents include the radius
+}
+
 int fsim_get_obstacles(const fsim_t* h, FsimObstacle* out, int cap, int* n) {
     if (!h) return FSIM_ERR_INVALID;
     const int m = cap < h->nobs ? cap : h->nobs;

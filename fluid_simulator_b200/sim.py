@@ -51,6 +51,7 @@ def load_library():
         "fsim_set_params": (i32, [vp, P(abi.Params)]),
         "fsim_set_obstacles": (i32, [vp, P(abi.Obstacle), i32]),
         "fsim_get_obstacles": (i32, [vp, P(abi.Obstacle), i32, P(i32)]),
+        "fsim_set_particle_radius": (i32, [vp, dbl]),
         "fsim_upload_particles": (i32, [vp, vp, i64]),
         "fsim_append_particles": (i32, [vp, vp, i64]),
         "fsim_remove_particles": (i32, [vp, vp, i64]),

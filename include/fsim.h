@@ -184,6 +184,8 @@ FSIM_API int fsim_set_params(fsim_t* h, const FsimParams* p);
 /* simulator->obstacles = clones (manager/simulationManager.cpp:202-207); list order is semantic (macGrid.cpp:247-259) */
 FSIM_API int fsim_set_obstacles(fsim_t* h, const FsimObstacle* obs, int n);
 FSIM_API int fsim_get_obstacles(const fsim_t* h, FsimObstacle* out, int cap, int* n);
+/* HashedParticles::setParticleR (hashedParticles.cpp:186-193): the radius enters the advect / push-out bounds */
+FSIM_API int fsim_set_particle_radius(fsim_t* h, double r);
 
 /* HashedParticles::getParticleAt/forEach write path, setParticleNum (hashedParticles.cpp:132-151,178-180) */
 FSIM_API int fsim_upload_particles(fsim_t* h, const double* aos15, int64_t n);

@@ -1,0 +1,100 @@
+"""Host side above the C ABI: the reference-shaped C++ facade (fluid_simulator_b200/host) builds on CPU, and on the GPU
+(i) a driver that uses it exactly like SimulationManager's constructor/worker agrees with the fp64 oracle, and (ii) the
+reference's own, unmodified manager/simulationManager.cpp runs on top of it (binary built where /root/reference exists)."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CPP = os.path.join(ROOT, "tests", "cpp")
+
+
+def _env():
+    env = dict(os.environ)
+    env.pop("CXX", None)
+    env.pop("CC", None)
+    return env
+
+
+def test_facade_builds_against_c_abi():
+    subprocess.check_call(["bash", os.path.join(CPP, "build_facade.sh")], env=_env())
+    assert os.path.exists(os.path.join(CPP, "build", "facade_smoke"))
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src/Simulator/manager"), reason="reference sources not present")
+def test_reference_manager_compiles_unmodified_against_facade():
+    subprocess.check_call(["bash", os.path.join(CPP, "build_dropin.sh")], env=_env())
+    assert os.path.exists(os.path.join(ROOT, "oracle", "_ref", "manager_on_b200"))
+
+
+def test_facade_headers_mirror_reference_signatures():
+    """The signatures SURVEY.md §8b lists as the drop-in surface are present in the facade headers."""
+    host = os.path.join(ROOT, "fluid_simulator_b200", "host", "simulator")
+    sim = open(os.path.join(host, "simulator.h")).read()
+    for sig in ("void setNewMacGrid(", "void setNewHashedParticles(", "void simulate(double dt)", "getStepDuration() const",
+                "std::vector<std::unique_ptr<genericfsim::obstacle::Obstacle>> obstacles", "SimulatorConfig config"):
+        assert sig in sim, sig
+    hp = open(os.path.join(host, "particles", "hashedParticles.h")).read()
+    for sig in ("HashedParticles(int num, double r, glm::dvec3 dimensions, glm::dvec3 cellD, bool zConst, double z)",
+                "void forEach(bool parallel, std::function<void(Particle&, int)>&& lambda)", "Particle& getParticleAt(int idx)",
+                "void setParticleNum(int num)", "void addParticles(", "void removeParticles(", "const bool zConst"):
+        assert sig in hp, sig
+    mg = open(os.path.join(host, "macGrid", "macGrid.h")).read()
+    for sig in ("MacGrid(glm::dvec3 targetDimensions, double resolution, bool twoD)", "virtual int solveIncompressibility(bool parallel, double dt) = 0",
+                "const glm::ivec3 gridSize", "double pressureK = 2.0, averagePressure = 2.0", "inline MacGridCell& cell(int x, int y, int z)"):
+        assert sig in mg, sig
+
+
+@pytest.mark.gpu
+def test_facade_matches_oracle(oracle_lib):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from fluid_simulator_b200 import abi, scenes
+    from oracle.oracle import OracleSim
+    exe = os.path.join(CPP, "build", "facade_smoke")
+    if not os.path.exists(exe):
+        subprocess.check_call(["bash", os.path.join(CPP, "build_facade.sh")], env=_env())
+    n, steps = 24, 3
+    out = subprocess.check_output([exe, str(n), str(steps)], text=True)
+    m = re.search(r"FACADE np=(\d+) ke=(\S+) ysum=(\S+) water=(\d+) solid=(\d+) v2ysum=(\S+) its=(-?\d+) gfx=(\d+)", out)
+    assert m, out
+    assert "FACADE basic=throws" in out
+    np_, ke, ysum, water, solid, v2ysum = int(m[1]), float(m[2]), float(m[3]), int(m[4]), int(m[5]), float(m[6])
+    # same scene through the oracle
+    nx, ny, nz = n // 2 - 1, n - 2, n - 2
+    xs, ys, zs, ss = np.meshgrid(np.arange(1, nx + 1), np.arange(1, ny + 1), np.arange(1, nz + 1), np.arange(8), indexing="ij")
+    pos = np.stack([xs + np.where(ss & 4, 0.75, 0.25), ys + np.where(ss & 2, 0.75, 0.25), zs + np.where(ss & 1, 0.75, 0.25)], axis=-1).reshape(-1, 3)
+    parts = np.zeros((pos.shape[0], 15))
+    parts[:, 0:3] = pos
+    o = OracleSim((n, n, n), 1.0, False, 0.25)
+    o.set_params(scenes.default_params(abi.FLIP, tol=1e-9))
+    o.set_obstacles([abi.make_obstacle(abi.SPHERE, pos=(0.3 * n, 0.3 * n, 0.5 * n), r=0.12 * n)])
+    o.upload_particles(parts)
+    for _ in range(steps):
+        o.step(0.005)
+    po = o.download_particles()
+    t = o.download_grid(abi.FIELD_TYPE)
+    assert np_ == po.shape[0] and int(m[8]) == np_
+    assert water == int((t == abi.WATER).sum()) and solid == int((t == abi.SOLID).sum())
+    assert abs(ke - 0.5 * (po[:, 3:6] ** 2).sum()) <= 1e-4 * ke
+    assert abs(ysum - po[:, 1].sum()) <= 1e-6 * abs(ysum)
+    assert abs(v2ysum - o.download_grid(abi.FIELD_V2)[:, 1].sum()) <= 1e-4 * abs(v2ysum)
+
+
+@pytest.mark.gpu
+def test_reference_manager_runs_on_b200_backend():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    exe = os.path.join(ROOT, "oracle", "_ref", "manager_on_b200")
+    if not os.path.exists(exe):
+        pytest.skip("drop-in binary not built (needs /root/reference at build time)")
+    out = subprocess.check_output([exe], text=True, timeout=120)
+    m = re.search(r"DROPIN particles=(\d+) grid=(\d+)x(\d+)x(\d+) ymean=(\S+) vmax=(\S+) its=(-?\d+)", out)
+    assert m, out
+    assert int(m[1]) == 30000 and (int(m[2]), int(m[3]), int(m[4])) == (40, 25, 20)
+    assert 0.0 < float(m[5]) < 25.0 and float(m[6]) > 0.0  # the fluid fell and moves
