@@ -18,6 +18,7 @@
 #include <cooperative_groups.h>
 
 #include "fsim_internal.h"
+#include "reduce.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -268,18 +269,21 @@ __global__ void __launch_bounds__(256) mg_first4_kernel(Lv L, const double* __re
                 const float d = (float)((cd[i] >> 6) & 7u);
                 xo.v[i] = d > 0.f ? OMEGA * bb.v[i] / d : 0.f;
             }
+        st4(b + c, bb);     // groups without WATER cells are never read (every consumer checks the code) => not written
+        st4(xout + c, xo);
     }
-    st4(b + c, bb);
-    st4(xout + c, xo);
 }
 
-__global__ void __launch_bounds__(256) mg_jacobi4_kernel(Lv L, const PcgScalars* __restrict__ sc, const float* __restrict__ b, const float* __restrict__ xin,
-                                                         float* __restrict__ xout) {
+// DOT: the last sweep of the cycle also accumulates sigma' = z.r against the fp64 CG residual (saves a pass over z and r)
+template <bool DOT>
+__global__ void __launch_bounds__(256) mg_jacobi4_kernel(Lv L, PcgScalars* __restrict__ sc, const float* __restrict__ b, const float* __restrict__ xin,
+                                                         float* __restrict__ xout, const double* __restrict__ r64, double* partials,
+                                                         unsigned int* counter) {
     if (sc->done) return;
     int64_t c; unsigned cd[4];
-    if (!group_of(L, c, cd)) return;
-    F4 xo = zero4();
-    if ((cd[0] | cd[1] | cd[2] | cd[3]) & CODE_ACTIVE) {
+    double acc[1] = {0.0};
+    if (group_of(L, c, cd) && ((cd[0] | cd[1] | cd[2] | cd[3]) & CODE_ACTIVE)) {
+        F4 xo = zero4();
         const Stencil4 s = load_stencil4(L, xin, c, cd);
         const F4 bb = ld4(b + c);
 #pragma unroll
@@ -289,8 +293,80 @@ __global__ void __launch_bounds__(256) mg_jacobi4_kernel(Lv L, const PcgScalars*
                 const float xi = s.c.v[i];
                 xo.v[i] = d > 0.f ? xi + OMEGA * (bb.v[i] - (d * xi - off4(s, i, cd[i]))) / d : 0.f;
             }
+        st4(xout + c, xo);
+        if (DOT) {
+            const double2 r0 = *reinterpret_cast<const double2*>(r64 + c), r1 = *reinterpret_cast<const double2*>(r64 + c + 2);
+            const double rr[4] = {r0.x, r0.y, r1.x, r1.y};
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                if (cd[i] & CODE_ACTIVE) acc[0] += (double)xo.v[i] * rr[i];
+        }
     }
-    st4(xout + c, xo);
+    if (DOT) {
+        double out[1];
+        const unsigned bid = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+        if (grid_reduce<1, 0>(acc, partials, counter, out, bid, gridDim.x * gridDim.y * gridDim.z)) sc->sigma_new = out[0];
+    }
+}
+
+// CG update fused with the first smoothing sweep of the next cycle (level 0, linear chunks of 4-cell groups):
+//   alpha = sigma / s.q ; p += alpha s ; r -= alpha q ; ||r||_inf ; b = r / scale ; x1 = omega b / diag
+constexpr int UF_CHUNK = 8192;
+__global__ void __launch_bounds__(256) mg_update_first4_kernel(Lv L, int64_t nc, PcgScalars* sc, PcgHostStatus* status, double* __restrict__ p,
+                                                               const double* __restrict__ sv, double* __restrict__ r,
+                                                               const double* __restrict__ q, float* __restrict__ b, float* __restrict__ xout,
+                                                               double* partials, unsigned int* counter) {
+    if (sc->done) return;
+    const double alpha = sc->sigma / sc->sq;
+    const bool bad = alpha != alpha;  // NaN => the reference breaks before touching p (bridsonSolverGrid.cpp:271-272)
+    const double inv_scale = sc->inv_scale;
+    double acc[1] = {0.0};
+    if (!bad) {
+        const int64_t cend = min((int64_t)(blockIdx.x + 1) * UF_CHUNK, nc);
+        for (int64_t c = (int64_t)blockIdx.x * UF_CHUNK + (int64_t)threadIdx.x * 4; c < cend; c += 256 * 4) {
+            const ushort4 t = *reinterpret_cast<const ushort4*>(L.code + c);
+            const unsigned cd[4] = {t.x, t.y, t.z, t.w};
+            if (!((cd[0] | cd[1] | cd[2] | cd[3]) & CODE_ACTIVE)) continue;
+            double pp[4], ss[4], rr[4], qq[4];
+#pragma unroll
+            for (int h2 = 0; h2 < 2; h2++) {
+                const double2 a0 = *reinterpret_cast<const double2*>(p + c + 2 * h2), a1 = *reinterpret_cast<const double2*>(sv + c + 2 * h2);
+                const double2 a2 = *reinterpret_cast<const double2*>(r + c + 2 * h2), a3 = *reinterpret_cast<const double2*>(q + c + 2 * h2);
+                pp[2 * h2] = a0.x; pp[2 * h2 + 1] = a0.y; ss[2 * h2] = a1.x; ss[2 * h2 + 1] = a1.y;
+                rr[2 * h2] = a2.x; rr[2 * h2 + 1] = a2.y; qq[2 * h2] = a3.x; qq[2 * h2 + 1] = a3.y;
+            }
+            F4 bb = zero4(), xo = zero4();
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                if (cd[i] & CODE_ACTIVE) {
+                    pp[i] += alpha * ss[i];
+                    rr[i] -= alpha * qq[i];
+                    acc[0] = fmax(acc[0], fabs(rr[i]));
+                    bb.v[i] = (float)(rr[i] * inv_scale);
+                    const float d = (float)((cd[i] >> 6) & 7u);
+                    xo.v[i] = d > 0.f ? OMEGA * bb.v[i] / d : 0.f;
+                }
+#pragma unroll
+            for (int h2 = 0; h2 < 2; h2++) {
+                *reinterpret_cast<double2*>(p + c + 2 * h2) = make_double2(pp[2 * h2], pp[2 * h2 + 1]);
+                *reinterpret_cast<double2*>(r + c + 2 * h2) = make_double2(rr[2 * h2], rr[2 * h2 + 1]);
+            }
+            st4(b + c, bb);
+            st4(xout + c, xo);
+        }
+    }
+    double out[1];
+    if (grid_reduce<0, 1>(acc, partials, counter, out)) {
+        const int it = sc->it;
+        if (bad) {
+            sc->nan_break = 1; sc->done = 1; sc->iterations = it;
+        } else {
+            sc->rmax = out[0];
+            if (out[0] < sc->tol) { sc->done = 1; sc->iterations = it; }                       // :280-281, 292
+            else if (it + 1 >= sc->max_it) { sc->done = 2; sc->iterations = sc->max_it; }       // iteration cap
+        }
+        if (sc->done) { status->done = sc->done; __threadfence_system(); }
+    }
 }
 
 // one thread = two coarse cells in x = a 4x2x2 block of fine cells
@@ -358,8 +434,8 @@ __global__ void __launch_bounds__(256) mg_prolong_jacobi4_kernel(Lv L, Lv C, con
                 const float xi = s.c.v[i];
                 xo.v[i] = d > 0.f ? xi + OMEGA * (bb.v[i] - (d * xi - off4(s, i, cd[i]))) / d : 0.f;
             }
+        st4(xout + c, xo);
     }
-    st4(xout + c, xo);
 }
 
 // Galerkin operator of level 1 from the cell flags: face weight = # WATER-WATER fine connections across the coarse
@@ -641,7 +717,7 @@ int alloc_level(fsim* h, MgLevel* m, bool fine) {
 }
 
 // one multigrid cycle on level l for the right-hand side m->b; returns the array holding the result
-int cycle(fsim* h, int l, bool zero_guess, float** result) {
+int cycle(fsim* h, int l, bool zero_guess, float** result, bool first_done = false, bool with_dot = false) {
     MgLevel* m = h->mg[l];
     const dim3 blk(32, 4, 2);
     const Lv L = view(h, m, l);
@@ -681,14 +757,15 @@ int cycle(fsim* h, int l, bool zero_guess, float** result) {
         KScope ks(h, kid);
         mg_pre2_kernel<<<grid_of(m, blk), blk, 0, h->stream>>>(L, sc, m->b, cur);
     } else {
-        KScope ks(h, kid, PRE);
+        KScope ks(h, kid, PRE - ((zero_guess && first_done) ? 1 : 0));
         for (int s = 0; s < PRE; s++) {
+            if (s == 0 && zero_guess && first_done) continue;  // x1 and b were written by the fused CG update
             if (s == 0 && zero_guess) {
                 if (v4) mg_first4_kernel<<<grd4, blk4, 0, h->stream>>>(L, h->r, sc, m->b, cur);
                 else if (fine) mg_first_kernel<true><<<grid_of(m, blk), blk, 0, h->stream>>>(L, h->r, sc, m->b, cur);
                 else mg_first_kernel<false><<<grid_of(m, blk), blk, 0, h->stream>>>(L, nullptr, sc, m->b, cur);
             } else {
-                if (v4) mg_jacobi4_kernel<<<grd4, blk4, 0, h->stream>>>(L, sc, m->b, cur, oth);
+                if (v4) mg_jacobi4_kernel<false><<<grd4, blk4, 0, h->stream>>>(L, h->scal, m->b, cur, oth, nullptr, nullptr, nullptr);
                 else if (fine) mg_jacobi_kernel<true><<<grid_of(m, blk), blk, 0, h->stream>>>(L, sc, m->b, cur, oth);
                 else mg_jacobi_kernel<false><<<grid_of(m, blk), blk, 0, h->stream>>>(L, sc, m->b, cur, oth);
                 float* t = cur; cur = oth; oth = t;
@@ -717,7 +794,9 @@ int cycle(fsim* h, int l, bool zero_guess, float** result) {
         else mg_prolong_jacobi_kernel<false><<<grid_of(m, blk), blk, 0, h->stream>>>(L, C, sc, m->b, cur, mc->xa, oth);
         { float* t = cur; cur = oth; oth = t; }
         for (int s = 1; s < POST; s++) {
-            if (v4) mg_jacobi4_kernel<<<grd4, blk4, 0, h->stream>>>(L, sc, m->b, cur, oth);
+            if (v4 && with_dot && s == POST - 1)
+                mg_jacobi4_kernel<true><<<grd4, blk4, 0, h->stream>>>(L, h->scal, m->b, cur, oth, h->r, h->partials, h->red_counter);
+            else if (v4) mg_jacobi4_kernel<false><<<grd4, blk4, 0, h->stream>>>(L, h->scal, m->b, cur, oth, nullptr, nullptr, nullptr);
             else if (fine) mg_jacobi_kernel<true><<<grid_of(m, blk), blk, 0, h->stream>>>(L, sc, m->b, cur, oth);
             else mg_jacobi_kernel<false><<<grid_of(m, blk), blk, 0, h->stream>>>(L, sc, m->b, cur, oth);
             float* t = cur; cur = oth; oth = t;
@@ -769,10 +848,25 @@ int mg_build(fsim* h) {
     return FSIM_OK;
 }
 
-// z32 = M^-1 r : one cycle from a zero guess on the fp64 CG residual h->r
-int mg_apply(fsim* h) {
+// the fused paths need the float4 level-0 kernels
+bool mg_can_fuse(const fsim* h) { return h->use_mg && !h->mg.empty() && h->mg[0]->gx % 4 == 0 && h->g.nc % 4 == 0; }
+
+// CG update (p, r, ||r||_inf, convergence flags) fused with the first smoothing sweep of the cycle that follows
+int mg_update_first(fsim* h) {
+    MgLevel* m = h->mg[0];
+    const Lv L = view(h, m, 0);
+    KScope ks(h, K_UPDATE);
+    mg_update_first4_kernel<<<div_up(h->g.nc, UF_CHUNK), 256, 0, h->stream>>>(L, h->g.nc, h->scal, h->status_dev, h->p, h->s, h->r, h->q, m->b,
+                                                                              m->xa, h->partials, h->red_counter);
+    FSIM_CHECK_LAUNCH(h);
+    return FSIM_OK;
+}
+
+// z32 = M^-1 r : one cycle from a zero guess on the fp64 CG residual h->r.  first_done: b and the first sweep were
+// produced by mg_update_first; with_dot: the last sweep also writes sigma' = z.r
+int mg_apply(fsim* h, bool first_done, bool with_dot) {
     float* res = nullptr;
-    int rc = cycle(h, 0, true, &res);
+    int rc = cycle(h, 0, true, &res, first_done, with_dot);
     if (rc) return rc;
     h->mg_z32 = res;
     FSIM_CHECK_LAUNCH(h);

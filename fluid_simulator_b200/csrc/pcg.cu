@@ -14,13 +14,16 @@
 //     last-block sum => deterministic, no fp64 atomics;
 //   * all scalars (sigma, alpha, beta, done flag, iteration count) stay on the device; the host only polls the done flag.
 #include "fsim_internal.h"
+#include "reduce.cuh"
 
-int mg_apply(fsim* h);  // z = M^-1 r   (mg.cu)
+int mg_apply(fsim* h, bool first_done, bool with_dot);  // z = M^-1 r   (mg.cu)
+int mg_update_first(fsim* h);
+bool mg_can_fuse(const fsim* h);
 bool mg_enabled(const fsim* h);
 
 namespace {
 
-constexpr int PT = 256;     // threads per block
+constexpr int PT = RED_THREADS;  // threads per block
 constexpr int CV = 2;       // consecutive cells per thread and trip (16-byte fp64 loads)
 constexpr int CHUNK = 8192; // cells per block of the reducing kernels: few partials => short fixed-order final sum
 
@@ -40,72 +43,6 @@ struct PcgArgs {
     double avg_pressure, pressure_k;
     int pressure_enabled, warm;
 };
-
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    return v;
-}
-__device__ __forceinline__ double warp_max(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, o));
-    return v;
-}
-
-// block reduction of NS sums followed by NM maxima; the last block to arrive folds all per-block partials in a fixed
-// order (bitwise reproducible) and its thread 0 returns true with the grid-wide totals in out[].
-template <int NS, int NM>
-__device__ __forceinline__ bool grid_reduce(double* vals, double* partials, unsigned int* counter, double* out) {
-    __shared__ double sh[NS + NM][PT / 32];
-    __shared__ bool last;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-#pragma unroll
-    for (int k = 0; k < NS + NM; k++) {
-        const double v = k < NS ? warp_sum(vals[k]) : warp_max(vals[k]);
-        if (lane == 0) sh[k][w] = v;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int k = 0; k < NS + NM; k++) {
-            double v = sh[k][0];
-            for (int i = 1; i < PT / 32; i++) v = k < NS ? v + sh[k][i] : fmax(v, sh[k][i]);
-            partials[(size_t)k * gridDim.x + blockIdx.x] = v;
-        }
-        __threadfence();
-        const unsigned t = atomicInc(counter, gridDim.x - 1);  // wraps back to 0 => self-resetting
-        last = (t == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!last) return false;
-    __threadfence();
-    double tot[NS + NM];
-#pragma unroll
-    for (int k = 0; k < NS + NM; k++) {
-        double v = 0.0;
-        for (unsigned i = threadIdx.x; i < gridDim.x; i += PT) {
-            const double x = __ldcg(partials + (size_t)k * gridDim.x + i);
-            v = k < NS ? v + x : fmax(v, x);
-        }
-        tot[k] = k < NS ? warp_sum(v) : warp_max(v);
-    }
-    __syncthreads();
-    if (lane == 0) {
-#pragma unroll
-        for (int k = 0; k < NS + NM; k++) sh[k][w] = tot[k];
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int k = 0; k < NS + NM; k++) {
-            double v = sh[k][0];
-            for (int i = 1; i < PT / 32; i++) v = k < NS ? v + sh[k][i] : fmax(v, sh[k][i]);
-            out[k] = v;
-        }
-        return true;
-    }
-    return false;
-}
 
 // iteration space of the chunked kernels: block b owns cells [b*CHUNK, (b+1)*CHUNK), a thread visits CV cells per trip
 #define FOR_CHUNK(c0, nc)                                                                                      \
@@ -297,6 +234,50 @@ __global__ void __launch_bounds__(PT) spmv_kernel(PcgArgs a) {
     if (grid_reduce<1, 0>(acc, a.partials, a.counter, out)) a.sc->sq = out[0];
 }
 
+// same as spmv_kernel<true> with four cells per thread and trip (gx % 4 == 0): 13 independent loads in flight per thread
+__global__ void __launch_bounds__(PT) spmv4_kernel(PcgArgs a) {
+    if (a.sc->done) return;
+    double acc[1] = {0.0};
+    const int64_t sy = a.g.sy, sz = a.g.sz;
+    const double scale = a.sc->scale;
+    const int64_t cend = min((int64_t)(blockIdx.x + 1) * CHUNK, a.g.nc);
+    for (int64_t c = (int64_t)blockIdx.x * CHUNK + (int64_t)threadIdx.x * 4; c < cend; c += PT * 4) {
+        const ushort4 t = *reinterpret_cast<const ushort4*>(a.code + c);
+        const unsigned cd[4] = {t.x, t.y, t.z, t.w};
+        const unsigned any = cd[0] | cd[1] | cd[2] | cd[3];
+        if (!(any & CODE_ACTIVE)) continue;
+        double sc[4], ym[4] = {0, 0, 0, 0}, yp[4] = {0, 0, 0, 0}, zm[4] = {0, 0, 0, 0}, zp[4] = {0, 0, 0, 0};
+        auto ld = [&](double* dst, const double* src) {
+            const double2 u = *reinterpret_cast<const double2*>(src), v = *reinterpret_cast<const double2*>(src + 2);
+            dst[0] = u.x; dst[1] = u.y; dst[2] = v.x; dst[3] = v.y;
+        };
+        ld(sc, a.s + c);
+        if (any & 4u) ld(ym, a.s + c - sy);
+        if (any & 8u) ld(yp, a.s + c + sy);
+        if (any & 16u) ld(zm, a.s + c - sz);
+        if (any & 32u) ld(zp, a.s + c + sz);
+        const double xl = (cd[0] & 1u) ? a.s[c - 1] : 0.0, xr = (cd[3] & 2u) ? a.s[c + 4] : 0.0;
+        double q[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            if (cd[i] & CODE_ACTIVE) {
+                double n = 0.0;
+                if (cd[i] & 1u) n += i == 0 ? xl : sc[i - 1];
+                if (cd[i] & 2u) n += i == 3 ? xr : sc[i + 1];
+                if (cd[i] & 4u) n += ym[i];
+                if (cd[i] & 8u) n += yp[i];
+                if (cd[i] & 16u) n += zm[i];
+                if (cd[i] & 32u) n += zp[i];
+                q[i] = scale * ((double)code_ns(cd[i]) * sc[i] - n);
+                acc[0] += sc[i] * q[i];
+            }
+        *reinterpret_cast<double2*>(a.q + c) = make_double2(q[0], q[1]);
+        *reinterpret_cast<double2*>(a.q + c + 2) = make_double2(q[2], q[3]);
+    }
+    double out[1];
+    if (grid_reduce<1, 0>(acc, a.partials, a.counter, out)) a.sc->sq = out[0];
+}
+
 // alpha = sigma / s.q ; p += alpha s ; r -= alpha q ; ||r||_inf ; (JACOBI: z = r / A_ii ; sigma' = z.r)   (:270-284)
 template <bool JACOBI>
 __global__ void __launch_bounds__(PT) update_kernel(PcgArgs a) {
@@ -389,12 +370,20 @@ __global__ void sigma_kernel(PcgScalars* sc, PcgHostStatus* status) {
 static int enqueue_iteration(fsim* h, const PcgArgs& a, bool vec, bool use_mg, int nbv) {
     {
         KScope ks(h, K_SPMV);
-        if (vec) spmv_kernel<true><<<nbv, PT, 0, h->stream>>>(a);
+        if (vec && a.g.gx % 4 == 0 && a.g.nc % 4 == 0) spmv4_kernel<<<nbv, PT, 0, h->stream>>>(a);
+        else if (vec) spmv_kernel<true><<<nbv, PT, 0, h->stream>>>(a);
         else spmv_kernel<false><<<nbv, PT, 0, h->stream>>>(a);
     }
-    if (use_mg) {
+    if (use_mg && mg_can_fuse(h)) {
+        // update fused with the cycle's first sweep, z.r fused with its last sweep: 2 passes and 2 launches fewer
+        int rc = mg_update_first(h);
+        if (rc) return rc;
+        rc = mg_apply(h, true, true);
+        if (rc) return rc;
+        if (a.z32 != h->mg_z32) return fsim_fail(h, FSIM_ERR_INVALID, "multigrid result buffer moved between cycles");
+    } else if (use_mg) {
         { KScope ks(h, K_UPDATE); update_kernel<false><<<nbv, PT, 0, h->stream>>>(a); }
-        int rc = mg_apply(h);
+        int rc = mg_apply(h, false, false);
         if (rc) return rc;
         if (a.z32 != h->mg_z32) return fsim_fail(h, FSIM_ERR_INVALID, "multigrid result buffer moved between cycles");
         KScope ks(h, K_UPDATE);
@@ -448,7 +437,7 @@ int k_project(fsim* h, double dt, int* iterations) {
     if (use_mg) {
         int rc = mg_build(h);
         if (rc) return rc;
-        rc = mg_apply(h);
+        rc = mg_apply(h, false, false);
         if (rc) return rc;
         a.z32 = h->mg_z32;
         KScope ks(h, K_PCG_INIT);
