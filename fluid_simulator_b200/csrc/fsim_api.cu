@@ -294,8 +294,8 @@ int fsim_create(const FsimGridDesc* desc, fsim_t** out) {
     A(dev_alloc(h, &h->d_obs, FSIM_MAX_OBS));
     A(dev_alloc(h, &h->scal, 1));
     h->red_blocks = (int)(g.nc / 256 + 2);  // one partial per 256-thread block of the widest solver launch
-    A(dev_alloc(h, &h->partials, (size_t)3 * h->red_blocks));
-    A(dev_alloc(h, &h->red_counter, 1));
+    A(dev_alloc(h, &h->partials, (size_t)3 * (h->red_blocks + h->red_blocks / 32 + 2)));
+    A(dev_alloc(h, &h->red_counter, (size_t)h->red_blocks / 32 + 4));
     const int64_t cap0 = desc->particle_capacity > 0 ? desc->particle_capacity : 0;
     // scan scratch: one entry per 4096-item tile of the larger of (cells, particle capacity); grown with capacity
     h->scan_block = nullptr;

@@ -124,7 +124,7 @@ __device__ __forceinline__ void p2g_pass(const P2GArgs& a, float* s_val, float* 
         }
 }
 
-__global__ void __launch_bounds__(NTHREADS) p2g_kernel(P2GArgs a) {
+__global__ void __launch_bounds__(NTHREADS, 2) p2g_kernel(P2GArgs a) {
     __shared__ float s[7][SN];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int wy = warp % TY, wz = warp / TY;

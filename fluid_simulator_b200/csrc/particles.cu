@@ -44,7 +44,7 @@ struct AdvectArgs {
     const DevObstacle* obs;
 };
 
-__global__ void __launch_bounds__(256) advect_kernel(AdvectArgs a) {
+__global__ void __launch_bounds__(256, 5) advect_kernel(AdvectArgs a) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n) return;
     D3 pos = mk(a.px[i], a.py[i], a.pz[i]);

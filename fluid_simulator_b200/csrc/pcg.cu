@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(PT) spmv_kernel(PcgArgs a) {
 }
 
 // same as spmv_kernel<true> with four cells per thread and trip (gx % 4 == 0): 13 independent loads in flight per thread
-__global__ void __launch_bounds__(PT) spmv4_kernel(PcgArgs a) {
+__global__ void __launch_bounds__(PT, 4) spmv4_kernel(PcgArgs a) {
     if (a.sc->done) return;
     double acc[1] = {0.0};
     const int64_t sy = a.g.sy, sz = a.g.sz;

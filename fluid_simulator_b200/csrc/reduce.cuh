@@ -15,43 +15,69 @@ __device__ __forceinline__ double warp_max(double v) {
     return v;
 }
 
-// block reduction of NS sums followed by NM maxima; the last block to arrive folds all per-block partials in a fixed
-// order (bitwise reproducible) and its thread 0 returns true with the grid-wide totals in out[].
+// Deterministic grid-wide reduction of NS sums followed by NM maxima.  Two-level arrival counters keep the same-address
+// atomic traffic low for grids of tens of thousands of blocks: blocks arrive in groups of RED_GROUP; the last block of a
+// group folds the group's per-block partials (fixed order) into one group partial and arrives at the top counter; the
+// last group folds the group partials (fixed order).  Exactly one thread of the grid returns true with the totals in out[].
+// partials: [(NS+NM)][nblocks + ngroups] doubles; counters: [1 + ngroups] unsigned, zero-initialised, self-resetting.
+constexpr unsigned RED_GROUP = 32;
+
 template <int NS, int NM>
-__device__ __forceinline__ bool grid_reduce(double* vals, double* partials, unsigned int* counter, double* out,
+__device__ __forceinline__ bool grid_reduce(double* vals, double* partials, unsigned int* counters, double* out,
                                             unsigned bid = blockIdx.x, unsigned nblocks = gridDim.x) {
     constexpr int PT = RED_THREADS;
+    constexpr int NV = NS + NM;
+    __shared__ double sh[NV][PT / 32];
+    __shared__ int role;  // 0: done, 1: last of its group, 2: last of the grid
     const unsigned tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
-    __shared__ double sh[NS + NM][PT / 32];
-    __shared__ bool last;
     const int lane = tid & 31, w = tid >> 5;
+    const unsigned ngroups = (nblocks + RED_GROUP - 1) / RED_GROUP;
+    const unsigned stride = nblocks + ngroups;  // per value: block partials followed by group partials
+    const unsigned grp = bid / RED_GROUP;
+    const unsigned gsize = min(RED_GROUP, nblocks - grp * RED_GROUP);
 #pragma unroll
-    for (int k = 0; k < NS + NM; k++) {
+    for (int k = 0; k < NV; k++) {
         const double v = k < NS ? warp_sum(vals[k]) : warp_max(vals[k]);
         if (lane == 0) sh[k][w] = v;
     }
     __syncthreads();
     if (tid == 0) {
 #pragma unroll
-        for (int k = 0; k < NS + NM; k++) {
+        for (int k = 0; k < NV; k++) {
             double v = sh[k][0];
             for (int i = 1; i < PT / 32; i++) v = k < NS ? v + sh[k][i] : fmax(v, sh[k][i]);
-            partials[(size_t)k * nblocks + bid] = v;
+            partials[(size_t)k * stride + bid] = v;
         }
         __threadfence();
-        const unsigned t = atomicInc(counter, nblocks - 1);  // wraps back to 0 => self-resetting
-        last = (t == nblocks - 1);
+        role = (atomicInc(counters + 1 + grp, gsize - 1) == gsize - 1) ? 1 : 0;  // wraps to 0 => self-resetting
     }
     __syncthreads();
-    if (!last) return false;
+    if (role == 0) return false;
     __threadfence();
-    double tot[NS + NM];
+    // last block of the group: fold the group's block partials in block order (one warp is plenty for <= 32 values)
+    if (w == 0) {
 #pragma unroll
-    for (int k = 0; k < NS + NM; k++) {
+        for (int k = 0; k < NV; k++) {
+            double v = ((unsigned)lane < gsize) ? __ldcg(partials + (size_t)k * stride + grp * RED_GROUP + lane) : 0.0;
+            // fixed-order serial fold by lane 0 through shuffles: tree order is fixed => reproducible
+            v = k < NS ? warp_sum(v) : warp_max(v);
+            if (lane == 0) partials[(size_t)k * stride + nblocks + grp] = v;
+        }
+        if (lane == 0) {
+            __threadfence();
+            role = (atomicInc(counters, ngroups - 1) == ngroups - 1) ? 2 : 0;
+        }
+    }
+    __syncthreads();
+    if (role != 2) return false;
+    __threadfence();
+    double tot[NV];
+#pragma unroll
+    for (int k = 0; k < NV; k++) {
         double v = 0.0;
-#pragma unroll 8
-        for (unsigned i = tid; i < nblocks; i += PT) {
-            const double x = __ldcg(partials + (size_t)k * nblocks + i);
+#pragma unroll 4
+        for (unsigned i = tid; i < ngroups; i += PT) {
+            const double x = __ldcg(partials + (size_t)k * stride + nblocks + i);
             v = k < NS ? v + x : fmax(v, x);
         }
         tot[k] = k < NS ? warp_sum(v) : warp_max(v);
@@ -59,12 +85,12 @@ __device__ __forceinline__ bool grid_reduce(double* vals, double* partials, unsi
     __syncthreads();
     if (lane == 0) {
 #pragma unroll
-        for (int k = 0; k < NS + NM; k++) sh[k][w] = tot[k];
+        for (int k = 0; k < NV; k++) sh[k][w] = tot[k];
     }
     __syncthreads();
     if (tid == 0) {
 #pragma unroll
-        for (int k = 0; k < NS + NM; k++) {
+        for (int k = 0; k < NV; k++) {
             double v = sh[k][0];
             for (int i = 1; i < PT / 32; i++) v = k < NS ? v + sh[k][i] : fmax(v, sh[k][i]);
             out[k] = v;
@@ -73,4 +99,3 @@ __device__ __forceinline__ bool grid_reduce(double* vals, double* partials, unsi
     }
     return false;
 }
-
