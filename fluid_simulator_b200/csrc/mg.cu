@@ -33,7 +33,8 @@ struct MgLevel {
 
 namespace {
 
-constexpr float OMEGA = 0.8f;
+constexpr float OMEGA = 0.8f;                    // coarsest-level Jacobi
+constexpr float OM_A = 1.389f, OM_B = 0.5617f;   // 2-step Chebyshev weights for D^-1 A on [0.5, 2]: pre-sweeps (A, B), post-sweeps (B, A)
 constexpr float OVER = 1.8f;
 constexpr int PRE = 2, POST = 2;
 constexpr int W_FIRST = 2, W_LAST = 2; // levels W_FIRST..W_LAST are visited twice per visit of their parent
@@ -95,7 +96,7 @@ __global__ void __launch_bounds__(256) mg_first_kernel(Lv L, const double* __res
         float bb;
         if (FINE) { bb = (float)(r64[c] * inv_scale); b[c] = bb; } else bb = b[c];
         const float d = FINE ? (float)((L.code[c] >> 6) & 7u) : L.diag[c];
-        v = d > 0.f ? OMEGA * bb / d : 0.f;
+        v = d > 0.f ? OM_A * bb / d : 0.f;
     } else if (FINE) b[c] = 0.f;
     xout[c] = v;
 }
@@ -103,7 +104,7 @@ __global__ void __launch_bounds__(256) mg_first_kernel(Lv L, const double* __res
 // damped Jacobi sweep: xout = xin + omega * (b - A xin) / diag
 template <bool FINE>
 __global__ void __launch_bounds__(256) mg_jacobi_kernel(Lv L, const PcgScalars* __restrict__ sc, const float* __restrict__ b, const float* __restrict__ xin,
-                                                         float* __restrict__ xout) {
+                                                         float* __restrict__ xout, float om) {
     if (sc->done) return;
     int x, y, z; int64_t c;
     if (!cell_of(L, x, y, z, c)) return;
@@ -112,7 +113,7 @@ __global__ void __launch_bounds__(256) mg_jacobi_kernel(Lv L, const PcgScalars* 
         float off;
         const float d = row<FINE>(L, c, xin, &off);
         const float xi = xin[c];
-        v = d > 0.f ? xi + OMEGA * (b[c] - (d * xi - off)) / d : 0.f;
+        v = d > 0.f ? xi + om * (b[c] - (d * xi - off)) / d : 0.f;
     }
     xout[c] = v;
 }
@@ -127,7 +128,7 @@ __global__ void __launch_bounds__(256) mg_pre2_kernel(Lv L, const PcgScalars* __
     const float d = L.diag[c];
     float v = 0.f;
     if (d > 0.f) {
-        auto x1 = [&](int64_t cn) -> float { const float dn = L.diag[cn]; return dn > 0.f ? OMEGA * b[cn] / dn : 0.f; };
+        auto x1 = [&](int64_t cn) -> float { const float dn = L.diag[cn]; return dn > 0.f ? OM_A * b[cn] / dn : 0.f; };
         const float w0 = L.wx[c - 1], w1 = L.wx[c], w2 = L.wy[c - L.sy], w3 = L.wy[c], w4 = L.wz[c - L.sz], w5 = L.wz[c];
         float off = 0.f;
         if (w0 > 0.f) off += w0 * x1(c - 1);
@@ -137,8 +138,8 @@ __global__ void __launch_bounds__(256) mg_pre2_kernel(Lv L, const PcgScalars* __
         if (w4 > 0.f) off += w4 * x1(c - L.sz);
         if (w5 > 0.f) off += w5 * x1(c + L.sz);
         const float bb = b[c];
-        const float xi = OMEGA * bb / d;
-        v = xi + OMEGA * (bb - (d * xi - off)) / d;
+        const float xi = OM_A * bb / d;
+        v = xi + OM_B * (bb - (d * xi - off)) / d;
     }
     xout[c] = v;
 }
@@ -203,7 +204,7 @@ __global__ void __launch_bounds__(256) mg_prolong_jacobi_kernel(Lv L, Lv C, cons
             if (w5 > 0.f) off += w5 * xc(x, y, z + 1, c + L.sz);
         }
         const float xi = xc(x, y, z, c);
-        v = d > 0.f ? xi + OMEGA * (b[c] - (d * xi - off)) / d : 0.f;
+        v = d > 0.f ? xi + OM_B * (b[c] - (d * xi - off)) / d : 0.f;
     }
     xout[c] = v;
 }
@@ -267,7 +268,7 @@ __global__ void __launch_bounds__(256) mg_first4_kernel(Lv L, const double* __re
             if (cd[i] & CODE_ACTIVE) {
                 bb.v[i] = (float)(rr[i] * inv_scale);
                 const float d = (float)((cd[i] >> 6) & 7u);
-                xo.v[i] = d > 0.f ? OMEGA * bb.v[i] / d : 0.f;
+                xo.v[i] = d > 0.f ? OM_A * bb.v[i] / d : 0.f;
             }
         st4(b + c, bb);     // groups without WATER cells are never read (every consumer checks the code) => not written
         st4(xout + c, xo);
@@ -278,7 +279,7 @@ __global__ void __launch_bounds__(256) mg_first4_kernel(Lv L, const double* __re
 template <bool DOT>
 __global__ void __launch_bounds__(256) mg_jacobi4_kernel(Lv L, PcgScalars* __restrict__ sc, const float* __restrict__ b, const float* __restrict__ xin,
                                                          float* __restrict__ xout, const double* __restrict__ r64, double* partials,
-                                                         unsigned int* counter) {
+                                                         unsigned int* counter, float om) {
     if (sc->done) return;
     int64_t c; unsigned cd[4];
     double acc[1] = {0.0};
@@ -291,7 +292,7 @@ __global__ void __launch_bounds__(256) mg_jacobi4_kernel(Lv L, PcgScalars* __res
             if (cd[i] & CODE_ACTIVE) {
                 const float d = (float)((cd[i] >> 6) & 7u);
                 const float xi = s.c.v[i];
-                xo.v[i] = d > 0.f ? xi + OMEGA * (bb.v[i] - (d * xi - off4(s, i, cd[i]))) / d : 0.f;
+                xo.v[i] = d > 0.f ? xi + om * (bb.v[i] - (d * xi - off4(s, i, cd[i]))) / d : 0.f;
             }
         st4(xout + c, xo);
         if (DOT) {
@@ -344,7 +345,7 @@ __global__ void __launch_bounds__(256) mg_update_first4_kernel(Lv L, int64_t nc,
                     acc[0] = fmax(acc[0], fabs(rr[i]));
                     bb.v[i] = (float)(rr[i] * inv_scale);
                     const float d = (float)((cd[i] >> 6) & 7u);
-                    xo.v[i] = d > 0.f ? OMEGA * bb.v[i] / d : 0.f;
+                    xo.v[i] = d > 0.f ? OM_A * bb.v[i] / d : 0.f;
                 }
 #pragma unroll
             for (int h2 = 0; h2 < 2; h2++) {
@@ -432,7 +433,7 @@ __global__ void __launch_bounds__(256) mg_prolong_jacobi4_kernel(Lv L, Lv C, con
             if (cd[i] & CODE_ACTIVE) {
                 const float d = (float)((cd[i] >> 6) & 7u);
                 const float xi = s.c.v[i];
-                xo.v[i] = d > 0.f ? xi + OMEGA * (bb.v[i] - (d * xi - off4(s, i, cd[i]))) / d : 0.f;
+                xo.v[i] = d > 0.f ? xi + OM_B * (bb.v[i] - (d * xi - off4(s, i, cd[i]))) / d : 0.f;
             }
         st4(xout + c, xo);
     }
@@ -555,13 +556,13 @@ __device__ __forceinline__ float t_row(const Lv& L, int c, const float* x, float
               L.wz[c] * x[c + L.sz] + L.wz[c - L.sz] * x[c - L.sz];
     return L.diag[c];
 }
-__device__ void t_jacobi(const Lv& L, const float* b, const float* xin, float* xout, int t0, int nt) {
+__device__ void t_jacobi(const Lv& L, const float* b, const float* xin, float* xout, int t0, int nt, float om) {
     const int nc = L.gx * L.gy * L.gz;
     for (int c = t0; c < nc; c += nt) {
         float off;
         const float d = t_row(L, c, xin, &off);
         const float xi = xin[c];
-        xout[c] = d > 0.f ? xi + OMEGA * (b[c] - (d * xi - off)) / d : 0.f;
+        xout[c] = d > 0.f ? xi + om * (b[c] - (d * xi - off)) / d : 0.f;
     }
 }
 __device__ void t_pre2(const Lv& L, const float* b, float* xout, int t0, int nt) {
@@ -575,9 +576,9 @@ __device__ void t_pre2(const Lv& L, const float* b, float* xout, int t0, int nt)
             float off = 0.f;
 #pragma unroll
             for (int k = 0; k < 6; k++)
-                if (w[k] > 0.f) { const float dn = L.diag[nb[k]]; if (dn > 0.f) off += w[k] * OMEGA * b[nb[k]] / dn; }
-            const float bb = b[c], xi = OMEGA * bb / d;
-            v = xi + OMEGA * (bb - (d * xi - off)) / d;
+                if (w[k] > 0.f) { const float dn = L.diag[nb[k]]; if (dn > 0.f) off += w[k] * OM_A * b[nb[k]] / dn; }
+            const float bb = b[c], xi = OM_A * bb / d;
+            v = xi + OM_B * (bb - (d * xi - off)) / d;
         }
         xout[c] = v;
     }
@@ -619,7 +620,7 @@ __device__ void t_prolong_jacobi(const Lv& L, const Lv& C, const float* b, const
             if (w4 > 0.f) off += w4 * xc(x, y, z - 1, c - L.sz);
             if (w5 > 0.f) off += w5 * xc(x, y, z + 1, c + L.sz);
             const float xi = xc(x, y, z, c);
-            v = xi + OMEGA * (b[c] - (d * xi - off)) / d;
+            v = xi + OM_B * (b[c] - (d * xi - off)) / d;
         }
         xout[c] = v;
     }
@@ -635,8 +636,8 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) mg_tail_kernel(TailArgs a) {
     for (int i = 0; i + 1 < a.n; i++) {
         const TailLevel& T = a.lv[i];
         if (i == 0 && !a.zero_guess) {
-            t_jacobi(T.L, T.b, T.xa, T.xb, t0, nt); cluster.sync();
-            t_jacobi(T.L, T.b, T.xb, T.xa, t0, nt); cluster.sync();
+            t_jacobi(T.L, T.b, T.xa, T.xb, t0, nt, OM_A); cluster.sync();
+            t_jacobi(T.L, T.b, T.xb, T.xa, t0, nt, OM_B); cluster.sync();
         } else {
             t_pre2(T.L, T.b, T.xa, t0, nt); cluster.sync();
         }
@@ -684,7 +685,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) mg_tail_kernel(TailArgs a) {
     for (int i = a.n - 2; i >= 0; i--) {
         const TailLevel& T = a.lv[i];
         t_prolong_jacobi(T.L, a.lv[i + 1].L, T.b, T.xa, a.lv[i + 1].xa, T.xb, t0, nt); cluster.sync();
-        t_jacobi(T.L, T.b, T.xb, T.xa, t0, nt);
+        t_jacobi(T.L, T.b, T.xb, T.xa, t0, nt, OM_A);
         if (i > 0) cluster.sync();
     }
 }
@@ -765,9 +766,10 @@ int cycle(fsim* h, int l, bool zero_guess, float** result, bool first_done = fal
                 else if (fine) mg_first_kernel<true><<<grid_of(m, blk), blk, 0, h->stream>>>(L, h->r, sc, m->b, cur);
                 else mg_first_kernel<false><<<grid_of(m, blk), blk, 0, h->stream>>>(L, nullptr, sc, m->b, cur);
             } else {
-                if (v4) mg_jacobi4_kernel<false><<<grd4, blk4, 0, h->stream>>>(L, h->scal, m->b, cur, oth, nullptr, nullptr, nullptr);
-                else if (fine) mg_jacobi_kernel<true><<<grid_of(m, blk), blk, 0, h->stream>>>(L, sc, m->b, cur, oth);
-                else mg_jacobi_kernel<false><<<grid_of(m, blk), blk, 0, h->stream>>>(L, sc, m->b, cur, oth);
+                const float om = s == 0 ? OM_A : OM_B;
+                if (v4) mg_jacobi4_kernel<false><<<grd4, blk4, 0, h->stream>>>(L, h->scal, m->b, cur, oth, nullptr, nullptr, nullptr, om);
+                else if (fine) mg_jacobi_kernel<true><<<grid_of(m, blk), blk, 0, h->stream>>>(L, sc, m->b, cur, oth, om);
+                else mg_jacobi_kernel<false><<<grid_of(m, blk), blk, 0, h->stream>>>(L, sc, m->b, cur, oth, om);
                 float* t = cur; cur = oth; oth = t;
             }
         }
@@ -794,11 +796,12 @@ int cycle(fsim* h, int l, bool zero_guess, float** result, bool first_done = fal
         else mg_prolong_jacobi_kernel<false><<<grid_of(m, blk), blk, 0, h->stream>>>(L, C, sc, m->b, cur, mc->xa, oth);
         { float* t = cur; cur = oth; oth = t; }
         for (int s = 1; s < POST; s++) {
+            const float om = OM_A;  // post-sweeps run the pre-sweep weights in reverse order (B in the fused prolongation sweep, then A)
             if (v4 && with_dot && s == POST - 1)
-                mg_jacobi4_kernel<true><<<grd4, blk4, 0, h->stream>>>(L, h->scal, m->b, cur, oth, h->r, h->partials, h->red_counter);
-            else if (v4) mg_jacobi4_kernel<false><<<grd4, blk4, 0, h->stream>>>(L, h->scal, m->b, cur, oth, nullptr, nullptr, nullptr);
-            else if (fine) mg_jacobi_kernel<true><<<grid_of(m, blk), blk, 0, h->stream>>>(L, sc, m->b, cur, oth);
-            else mg_jacobi_kernel<false><<<grid_of(m, blk), blk, 0, h->stream>>>(L, sc, m->b, cur, oth);
+                mg_jacobi4_kernel<true><<<grd4, blk4, 0, h->stream>>>(L, h->scal, m->b, cur, oth, h->r, h->partials, h->red_counter, om);
+            else if (v4) mg_jacobi4_kernel<false><<<grd4, blk4, 0, h->stream>>>(L, h->scal, m->b, cur, oth, nullptr, nullptr, nullptr, om);
+            else if (fine) mg_jacobi_kernel<true><<<grid_of(m, blk), blk, 0, h->stream>>>(L, sc, m->b, cur, oth, om);
+            else mg_jacobi_kernel<false><<<grid_of(m, blk), blk, 0, h->stream>>>(L, sc, m->b, cur, oth, om);
             float* t = cur; cur = oth; oth = t;
         }
     }

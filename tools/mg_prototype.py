@@ -221,3 +221,38 @@ def sweep3(n, kind="dam"):
                   dict(visits={2: 2}, pre_l={2: 4, 3: 4}, post_l={2: 4, 3: 4}), dict(visits={}, pre_l={1: 4, 2: 8, 3: 8}, post_l={1: 4, 2: 8, 3: 8})]:
         cfg = dict(base); cfg.update(extra)
         t0 = time.time(); x, it = pcg(A, b, lambda r: vcycle3(levels, 0, r, cfg), 1e-6); print(extra, "its", it, "%.1fs" % (time.time() - t0))
+
+def smooth_seq(L, x, b, omegas):
+    A, D = L["A"], L["D"]
+    for om in omegas:
+        x = x + om * (b - A @ x) / D
+    return x
+
+def vcycle4(levels, l, b, cfg):
+    L = levels[l]
+    if l == len(levels) - 1:
+        return smooth(L, np.zeros_like(b), b, "jacobi", cfg["coarse_sweeps"], omega=0.8)
+    oms = cfg["omegas_l"].get(l, cfg["omegas"])
+    x = smooth_seq(L, np.zeros_like(b), b, oms)
+    rc = L["P"].T @ (b - L["A"] @ x)
+    ec = np.zeros(levels[l + 1]["A"].shape[0])
+    for v in range(cfg["visits"].get(l + 1, 1) if l + 1 < len(levels) - 1 else 1):
+        ec = ec + vcycle4(levels, l + 1, rc - levels[l + 1]["A"] @ ec, cfg)
+    x = x + cfg["over"] * (L["P"] @ ec)
+    return smooth_seq(L, x, b, oms[::-1])
+
+def sweep4(n, kind="dam"):
+    t = build(n, kind); A, idx = assemble(t); A = A * 0.005
+    gdt = -39.24 * 0.005
+    vy = np.zeros(t.shape); up = np.roll(t, -1, axis=1)
+    vy[(t != SOLID) & (up != SOLID)] = gdt
+    b = -(vy - np.roll(vy, 1, axis=1))[t == WATER]
+    b = b + np.random.default_rng(0).normal(0, 1.0, b.shape)
+    levels = hierarchy(t, A, idx, min_cells=600)
+    print(n, kind, "levels", [L["A"].shape[0] for L in levels])
+    for oms, over, extra in [((0.8, 0.8), 1.8, {}), ((1.389, 0.5617), 1.8, {}), ((1.2, 0.6), 1.8, {}), ((1.0, 0.67), 1.8, {}), ((1.389, 0.5617), 2.0, {}),
+                      ((1.1, 0.62), 1.8, {}), ((0.9, 0.9), 1.8, {}), ((1.0, 1.0), 1.8, {}), ((1.5, 0.75, 0.5), 1.8, {}), ((0.8, 0.8, 0.8), 1.8, {}),
+                      ((0.8, 0.8), 1.8, {1: (0.8, 0.8, 0.8), 2: (0.8,) * 4, 3: (0.8,) * 4}),
+                      ((1.389, 0.5617), 1.8, {1: (1.5, 0.75, 0.5), 2: (1.5, 0.75, 0.5), 3: (1.5, 0.75, 0.5)})]:
+        cfg = dict(omegas=oms, over=over, coarse_sweeps=30, visits={2: 2}, omegas_l=extra)
+        t0 = time.time(); x, it = pcg(A, b, lambda r: vcycle4(levels, 0, r, cfg), 1e-6); print(oms, over, extra, "its", it, "%.1fs" % (time.time() - t0))
