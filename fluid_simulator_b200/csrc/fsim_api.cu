@@ -264,7 +264,7 @@ int fsim_create(const FsimGridDesc* desc, fsim_t** out) {
     p.push_apart_enabled = 1; p.pressure_enabled = 1; p.max_iterations = 80; p.pressure_k = 2.0;
     p.average_pressure = 2.0; p.fluid_density = 1.0; p.residual_tolerance = 1e-6;
     h->nobs = 0;
-    h->np = 0; h->cap = 0; h->cur = 0; h->have_c = false; h->track_ids = true; h->sorted = false; h->kill_pending = false;
+    h->np = 0; h->cap = 0; h->cur = 0; h->have_c = false; h->track_ids = true; h->sorted = false; h->binned = false; h->kill_pending = false;
     memset(h->ps, 0, sizeof(h->ps));
     h->key = h->rank = nullptr; h->kill = nullptr;
     h->next_id = 0; h->gfx = nullptr; h->gfx_cap = 0;
@@ -415,7 +415,7 @@ int fsim_upload_particles(fsim_t* h, const double* aos15, int64_t n) {
     h->np = n;
     TRY(k_iota_ids(h, 0, n, 0));
     h->next_id = (uint32_t)n;
-    h->sorted = false; h->kill_pending = false;
+    h->sorted = false; h->binned = false; h->kill_pending = false;
     return FSIM_OK;
 }
 
@@ -428,7 +428,7 @@ int fsim_append_particles(fsim_t* h, const double* aos15, int64_t n) {
     TRY(k_iota_ids(h, h->np, n, h->next_id));  // ids continue after the largest id ever handed out
     h->next_id += (uint32_t)n;
     h->np += n;
-    h->sorted = false;
+    h->sorted = false; h->binned = false;
     return FSIM_OK;
 }
 
@@ -506,7 +506,7 @@ int fsim_upload_particles_f32(fsim_t* h, const float* pos, const float* vel, con
     h->np = n;
     TRY(k_iota_ids(h, 0, n, 0));
     h->next_id = (uint32_t)n;
-    h->sorted = false; h->kill_pending = false;
+    h->sorted = false; h->binned = false; h->kill_pending = false;
     return FSIM_OK;
 }
 
@@ -583,7 +583,7 @@ int fsim_step(fsim_t* h, double dt, int* pcg_iterations) {
     FSIM_CUDA(h, cudaEventRecord(h->ev[0], h->stream));
     if (h->par.spawning_enabled) TRY(fsim_stage_spawn(h, dt));
     // advect + obstacle push-out + stopParticles are one pass over the particles (push-apart is not on this path)
-    TRY(k_advect(h, dt, true, true, h->par.stop_particles != 0));
+    TRY(k_advect(h, dt, true, true, h->par.stop_particles != 0, /*do_bin=*/true));
     FSIM_CUDA(h, cudaEventRecord(h->ev[1], h->stream));
     TRY(k_sort(h));
     FSIM_CUDA(h, cudaEventRecord(h->ev[2], h->stream));

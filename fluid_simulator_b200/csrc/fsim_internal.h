@@ -102,6 +102,7 @@ struct fsim {
     uint8_t* kill;            // [cap] sink-capture flags written by the advect kernel
     bool kill_pending;        // kill[] holds flags the next sort must honour
     bool sorted;  // particles are in cell-binned order consistent with cell_start
+    bool binned;  // key / rank / cnt are current for the particle arrays (the fused advect kernel produced them)
 
     // grid
     uint32_t *cnt, *cell_start;  // [nc], [nc+1]
@@ -198,7 +199,7 @@ struct KScope {
 
 // ---- kernels' host launchers (one per stage file) ----------------------------------------------------
 int k_upload_obstacles(fsim* h);
-int k_advect(fsim* h, double dt, bool do_advect, bool do_pushout, bool do_stop);
+int k_advect(fsim* h, double dt, bool do_advect, bool do_pushout, bool do_stop, bool do_bin = false);
 int k_sort(fsim* h);  // key/count -> scan -> reorder; updates np when particles were removed
 int k_p2g(fsim* h);
 int k_classify(fsim* h, double dt);

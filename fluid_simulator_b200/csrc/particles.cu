@@ -42,16 +42,23 @@ struct AdvectArgs {
     int zconst, despawn, nobs;
     int do_advect, do_pushout, do_stop;
     const DevObstacle* obs;
+    // fused binning (fsim_step): key / rank / histogram straight from the registers that hold the new position
+    int do_bin;
+    GridDims g;
+    uint32_t *cnt, *key, *rank;
 };
 
-__global__ void __launch_bounds__(256, 5) advect_kernel(AdvectArgs a) {
+__device__ __forceinline__ uint32_t cell_key(const GridDims& g, float x, float y, float z);
+
+__global__ void __launch_bounds__(256, 4) advect_kernel(AdvectArgs a) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.n) return;
-    D3 pos = mk(a.px[i], a.py[i], a.pz[i]);
-    D3 v = mk(a.vx[i], a.vy[i], a.vz[i]);
+    const bool live = i < a.n;
+    if (!live && !a.do_bin) return;  // with fused binning whole warps stay for the __match_any_sync below
+    D3 pos = mk(0, 0, 0), v = mk(0, 0, 0);
+    if (live) { pos = mk(a.px[i], a.py[i], a.pz[i]); v = mk(a.vx[i], a.vy[i], a.vz[i]); }
     bool killed = false;
 
-    if (a.do_advect) {
+    if (a.do_advect && live) {
         const double dt = a.dt, pr = a.pr;
         double t = 0;
         int run = 0;
@@ -140,7 +147,7 @@ __global__ void __launch_bounds__(256, 5) advect_kernel(AdvectArgs a) {
         pos.z = clampd(pos.z, a.lo.z, a.hi.z);
     }
 
-    if (a.do_pushout && !killed) {  // simulator.cpp:253-312; obstacles in list order, per particle independent
+    if (a.do_pushout && !killed && live) {  // simulator.cpp:253-312; obstacles in list order, per particle independent
         const double pr = a.pr;
         for (int k = 0; k < a.nobs; k++) {
             const DevObstacle& ob = a.obs[k];
@@ -179,9 +186,26 @@ __global__ void __launch_bounds__(256, 5) advect_kernel(AdvectArgs a) {
     }
     if (a.do_stop) v = mk(0, 0, 0);
 
-    a.px[i] = (float)pos.x; a.py[i] = (float)pos.y; a.pz[i] = (float)pos.z;
-    a.vx[i] = (float)v.x; a.vy[i] = (float)v.y; a.vz[i] = (float)v.z;
-    if (a.kill && a.do_advect) a.kill[i] = killed ? 1 : 0;
+    const float fx = (float)pos.x, fy = (float)pos.y, fz = (float)pos.z;
+    if (live) {
+        a.px[i] = fx; a.py[i] = fy; a.pz[i] = fz;
+        a.vx[i] = (float)v.x; a.vy[i] = (float)v.y; a.vz[i] = (float)v.z;
+        if (a.kill && a.do_advect) a.kill[i] = killed ? 1 : 0;
+    }
+    if (a.do_bin) {  // same as bin_kernel, on the stored (fp32-rounded) position
+        uint32_t k = INVALID_KEY;
+        if (live && !killed) k = cell_key(a.g, fx, fy, fz);
+        const unsigned peers = __match_any_sync(0xffffffffu, k);
+        const int lane = threadIdx.x & 31;
+        const int leader = __ffs(peers) - 1;
+        uint32_t base = 0;
+        if (lane == leader && k != INVALID_KEY) base = atomicAdd(&a.cnt[k], (uint32_t)__popc(peers));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (live) {
+            a.key[i] = k;
+            a.rank[i] = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+        }
+    }
 }
 
 // particle -> device cell key; the index is ivec3(pos * cellDInv) evaluated in fp64 on the stored fp32 position,
@@ -415,7 +439,8 @@ ReorderArgs reorder_args(fsim* h) {
 
 }  // namespace
 
-int k_advect(fsim* h, double dt, bool do_advect, bool do_pushout, bool do_stop) {
+int k_advect(fsim* h, double dt, bool do_advect, bool do_pushout, bool do_stop, bool do_bin) {
+    h->binned = false;
     if (h->np == 0) return FSIM_OK;
     AdvectArgs a;
     ParticleSet& p = h->ps[h->cur];
@@ -438,14 +463,15 @@ int k_advect(fsim* h, double dt, bool do_advect, bool do_pushout, bool do_stop) 
     { KScope ks(h, K_ADVECT); advect_kernel<<<div_up(h->np, 256), 256, 0, h->stream>>>(a); }
     FSIM_CHECK_LAUNCH(h);
     h->sorted = false;
+    h->binned = do_bin;
     if (do_advect && h->par.despawning_enabled) h->kill_pending = true;
     return FSIM_OK;
 }
 
 int k_sort(fsim* h) {
     const GridDims& g = h->g;
-    { KScope ks(h, K_MEMSET); FSIM_CUDA(h, cudaMemsetAsync(h->cnt, 0, sizeof(uint32_t) * g.nc, h->stream)); }
-    if (h->np > 0) {
+    if (!h->binned) { KScope ks(h, K_MEMSET); FSIM_CUDA(h, cudaMemsetAsync(h->cnt, 0, sizeof(uint32_t) * g.nc, h->stream)); }
+    if (h->np > 0 && !h->binned) {
         ParticleSet& p = h->ps[h->cur];
         KScope ks(h, K_BIN);
         bin_kernel<<<div_up(h->np, 256), 256, 0, h->stream>>>(g, p.pos[0], p.pos[1], p.pos[2],
@@ -468,6 +494,7 @@ int k_sort(fsim* h) {
         h->kill_pending = false;
     }
     h->sorted = true;
+    h->binned = false;
     return FSIM_OK;
 }
 
@@ -492,7 +519,7 @@ int k_compact_remove(fsim* h, const int32_t* dev_ids, int64_t n) {
     FSIM_CUDA(h, cudaStreamSynchronize(h->stream));
     h->cur ^= 1;
     h->np = total;
-    h->sorted = false;
+    h->sorted = false; h->binned = false;
     return FSIM_OK;
 }
 
