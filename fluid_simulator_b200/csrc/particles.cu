@@ -460,6 +460,8 @@ int k_advect(fsim* h, double dt, bool do_advect, bool do_pushout, bool do_stop, 
     a.do_advect = do_advect; a.do_pushout = do_pushout; a.do_stop = do_stop;
     a.obs = h->d_obs;
     a.kill = h->kill;
+    a.do_bin = do_bin; a.g = h->g; a.cnt = h->cnt; a.key = h->key; a.rank = h->rank;
+    if (do_bin) { KScope ks(h, K_MEMSET); FSIM_CUDA(h, cudaMemsetAsync(h->cnt, 0, sizeof(uint32_t) * h->g.nc, h->stream)); }
     { KScope ks(h, K_ADVECT); advect_kernel<<<div_up(h->np, 256), 256, 0, h->stream>>>(a); }
     FSIM_CHECK_LAUNCH(h);
     h->sorted = false;
