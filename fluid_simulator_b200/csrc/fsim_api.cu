@@ -274,7 +274,7 @@ int fsim_create(const FsimGridDesc* desc, fsim_t** out) {
     h->launches = h->last_step_launches = 0; h->last_step_ms = 0;
     h->prof_mask = 0;
     h->mg_z32 = nullptr; h->mg_inv_scale = 1.0;
-    h->pcg_graph = nullptr; h->pcg_graph_launches = 0; memset(h->pcg_graph_class, 0, sizeof(h->pcg_graph_class));
+    h->pcg_graph = nullptr; h->pcg_graph_failed = false; h->pcg_graph_launches = 0; memset(h->pcg_graph_class, 0, sizeof(h->pcg_graph_class));
     { const char* e = getenv("FSIM_NO_GRAPH"); h->use_graph = !(e && e[0] == '1'); }
     { const char* e = getenv("FSIM_NO_WARM_START"); h->warm_start = !(e && e[0] == '1'); }
     h->status_host = nullptr; h->status_dev = nullptr;

@@ -120,7 +120,8 @@ struct fsim {
     PcgScalars* scal_host;                 // pinned
     PcgHostStatus* status_host;            // pinned + mapped
     PcgHostStatus* status_dev;             // device alias of status_host
-    cudaGraphExec_t pcg_graph;             // one PCG iteration (SpMV, update, multigrid cycle, dot, direction)
+    cudaGraphExec_t pcg_graph;             // device-side WHILE loop around one PCG iteration (SpMV, update, multigrid cycle, direction)
+    bool pcg_graph_failed;                 // conditional graph nodes unavailable: host-driven loop
     int pcg_graph_launches;                // kernels per graph launch
     int pcg_graph_class[K_COUNT];          // ... per kernel class
     bool use_graph, warm_start;

@@ -13,6 +13,8 @@
 //     consecutive cells (16-byte loads of the fp64 vectors); reductions are warp shuffle -> block -> fixed-order
 //     last-block sum => deterministic, no fp64 atomics;
 //   * all scalars (sigma, alpha, beta, done flag, iteration count) stay on the device; the host only polls the done flag.
+#include <cstdio>
+
 #include "fsim_internal.h"
 #include "reduce.cuh"
 
@@ -355,6 +357,11 @@ __global__ void __launch_bounds__(PT) direction_kernel(PcgArgs a) {
         a.s[c] = a.s[c] * beta + (a.z32 ? (double)a.z32[c] : a.z[c]);
     }
 }
+// loop condition of the device-side WHILE graph: keep iterating until an update kernel has set the done flag
+__global__ void loop_condition_kernel(cudaGraphConditionalHandle handle, const PcgScalars* sc) {
+    cudaGraphSetConditional(handle, sc->done ? 0u : 1u);
+}
+
 // closes iteration `it`: sigma <- sigma', it <- it + 1, progress published to the host-mapped status word
 __global__ void sigma_kernel(PcgScalars* sc, PcgHostStatus* status) {
     if (sc->done) return;
@@ -448,43 +455,81 @@ int k_project(fsim* h, double dt, int* iterations) {
     }
     FSIM_CHECK_LAUNCH(h);
 
-    const bool graph = h->use_graph && h->prof_mask == 0;
-    if (graph && !h->pcg_graph) {  // capture one iteration once; every argument is a fixed device pointer
-        cudaGraph_t gr = nullptr;
-        const int64_t l0 = h->launches;
-        int64_t c0[K_COUNT];
-        memcpy(c0, h->launch_n, sizeof(c0));
-        FSIM_CUDA(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-        int rc = enqueue_iteration(h, a, vec, use_mg, nbv);
-        cudaError_t e = cudaStreamEndCapture(h->stream, &gr);
-        if (rc) return rc;
-        if (e != cudaSuccess) return fsim_fail(h, FSIM_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
-        FSIM_CUDA(h, cudaGraphInstantiate(&h->pcg_graph, gr, 0));
-        cudaGraphDestroy(gr);
-        h->pcg_graph_launches = (int)(h->launches - l0);
-        for (int k = 0; k < K_COUNT; k++) { h->pcg_graph_class[k] = (int)(h->launch_n[k] - c0[k]); h->launch_n[k] = c0[k]; }
-        h->launches = l0;  // capture does not execute
+    // The whole PCG loop runs on the device: a CUDA graph whose body (one iteration, captured once -- every argument is a
+    // fixed device pointer and all solve parameters live in device memory) sits inside a conditional WHILE node; a
+    // one-thread kernel re-arms the condition from the done flag.  The host launches it once and never polls.
+    bool graph = h->use_graph && h->prof_mask == 0;
+    if (graph && !h->pcg_graph && !h->pcg_graph_failed) {
+        cudaGraph_t gr = nullptr, body = nullptr;
+        cudaGraphConditionalHandle handle;
+        cudaGraphNode_t set_node, cond_node;
+        bool ok = cudaGraphCreate(&gr, 0) == cudaSuccess &&
+                  cudaGraphConditionalHandleCreate(&handle, gr, 1, cudaGraphCondAssignDefault) == cudaSuccess;
+        if (ok) {
+            void* kargs[2] = {(void*)&handle, (void*)&h->scal};
+            cudaKernelNodeParams kp = {};
+            kp.func = (void*)loop_condition_kernel;
+            kp.gridDim = dim3(1); kp.blockDim = dim3(1); kp.sharedMemBytes = 0; kp.kernelParams = kargs; kp.extra = nullptr;
+            ok = cudaGraphAddKernelNode(&set_node, gr, nullptr, 0, &kp) == cudaSuccess;
+        }
+        if (ok) {
+            cudaGraphNodeParams cp = {};
+            cp.type = cudaGraphNodeTypeConditional;
+            cp.conditional.handle = handle;
+            cp.conditional.type = cudaGraphCondTypeWhile;
+            cp.conditional.size = 1;
+            ok = cudaGraphAddNode(&cond_node, gr, &set_node, 1, &cp) == cudaSuccess;
+            if (ok) body = cp.conditional.phGraph_out[0];
+        }
+        if (ok) {
+            const int64_t l0 = h->launches;
+            int64_t c0[K_COUNT];
+            memcpy(c0, h->launch_n, sizeof(c0));
+            ok = cudaStreamBeginCaptureToGraph(h->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+            if (ok) {
+                const int rc = enqueue_iteration(h, a, vec, use_mg, nbv);
+                loop_condition_kernel<<<1, 1, 0, h->stream>>>(handle, h->scal);
+                cudaGraph_t dummy = nullptr;
+                const cudaError_t e = cudaStreamEndCapture(h->stream, &dummy);
+                ok = rc == FSIM_OK && e == cudaSuccess;
+            }
+            h->pcg_graph_launches = (int)(h->launches - l0) + 1;
+            for (int k = 0; k < K_COUNT; k++) { h->pcg_graph_class[k] = (int)(h->launch_n[k] - c0[k]); h->launch_n[k] = c0[k]; }
+            h->launches = l0;  // capture does not execute
+        }
+        if (ok) ok = cudaGraphInstantiate(&h->pcg_graph, gr, 0) == cudaSuccess;
+        if (gr) cudaGraphDestroy(gr);
+        if (!ok) {  // older driver / unsupported node: fall back to enqueueing iterations from the host
+            const cudaError_t why = cudaGetLastError();
+            fprintf(stderr, "libfsim_b200: device-side PCG loop graph unavailable (%s); using the host-driven loop\n", cudaGetErrorString(why));
+            h->pcg_graph = nullptr;
+            h->pcg_graph_failed = true;
+        }
     }
-    // the host never blocks on the stream inside the loop: it polls the host-mapped status word and keeps at most
-    // two iterations in flight; kernels of an iteration enqueued after convergence see done != 0 and exit immediately
-    for (int it = 0; it < max_it; it++) {
-        if (h->status_host->done) break;
-        if (graph) {
-            FSIM_CUDA(h, cudaGraphLaunch(h->pcg_graph, h->stream));
-            h->launches += h->pcg_graph_launches;
-            for (int k = 0; k < K_COUNT; k++) h->launch_n[k] += h->pcg_graph_class[k];
-        } else {
+    graph = graph && h->pcg_graph;
+    if (graph) {
+        FSIM_CUDA(h, cudaGraphLaunch(h->pcg_graph, h->stream));
+    } else {
+        // host-driven loop: polls the host-mapped status word (no stream sync), at most two iterations in flight;
+        // kernels of an iteration enqueued after convergence see done != 0 and exit immediately
+        for (int it = 0; it < max_it; it++) {
+            if (h->status_host->done) break;
             int rc = enqueue_iteration(h, a, vec, use_mg, nbv);
             if (rc) return rc;
-        }
-        while (!h->status_host->done && it + 1 - h->status_host->it_done > 1) {
-            if (cudaStreamQuery(h->stream) != cudaErrorNotReady) break;  // drained (or failed): flags are final
+            while (!h->status_host->done && it + 1 - h->status_host->it_done > 1) {
+                if (cudaStreamQuery(h->stream) != cudaErrorNotReady) break;  // drained (or failed): flags are final
+            }
         }
     }
     FSIM_CHECK_LAUNCH(h);
     FSIM_CUDA(h, cudaMemcpyAsync(h->scal_host, h->scal, sizeof(PcgScalars), cudaMemcpyDeviceToHost, h->stream));
     FSIM_CUDA(h, cudaStreamSynchronize(h->stream));
     const PcgScalars& s = *h->scal_host;
+    if (graph) {  // the device decided how many iterations ran: account their launches now
+        const int ran = s.early_out ? 0 : s.it + ((s.done == 1 || s.nan_break) ? 1 : 0);
+        h->launches += (int64_t)h->pcg_graph_launches * ran + 1;
+        for (int k = 0; k < K_COUNT; k++) h->launch_n[k] += (int64_t)h->pcg_graph_class[k] * ran;
+    }
     h->solve.iterations = s.early_out ? 0 : (s.done ? s.iterations : max_it);
     h->solve.early_out = s.early_out;
     h->solve.rhs_sumsq = s.rhs_sumsq;
