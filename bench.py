@@ -26,7 +26,7 @@ DT = 0.005
 # ALGORITHMIC bytes: compulsory fp32-SoA traffic only
 B_PARTICLE = {0: 72, 1: 84, 2: 144}   # PIC / FLIP / APIC bytes per particle-update (two compulsory particle passes)
 B_CELL = 205                          # bytes per cell per step for the grid stages
-B_IT_CG = 106                         # fp64 CG core per fluid cell per iteration: SpMV R8+1 W8, p/r/s updates 3x(R8+W8) .. see DESIGN.md
+B_IT = 174                            # bytes per fluid cell per PCG iteration: fp64 CG core 86 + multigrid cycle 88
 
 
 def peaks():
@@ -171,7 +171,8 @@ def main():
     # weak scaling over ranks: every rank advances its own N^3 dam break (independent replicas of the workload);
     # z-slab sharding of ONE domain with NCCL halos is the next step
     t_gen = time.perf_counter()
-    pos = scenes.block_positions_f32(1, n // 2, 1, n - 1, 1, n - 1)
+    from fluid_simulator_b200 import dist as fdist
+    pos = scenes.block_positions_f32(1, n // 2, 1, n - 1, 1, n - 1, seed=fdist.replica_seed(scenes.SEED, rank))
     np_local = pos.shape[0]
     sim = FluidSim((float(n),) * 3, 1.0, False, 0.25, capacity=np_local, device=local_rank)
     sim.set_id_tracking(False)  # ids are test support; the hot path does not carry them
@@ -222,12 +223,8 @@ def main():
     nf = int(info.fluid_cells)
     timings = sim.timings()
 
-    t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms_max = float(t.item())
+    total_units, dev_ms_max, value = fdist.aggregate(dist, "cuda", np_local * args.steps, dev_ms, world)
     total_particles = np_local * world
-    value = total_particles * args.steps / (dev_ms_max * 1e-3)
 
     # ---- end-to-end through the C ABI with host buffers: per step set_params + set_obstacles (H2D) + simulate + the
     # manager's gfx export into pinned host memory (D2H 20 B/particle), what simulationThreadWorker does per iteration
@@ -262,18 +259,28 @@ def main():
     peak, peak_src = peaks()
     its_mean = float(np.mean(step_its))
     # per-launch algorithmic bytes of the dominant kernel class
-    alg = {"spmv": nf * (8 + 8 + 8) + n ** 3 * 1, "pcg_update": nf * (8 * 3 + 8 * 3 + 8) + n ** 3 * 1, "pcg_direction": nf * 24 + n ** 3,
-           "p2g": np_local * (24 if transfer != abi.APIC else 60) + n ** 3 * (8 + 28), "g2p": np_local * (36 if transfer == abi.FLIP else 24 if transfer == abi.PIC else 60) + n ** 3 * 24,
-           "advect": np_local * 48, "bin": np_local * 20, "reorder": np_local * 56, "mg": nf * 83}
+    pb = {abi.PIC: 24, abi.FLIP: 24, abi.APIC: 60}[transfer]
+    nc = n ** 3
+    alg = {"advect": np_local * 2 * pb,                      # pass A: read + write pos, vel (+C)
+           "p2g": np_local * pb + nc * (8 + 28),             # particles in, bin table, 7 accumulator channels out
+           "g2p": np_local * (36 if transfer == abi.FLIP else pb + (12 if transfer == abi.PIC else 48)) + nc * (24 if transfer == abi.FLIP else 12),
+           "reorder": np_local * (2 * pb + 8), "bin": np_local * 20,   # sort passes: implementation overhead, listed with their own minimal traffic
+           "spmv": nf * 16 + nc * 2, "pcg_update": nf * 56 + nc * 2, "pcg_direction": nf * 20 + nc * 2,
+           "mg": nf * 15 + nc * 2,                          # average level-0 multigrid kernel (jacobi 14, restrict 10, prolong 14, jacobi+dot 22 B)
+           "mg_level1": (nc // 8) * 28, "finalize": nc * 53, "extrapolate": nc * 25, "classify": nc * 5, "rhs": nc * 17 + nf * 28}
+    traffic_path = os.path.join(ROOT, "profiles", "r1_dram_traffic_256_flip.json")
+    traffic = None
+    if n == 256 and transfer == abi.FLIP and os.path.exists(traffic_path):
+        traffic = json.load(open(traffic_path)).get(dominant)
     dom_ms, dom_n, _ = prof[dominant]
     roofline = None
     if dom_n > 0 and dominant in alg:
         ach = alg[dominant] / (dom_ms / dom_n * 1e-3) / 1e9
         roofline = {"kernel": dominant, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": None, "peak_source": peak_src, "avg_launch_ms": dom_ms / dom_n, "launches_timed": dom_n,
+                    "traffic": traffic, "peak_source": peak_src, "avg_launch_ms": dom_ms / dom_n, "launches_timed": dom_n,
                     "algorithmic_bytes_per_launch": alg[dominant], "share_of_step": (dom_ms / prof_steps) / sum(v[0] / prof_steps for v in prof.values()),
                     "timed_in": f"{prof_steps} event-bracketed steps right after the timed region"}
-    b_step = np_local * B_PARTICLE[transfer] + n ** 3 * B_CELL + its_mean * nf * B_IT_CG
+    b_step = np_local * B_PARTICLE[transfer] + n ** 3 * B_CELL + its_mean * nf * B_IT
     step_frac = b_step / (dev_ms_max / args.steps * 1e-3) / 1e9 / peak
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
