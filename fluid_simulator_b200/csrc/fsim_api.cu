@@ -128,8 +128,10 @@ void fold_timings(fsim* h) {
                  us_proj = ms[4] * 1e3, us_ext = ms[5] * 1e3, us_g2p = ms[6] * 1e3;
     FsimTimings& t = h->timings;
     const double f = 0.9;  // slidingAvgFactor, simulator.cpp:52
-    t.simulate_particles = (int64_t)(t.simulate_particles * f + us_adv * (1 - f));
-    t.push_particles_apart = (int64_t)(t.push_particles_apart * f);
+    t.simulate_particles = (int64_t)(t.simulate_particles * f + (us_adv - (h->push_timed ? 0.0 : 0.0)) * (1 - f));
+    double us_push = 0;
+    if (h->push_timed) { float pm = 0; cudaEventElapsedTime(&pm, h->ev[9], h->ev[15]); us_push = pm * 1e3; }
+    t.push_particles_apart = (int64_t)(t.push_particles_apart * f + us_push * (1 - f));
     t.push_particles_out_of_obstacles = (int64_t)(t.push_particles_out_of_obstacles * f);  // fused into the advect kernel
     t.p2g_transfer = (int64_t)(t.p2g_transfer * f + (us_sort + us_p2g) * (1 - f));
     t.incompressibility_prep = (int64_t)(t.incompressibility_prep * f + us_prep * (1 - f));
@@ -137,7 +139,7 @@ void fold_timings(fsim* h) {
     t.velocity_extrapolation = (int64_t)(t.velocity_extrapolation * f + us_ext * (1 - f));
     t.g2p_transfer = (int64_t)(t.g2p_transfer * f + us_g2p * (1 - f));
     t.incompressibility_it_count = h->solve.iterations;
-    t.last_raw_us[0] = us_adv; t.last_raw_us[1] = 0; t.last_raw_us[2] = 0; t.last_raw_us[3] = us_p2g;
+    t.last_raw_us[0] = us_adv; t.last_raw_us[1] = us_push; t.last_raw_us[2] = 0; t.last_raw_us[3] = us_p2g;
     t.last_raw_us[4] = us_prep; t.last_raw_us[5] = us_proj; t.last_raw_us[6] = us_ext; t.last_raw_us[7] = us_g2p;
     t.last_sort_us = us_sort;
     float total;
@@ -268,6 +270,7 @@ int fsim_create(const FsimGridDesc* desc, fsim_t** out) {
     memset(h->ps, 0, sizeof(h->ps));
     h->key = h->rank = nullptr; h->kill = nullptr;
     h->next_id = 0; h->gfx = nullptr; h->gfx_cap = 0;
+    h->copy_stream = nullptr; h->gfx_ready = nullptr; h->gfx_copied = nullptr; h->gfx_inflight = false;
     h->pressure_valid = false; h->ev_valid = false;
     memset(&h->timings, 0, sizeof(h->timings));
     memset(&h->solve, 0, sizeof(h->solve));
@@ -340,6 +343,9 @@ int fsim_destroy(fsim_t* h) {
     cudaFree(h->dens);
     cudaFree(h->p); cudaFree(h->rhs); cudaFree(h->r); cudaFree(h->s); cudaFree(h->q); cudaFree(h->z);
     cudaFree(h->d_obs); cudaFree(h->scal); cudaFree(h->partials); cudaFree(h->red_counter);
+    if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
+    if (h->gfx_ready) cudaEventDestroy(h->gfx_ready);
+    if (h->gfx_copied) cudaEventDestroy(h->gfx_copied);
     cudaFree(h->stage); cudaFree(h->gfx);
     for (const ProfRec& r : h->prof_recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     for (cudaEvent_t e : h->prof_free) cudaEventDestroy(e);
@@ -562,6 +568,11 @@ int fsim_stage_advect(fsim_t* h, double dt) {
     if (h->kill_pending) TRY(k_sort(h));  // removeParticles at the end of advectParticles (simulator.cpp:250)
     return FSIM_OK;
 }
+int fsim_stage_push_apart(fsim_t* h) {  /* updateParticleIntersectionHash + pushParticlesApart, simulator.cpp:61-64 */
+    BIND(h);
+    TRY(ensure_sorted(h));
+    return k_push_apart(h);
+}
 int fsim_stage_push_out(fsim_t* h) { BIND(h); return k_advect(h, 0.0, false, true, false); }
 int fsim_stage_p2g(fsim_t* h) {
     BIND(h);
@@ -582,8 +593,20 @@ int fsim_step(fsim_t* h, double dt, int* pcg_iterations) {
     const int64_t l0 = h->launches;
     FSIM_CUDA(h, cudaEventRecord(h->ev[0], h->stream));
     if (h->par.spawning_enabled) TRY(fsim_stage_spawn(h, dt));
-    // advect + obstacle push-out + stopParticles are one pass over the particles (push-apart is not on this path)
-    TRY(k_advect(h, dt, true, true, h->par.stop_particles != 0, /*do_bin=*/true));
+    if (h->par.push_apart_enabled) {
+        // simulate() order (simulator.cpp:57-74): advect -> push apart -> push out of obstacles -> stop
+        TRY(k_advect(h, dt, true, false, false, /*do_bin=*/true));
+        FSIM_CUDA(h, cudaEventRecord(h->ev[9], h->stream));
+        TRY(k_sort(h));
+        TRY(k_push_apart(h));
+        FSIM_CUDA(h, cudaEventRecord(h->ev[10 + 5], h->stream));
+        TRY(k_advect(h, dt, false, true, h->par.stop_particles != 0, /*do_bin=*/true));
+        h->push_timed = true;
+    } else {
+        // advect + obstacle push-out + stopParticles are one pass over the particles
+        TRY(k_advect(h, dt, true, true, h->par.stop_particles != 0, /*do_bin=*/true));
+        h->push_timed = false;
+    }
     FSIM_CUDA(h, cudaEventRecord(h->ev[1], h->stream));
     TRY(k_sort(h));
     FSIM_CUDA(h, cudaEventRecord(h->ev[2], h->stream));
@@ -673,6 +696,40 @@ int fsim_export_gfx(fsim_t* h, FsimParticleGfx* out, int64_t cap, int64_t* n) {
     return FSIM_OK;
 }
 
+int fsim_export_gfx_async(fsim_t* h, FsimParticleGfx* out, int64_t cap, int64_t* n) {
+    BIND(h);
+    if (n) *n = h->np;
+    const int64_t m = std::min(cap, h->np);
+    if (m <= 0 || !out) return FSIM_OK;
+    if (!h->copy_stream) {
+        FSIM_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        FSIM_CUDA(h, cudaEventCreateWithFlags(&h->gfx_ready, cudaEventDisableTiming));
+        FSIM_CUDA(h, cudaEventCreateWithFlags(&h->gfx_copied, cudaEventDisableTiming));
+    }
+    // the device staging buffer is reused: the new export kernel must not overwrite it before the previous copy has left
+    if (h->gfx_inflight) FSIM_CUDA(h, cudaStreamWaitEvent(h->stream, h->gfx_copied, 0));
+    if (!(h->gfx && h->gfx_cap >= h->np)) {
+        if (h->gfx_inflight) FSIM_CUDA(h, cudaEventSynchronize(h->gfx_copied));
+        TRY(ensure_gfx(h));
+    }
+    TRY(k_export_gfx(h, h->gfx));
+    FSIM_CUDA(h, cudaEventRecord(h->gfx_ready, h->stream));
+    FSIM_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->gfx_ready, 0));
+    FSIM_CUDA(h, cudaMemcpyAsync(out, h->gfx, sizeof(FsimParticleGfx) * m, cudaMemcpyDeviceToHost, h->copy_stream));
+    FSIM_CUDA(h, cudaEventRecord(h->gfx_copied, h->copy_stream));
+    h->gfx_inflight = true;
+    return FSIM_OK;
+}
+
+int fsim_export_gfx_wait(fsim_t* h) {
+    BIND(h);
+    if (h->gfx_inflight) {
+        FSIM_CUDA(h, cudaEventSynchronize(h->gfx_copied));
+        h->gfx_inflight = false;
+    }
+    return FSIM_OK;
+}
+
 int fsim_get_step_durations(const fsim_t* hc, FsimTimings* out) {
     fsim* h = const_cast<fsim*>(hc);
     BIND(h);
@@ -700,7 +757,7 @@ int fsim_get_last_step_stats(const fsim_t* hc, double* device_ms, int64_t* kerne
 
 static const char* const kKernelNames[K_COUNT] = {"advect", "bin", "scan", "reorder", "p2g", "classify", "finalize", "rhs",
                                                     "pcg_init", "spmv", "pcg_update", "pcg_direction", "mg", "mg_level1", "mg_coarse", "pressure_apply",
-                                                    "extrapolate", "g2p", "gfx", "memset"};
+                                                    "extrapolate", "g2p", "gfx", "memset", "push_apart"};
 
 int fsim_kernel_class_count(void) { return K_COUNT; }
 const char* fsim_kernel_class_name(int kid) { return (kid >= 0 && kid < K_COUNT) ? kKernelNames[kid] : ""; }
@@ -732,14 +789,14 @@ int fsim_profile_read(fsim_t* h, double* total_ms, int64_t* profiled_launches, i
 
 int fsim_timer_record(fsim_t* h, int slot) {
     BIND(h);
-    if (slot < 0 || slot > 5) return fsim_fail(h, FSIM_ERR_INVALID, "timer slot out of range");
+    if (slot < 0 || slot > 4) return fsim_fail(h, FSIM_ERR_INVALID, "timer slot out of range");
     FSIM_CUDA(h, cudaEventRecord(h->ev[10 + slot], h->stream));
     return FSIM_OK;
 }
 
 int fsim_timer_elapsed_ms(fsim_t* h, int slot_begin, int slot_end, double* ms) {
     BIND(h);
-    if (slot_begin < 0 || slot_begin > 5 || slot_end < 0 || slot_end > 5 || !ms) return fsim_fail(h, FSIM_ERR_INVALID, "bad timer slots");
+    if (slot_begin < 0 || slot_begin > 4 || slot_end < 0 || slot_end > 4 || !ms) return fsim_fail(h, FSIM_ERR_INVALID, "bad timer slots");
     FSIM_CUDA(h, cudaEventSynchronize(h->ev[10 + slot_end]));
     float f = 0.f;
     FSIM_CUDA(h, cudaEventElapsedTime(&f, h->ev[10 + slot_begin], h->ev[10 + slot_end]));

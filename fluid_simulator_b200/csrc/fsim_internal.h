@@ -73,7 +73,7 @@ struct MgLevel;
 // kernel classes for launch counting and the optional per-launch CUDA-event profiling (fsim_profile_*)
 enum KernelId {
     K_ADVECT = 0, K_BIN, K_SCAN, K_REORDER, K_P2G, K_CLASSIFY, K_FINALIZE, K_RHS, K_PCG_INIT, K_SPMV, K_UPDATE,
-    K_DIRECTION, K_MG, K_MG1, K_MG2, K_APPLY, K_EXTRAP, K_G2P, K_GFX, K_MEMSET, K_COUNT
+    K_DIRECTION, K_MG, K_MG1, K_MG2, K_APPLY, K_EXTRAP, K_G2P, K_GFX, K_MEMSET, K_PUSH, K_COUNT
 };
 struct ProfRec { int kid; cudaEvent_t e0, e1; };
 
@@ -98,6 +98,9 @@ struct fsim {
     uint32_t next_id;         // next persistent particle id to hand out
     FsimParticleGfx* gfx;     // device buffer of the gfx export, [gfx_cap]
     int64_t gfx_cap;
+    cudaStream_t copy_stream;  // D2H of the async gfx export
+    cudaEvent_t gfx_ready, gfx_copied;
+    bool gfx_inflight;
     uint32_t *key, *rank;     // [cap+1] each
     uint8_t* kill;            // [cap] sink-capture flags written by the advect kernel
     bool kill_pending;        // kill[] holds flags the next sort must honour
@@ -139,6 +142,7 @@ struct fsim {
     // timing
     cudaEvent_t ev[16];
     bool ev_valid;
+    bool push_timed;  // the last step ran the push-apart pass (ev[9]..ev[15] bracket it)
     FsimTimings timings;
     FsimSolveInfo solve;
     double last_step_ms;
@@ -201,7 +205,8 @@ struct KScope {
 // ---- kernels' host launchers (one per stage file) ----------------------------------------------------
 int k_upload_obstacles(fsim* h);
 int k_advect(fsim* h, double dt, bool do_advect, bool do_pushout, bool do_stop, bool do_bin = false);
-int k_sort(fsim* h);  // key/count -> scan -> reorder; updates np when particles were removed
+int k_sort(fsim* h);
+int k_push_apart(fsim* h);  // key/count -> scan -> reorder; updates np when particles were removed
 int k_p2g(fsim* h);
 int k_classify(fsim* h, double dt);
 int k_post_p2g_only(fsim* h, double gravity_increment);

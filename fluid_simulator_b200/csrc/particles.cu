@@ -8,6 +8,9 @@
 //   reorder_kernel     scatter into cell-binned SoA order (drops particles captured by a sink = removeParticles,
 //                      hashedParticles.cpp:158-172)
 //   layout conversion between the reference's AoS fp64 `Particle` (particle.h:8-12) and the device SoA fp32
+#include <algorithm>
+#include <cmath>
+
 #include "fsim_internal.h"
 
 #define INVALID_KEY 0xFFFFFFFFu
@@ -341,6 +344,55 @@ __global__ void __launch_bounds__(256) reorder_kernel(ReorderArgs a) {
     if (a.src_id) a.dst_id[d] = a.src_id[i];
 }
 
+// ---- push-apart (HashedParticles::pushParticlesApart, hashedParticles.cpp:64-107; SURVEY §8f "next #1") ----------
+// The reference walks a hash grid of spacing 2r and separates every overlapping pair in place (each thread moves both
+// particles; racy and order-dependent by construction).  Here the particles are already cell-binned on the MAC grid, so a
+// thread finds its neighbours in the (2R+1)^2 x-runs of cells around its own cell (R = ceil(2r / h)) and applies the sum
+// of its half-overlaps, computed from the positions at the start of the pass (Jacobi form): an isolated pair ends
+// exactly 2r apart, as in the reference.  Equivalence with the reference is statistical (it is with itself, too).
+struct PushApartArgs {
+    GridDims g;
+    const float *px, *py, *pz;
+    float *ox, *oy, *oz;
+    const uint32_t* cell_start;
+    int64_t n;
+    float d, d2;       // 2r, (2r)^2
+    int R;             // search radius in cells
+    float lo[3], hi[3];
+    int zconst;
+    float zval;
+};
+
+__global__ void __launch_bounds__(256) push_apart_kernel(PushApartArgs a) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const GridDims& g = a.g;
+    const float x = a.px[i], y = a.py[i], z = a.pz[i];
+    const int cx = min(max((int)((double)x * g.dihx), 0), g.gx - 1), cy = min(max((int)((double)y * g.dihy), 0), g.gy - 1),
+              cz = min(max((int)((double)z * g.dihz), 0), g.gz - 1);
+    float dx = 0.f, dy = 0.f, dz = 0.f;
+    const int x0 = max(cx - a.R, 0), x1 = min(cx + a.R, g.gx - 1);
+    for (int zz = max(cz - a.R, 0); zz <= min(cz + a.R, g.gz - 1); zz++)
+        for (int yy = max(cy - a.R, 0); yy <= min(cy + a.R, g.gy - 1); yy++) {
+            const int64_t row = ((int64_t)zz * g.gy + yy) * g.gx;
+            const uint32_t jb = a.cell_start[row + x0], je = a.cell_start[row + x1 + 1];
+            for (uint32_t j = jb; j < je; j++) {
+                if (j == (uint32_t)i) continue;
+                const float ex = x - a.px[j], ey = y - a.py[j], ez = z - a.pz[j];
+                const float r2 = ex * ex + ey * ey + ez * ez;
+                if (r2 > a.d2 || r2 < 1e-8f) continue;  // hashedParticles.cpp:88-89
+                const float dist = sqrtf(r2);
+                const float t = (a.d - dist) / dist * 0.5f;
+                dx += ex * t; dy += ey * t; dz += ez * t;
+            }
+        }
+    float nx = x + dx, ny = y + dy, nz = z + dz;
+    nx = fminf(fmaxf(nx, a.lo[0]), a.hi[0]);
+    ny = fminf(fmaxf(ny, a.lo[1]), a.hi[1]);
+    nz = a.zconst ? a.zval : fminf(fmaxf(nz, a.lo[2]), a.hi[2]);
+    a.ox[i] = nx; a.oy[i] = ny; a.oz[i] = nz;
+}
+
 // ---- layout conversion ---------------------------------------------------------------------------------
 struct SoA { float* ch[15]; int nch; };
 
@@ -497,6 +549,30 @@ int k_sort(fsim* h) {
     }
     h->sorted = true;
     h->binned = false;
+    return FSIM_OK;
+}
+
+int k_push_apart(fsim* h) {  // requires cell-binned particles (k_sort)
+    if (h->np == 0) return FSIM_OK;
+    PushApartArgs a;
+    a.g = h->g;
+    ParticleSet &p = h->ps[h->cur], &o = h->ps[h->cur ^ 1];
+    a.px = p.pos[0]; a.py = p.pos[1]; a.pz = p.pos[2];
+    a.ox = o.pos[0]; a.oy = o.pos[1]; a.oz = o.pos[2];
+    a.cell_start = h->cell_start; a.n = h->np;
+    const double r = h->particle_r;
+    a.d = (float)(2.0 * r); a.d2 = a.d * a.d;
+    const double hmin = std::min(h->info.cell_d[0], std::min(h->info.cell_d[1], h->info.cell_d[2]));
+    a.R = std::max(1, (int)std::ceil(2.0 * r / hmin));
+    for (int k = 0; k < 3; k++) {  // particleLow / particleHigh, hashedParticles.cpp:67-68
+        a.lo[k] = (float)(h->info.cell_d[k] + r * 1.01);
+        a.hi[k] = (float)(h->info.dimensions[k] - (h->info.cell_d[k] + r * 1.01));
+    }
+    a.zconst = h->zconst; a.zval = (float)h->zval;
+    { KScope ks(h, K_PUSH); push_apart_kernel<<<div_up(h->np, 256), 256, 0, h->stream>>>(a); }
+    FSIM_CHECK_LAUNCH(h);
+    for (int k = 0; k < 3; k++) std::swap(p.pos[k], o.pos[k]);  // velocities, C and ids stay where they are
+    h->sorted = false; h->binned = false;
     return FSIM_OK;
 }
 

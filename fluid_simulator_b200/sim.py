@@ -64,6 +64,7 @@ def load_library():
         "fsim_step": (i32, [vp, dbl, P(i32)]),
         "fsim_stage_spawn": (i32, [vp, dbl]),
         "fsim_stage_advect": (i32, [vp, dbl]),
+        "fsim_stage_push_apart": (i32, [vp]),
         "fsim_stage_push_out": (i32, [vp]),
         "fsim_stage_p2g": (i32, [vp]),
         "fsim_stage_classify": (i32, [vp, dbl]),
@@ -75,6 +76,8 @@ def load_library():
         "fsim_upload_grid": (i32, [vp, i32, vp, i64]),
         "fsim_download_particle_cells": (i32, [vp, vp, i64]),
         "fsim_export_gfx": (i32, [vp, vp, i64, P(i64)]),
+        "fsim_export_gfx_async": (i32, [vp, vp, i64, P(i64)]),
+        "fsim_export_gfx_wait": (i32, [vp]),
         "fsim_get_step_durations": (i32, [vp, P(abi.Timings)]),
         "fsim_get_solve_info": (i32, [vp, P(abi.SolveInfo)]),
         "fsim_get_last_step_stats": (i32, [vp, P(dbl), P(i64)]),
@@ -213,6 +216,7 @@ class FluidSim:
 
     def stage_spawn(self, dt): self._ck(self.L.fsim_stage_spawn(self.h, dt))
     def stage_advect(self, dt): self._ck(self.L.fsim_stage_advect(self.h, dt))
+    def stage_push_apart(self): self._ck(self.L.fsim_stage_push_apart(self.h))
     def stage_push_out(self): self._ck(self.L.fsim_stage_push_out(self.h))
     def stage_p2g(self, dt=0.0): self._ck(self.L.fsim_stage_p2g(self.h))
     def stage_classify(self, dt): self._ck(self.L.fsim_stage_classify(self.h, dt))
@@ -252,6 +256,14 @@ class FluidSim:
         n = C.c_int64()
         self._ck(self.L.fsim_export_gfx(self.h, ptr, cap, C.byref(n)))
         return int(n.value)
+
+    def export_gfx_async_ptr(self, ptr, cap):
+        """Enqueues the gfx export; the copy into `ptr` (pinned host memory) overlaps the following steps."""
+        n = C.c_int64()
+        self._ck(self.L.fsim_export_gfx_async(self.h, ptr, cap, C.byref(n)))
+        return int(n.value)
+
+    def export_gfx_wait(self): self._ck(self.L.fsim_export_gfx_wait(self.h))
 
     # --- introspection --------------------------------------------------------------------------
     def step_durations(self):

@@ -247,3 +247,42 @@ def test_properties_at_scale(gpu):
     diag(test="scale/128", its=its, fluid=int(info.fluid_cells), rmax=info.residual_max, stats=g.last_step_stats(),
          timings=g.step_durations())
     assert info.residual_max < 1e-6 and not info.early_out
+
+
+def _pair_stats(pos, d):
+    """fraction of particles that have a neighbour closer than 0.9*d, and the mean nearest-neighbour distance (2D scene)"""
+    from scipy.spatial import cKDTree
+    t = cKDTree(pos[:, 0:2])
+    dist, _ = t.query(pos[:, 0:2], k=2)
+    nn = dist[:, 1]
+    return float((nn < 0.9 * d).mean()), float(nn.mean())
+
+
+def test_push_apart_statistical_parity(gpu):
+    """pushParticlesApart is racy / order dependent in the reference, so parity is statistical:
+    after 60 steps of the 2D preset (push-apart ON) overlap statistics, kinetic energy and centre of mass agree with the
+    compiled reference, and both differ clearly from a run with push-apart off."""
+    from oracle import refsim
+    if not refsim.available():
+        pytest.skip("oracle/_ref not built")
+    sc = scenes.dam_break_2d(48, push_apart_enabled=True)
+    r = refsim.RefSim(sc.dims, sc.resolution, sc.two_d, sc.particle_radius)
+    g = gpu(sc.dims, sc.resolution, sc.two_d, sc.particle_radius)
+    g_off = gpu(sc.dims, sc.resolution, sc.two_d, sc.particle_radius)
+    for s in (r, g):
+        s.set_params(sc.params); s.upload_particles(sc.particles)
+    g_off.set_params(scenes.dam_break_2d(48).params); g_off.upload_particles(sc.particles)
+    for _ in range(60):
+        r.step(sc.dt); g.step(sc.dt); g_off.step(sc.dt)
+    pr, pg, po = r.download_particles(), g.download_particles(), g_off.download_particles()
+    d = 2 * sc.particle_radius
+    fr, mr = _pair_stats(pr, d); fg, mg = _pair_stats(pg, d); fo, mo = _pair_stats(po, d)
+    ke = lambda p: 0.5 * (p[:, 3:6] ** 2).sum()
+    diag(test="push_apart/2d", close_frac_ref=fr, close_frac_gpu=fg, close_frac_off=fo, nn_ref=mr, nn_gpu=mg, nn_off=mo,
+         ke_ref=ke(pr), ke_gpu=ke(pg), com_ref=pr[:, 0:2].mean(0).tolist(), com_gpu=pg[:, 0:2].mean(0).tolist(),
+         push_us=g.step_durations()["PushParticlesApart"])
+    assert fg < 0.5 * fo + 0.02                 # push-apart removes most close pairs ...
+    assert abs(mg - mr) < 0.1 * mr              # ... and spaces particles like the reference does (mean nearest neighbour)
+    assert abs(ke(pg) - ke(pr)) < 0.15 * ke(pr)
+    assert np.abs(pg[:, 0:2].mean(0) - pr[:, 0:2].mean(0)).max() < 1.0
+    assert g.step_durations()["PushParticlesApart"] > 0
