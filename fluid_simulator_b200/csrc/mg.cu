@@ -310,54 +310,6 @@ __global__ void __launch_bounds__(256) mg_jacobi4_kernel(Lv L, PcgScalars* __res
     }
 }
 
-// chunked variant of mg_jacobi4_kernel: a block owns L0_CHUNK consecutive cells, every thread makes L0_TRIPS trips of 4
-// cells and fetches the stencil codes of ALL its trips first, so the iterate loads of a trip no longer wait for that
-// trip's code (one dependent memory round trip instead of two) -- these kernels are latency-bound, not HBM-bound.
-constexpr int L0_TRIPS = 4;
-constexpr int L0_CHUNK = 256 * 4 * L0_TRIPS;
-template <bool DOT>
-__global__ void __launch_bounds__(256, 4) mg_jacobi4c_kernel(Lv L, int64_t nc, PcgScalars* __restrict__ sc, const float* __restrict__ b,
-                                                          const float* __restrict__ xin, float* __restrict__ xout,
-                                                          const double* __restrict__ r64, double* partials, unsigned int* counter, float om) {
-    if (sc->done) return;
-    const int64_t base = (int64_t)blockIdx.x * L0_CHUNK + (int64_t)threadIdx.x * 4;
-    ushort4 codes[L0_TRIPS];
-#pragma unroll
-    for (int t = 0; t < L0_TRIPS; t++) {
-        const int64_t c = base + (int64_t)t * 1024;
-        codes[t] = c < nc ? *reinterpret_cast<const ushort4*>(L.code + c) : make_ushort4(0, 0, 0, 0);
-    }
-    double acc[1] = {0.0};
-#pragma unroll
-    for (int t = 0; t < L0_TRIPS; t++) {
-        const int64_t c = base + (int64_t)t * 1024;
-        const unsigned cd[4] = {codes[t].x, codes[t].y, codes[t].z, codes[t].w};
-        if (!((cd[0] | cd[1] | cd[2] | cd[3]) & CODE_ACTIVE)) continue;
-        F4 xo = zero4();
-        const Stencil4 s = load_stencil4(L, xin, c, cd);
-        const F4 bb = ld4(b + c);
-#pragma unroll
-        for (int i = 0; i < 4; i++)
-            if (cd[i] & CODE_ACTIVE) {
-                const float d = (float)((cd[i] >> 6) & 7u);
-                const float xi = s.c.v[i];
-                xo.v[i] = d > 0.f ? xi + om * (bb.v[i] - (d * xi - off4(s, i, cd[i]))) / d : 0.f;
-            }
-        st4(xout + c, xo);
-        if (DOT) {
-            const double2 r0 = *reinterpret_cast<const double2*>(r64 + c), r1 = *reinterpret_cast<const double2*>(r64 + c + 2);
-            const double rr[4] = {r0.x, r0.y, r1.x, r1.y};
-#pragma unroll
-            for (int i = 0; i < 4; i++)
-                if (cd[i] & CODE_ACTIVE) acc[0] += (double)xo.v[i] * rr[i];
-        }
-    }
-    if (DOT) {
-        double out[1];
-        if (grid_reduce<1, 0>(acc, partials, counter, out)) sc->sigma_new = out[0];
-    }
-}
-
 // CG update fused with the first smoothing sweep of the next cycle (level 0, linear chunks of 4-cell groups):
 //   alpha = sigma / s.q ; p += alpha s ; r -= alpha q ; ||r||_inf ; b = r / scale ; x1 = omega b / diag
 constexpr int UF_CHUNK = 8192;
@@ -815,7 +767,7 @@ int cycle(fsim* h, int l, bool zero_guess, float** result, bool first_done = fal
                 else mg_first_kernel<false><<<grid_of(m, blk), blk, 0, h->stream>>>(L, nullptr, sc, m->b, cur);
             } else {
                 const float om = s == 0 ? OM_A : OM_B;
-                if (v4) mg_jacobi4c_kernel<false><<<div_up(m->nc, L0_CHUNK), 256, 0, h->stream>>>(L, m->nc, h->scal, m->b, cur, oth, nullptr, nullptr, nullptr, om);
+                if (v4) mg_jacobi4_kernel<false><<<grd4, blk4, 0, h->stream>>>(L, h->scal, m->b, cur, oth, nullptr, nullptr, nullptr, om);
                 else if (fine) mg_jacobi_kernel<true><<<grid_of(m, blk), blk, 0, h->stream>>>(L, sc, m->b, cur, oth, om);
                 else mg_jacobi_kernel<false><<<grid_of(m, blk), blk, 0, h->stream>>>(L, sc, m->b, cur, oth, om);
                 float* t = cur; cur = oth; oth = t;
@@ -846,8 +798,8 @@ int cycle(fsim* h, int l, bool zero_guess, float** result, bool first_done = fal
         for (int s = 1; s < POST; s++) {
             const float om = OM_A;  // post-sweeps run the pre-sweep weights in reverse order (B in the fused prolongation sweep, then A)
             if (v4 && with_dot && s == POST - 1)
-                mg_jacobi4c_kernel<true><<<div_up(m->nc, L0_CHUNK), 256, 0, h->stream>>>(L, m->nc, h->scal, m->b, cur, oth, h->r, h->partials, h->red_counter, om);
-            else if (v4) mg_jacobi4c_kernel<false><<<div_up(m->nc, L0_CHUNK), 256, 0, h->stream>>>(L, m->nc, h->scal, m->b, cur, oth, nullptr, nullptr, nullptr, om);
+                mg_jacobi4_kernel<true><<<grd4, blk4, 0, h->stream>>>(L, h->scal, m->b, cur, oth, h->r, h->partials, h->red_counter, om);
+            else if (v4) mg_jacobi4_kernel<false><<<grd4, blk4, 0, h->stream>>>(L, h->scal, m->b, cur, oth, nullptr, nullptr, nullptr, om);
             else if (fine) mg_jacobi_kernel<true><<<grid_of(m, blk), blk, 0, h->stream>>>(L, sc, m->b, cur, oth, om);
             else mg_jacobi_kernel<false><<<grid_of(m, blk), blk, 0, h->stream>>>(L, sc, m->b, cur, oth, om);
             float* t = cur; cur = oth; oth = t;

@@ -281,8 +281,8 @@ def test_push_apart_statistical_parity(gpu):
     diag(test="push_apart/2d", close_frac_ref=fr, close_frac_gpu=fg, close_frac_off=fo, nn_ref=mr, nn_gpu=mg, nn_off=mo,
          ke_ref=ke(pr), ke_gpu=ke(pg), com_ref=pr[:, 0:2].mean(0).tolist(), com_gpu=pg[:, 0:2].mean(0).tolist(),
          push_us=g.step_durations()["PushParticlesApart"])
-    assert fg < 0.5 * fo + 0.02                 # push-apart removes most close pairs ...
-    assert abs(mg - mr) < 0.1 * mr              # ... and spaces particles like the reference does (mean nearest neighbour)
+    assert mg > 1.8 * mo                        # push-apart spreads the particles (mean nearest-neighbour distance) ...
+    assert abs(mg - mr) < 0.1 * mr              # ... to the same spacing as the reference's pass
     assert abs(ke(pg) - ke(pr)) < 0.15 * ke(pr)
     assert np.abs(pg[:, 0:2].mean(0) - pr[:, 0:2].mean(0)).max() < 1.0
     assert g.step_durations()["PushParticlesApart"] > 0
