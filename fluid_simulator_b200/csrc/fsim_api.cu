@@ -280,6 +280,8 @@ int fsim_create(const FsimGridDesc* desc, fsim_t** out) {
     h->pcg_graph = nullptr; h->pcg_graph_failed = false; h->pcg_graph_launches = 0; memset(h->pcg_graph_class, 0, sizeof(h->pcg_graph_class));
     { const char* e = getenv("FSIM_NO_GRAPH"); h->use_graph = !(e && e[0] == '1'); }
     { const char* e = getenv("FSIM_NO_WARM_START"); h->warm_start = !(e && e[0] == '1'); }
+    { const char* e = getenv("FSIM_WARM_EXTRAPOLATE"); h->warm_extrapolate = !(e && e[0] == '0'); }
+    h->warm_history = 0; h->p_prev = nullptr;
     h->status_host = nullptr; h->status_dev = nullptr;
     { const char* e = getenv("FSIM_PRECOND"); h->use_mg = !(e && strcmp(e, "jacobi") == 0); }
     memset(h->prof_ms, 0, sizeof(h->prof_ms)); memset(h->prof_n, 0, sizeof(h->prof_n)); memset(h->launch_n, 0, sizeof(h->launch_n));
@@ -294,6 +296,7 @@ int fsim_create(const FsimGridDesc* desc, fsim_t** out) {
     A(dev_alloc(h, &h->dens, g.nc));
     A(dev_alloc(h, &h->p, g.nc)); A(dev_alloc(h, &h->rhs, g.nc)); A(dev_alloc(h, &h->r, g.nc));
     A(dev_alloc(h, &h->s, g.nc)); A(dev_alloc(h, &h->q, g.nc)); A(dev_alloc(h, &h->z, g.nc));
+    A(dev_alloc(h, &h->p_prev, g.nc));
     A(dev_alloc(h, &h->d_obs, FSIM_MAX_OBS));
     A(dev_alloc(h, &h->scal, 1));
     h->red_blocks = (int)(g.nc / 256 + 2);  // one partial per 256-thread block of the widest solver launch
@@ -341,7 +344,7 @@ int fsim_destroy(fsim_t* h) {
     cudaFree(h->cnt); cudaFree(h->cell_start); cudaFree(h->scan_block); cudaFree(h->flags); cudaFree(h->code);
     for (int a = 0; a < 3; a++) { cudaFree(h->u[a]); cudaFree(h->u2[a]); cudaFree(h->wsum[a]); }
     cudaFree(h->dens);
-    cudaFree(h->p); cudaFree(h->rhs); cudaFree(h->r); cudaFree(h->s); cudaFree(h->q); cudaFree(h->z);
+    cudaFree(h->p); cudaFree(h->rhs); cudaFree(h->r); cudaFree(h->s); cudaFree(h->q); cudaFree(h->z); cudaFree(h->p_prev);
     cudaFree(h->d_obs); cudaFree(h->scal); cudaFree(h->partials); cudaFree(h->red_counter);
     if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
     if (h->gfx_ready) cudaEventDestroy(h->gfx_ready);

@@ -127,7 +127,9 @@ struct fsim {
     bool pcg_graph_failed;                 // conditional graph nodes unavailable: host-driven loop
     int pcg_graph_launches;                // kernels per graph launch
     int pcg_graph_class[K_COUNT];          // ... per kernel class
-    bool use_graph, warm_start;
+    bool use_graph, warm_start, warm_extrapolate;
+    int warm_history;   // consecutive solves whose pressure is available for the warm start
+    float* p_prev;      // pressure of the step before the last one (fp32)
     double* partials;                      // reduction partials [3][max_blocks]
     unsigned int* red_counter;
     int red_blocks;

@@ -36,6 +36,7 @@ struct PcgArgs {
     const float* u2[3];
     const float* dens;
     double *p, *rhs, *r, *s, *q, *z;
+    float* p_prev;     // last step's converged pressure (fp32 copy) for the extrapolated warm start
     const float* z32;  // multigrid result (fp32) when the multigrid preconditioner is active, else nullptr
     PcgScalars* sc;
     double* partials;  // [3][gridDim.x]
@@ -81,8 +82,19 @@ __global__ void __launch_bounds__(PT) rhs_kernel(PcgArgs a) {
         }
         a.code[c] = (uint16_t)code;
         a.rhs[c] = rhs;
-        if (!a.warm) { a.r[c] = rhs; a.p[c] = 0.0; }
-        else if (!(code & CODE_ACTIVE)) a.p[c] = 0.0;  // warm start keeps last step's pressure on WATER cells only
+        if (!a.warm) { a.r[c] = rhs; a.p[c] = 0.0; if (a.p_prev) a.p_prev[c] = 0.f; }
+        else {
+            // warm start from last step's pressure, linearly extrapolated in time where two previous solutions exist
+            // (initial guess only: the converged field does not depend on it)
+            const double p1 = (code & CODE_ACTIVE) ? a.p[c] : 0.0;
+            double guess = p1;
+            if (a.p_prev) {
+                const double p0 = (double)a.p_prev[c];
+                if (a.warm > 1 && p1 != 0.0 && p0 != 0.0) guess = 2.0 * p1 - p0;
+                a.p_prev[c] = (float)p1;
+            }
+            a.p[c] = (code & CODE_ACTIVE) ? guess : 0.0;
+        }
     }
     double out[2];
     if (grid_reduce<2, 0>(acc, a.partials, a.counter, out)) {
@@ -237,11 +249,16 @@ __global__ void __launch_bounds__(PT) spmv_kernel(PcgArgs a) {
 }
 
 // same as spmv_kernel<true> with four cells per thread and trip (gx % 4 == 0): 13 independent loads in flight per thread
+// LAZY: the search-direction update of the previous iteration, s <- z + beta s (:284-289), is not a pass of its own: it is
+// evaluated on the fly at the 7 stencil points here (reads z as well) and written back by the fused update kernel.
+template <bool LAZY>
 __global__ void __launch_bounds__(PT, 4) spmv4_kernel(PcgArgs a) {
     if (a.sc->done) return;
     double acc[1] = {0.0};
     const int64_t sy = a.g.sy, sz = a.g.sz;
     const double scale = a.sc->scale;
+    const bool first = a.sc->it == 0;  // iteration 0: s = z was written by the start kernel
+    const double gam = (LAZY && !first) ? 1.0 : 0.0, bet = (LAZY && !first) ? a.sc->sigma_new / a.sc->sigma : 1.0;
     const int64_t cend = min((int64_t)(blockIdx.x + 1) * CHUNK, a.g.nc);
     for (int64_t c = (int64_t)blockIdx.x * CHUNK + (int64_t)threadIdx.x * 4; c < cend; c += PT * 4) {
         const ushort4 t = *reinterpret_cast<const ushort4*>(a.code + c);
@@ -249,16 +266,25 @@ __global__ void __launch_bounds__(PT, 4) spmv4_kernel(PcgArgs a) {
         const unsigned any = cd[0] | cd[1] | cd[2] | cd[3];
         if (!(any & CODE_ACTIVE)) continue;
         double sc[4], ym[4] = {0, 0, 0, 0}, yp[4] = {0, 0, 0, 0}, zm[4] = {0, 0, 0, 0}, zp[4] = {0, 0, 0, 0};
-        auto ld = [&](double* dst, const double* src) {
-            const double2 u = *reinterpret_cast<const double2*>(src), v = *reinterpret_cast<const double2*>(src + 2);
+        auto ld = [&](double* dst, int64_t at) {
+            const double2 u = *reinterpret_cast<const double2*>(a.s + at), v = *reinterpret_cast<const double2*>(a.s + at + 2);
             dst[0] = u.x; dst[1] = u.y; dst[2] = v.x; dst[3] = v.y;
+            if (LAZY) {
+                const float4 zz = *reinterpret_cast<const float4*>(a.z32 + at);
+                dst[0] = gam * (double)zz.x + bet * dst[0]; dst[1] = gam * (double)zz.y + bet * dst[1];
+                dst[2] = gam * (double)zz.z + bet * dst[2]; dst[3] = gam * (double)zz.w + bet * dst[3];
+            }
         };
-        ld(sc, a.s + c);
-        if (any & 4u) ld(ym, a.s + c - sy);
-        if (any & 8u) ld(yp, a.s + c + sy);
-        if (any & 16u) ld(zm, a.s + c - sz);
-        if (any & 32u) ld(zp, a.s + c + sz);
-        const double xl = (cd[0] & 1u) ? a.s[c - 1] : 0.0, xr = (cd[3] & 2u) ? a.s[c + 4] : 0.0;
+        auto ld1 = [&](int64_t at) -> double {
+            const double v = a.s[at];
+            return LAZY ? gam * (double)a.z32[at] + bet * v : v;
+        };
+        ld(sc, c);
+        if (any & 4u) ld(ym, c - sy);
+        if (any & 8u) ld(yp, c + sy);
+        if (any & 16u) ld(zm, c - sz);
+        if (any & 32u) ld(zp, c + sz);
+        const double xl = (cd[0] & 1u) ? ld1(c - 1) : 0.0, xr = (cd[3] & 2u) ? ld1(c + 4) : 0.0;
         double q[4] = {0, 0, 0, 0};
 #pragma unroll
         for (int i = 0; i < 4; i++)
@@ -375,9 +401,11 @@ __global__ void sigma_kernel(PcgScalars* sc, PcgHostStatus* status) {
 
 // one PCG iteration: SpMV -> update -> (multigrid cycle -> z.r | fused diagonal) -> direction -> close
 static int enqueue_iteration(fsim* h, const PcgArgs& a, bool vec, bool use_mg, int nbv) {
+    const bool lazy = use_mg && mg_can_fuse(h);  // fused path: SpMV(+direction) -> update(+direction, +first sweep) -> cycle(+z.r)
     {
         KScope ks(h, K_SPMV);
-        if (vec && a.g.gx % 4 == 0 && a.g.nc % 4 == 0) spmv4_kernel<<<nbv, PT, 0, h->stream>>>(a);
+        if (lazy) spmv4_kernel<true><<<nbv, PT, 0, h->stream>>>(a);
+        else if (vec && a.g.gx % 4 == 0 && a.g.nc % 4 == 0) spmv4_kernel<false><<<nbv, PT, 0, h->stream>>>(a);
         else if (vec) spmv_kernel<true><<<nbv, PT, 0, h->stream>>>(a);
         else spmv_kernel<false><<<nbv, PT, 0, h->stream>>>(a);
     }
@@ -388,6 +416,7 @@ static int enqueue_iteration(fsim* h, const PcgArgs& a, bool vec, bool use_mg, i
         rc = mg_apply(h, true, true);
         if (rc) return rc;
         if (a.z32 != h->mg_z32) return fsim_fail(h, FSIM_ERR_INVALID, "multigrid result buffer moved between cycles");
+        return FSIM_OK;  // direction and iteration bookkeeping are folded into the kernels above
     } else if (use_mg) {
         { KScope ks(h, K_UPDATE); update_kernel<false><<<nbv, PT, 0, h->stream>>>(a); }
         int rc = mg_apply(h, false, false);
@@ -420,7 +449,8 @@ int k_project(fsim* h, double dt, int* iterations) {
     a.inv_h = 1.0 / hcell;
     a.avg_pressure = h->par.average_pressure; a.pressure_k = h->par.pressure_k;
     a.pressure_enabled = h->par.pressure_enabled;
-    a.warm = h->warm_start && h->pressure_valid;
+    a.warm = (h->warm_start && h->pressure_valid) ? (h->warm_extrapolate && h->warm_history >= 2 ? 2 : 1) : 0;
+    a.p_prev = h->warm_extrapolate ? h->p_prev : nullptr;
     a.z32 = nullptr;
     const int nb1 = div_up(g.nc, PT);        // one cell per thread
     const int nbv = div_up(g.nc, CHUNK);     // chunked kernels
@@ -537,6 +567,7 @@ int k_project(fsim* h, double dt, int* iterations) {
     h->solve.fluid_cells = s.fluid_cells;
     if (iterations) *iterations = h->solve.iterations;
     h->pressure_valid = !s.early_out;
+    h->warm_history = s.early_out ? 0 : h->warm_history + 1;
     if (!s.early_out) return k_pressure_apply(h, dt);  // the early-out returns before applying anything (:257-258)
     return FSIM_OK;
 }
