@@ -314,15 +314,11 @@ __global__ void __launch_bounds__(256) mg_jacobi4_kernel(Lv L, PcgScalars* __res
 //   alpha = sigma / s.q ; p += alpha s ; r -= alpha q ; ||r||_inf ; b = r / scale ; x1 = omega b / diag
 constexpr int UF_CHUNK = 8192;
 __global__ void __launch_bounds__(256) mg_update_first4_kernel(Lv L, int64_t nc, PcgScalars* sc, PcgHostStatus* status, double* __restrict__ p,
-                                                               double* __restrict__ sv, double* __restrict__ r,
+                                                               const double* __restrict__ sv, double* __restrict__ r,
                                                                const double* __restrict__ q, float* __restrict__ b, float* __restrict__ xout,
-                                                               const float* __restrict__ z32, double* partials, unsigned int* counter) {
+                                                               double* partials, unsigned int* counter) {
     if (sc->done) return;
-    // lazy search direction (see spmv4_kernel<true>): s <- z + beta s is materialised here, one pass late
-    const bool first = sc->it == 0;
-    const double gam = first ? 0.0 : 1.0, bet = first ? 1.0 : sc->sigma_new / sc->sigma;
-    const double sig = first ? sc->sigma : sc->sigma_new;  // sigma of THIS iteration
-    const double alpha = sig / sc->sq;
+    const double alpha = sc->sigma / sc->sq;
     const bool bad = alpha != alpha;  // NaN => the reference breaks before touching p (bridsonSolverGrid.cpp:271-272)
     const double inv_scale = sc->inv_scale;
     double acc[1] = {0.0};
@@ -340,11 +336,6 @@ __global__ void __launch_bounds__(256) mg_update_first4_kernel(Lv L, int64_t nc,
                 pp[2 * h2] = a0.x; pp[2 * h2 + 1] = a0.y; ss[2 * h2] = a1.x; ss[2 * h2 + 1] = a1.y;
                 rr[2 * h2] = a2.x; rr[2 * h2 + 1] = a2.y; qq[2 * h2] = a3.x; qq[2 * h2 + 1] = a3.y;
             }
-            if (!first) {
-                const float4 zz = *reinterpret_cast<const float4*>(z32 + c);
-                ss[0] = gam * (double)zz.x + bet * ss[0]; ss[1] = gam * (double)zz.y + bet * ss[1];
-                ss[2] = gam * (double)zz.z + bet * ss[2]; ss[3] = gam * (double)zz.w + bet * ss[3];
-            }
             F4 bb = zero4(), xo = zero4();
 #pragma unroll
             for (int i = 0; i < 4; i++)
@@ -360,7 +351,6 @@ __global__ void __launch_bounds__(256) mg_update_first4_kernel(Lv L, int64_t nc,
             for (int h2 = 0; h2 < 2; h2++) {
                 *reinterpret_cast<double2*>(p + c + 2 * h2) = make_double2(pp[2 * h2], pp[2 * h2 + 1]);
                 *reinterpret_cast<double2*>(r + c + 2 * h2) = make_double2(rr[2 * h2], rr[2 * h2 + 1]);
-                if (!first) *reinterpret_cast<double2*>(sv + c + 2 * h2) = make_double2(ss[2 * h2], ss[2 * h2 + 1]);
             }
             st4(b + c, bb);
             st4(xout + c, xo);
@@ -377,12 +367,6 @@ __global__ void __launch_bounds__(256) mg_update_first4_kernel(Lv L, int64_t nc,
             else if (it + 1 >= sc->max_it) { sc->done = 2; sc->iterations = sc->max_it; }       // iteration cap
         }
         if (sc->done) { status->done = sc->done; __threadfence_system(); }
-        else {  // close the iteration: sigma <- sigma of this iteration; the cycle that follows writes sigma_new
-            sc->sigma = sig;
-            sc->it = it + 1;
-            status->it_done = it + 1;
-            __threadfence_system();
-        }
     }
 }
 
@@ -876,7 +860,7 @@ int mg_update_first(fsim* h) {
     const Lv L = view(h, m, 0);
     KScope ks(h, K_UPDATE);
     mg_update_first4_kernel<<<div_up(h->g.nc, UF_CHUNK), 256, 0, h->stream>>>(L, h->g.nc, h->scal, h->status_dev, h->p, h->s, h->r, h->q, m->b,
-                                                                              m->xa, h->mg_z32, h->partials, h->red_counter);
+                                                                              m->xa, h->partials, h->red_counter);
     FSIM_CHECK_LAUNCH(h);
     return FSIM_OK;
 }

@@ -249,16 +249,11 @@ __global__ void __launch_bounds__(PT) spmv_kernel(PcgArgs a) {
 }
 
 // same as spmv_kernel<true> with four cells per thread and trip (gx % 4 == 0): 13 independent loads in flight per thread
-// LAZY: the search-direction update of the previous iteration, s <- z + beta s (:284-289), is not a pass of its own: it is
-// evaluated on the fly at the 7 stencil points here (reads z as well) and written back by the fused update kernel.
-template <bool LAZY>
 __global__ void __launch_bounds__(PT, 4) spmv4_kernel(PcgArgs a) {
     if (a.sc->done) return;
     double acc[1] = {0.0};
     const int64_t sy = a.g.sy, sz = a.g.sz;
     const double scale = a.sc->scale;
-    const bool first = a.sc->it == 0;  // iteration 0: s = z was written by the start kernel
-    const double gam = (LAZY && !first) ? 1.0 : 0.0, bet = (LAZY && !first) ? a.sc->sigma_new / a.sc->sigma : 1.0;
     const int64_t cend = min((int64_t)(blockIdx.x + 1) * CHUNK, a.g.nc);
     for (int64_t c = (int64_t)blockIdx.x * CHUNK + (int64_t)threadIdx.x * 4; c < cend; c += PT * 4) {
         const ushort4 t = *reinterpret_cast<const ushort4*>(a.code + c);
@@ -266,25 +261,16 @@ __global__ void __launch_bounds__(PT, 4) spmv4_kernel(PcgArgs a) {
         const unsigned any = cd[0] | cd[1] | cd[2] | cd[3];
         if (!(any & CODE_ACTIVE)) continue;
         double sc[4], ym[4] = {0, 0, 0, 0}, yp[4] = {0, 0, 0, 0}, zm[4] = {0, 0, 0, 0}, zp[4] = {0, 0, 0, 0};
-        auto ld = [&](double* dst, int64_t at) {
-            const double2 u = *reinterpret_cast<const double2*>(a.s + at), v = *reinterpret_cast<const double2*>(a.s + at + 2);
+        auto ld = [&](double* dst, const double* src) {
+            const double2 u = *reinterpret_cast<const double2*>(src), v = *reinterpret_cast<const double2*>(src + 2);
             dst[0] = u.x; dst[1] = u.y; dst[2] = v.x; dst[3] = v.y;
-            if (LAZY) {
-                const float4 zz = *reinterpret_cast<const float4*>(a.z32 + at);
-                dst[0] = gam * (double)zz.x + bet * dst[0]; dst[1] = gam * (double)zz.y + bet * dst[1];
-                dst[2] = gam * (double)zz.z + bet * dst[2]; dst[3] = gam * (double)zz.w + bet * dst[3];
-            }
         };
-        auto ld1 = [&](int64_t at) -> double {
-            const double v = a.s[at];
-            return LAZY ? gam * (double)a.z32[at] + bet * v : v;
-        };
-        ld(sc, c);
-        if (any & 4u) ld(ym, c - sy);
-        if (any & 8u) ld(yp, c + sy);
-        if (any & 16u) ld(zm, c - sz);
-        if (any & 32u) ld(zp, c + sz);
-        const double xl = (cd[0] & 1u) ? ld1(c - 1) : 0.0, xr = (cd[3] & 2u) ? ld1(c + 4) : 0.0;
+        ld(sc, a.s + c);
+        if (any & 4u) ld(ym, a.s + c - sy);
+        if (any & 8u) ld(yp, a.s + c + sy);
+        if (any & 16u) ld(zm, a.s + c - sz);
+        if (any & 32u) ld(zp, a.s + c + sz);
+        const double xl = (cd[0] & 1u) ? a.s[c - 1] : 0.0, xr = (cd[3] & 2u) ? a.s[c + 4] : 0.0;
         double q[4] = {0, 0, 0, 0};
 #pragma unroll
         for (int i = 0; i < 4; i++)
@@ -401,11 +387,9 @@ __global__ void sigma_kernel(PcgScalars* sc, PcgHostStatus* status) {
 
 // one PCG iteration: SpMV -> update -> (multigrid cycle -> z.r | fused diagonal) -> direction -> close
 static int enqueue_iteration(fsim* h, const PcgArgs& a, bool vec, bool use_mg, int nbv) {
-    const bool lazy = use_mg && mg_can_fuse(h);  // fused path: SpMV(+direction) -> update(+direction, +first sweep) -> cycle(+z.r)
     {
         KScope ks(h, K_SPMV);
-        if (lazy) spmv4_kernel<true><<<nbv, PT, 0, h->stream>>>(a);
-        else if (vec && a.g.gx % 4 == 0 && a.g.nc % 4 == 0) spmv4_kernel<false><<<nbv, PT, 0, h->stream>>>(a);
+        if (vec && a.g.gx % 4 == 0 && a.g.nc % 4 == 0) spmv4_kernel<<<nbv, PT, 0, h->stream>>>(a);
         else if (vec) spmv_kernel<true><<<nbv, PT, 0, h->stream>>>(a);
         else spmv_kernel<false><<<nbv, PT, 0, h->stream>>>(a);
     }
@@ -416,7 +400,6 @@ static int enqueue_iteration(fsim* h, const PcgArgs& a, bool vec, bool use_mg, i
         rc = mg_apply(h, true, true);
         if (rc) return rc;
         if (a.z32 != h->mg_z32) return fsim_fail(h, FSIM_ERR_INVALID, "multigrid result buffer moved between cycles");
-        return FSIM_OK;  // direction and iteration bookkeeping are folded into the kernels above
     } else if (use_mg) {
         { KScope ks(h, K_UPDATE); update_kernel<false><<<nbv, PT, 0, h->stream>>>(a); }
         int rc = mg_apply(h, false, false);
