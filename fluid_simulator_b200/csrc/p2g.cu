@@ -5,8 +5,8 @@
 // Design: particles are cell-binned, so the scatter is tile-local.  One CTA owns a
 // 32x4x4 tile of cells, one THREAD owns one cell and walks that cell's particles sequentially.  All
 // particles of a cell touch the same 2x3x3 (staggered axis) / 3x3x3 (cell-centred) node neighbourhood,
-// so the thread accumulates the whole neighbourhood in REGISTERS (hat weights are exactly 0 outside the
-// 2x2x2 bracket the reference picks, macGrid.cpp:142-148) and only then folds it into a shared-memory
+// so the thread accumulates the whole neighbourhood in REGISTERS with packed fp32x2 FMAs (FFMA2; hat weights are
+// exactly 0 outside the 2x2x2 bracket the reference picks, macGrid.cpp:142-148) and only then folds it into a shared-memory
 // tile with plain read-modify-writes in 9 conflict-free phases: in phase (dy,dz) warp (j,k) owns row
 // (j+dy,k+dz), lanes own distinct x -- no shared-memory atomics (fp32 smem atomicAdd is a CAS loop on
 // sm_100a) and a deterministic summation order inside the tile.  The tile (+1-cell halo) is flushed with
@@ -39,85 +39,131 @@ __device__ __forceinline__ void centred_w(float f, float w[3]) {
     w[2] = fmaxf(0.f, a);
 }
 
-// One staggered pass.  AXIS = 0,1,2: face grid of that axis (2 nodes along AXIS, 3 along the others), values + weights.
-// AXIS = 3: cell-centred density (3x3x3 nodes, weights only).
+// packed fp32x2 FMA (sm_100 FFMA2): d = a * b + c on both halves; the mov.b64 packing is free after register allocation
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    float2 d;
+    asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d.x), "=f"(d.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+}
+
+// fold one register value into the shared tile (plain read-modify-write: the phase structure makes it conflict-free)
+__device__ __forceinline__ void fold(float* s, int id, float v, bool on) {
+    if (on && v != 0.f) s[id] += v;
+}
+
+// One staggered face pass, AXIS = 0,1,2: 2 nodes along AXIS (the pair a packed FFMA2 works on), 3 along the other two
+// dimensions B < C.  Per particle and node pair: weights += (wA0, wA1) * wB*wC ; values += (wA0*val0, wA1*val1) * wB*wC,
+// val_n = v + c[AXIS] . (face_n - particle) (APIC, simulator.cpp:327-328) or v (PIC / FLIP, :324).
 template <int AXIS>
-__device__ __forceinline__ void p2g_pass(const P2GArgs& a, float* s_val, float* s_w, bool active, int x, int y, int z,
-                                         uint32_t start, uint32_t n, int lane, int wy, int wz) {
-    constexpr int NX = (AXIS == 0) ? 2 : 3, NY = (AXIS == 1) ? 2 : 3, NZ = (AXIS == 2) ? 2 : 3;
-    float accw[NZ][NY][NX];
-    float accv[NZ][NY][NX];
+__device__ __forceinline__ void p2g_face_pass(const P2GArgs& a, float* s_val, float* s_w, bool active, int x, int y, int z,
+                                              uint32_t start, uint32_t n, int lane, int wy, int wz) {
+    constexpr int B = AXIS == 0 ? 1 : 0, C = AXIS == 2 ? 1 : 2;
+    float2 aw[3][3], av[3][3];  // [c][b]
 #pragma unroll
-    for (int k = 0; k < NZ; k++)
+    for (int c = 0; c < 3; c++)
 #pragma unroll
-        for (int j = 0; j < NY; j++)
-#pragma unroll
-            for (int i = 0; i < NX; i++) { accw[k][j][i] = 0.f; accv[k][j][i] = 0.f; }
+        for (int b = 0; b < 3; b++) { aw[c][b] = make_float2(0.f, 0.f); av[c][b] = make_float2(0.f, 0.f); }
 
     if (active) {
         const float* vel = AXIS == 0 ? a.vx : (AXIS == 1 ? a.vy : a.vz);
+        const float hh[3] = {a.g.hx, a.g.hy, a.g.hz};
         for (uint32_t t = 0; t < n; t++) {
             const uint32_t p = start + t;
-            const float fx = fmaf(__ldg(a.px + p), a.g.ihx, -(float)x);  // single rounding
-            const float fy = fmaf(__ldg(a.py + p), a.g.ihy, -(float)y);
-            const float fz = fmaf(__ldg(a.pz + p), a.g.ihz, -(float)z);
-            float wx[3], wy_[3], wz_[3];
-            // offsets (in cells) from the particle to node i along each dimension, for the APIC term
-            float ox[3], oy[3], oz[3];
-            if (AXIS == 0) { wx[0] = 1.f - fx; wx[1] = fx; wx[2] = 0.f; ox[0] = -fx; ox[1] = 1.f - fx; ox[2] = 0.f; }
-            else { centred_w(fx, wx); ox[0] = -0.5f - fx; ox[1] = 0.5f - fx; ox[2] = 1.5f - fx; }
-            if (AXIS == 1) { wy_[0] = 1.f - fy; wy_[1] = fy; wy_[2] = 0.f; oy[0] = -fy; oy[1] = 1.f - fy; oy[2] = 0.f; }
-            else { centred_w(fy, wy_); oy[0] = -0.5f - fy; oy[1] = 0.5f - fy; oy[2] = 1.5f - fy; }
-            if (AXIS == 2) { wz_[0] = 1.f - fz; wz_[1] = fz; wz_[2] = 0.f; oz[0] = -fz; oz[1] = 1.f - fz; oz[2] = 0.f; }
-            else { centred_w(fz, wz_); oz[0] = -0.5f - fz; oz[1] = 0.5f - fz; oz[2] = 1.5f - fz; }
-            if (AXIS == 3) {
-#pragma unroll
-                for (int k = 0; k < NZ; k++)
-#pragma unroll
-                    for (int j = 0; j < NY; j++) {
-                        const float wyz = wy_[j] * wz_[k];
-#pragma unroll
-                        for (int i = 0; i < NX; i++) accw[k][j][i] += wx[i] * wyz;
-                    }
-            } else {
-                const float v = __ldg(vel + p);
-                float cx = 0.f, cy = 0.f, cz = 0.f;
-                if (a.apic) {  // c[AXIS] . (face.pos - particle.pos), simulator.cpp:327-328
-                    cx = __ldg(a.c[3 * (AXIS % 3) + 0] + p) * a.g.hx;
-                    cy = __ldg(a.c[3 * (AXIS % 3) + 1] + p) * a.g.hy;
-                    cz = __ldg(a.c[3 * (AXIS % 3) + 2] + p) * a.g.hz;
-                }
-#pragma unroll
-                for (int k = 0; k < NZ; k++)
-#pragma unroll
-                    for (int j = 0; j < NY; j++) {
-                        const float wyz = wy_[j] * wz_[k];
-                        const float vyz = v + cy * oy[j] + cz * oz[k];
-#pragma unroll
-                        for (int i = 0; i < NX; i++) {
-                            const float w = wx[i] * wyz;
-                            accw[k][j][i] += w;
-                            accv[k][j][i] += w * (vyz + cx * ox[i]);
-                        }
-                    }
+            float f[3];
+            f[0] = fmaf(__ldg(a.px + p), a.g.ihx, -(float)x);  // single rounding
+            f[1] = fmaf(__ldg(a.py + p), a.g.ihy, -(float)y);
+            f[2] = fmaf(__ldg(a.pz + p), a.g.ihz, -(float)z);
+            const float2 wA = make_float2(1.f - f[AXIS], f[AXIS]);
+            float wB[3], wC[3];
+            centred_w(f[B], wB);
+            centred_w(f[C], wC);
+            const float v = __ldg(vel + p);
+            float2 wav = make_float2(wA.x * v, wA.y * v), P = make_float2(0.f, 0.f);
+            float cB = 0.f, cC = 0.f;
+            if (a.apic) {
+                const float cA = __ldg(a.c[3 * AXIS + AXIS] + p) * hh[AXIS];
+                cB = __ldg(a.c[3 * AXIS + B] + p) * hh[B];
+                cC = __ldg(a.c[3 * AXIS + C] + p) * hh[C];
+                P = make_float2(wA.x * cA * (-f[AXIS]), wA.y * cA * (1.f - f[AXIS]));  // offsets to the two faces along AXIS
             }
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+#pragma unroll
+                for (int b = 0; b < 3; b++) {
+                    const float wbc = wB[b] * wC[c];
+                    const float2 w2 = make_float2(wbc, wbc);
+                    aw[c][b] = ffma2(wA, w2, aw[c][b]);
+                    float2 tv = wav;
+                    if (a.apic) {
+                        const float base = v + cB * ((float)b - 0.5f - f[B]) + cC * ((float)c - 0.5f - f[C]);
+                        tv = ffma2(wA, make_float2(base, base), P);
+                    }
+                    av[c][b] = ffma2(tv, w2, av[c][b]);
+                }
         }
     }
-
-    // fold the register neighbourhood into the shared tile: phase (k,j) -> warp (wy,wz) owns row (wy+j, wz+k)
+    // fold: phases over (k, j), lanes along x.  (i,j,k) -> (pair half, b, c) depends on which dimension is staggered.
+    constexpr int NX = (AXIS == 0) ? 2 : 3, NY = (AXIS == 1) ? 2 : 3, NZ = (AXIS == 2) ? 2 : 3;
 #pragma unroll
     for (int k = 0; k < NZ; k++)
 #pragma unroll
         for (int j = 0; j < NY; j++) {
-            // node index along each dim: staggered axis -> {c-1, c} ; centred -> {c-1, c, c+1}; smem index = cell_local + 1 + (node - c)
             const int row = sidx(0, wy + j, wz + k);
 #pragma unroll
             for (int i = 0; i < NX; i++) {
+                const int half = AXIS == 0 ? i : (AXIS == 1 ? j : k);
+                const int bb = AXIS == 0 ? j : i;
+                const int cc = AXIS == 2 ? j : k;
+                const float w = half ? aw[cc][bb].y : aw[cc][bb].x;
+                const float vv = half ? av[cc][bb].y : av[cc][bb].x;
                 const int id = row + lane + i;
-                if (active && accw[k][j][i] != 0.f) {
-                    s_w[id] += accw[k][j][i];
-                    if (AXIS != 3) s_val[id] += accv[k][j][i];
+                if (active && w != 0.f) { s_w[id] += w; s_val[id] += vv; }
+                __syncwarp();
+            }
+            __syncthreads();
+        }
+}
+
+// cell-centred density pass (avgPNum, simulator.cpp:362-366): 3x3x3 nodes, weights only; x nodes packed as (0,1),(2,-)
+__device__ __forceinline__ void p2g_density_pass(const P2GArgs& a, float* s_w, bool active, int x, int y, int z, uint32_t start,
+                                                 uint32_t n, int lane, int wy, int wz) {
+    float2 aw[3][3][2];
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) { aw[k][j][0] = make_float2(0.f, 0.f); aw[k][j][1] = make_float2(0.f, 0.f); }
+    if (active) {
+        for (uint32_t t = 0; t < n; t++) {
+            const uint32_t p = start + t;
+            const float fx = fmaf(__ldg(a.px + p), a.g.ihx, -(float)x);
+            const float fy = fmaf(__ldg(a.py + p), a.g.ihy, -(float)y);
+            const float fz = fmaf(__ldg(a.pz + p), a.g.ihz, -(float)z);
+            float wx[3], wy_[3], wz_[3];
+            centred_w(fx, wx); centred_w(fy, wy_); centred_w(fz, wz_);
+            const float2 wx01 = make_float2(wx[0], wx[1]), wx2 = make_float2(wx[2], 0.f);
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+#pragma unroll
+                for (int j = 0; j < 3; j++) {
+                    const float wyz = wy_[j] * wz_[k];
+                    const float2 w2 = make_float2(wyz, wyz);
+                    aw[k][j][0] = ffma2(wx01, w2, aw[k][j][0]);
+                    aw[k][j][1] = ffma2(wx2, w2, aw[k][j][1]);
                 }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            const int row = sidx(0, wy + j, wz + k);
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                const float w = i == 0 ? aw[k][j][0].x : (i == 1 ? aw[k][j][0].y : aw[k][j][1].x);
+                if (active && w != 0.f) s_w[row + lane + i] += w;
                 __syncwarp();
             }
             __syncthreads();
@@ -143,10 +189,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) p2g_kernel(P2GArgs a) {
     __syncthreads();
 
     const bool active = n > 0;
-    p2g_pass<0>(a, s[0], s[3], active, x, y, z, start, n, lane, wy, wz);
-    p2g_pass<1>(a, s[1], s[4], active, x, y, z, start, n, lane, wy, wz);
-    p2g_pass<2>(a, s[2], s[5], active, x, y, z, start, n, lane, wy, wz);
-    p2g_pass<3>(a, nullptr, s[6], active, x, y, z, start, n, lane, wy, wz);
+    p2g_face_pass<0>(a, s[0], s[3], active, x, y, z, start, n, lane, wy, wz);
+    p2g_face_pass<1>(a, s[1], s[4], active, x, y, z, start, n, lane, wy, wz);
+    p2g_face_pass<2>(a, s[2], s[5], active, x, y, z, start, n, lane, wy, wz);
+    p2g_density_pass(a, s[6], active, x, y, z, start, n, lane, wy, wz);
 
     // flush tile + halo: one RED per touched node and channel (x fastest => coalesced)
     for (int i = threadIdx.x; i < SN; i += NTHREADS) {

@@ -70,13 +70,26 @@ __global__ void __launch_bounds__(256, 4) advect_kernel(AdvectArgs a) {
             run++;
             double minT = 1e6;
             int minAxis = 0;
+            // time to the nearest wall (simulator.cpp:156-169).  Division-free pre-check first: a wall can only be reached
+            // within the remaining time if gap <= |v| * (dt - t); the margin keeps the skip conservative, so the exact
+            // fp64 divisions below still decide every close call (almost no particle needs them).
+            const double rem = (dt - t) * (1.0 + 1e-9);
+            bool near = false;
 #pragma unroll
             for (int axis = 0; axis < 3; axis++) {
                 const double c = comp(v, axis);
-                double tmp = 1e6;
-                if (c > 1e-6) tmp = (comp(a.hi, axis) - comp(pos, axis)) / c;
-                else if (c < -1e-6) tmp = (comp(pos, axis) - comp(a.lo, axis)) / -c;
-                if (tmp < minT) { minT = tmp; minAxis = axis; }
+                if (c > 1e-6) near |= (comp(a.hi, axis) - comp(pos, axis)) <= c * rem;
+                else if (c < -1e-6) near |= (comp(pos, axis) - comp(a.lo, axis)) <= -c * rem;
+            }
+            if (near) {
+#pragma unroll
+                for (int axis = 0; axis < 3; axis++) {
+                    const double c = comp(v, axis);
+                    double tmp = 1e6;
+                    if (c > 1e-6) tmp = (comp(a.hi, axis) - comp(pos, axis)) / c;
+                    else if (c < -1e-6) tmp = (comp(pos, axis) - comp(a.lo, axis)) / -c;
+                    if (tmp < minT) { minT = tmp; minAxis = axis; }
+                }
             }
             if (minT <= (dt - t)) {  // wall bounce, restitution 0.3 (simulator.cpp:171-176)
                 pos = pos + (v * minT) * 0.999;
