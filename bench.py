@@ -133,6 +133,7 @@ def main():
     ap.add_argument("--cpu-warmup", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--obstacle-box", action="store_true", help="add the static box of SURVEY cfg 3 (size (24,96,N) at (0.7N,48,0.5N))")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -177,6 +178,8 @@ def main():
     sim = FluidSim((float(n),) * 3, 1.0, False, 0.25, capacity=np_local, device=local_rank)
     sim.set_id_tracking(False)  # ids are test support; the hot path does not carry them
     sim.set_params(scene_params(n, transfer))
+    if args.obstacle_box:
+        sim.set_obstacles([scenes.cfg3_box(n)])
     sim.upload_particles_f32(pos)
     del pos
     t_gen = time.perf_counter() - t_gen
@@ -241,7 +244,7 @@ def main():
         t0 = time.perf_counter()
         for i in range(k):
             sim.set_params(params)
-            sim.set_obstacles([])
+            sim.set_obstacles([scenes.cfg3_box(n)] if args.obstacle_box else [])
             sim.step(DT)
             sim.export_gfx_wait()                     # buffer (i-1)%2 has landed and may be consumed
             sim.export_gfx_async_ptr(gfx[i % 2].data_ptr(), np_local)

@@ -11,6 +11,7 @@ OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_COMM = 0, 1, 2, 3, 4
 PIC, FLIP, APIC = 0, 1, 2
 WATER, AIR, SOLID = 0, 1, 2
 BOX, SPHERE, SOURCE, SINK = 0, 1, 2, 3
+SOLVER_BRIDSON, SOLVER_BASIC = 0, 1
 MAX_OBSTACLES = 32
 (FIELD_TYPE, FIELD_V, FIELD_V2, FIELD_WSUM, FIELD_AVGPNUM, FIELD_PRESSURE, FIELD_RHS, FIELD_PCOUNT) = range(8)
 
@@ -30,7 +31,7 @@ class Params(C.Structure):
     _fields_ = [("transfer_type", C.c_int32), ("flip_ratio", C.c_float), ("gravity", C.c_float),
                 ("gravity_enabled", C.c_int32), ("push_apart_enabled", C.c_int32), ("spawning_enabled", C.c_int32),
                 ("despawning_enabled", C.c_int32), ("stop_particles", C.c_int32), ("top_solid", C.c_int32),
-                ("pressure_enabled", C.c_int32), ("max_iterations", C.c_int32), ("reserved0", C.c_int32),
+                ("pressure_enabled", C.c_int32), ("max_iterations", C.c_int32), ("solver_type", C.c_int32),
                 ("pressure_k", C.c_double), ("average_pressure", C.c_double), ("fluid_density", C.c_double),
                 ("residual_tolerance", C.c_double)]
 
@@ -72,7 +73,7 @@ class SolveInfo(C.Structure):
 def make_params(transfer_type=FLIP, flip_ratio=0.99, gravity=150.0, gravity_enabled=True, push_apart_enabled=False,
                 spawning_enabled=False, despawning_enabled=False, stop_particles=False, top_solid=False,
                 pressure_enabled=True, max_iterations=80, pressure_k=2.0, average_pressure=2.0, fluid_density=1.0,
-                residual_tolerance=1e-6):
+                residual_tolerance=1e-6, solver_type=0):
     """Defaults are the reference's struct defaults (simulator.h:30-39, macGrid.h:173-179) except
     push_apart_enabled (SURVEY §8(f) next #1)."""
     p = Params()
@@ -91,6 +92,7 @@ def make_params(transfer_type=FLIP, flip_ratio=0.99, gravity=150.0, gravity_enab
     p.average_pressure = average_pressure
     p.fluid_density = fluid_density
     p.residual_tolerance = residual_tolerance
+    p.solver_type = int(solver_type)
     return p
 
 

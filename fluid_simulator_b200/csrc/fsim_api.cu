@@ -372,6 +372,7 @@ int fsim_set_params(fsim_t* h, const FsimParams* p) {
     if (!p) return fsim_fail(h, FSIM_ERR_INVALID, "null params");
     if (p->transfer_type < 0 || p->transfer_type > 2) return fsim_fail(h, FSIM_ERR_INVALID, "bad transfer type %d", p->transfer_type);
     if (!(p->fluid_density > 0)) return fsim_fail(h, FSIM_ERR_INVALID, "fluid density must be > 0");
+    if (p->solver_type != FSIM_SOLVER_BRIDSON && p->solver_type != FSIM_SOLVER_BASIC) return fsim_fail(h, FSIM_ERR_INVALID, "bad solver type %d", p->solver_type);
     h->par = *p;
     if (p->transfer_type == FSIM_TRANSFER_APIC) TRY(ensure_c(h));
     return FSIM_OK;

@@ -213,6 +213,7 @@ int k_p2g(fsim* h);
 int k_classify(fsim* h, double dt);
 int k_post_p2g_only(fsim* h, double gravity_increment);
 int k_pressure_apply(fsim* h, double dt);
+int k_project_basic(fsim* h, int* iterations);
 int k_project(fsim* h, double dt, int* iterations);
 int k_extrapolate(fsim* h);
 int k_g2p(fsim* h);

@@ -192,6 +192,42 @@ __global__ void __launch_bounds__(256) extrapolate_kernel(ExtrapArgs a) {
     }
 }
 
+// BasicMacGrid::solveIncompressibility (basicMacGrid.cpp:15-102): red-black Gauss-Seidel with over-relaxation 1.98 acting
+// directly on the face velocities; one launch per colour ((x+y+z) odd first, then even).  Cells of one colour share no
+// face, so the in-place update is race-free and -- unlike the PCG -- reproduces the reference sweep for sweep.
+struct BasicArgs {
+    GridDims g;
+    const uint8_t* flags;
+    float* u2[3];
+    const float* dens;
+    double avg_pressure, pressure_k;
+    int pressure_enabled, parity;
+};
+
+__global__ void __launch_bounds__(256) basic_sor_kernel(BasicArgs a) {
+    const GridDims& g = a.g;
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= g.nc) return;
+    const int x = (int)(c % g.gx), y = (int)((c / g.gx) % g.gy), z = (int)(c / ((int64_t)g.gx * g.gy));
+    if (((x + y + z) & 1) != a.parity) return;
+    if (x < 1 || y < 1 || z < 1 || x >= g.gx - 1 || y >= g.gy - 1 || z >= g.gz - 1) return;
+    if ((a.flags[c] & FL_TYPE_MASK) != FSIM_CELL_WATER) return;
+    const int s1 = (a.flags[c + g.sz] & FL_TYPE_MASK) != FSIM_CELL_SOLID, s2 = (a.flags[c - g.sz] & FL_TYPE_MASK) != FSIM_CELL_SOLID;
+    const int s3 = (a.flags[c + g.sy] & FL_TYPE_MASK) != FSIM_CELL_SOLID, s4 = (a.flags[c - g.sy] & FL_TYPE_MASK) != FSIM_CELL_SOLID;
+    const int s5 = (a.flags[c + 1] & FL_TYPE_MASK) != FSIM_CELL_SOLID, s6 = (a.flags[c - 1] & FL_TYPE_MASK) != FSIM_CELL_SOLID;
+    const int s = s1 + s2 + s3 + s4 + s5 + s6;
+    if (s == 0) return;
+    double d = -(double)a.u2[0][c] - (double)a.u2[1][c] - (double)a.u2[2][c] + (double)a.u2[0][c - 1] + (double)a.u2[1][c - g.sy] +
+               (double)a.u2[2][c - g.sz] + (a.pressure_enabled ? ((double)a.dens[c] - a.avg_pressure) * a.pressure_k : 0.0);
+    d = d * 1.98 / s;
+    if (s1) a.u2[2][c] = (float)((double)a.u2[2][c] + d);
+    if (s2) a.u2[2][c - g.sz] = (float)((double)a.u2[2][c - g.sz] - d);
+    if (s3) a.u2[1][c] = (float)((double)a.u2[1][c] + d);
+    if (s4) a.u2[1][c - g.sy] = (float)((double)a.u2[1][c - g.sy] - d);
+    if (s5) a.u2[0][c] = (float)((double)a.u2[0][c] + d);
+    if (s6) a.u2[0][c - 1] = (float)((double)a.u2[0][c - 1] - d);
+}
+
 // ---- transposing download / upload (device x-fastest <-> reference z-fastest) ---------------------------
 struct XferArgs {
     GridDims g;
@@ -288,6 +324,27 @@ int k_pressure_apply(fsim* h, double dt) {
     a.scale = dt / (h->par.fluid_density * h->info.cell_d[0]);
     { KScope ks(h, K_APPLY); pressure_apply_kernel<<<div_up(g.nc, 256), 256, 0, h->stream>>>(a); }
     FSIM_CHECK_LAUNCH(h);
+    return FSIM_OK;
+}
+
+int k_project_basic(fsim* h, int* iterations) {
+    const GridDims& g = h->g;
+    BasicArgs a;
+    a.g = g; a.flags = h->flags; a.dens = h->dens;
+    for (int ax = 0; ax < 3; ax++) a.u2[ax] = h->u2[ax];
+    a.avg_pressure = h->par.average_pressure; a.pressure_k = h->par.pressure_k; a.pressure_enabled = h->par.pressure_enabled;
+    const int n = h->par.max_iterations;
+    for (int it = 0; it < n; it++)
+        for (int colour = 1; colour >= 0; colour--) {  // odd cells first (z starts at 1 + (x+y)%2), then even
+            a.parity = colour;
+            KScope ks(h, K_APPLY);
+            basic_sor_kernel<<<div_up(g.nc, 256), 256, 0, h->stream>>>(a);
+        }
+    FSIM_CHECK_LAUNCH(h);
+    h->solve.iterations = n; h->solve.early_out = 0; h->solve.rhs_sumsq = 0; h->solve.residual_max = 0; h->solve.fluid_cells = 0;
+    h->pressure_valid = false;
+    h->warm_history = 0;
+    if (iterations) *iterations = n;  // the reference returns incompressibilityMaxIterationCount (basicMacGrid.cpp:10)
     return FSIM_OK;
 }
 

@@ -420,6 +420,7 @@ static int enqueue_iteration(fsim* h, const PcgArgs& a, bool vec, bool use_mg, i
 }
 
 int k_project(fsim* h, double dt, int* iterations) {
+    if (h->par.solver_type == FSIM_SOLVER_BASIC) return k_project_basic(h, iterations);
     const GridDims& g = h->g;
     PcgArgs a;
     a.g = g; a.flags = h->flags; a.code = h->code;

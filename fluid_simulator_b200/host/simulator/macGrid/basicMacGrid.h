@@ -1,17 +1,15 @@
-// macGrid/basicMacGrid.h:7-16 is the GUI's alternative red-black SOR solver; it is outside the path this backend
-// accelerates.  The type exists so that SimulationManager compiles unchanged; selecting it throws.
+// B200 facade of macGrid/basicMacGrid.h:7-16: the GUI's alternative solver (red-black Gauss-Seidel with SOR 1.98 on the
+// face velocities, a fixed number of sweeps).  Selecting it makes Simulator::simulate run FSIM_SOLVER_BASIC on the device
+// (grid.cu basic_sor_kernel) instead of the PCG projection.
 #pragma once
-#include <stdexcept>
 #include "macGrid.h"
 
 namespace genericfsim::macgrid {
 
 class BasicMacGrid : public MacGrid {
 public:
-    BasicMacGrid(glm::dvec3 targetDimensions, double resolution, bool twoD) : MacGrid(targetDimensions, resolution, twoD) {
-        throw std::runtime_error("BasicMacGrid (red-black SOR) is not provided by the B200 backend; use GridSolverType::BRIDSON");
-    }
-    int solveIncompressibility(bool, double) override { return 0; }
+    BasicMacGrid(glm::dvec3 targetDimensions, double resolution, bool twoD) : MacGrid(targetDimensions, resolution, twoD) {}
+    int solveIncompressibility(bool parallel, double dt) override;
 };
 
 }  // namespace genericfsim::macgrid

@@ -55,6 +55,10 @@ extern "C" {
 #define FSIM_TRANSFER_FLIP 1
 #define FSIM_TRANSFER_APIC 2
 
+/* SimulationConfig::GridSolverType (manager/simulationManager.h:35-38) */
+#define FSIM_SOLVER_BRIDSON 0 /* BridsonSolverGrid: PCG projection (bridsonSolverGrid.cpp:244-293) */
+#define FSIM_SOLVER_BASIC 1   /* BasicMacGrid: red-black SOR on the face velocities (basicMacGrid.cpp:15-102) */
+
 /* MacGridCell::CellType (macGrid/macGridCell.h:30-32) */
 #define FSIM_CELL_WATER 0
 #define FSIM_CELL_AIR 1
@@ -114,7 +118,7 @@ typedef struct FsimParams {
     int32_t top_solid;           /* isTopOfContainerSolid */
     int32_t pressure_enabled;
     int32_t max_iterations;      /* incompressibilityMaxIterationCount */
-    int32_t reserved0;
+    int32_t solver_type;         /* SimulationConfig::GridSolverType (manager/simulationManager.h:35-38): FSIM_SOLVER_* */
     double pressure_k;
     double average_pressure;
     double fluid_density;

@@ -27,7 +27,7 @@ COMMON="-std=c++20 -O2 -fPIC -w -I$HERE/ref_shim -I$SRC -I$SRC/macGrid -I$SRC/pa
 build_variant() {  # $1 = suffix, $2.. = extra flags
     local sfx="$1"; shift
     local objs=()
-    for tu in simulator.cpp macGrid/macGrid.cpp particles/hashedParticles.cpp; do
+    for tu in simulator.cpp macGrid/macGrid.cpp macGrid/basicMacGrid.cpp particles/hashedParticles.cpp; do
         local o="$OUT/obj/$(basename "$tu" .cpp)$sfx.o"
         $CXX $COMMON "$@" -c "$SRC/$tu" -o "$o" &
         objs+=("$o")

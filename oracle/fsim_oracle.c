@@ -683,8 +683,11 @@ static void apply_pressure(Oracle* o, double dt, const double* pr) {
     }
 }
 
+static int project_basic(Oracle* o);
+
 /* BridsonSolverGrid::solveIncompressibility bridsonSolverGrid.cpp:244-293 */
 int oracle_stage_project(Oracle* o, double dt) {
+    if (o->par.solver_type == FSIM_SOLVER_BASIC) return project_basic(o);
     const int n = o->nfluid;
     double* pressure = (double*)calloc(n > 0 ? n : 1, sizeof(double));
     double* z = (double*)calloc(n > 0 ? n : 1, sizeof(double));
@@ -734,6 +737,40 @@ done:
     o->solve.iterations = it;
     free(pressure); free(z); free(q); free(r); free(s); free(pre); free(A);
     return it;
+}
+
+/* BasicMacGrid::solveIncompressibility basicMacGrid.cpp:5-102 (the parallel branch's red-black order: it is the one a
+ * release build runs, and it is deterministic because cells of one colour share no face) */
+static int project_basic(Oracle* o) {
+    const double overRelaxation = 1.98;
+    const i3 g = o->gs;
+    for (int n = 0; n < o->par.max_iterations; n++)
+        for (int pass = 0; pass < 2; pass++)
+            for (int x = 1; x < g.x - 1; x++)
+                for (int y = 1; y < g.y - 1; y++)
+                    for (int z = (pass == 0 ? 1 + ((x + y) % 2) : 2 - ((x + y) % 2)); z < g.z - 1; z += 2) {
+                        const int64_t c = cidx(o, x, y, z);
+                        if (o->type[c] != FSIM_CELL_WATER) continue;
+                        const int64_t xm = cidx(o, x - 1, y, z), ym = cidx(o, x, y - 1, z), zm = cidx(o, x, y, z - 1);
+                        const int s1 = o->type[cidx(o, x, y, z + 1)] != FSIM_CELL_SOLID, s2 = o->type[zm] != FSIM_CELL_SOLID;
+                        const int s3 = o->type[cidx(o, x, y + 1, z)] != FSIM_CELL_SOLID, s4 = o->type[ym] != FSIM_CELL_SOLID;
+                        const int s5 = o->type[cidx(o, x + 1, y, z)] != FSIM_CELL_SOLID, s6 = o->type[xm] != FSIM_CELL_SOLID;
+                        const int s = s1 + s2 + s3 + s4 + s5 + s6;
+                        if (s == 0) continue;
+                        double d = -o->v2[3 * c + 0] - o->v2[3 * c + 1] - o->v2[3 * c + 2] + o->v2[3 * xm + 0] + o->v2[3 * ym + 1] + o->v2[3 * zm + 2] +
+                                   (o->par.pressure_enabled ? (o->avgp[c] - o->par.average_pressure) * o->par.pressure_k : 0.0);
+                        d = d * overRelaxation / s;
+                        if (s1) o->v2[3 * c + 2] += d;
+                        if (s2) o->v2[3 * zm + 2] -= d;
+                        if (s3) o->v2[3 * c + 1] += d;
+                        if (s4) o->v2[3 * ym + 1] -= d;
+                        if (s5) o->v2[3 * c + 0] += d;
+                        if (s6) o->v2[3 * xm + 0] -= d;
+                    }
+    o->pressure_valid = 0;
+    memset(&o->solve, 0, sizeof(o->solve));
+    o->solve.iterations = o->par.max_iterations;
+    return o->par.max_iterations;
 }
 
 /* MacGrid::extrapolateVelocities macGrid.cpp:294-336 */

@@ -28,6 +28,7 @@
 #define protected public
 #include "simulator.h"
 #include "macGrid/bridsonSolverGrid.h"
+#include "macGrid/basicMacGrid.h"
 #include "util/paralellDefine.h"
 #include "util/interpolation.h"
 #undef private
@@ -46,7 +47,8 @@ std::vector<double> g_ref_last_pressure;
 
 namespace {
 struct Ref {
-    std::shared_ptr<BridsonSolverGrid> grid;
+    std::shared_ptr<MacGrid> grid;
+    BridsonSolverGrid* bridson = nullptr;  // non-null when the PCG grid is in use
     std::shared_ptr<HashedParticles> particles;
     std::shared_ptr<Simulator> sim;
     double wall_s_last = 0;
@@ -59,7 +61,14 @@ void* ref_create(const FsimGridDesc* d) {
     auto* r = new Ref;
     glm::dvec3 dims(d->target_dims[0], d->target_dims[1], d->target_dims[2]);
     // SimulationManager ctor (manager/simulationManager.cpp:16-28): resolution is a float there
-    r->grid = std::make_shared<BridsonSolverGrid>(dims, (float)d->resolution, d->two_d != 0, 1.0);
+    // reserved0 = 1 selects the GUI's alternative BasicMacGrid (SimulationConfig::GridSolverType::BASIC)
+    if (d->reserved0 == 1) {
+        r->grid = std::make_shared<BasicMacGrid>(dims, (float)d->resolution, d->two_d != 0);
+    } else {
+        auto b = std::make_shared<BridsonSolverGrid>(dims, (float)d->resolution, d->two_d != 0, 1.0);
+        r->bridson = b.get();
+        r->grid = b;
+    }
     r->particles = std::make_shared<HashedParticles>(0, d->particle_radius, r->grid->dimensions, r->grid->cellD,
                                                      d->two_d != 0, dims.z / 2);
     r->sim = std::make_shared<Simulator>(Simulator::SimulatorConfig(), r->particles, r->grid);
@@ -231,8 +240,9 @@ int ref_get_grid(void* h, int field, void* out) {
     if (field == FSIM_FIELD_RHS) {
         double* o = (double*)out;
         std::fill(o, o + nc, 0.0);
-        g.fluidCellCount = (int)g.fluidCellPositions.size();  // solveIncompressibility does this first (bridsonSolverGrid.cpp:245)
-        std::vector<double> rhs = g.calculateRHS(true);
+        if (!r->bridson) return 0;
+        r->bridson->fluidCellCount = (int)g.fluidCellPositions.size();  // solveIncompressibility does this first (bridsonSolverGrid.cpp:245)
+        std::vector<double> rhs = r->bridson->calculateRHS(true);
         for (size_t i = 0; i < rhs.size(); i++) {
             glm::ivec3 p = g.fluidCellPositions[i];
             o[(int64_t)p.x * g.gridSize.y * g.gridSize.z + p.y * g.gridSize.z + p.z] = rhs[i];

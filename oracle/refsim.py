@@ -72,13 +72,14 @@ def _load(serial):
 class RefSim:
     """The reference's BridsonSolverGrid + HashedParticles + Simulator, driven headless."""
 
-    def __init__(self, dims, resolution=1.0, two_d=False, particle_radius=0.25, serial=False, **_):
+    def __init__(self, dims, resolution=1.0, two_d=False, particle_radius=0.25, serial=False, basic_solver=False, **_):
         self.L = _load(serial)
         d = abi.GridDesc()
         d.target_dims[:] = dims
         d.resolution = resolution
         d.two_d = int(two_d)
         d.particle_radius = particle_radius
+        d.reserved0 = 1 if basic_solver else 0  # BasicMacGrid instead of BridsonSolverGrid
         self.h = self.L.ref_create(C.byref(d))
         self.info = abi.GridInfo()
         self.L.ref_get_grid_info(self.h, C.byref(self.info))

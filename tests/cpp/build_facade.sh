@@ -5,7 +5,7 @@ HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 ROOT="$(cd "$HERE/../.." && pwd)"
 HOST="$ROOT/fluid_simulator_b200/host"
 mkdir -p "$HERE/build"
-/usr/bin/g++ -std=c++20 -O2 -fopenmp -I"$HOST" "$HERE/facade_smoke.cpp" "$HOST/facade.cpp" -include "$HOST/simulator/macGrid/basicMacGrid.h" \
+/usr/bin/g++ -std=c++20 -O2 -fopenmp -I"$HOST" "$HERE/facade_smoke.cpp" "$HOST/facade.cpp" \
     -L"$ROOT/fluid_simulator_b200" -lfsim_b200 -Wl,-rpath,"$ROOT/fluid_simulator_b200" -Wl,-rpath,/usr/local/cuda/lib64 -L/usr/local/cuda/lib64 -lcudart \
     -o "$HERE/build/facade_smoke"
 echo "built $HERE/build/facade_smoke"

@@ -286,3 +286,52 @@ def test_push_apart_statistical_parity(gpu):
     assert abs(ke(pg) - ke(pr)) < 0.15 * ke(pr)
     assert np.abs(pg[:, 0:2].mean(0) - pr[:, 0:2].mean(0)).max() < 1.0
     assert g.step_durations()["PushParticlesApart"] > 0
+
+
+def test_basic_solver_parity(gpu, oracle_lib):
+    """SURVEY §8f #4: GridSolverType::BASIC -- 30 red-black SOR(1.98) sweeps on the face velocities, sweep for sweep."""
+    sc = scenes.dam_break_3d(24, abi.FLIP, solver_type=abi.SOLVER_BASIC, max_iterations=30)
+    g, o = make_pair(gpu, sc, oracle_lib)
+    for _ in range(2):
+        assert g.step(sc.dt) == o.step(sc.dt) == 30
+    compare_state("basic_solver", g, o, NO_P, tol=1e-4)
+
+
+def test_cfg4_full_scale_source_sink_moving_box(gpu):
+    """SURVEY §8d cfg 4 at full size: 3D PIC, 192^3, 27.4 M particles, source (2000 particles/step), sink, sinusoidally
+    moving box.  No CPU oracle at this size (minutes per step): size-independent properties instead -- particle
+    bookkeeping (spawned - despawned), flags of the three obstacle kinds, every particle stays inside the container."""
+    n = 192
+    pos = scenes.block_positions_f32(1, n // 2, 1, n - 1, 1, n - 1)
+    n0 = pos.shape[0]
+    assert n0 == 27436000
+    g = gpu((float(n),) * 3, 1.0, False, 0.25, capacity=n0 + 64000)
+    g.set_id_tracking(False)
+    g.set_params(scenes.default_params(abi.PIC, spawning_enabled=True, despawning_enabled=True))
+    g.upload_particles_f32(pos)
+    del pos
+    dt = 0.005
+    counts = [n0]
+    obs = None
+    for st in range(4):
+        new = scenes.cfg4_obstacles(n, st, dt)
+        if obs is not None:
+            new[0].last_spawn_fraction = g.get_obstacles()[0].last_spawn_fraction
+        obs = new
+        g.set_obstacles(obs)
+        g.srand(100 + st)
+        g.step(dt)
+        counts.append(g.particle_count())
+    spawned = 4 * 2000                                  # rate 4e5/s * dt 0.005
+    assert n0 < counts[-1] <= n0 + spawned              # sink is outside the block in the first steps: growth only
+    t = g.download_grid(abi.FIELD_TYPE).reshape(n, n, n)
+    sx, sy, sz = int(0.25 * n), int(0.8 * n), int(0.5 * n)
+    assert t[sx, sy, sz] == abi.SOLID                   # the source sphere is solid on the grid (macGrid.cpp:235)
+    kx, ky, kz = int(0.8 * n), int(0.08 * n), int(0.5 * n)
+    assert t[kx, ky, kz] != abi.SOLID                   # the sink is not
+    bx = int(0.6 * n + 0.1 * n * np.sin(2 * np.pi * 3 / 200.0))
+    assert t[bx, int(0.25 * n), sz] == abi.SOLID        # the moving box, at its step-3 position
+    p, _ = g.download_particles_f32()
+    lo, hi = 1.0 + 0.25 * 1.01 - 1e-4, n - (1.0 + 0.25 * 1.01) + 1e-4
+    assert p.min() >= lo and p.max() <= hi
+    diag(test="cfg4/192", counts=counts, stats=g.last_step_stats(), timings=g.step_durations())
