@@ -9,12 +9,12 @@
 //    stencil whose face weight is the NUMBER of WATER-WATER fine connections across the coarse face and whose diagonal
 //    adds the WATER-AIR (Dirichlet) connections -- free surfaces, solid walls and obstacles are represented exactly on
 //    every level, no geometric heuristics.  Level 0 is matrix-free (1-byte flags); levels >= 1 store 4 floats per cell.
-//  * smoother: damped Jacobi (omega 0.8), 2 pre + 2 post sweeps, identical on the way down and up => symmetric cycle.
-//  * plain aggregation under-corrects smooth modes by ~2x; the coarse correction is scaled by 1.8 and the first two
-//    coarse levels are visited twice (W recursion) -- tools/mg_prototype.py: 8-9 PCG iterations at 128^3 where
-//    MIC(0) needs 80, independent of the grid size.
+//  * smoother: Jacobi with 2-step Chebyshev weights (pre: 1.389, 0.5617; post: reversed) => symmetric cycle.
+//  * plain aggregation under-corrects smooth modes by ~2x; the coarse correction is scaled by 1.8 and level 2 is
+//    visited twice (W recursion there only) -- tools/mg_prototype.py: 8-10 PCG iterations at 128^3..256^3 where
+//    MIC(0) needs 80..155.
 //  * fp32 throughout (it only has to be an approximate inverse); the CG recurrence around it is fp64 (pcg.cu).
-// Every kernel is a one-thread-per-cell 7-point stencil, x fastest => coalesced, HBM/L2-bound.
+// Level-0 kernels process 4 cells per thread (float4 / ushort4); small levels run in one thread-block-cluster launch.
 #include <cooperative_groups.h>
 
 #include "fsim_internal.h"
@@ -493,44 +493,6 @@ __global__ void __launch_bounds__(256) mg_buildn_kernel(Lv L, Lv C, float* __res
                 }
             }
     wx[cc] = w[0]; wy[cc] = w[1]; wz[cc] = w[2]; diag[cc] = d > 0.f ? d : 0.f;
-}
-
-// coarsest level: COARSE_SWEEPS damped Jacobi sweeps inside one CTA (one thread per cell, iterate in shared memory)
-__global__ void __launch_bounds__(COARSE_MAX) mg_coarse_kernel(Lv L, const PcgScalars* __restrict__ sc, const float* __restrict__ b,
-                                                                const float* __restrict__ xin, float* __restrict__ xout, int zero_guess,
-                                                                int sweeps) {
-    __shared__ float xs[2][COARSE_MAX];
-    if (sc->done) return;
-    const int c = threadIdx.x;
-    const int nc = L.gx * L.gy * L.gz;
-    const bool in = c < nc;
-    float d = 0.f, w[6] = {0, 0, 0, 0, 0, 0}, bb = 0.f;
-    int nb[6] = {0, 0, 0, 0, 0, 0};
-    if (in) {
-        d = L.diag[c];
-        bb = b[c];
-        w[0] = L.wx[c - 1]; w[1] = L.wx[c]; w[2] = L.wy[c - L.sy]; w[3] = L.wy[c]; w[4] = L.wz[c - L.sz]; w[5] = L.wz[c];
-        nb[0] = c - 1; nb[1] = c + 1; nb[2] = c - L.sy; nb[3] = c + L.sy; nb[4] = c - L.sz; nb[5] = c + L.sz;
-#pragma unroll
-        for (int k = 0; k < 6; k++)
-            if (!(w[k] > 0.f) || nb[k] < 0 || nb[k] >= nc) { w[k] = 0.f; nb[k] = c; }
-    }
-    xs[0][c] = (in && !zero_guess) ? xin[c] : 0.f;
-    __syncthreads();
-    int cur = 0;
-    for (int s = 0; s < sweeps; s++) {
-        float v = 0.f;
-        if (in && d > 0.f) {
-            const float* xv = xs[cur];
-            const float off = w[0] * xv[nb[0]] + w[1] * xv[nb[1]] + w[2] * xv[nb[2]] + w[3] * xv[nb[3]] + w[4] * xv[nb[4]] + w[5] * xv[nb[5]];
-            const float xi = xv[c];
-            v = xi + OMEGA * (bb - (d * xi - off)) / d;
-        }
-        xs[cur ^ 1][c] = v;
-        __syncthreads();
-        cur ^= 1;
-    }
-    if (in) xout[c] = xs[cur][c];
 }
 
 // ---- the small end of the hierarchy in ONE launch -----------------------------------------------------------------

@@ -49,11 +49,6 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
     return d;
 }
 
-// fold one register value into the shared tile (plain read-modify-write: the phase structure makes it conflict-free)
-__device__ __forceinline__ void fold(float* s, int id, float v, bool on) {
-    if (on && v != 0.f) s[id] += v;
-}
-
 // One staggered face pass, AXIS = 0,1,2: 2 nodes along AXIS (the pair a packed FFMA2 works on), 3 along the other two
 // dimensions B < C.  Per particle and node pair: weights += (wA0, wA1) * wB*wC ; values += (wA0*val0, wA1*val1) * wB*wC,
 // val_n = v + c[AXIS] . (face_n - particle) (APIC, simulator.cpp:327-328) or v (PIC / FLIP, :324).
