@@ -246,8 +246,8 @@ def main():
             sim.set_params(params)
             sim.set_obstacles([scenes.cfg3_box(n)] if args.obstacle_box else [])
             sim.step(DT)
-            sim.export_gfx_wait()                     # buffer (i-1)%2 has landed and may be consumed
             sim.export_gfx_async_ptr(gfx[i % 2].data_ptr(), np_local)
+            sim.export_gfx_wait_previous()            # buffer (i-1)%2 has landed and may be consumed
         sim.export_gfx_wait()
         barrier()
         el = time.perf_counter() - t0
@@ -277,6 +277,8 @@ def main():
            "spmv": nf * 16 + nc * 2, "pcg_update": nf * 56 + nc * 2, "pcg_direction": nf * 20 + nc * 2,
            "mg": nf * 15 + nc * 2,                          # average level-0 multigrid kernel (jacobi 14, restrict 10, prolong 14, jacobi+dot 22 B)
            "mg_level1": (nc // 8) * 28, "finalize": nc * 53, "extrapolate": nc * 25, "classify": nc * 5, "rhs": nc * 17 + nf * 28}
+    if not prof.get("g2p", (0, 0, 0))[2]:  # the G2P ran inside the fused G2P + advect + bin kernel: its grid reads and key/rank writes join that pass
+        alg["advect"] += nc * (24 if transfer == abi.FLIP else 12) + np_local * ((36 if transfer == abi.APIC else 0) + 8)
     traffic_path = os.path.join(ROOT, "profiles", "r1_dram_traffic_256_flip.json")
     traffic = None
     if n == 256 and transfer == abi.FLIP and os.path.exists(traffic_path):

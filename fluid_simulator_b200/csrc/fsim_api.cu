@@ -150,6 +150,15 @@ void fold_timings(fsim* h) {
 
 int ensure_sorted(fsim* h) { return h->sorted ? FSIM_OK : k_sort(h); }
 
+// fsim_step leaves its G2P to the next step's fused kernel; everything else that reads or writes particle velocities, or
+// writes the grid velocities, first brings the particles up to date
+int flush_g2p(fsim* h) { return h->g2p_pending ? k_g2p(h) : FSIM_OK; }
+#define BIND_FLUSH(h)  \
+    do {               \
+        BIND(h);       \
+        TRY(flush_g2p(h)); \
+    } while (0)
+
 int ensure_gfx(fsim* h) {
     if (h->gfx && h->gfx_cap >= h->np) return FSIM_OK;
     cudaFree(h->gfx);
@@ -270,7 +279,9 @@ int fsim_create(const FsimGridDesc* desc, fsim_t** out) {
     memset(h->ps, 0, sizeof(h->ps));
     h->key = h->rank = nullptr; h->kill = nullptr;
     h->next_id = 0; h->gfx = nullptr; h->gfx_cap = 0;
-    h->copy_stream = nullptr; h->gfx_ready = nullptr; h->gfx_copied = nullptr; h->gfx_inflight = false;
+    h->copy_stream = nullptr; h->gfx_slot = 0;
+    { const char* e = getenv("FSIM_NO_LAZY_G2P"); h->lazy_g2p = !(e && e[0] == '1'); h->g2p_pending = false; }
+    for (int k = 0; k < 2; k++) { h->gfx_async[k] = nullptr; h->gfx_async_cap[k] = 0; h->gfx_ready[k] = h->gfx_copied[k] = nullptr; h->gfx_inflight[k] = false; }
     h->pressure_valid = false; h->ev_valid = false;
     memset(&h->timings, 0, sizeof(h->timings));
     memset(&h->solve, 0, sizeof(h->solve));
@@ -347,8 +358,11 @@ int fsim_destroy(fsim_t* h) {
     cudaFree(h->p); cudaFree(h->rhs); cudaFree(h->r); cudaFree(h->s); cudaFree(h->q); cudaFree(h->z); cudaFree(h->p_prev);
     cudaFree(h->d_obs); cudaFree(h->scal); cudaFree(h->partials); cudaFree(h->red_counter);
     if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
-    if (h->gfx_ready) cudaEventDestroy(h->gfx_ready);
-    if (h->gfx_copied) cudaEventDestroy(h->gfx_copied);
+    for (int k = 0; k < 2; k++) {
+        if (h->gfx_ready[k]) cudaEventDestroy(h->gfx_ready[k]);
+        if (h->gfx_copied[k]) cudaEventDestroy(h->gfx_copied[k]);
+        cudaFree(h->gfx_async[k]);
+    }
     cudaFree(h->stage); cudaFree(h->gfx);
     for (const ProfRec& r : h->prof_recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     for (cudaEvent_t e : h->prof_free) cudaEventDestroy(e);
@@ -373,6 +387,7 @@ int fsim_set_params(fsim_t* h, const FsimParams* p) {
     if (p->transfer_type < 0 || p->transfer_type > 2) return fsim_fail(h, FSIM_ERR_INVALID, "bad transfer type %d", p->transfer_type);
     if (!(p->fluid_density > 0)) return fsim_fail(h, FSIM_ERR_INVALID, "fluid density must be > 0");
     if (p->solver_type != FSIM_SOLVER_BRIDSON && p->solver_type != FSIM_SOLVER_BASIC) return fsim_fail(h, FSIM_ERR_INVALID, "bad solver type %d", p->solver_type);
+    if (p->transfer_type != h->par.transfer_type || p->flip_ratio != h->par.flip_ratio) TRY(flush_g2p(h));  // a pending G2P uses the old blend
     h->par = *p;
     if (p->transfer_type == FSIM_TRANSFER_APIC) TRY(ensure_c(h));
     return FSIM_OK;
@@ -416,7 +431,7 @@ static int upload_aos(fsim* h, const double* aos15, int64_t first, int64_t n) {
 }
 
 int fsim_upload_particles(fsim_t* h, const double* aos15, int64_t n) {
-    BIND(h);
+    BIND_FLUSH(h);
     if (n < 0 || (n > 0 && !aos15)) return fsim_fail(h, FSIM_ERR_INVALID, "bad particle buffer");
     if (n >= (int64_t(1) << 31)) return fsim_fail(h, FSIM_ERR_NOMEM, "too many particles");
     h->np = 0;
@@ -430,7 +445,7 @@ int fsim_upload_particles(fsim_t* h, const double* aos15, int64_t n) {
 }
 
 int fsim_append_particles(fsim_t* h, const double* aos15, int64_t n) {
-    BIND(h);
+    BIND_FLUSH(h);
     if (n < 0 || (n > 0 && !aos15)) return fsim_fail(h, FSIM_ERR_INVALID, "bad particle buffer");
     if (n == 0) return FSIM_OK;
     TRY(ensure_capacity(h, h->np + n));
@@ -443,7 +458,7 @@ int fsim_append_particles(fsim_t* h, const double* aos15, int64_t n) {
 }
 
 int fsim_remove_particles(fsim_t* h, const int32_t* ids, int64_t n) {
-    BIND(h);
+    BIND_FLUSH(h);
     if (n < 0 || (n > 0 && !ids)) return fsim_fail(h, FSIM_ERR_INVALID, "bad id buffer");
     if (n == 0) return FSIM_OK;
     if ((size_t)n * sizeof(int32_t) > h->stage_bytes) return fsim_fail(h, FSIM_ERR_NOMEM, "too many ids in one call");
@@ -458,7 +473,7 @@ int fsim_particle_count(const fsim_t* h, int64_t* n) {
 }
 
 int fsim_download_particles(fsim_t* h, double* aos15, int64_t cap, int64_t* n) {
-    BIND(h);
+    BIND_FLUSH(h);
     if (n) *n = h->np;
     if (!aos15) return FSIM_OK;
     const int64_t total = std::min(cap, h->np);
@@ -496,7 +511,7 @@ int fsim_set_id_tracking(fsim_t* h, int on) {
 }
 
 int fsim_upload_particles_f32(fsim_t* h, const float* pos, const float* vel, const float* c, int64_t n) {
-    BIND(h);
+    BIND_FLUSH(h);
     if (n < 0 || (n > 0 && !pos)) return fsim_fail(h, FSIM_ERR_INVALID, "bad particle buffer");
     h->np = 0;
     TRY(ensure_capacity(h, n));
@@ -521,7 +536,7 @@ int fsim_upload_particles_f32(fsim_t* h, const float* pos, const float* vel, con
 }
 
 int fsim_download_particles_f32(fsim_t* h, float* pos, float* vel, float* c, int64_t cap, int64_t* n) {
-    BIND(h);
+    BIND_FLUSH(h);
     if (n) *n = h->np;
     const int64_t total = std::min(cap, h->np);
     const int64_t per = 3 + 3 + 9;
@@ -567,28 +582,28 @@ int fsim_stage_spawn(fsim_t* h, double dt) {
 }
 
 int fsim_stage_advect(fsim_t* h, double dt) {
-    BIND(h);
+    BIND_FLUSH(h);
     TRY(k_advect(h, dt, true, false, false));
     if (h->kill_pending) TRY(k_sort(h));  // removeParticles at the end of advectParticles (simulator.cpp:250)
     return FSIM_OK;
 }
 int fsim_stage_push_apart(fsim_t* h) {  /* updateParticleIntersectionHash + pushParticlesApart, simulator.cpp:61-64 */
-    BIND(h);
+    BIND_FLUSH(h);
     TRY(ensure_sorted(h));
     return k_push_apart(h);
 }
-int fsim_stage_push_out(fsim_t* h) { BIND(h); return k_advect(h, 0.0, false, true, false); }
+int fsim_stage_push_out(fsim_t* h) { BIND_FLUSH(h); return k_advect(h, 0.0, false, true, false); }
 int fsim_stage_p2g(fsim_t* h) {
-    BIND(h);
+    BIND_FLUSH(h);
     if (h->par.stop_particles) TRY(k_advect(h, 0.0, false, false, true));
     TRY(ensure_sorted(h));
     return k_p2g(h);
 }
-int fsim_stage_classify(fsim_t* h, double dt) { BIND(h); TRY(ensure_sorted(h)); return k_classify(h, dt); }
-int fsim_stage_post_p2g_update(fsim_t* h, double gravity_increment) { BIND(h); return k_post_p2g_only(h, gravity_increment); }
-int fsim_stage_project(fsim_t* h, double dt, int* iterations) { BIND(h); return k_project(h, dt, iterations); }
-int fsim_stage_extrapolate(fsim_t* h) { BIND(h); return k_extrapolate(h); }
-int fsim_stage_g2p(fsim_t* h) { BIND(h); TRY(ensure_sorted(h)); return k_g2p(h); }
+int fsim_stage_classify(fsim_t* h, double dt) { BIND_FLUSH(h); TRY(ensure_sorted(h)); return k_classify(h, dt); }
+int fsim_stage_post_p2g_update(fsim_t* h, double gravity_increment) { BIND_FLUSH(h); return k_post_p2g_only(h, gravity_increment); }
+int fsim_stage_project(fsim_t* h, double dt, int* iterations) { BIND_FLUSH(h); return k_project(h, dt, iterations); }
+int fsim_stage_extrapolate(fsim_t* h) { BIND_FLUSH(h); return k_extrapolate(h); }
+int fsim_stage_g2p(fsim_t* h) { BIND_FLUSH(h); TRY(ensure_sorted(h)); return k_g2p(h); }
 
 // Simulator::simulate (simulator.cpp:51-100)
 int fsim_step(fsim_t* h, double dt, int* pcg_iterations) {
@@ -597,9 +612,12 @@ int fsim_step(fsim_t* h, double dt, int* pcg_iterations) {
     const int64_t l0 = h->launches;
     FSIM_CUDA(h, cudaEventRecord(h->ev[0], h->stream));
     if (h->par.spawning_enabled) TRY(fsim_stage_spawn(h, dt));
+    // the G2P the previous step deferred runs inside this step's first particle pass (same arithmetic, one HBM round trip less)
+    const bool fuse = h->g2p_pending && h->sorted && h->np > 0;
+    if (!fuse) TRY(flush_g2p(h));
     if (h->par.push_apart_enabled) {
         // simulate() order (simulator.cpp:57-74): advect -> push apart -> push out of obstacles -> stop
-        TRY(k_advect(h, dt, true, false, false, /*do_bin=*/true));
+        TRY(k_advect(h, dt, true, false, false, /*do_bin=*/true, fuse));
         FSIM_CUDA(h, cudaEventRecord(h->ev[9], h->stream));
         TRY(k_sort(h));
         TRY(k_push_apart(h));
@@ -608,7 +626,7 @@ int fsim_step(fsim_t* h, double dt, int* pcg_iterations) {
         h->push_timed = true;
     } else {
         // advect + obstacle push-out + stopParticles are one pass over the particles
-        TRY(k_advect(h, dt, true, true, h->par.stop_particles != 0, /*do_bin=*/true));
+        TRY(k_advect(h, dt, true, true, h->par.stop_particles != 0, /*do_bin=*/true, fuse));
         h->push_timed = false;
     }
     FSIM_CUDA(h, cudaEventRecord(h->ev[1], h->stream));
@@ -623,7 +641,8 @@ int fsim_step(fsim_t* h, double dt, int* pcg_iterations) {
     FSIM_CUDA(h, cudaEventRecord(h->ev[5], h->stream));
     TRY(k_extrapolate(h));
     FSIM_CUDA(h, cudaEventRecord(h->ev[6], h->stream));
-    TRY(k_g2p(h));
+    if (h->lazy_g2p) h->g2p_pending = true;
+    else TRY(k_g2p(h));
     FSIM_CUDA(h, cudaEventRecord(h->ev[7], h->stream));
     FSIM_CUDA(h, cudaEventRecord(h->ev[8], h->stream));
     h->ev_valid = true;
@@ -655,7 +674,7 @@ int fsim_download_grid(fsim_t* h, int field, void* out, int64_t out_bytes) {
 }
 
 int fsim_upload_grid(fsim_t* h, int field, const void* in, int64_t in_bytes) {
-    BIND(h);
+    BIND_FLUSH(h);
     const int64_t nc = h->g.nc;
     int64_t need = 0;
     switch (field) {
@@ -689,7 +708,7 @@ int fsim_download_particle_cells(fsim_t* h, int32_t* out, int64_t cap) {
 }
 
 int fsim_export_gfx(fsim_t* h, FsimParticleGfx* out, int64_t cap, int64_t* n) {
-    BIND(h);
+    BIND_FLUSH(h);
     if (n) *n = h->np;
     const int64_t m = std::min(cap, h->np);
     if (m <= 0 || !out) return FSIM_OK;
@@ -701,35 +720,53 @@ int fsim_export_gfx(fsim_t* h, FsimParticleGfx* out, int64_t cap, int64_t* n) {
 }
 
 int fsim_export_gfx_async(fsim_t* h, FsimParticleGfx* out, int64_t cap, int64_t* n) {
-    BIND(h);
+    BIND_FLUSH(h);
     if (n) *n = h->np;
     const int64_t m = std::min(cap, h->np);
     if (m <= 0 || !out) return FSIM_OK;
     if (!h->copy_stream) {
         FSIM_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-        FSIM_CUDA(h, cudaEventCreateWithFlags(&h->gfx_ready, cudaEventDisableTiming));
-        FSIM_CUDA(h, cudaEventCreateWithFlags(&h->gfx_copied, cudaEventDisableTiming));
+        for (int k = 0; k < 2; k++) {
+            FSIM_CUDA(h, cudaEventCreateWithFlags(&h->gfx_ready[k], cudaEventDisableTiming));
+            FSIM_CUDA(h, cudaEventCreateWithFlags(&h->gfx_copied[k], cudaEventDisableTiming));
+        }
     }
-    // the device staging buffer is reused: the new export kernel must not overwrite it before the previous copy has left
-    if (h->gfx_inflight) FSIM_CUDA(h, cudaStreamWaitEvent(h->stream, h->gfx_copied, 0));
-    if (!(h->gfx && h->gfx_cap >= h->np)) {
-        if (h->gfx_inflight) FSIM_CUDA(h, cudaEventSynchronize(h->gfx_copied));
-        TRY(ensure_gfx(h));
+    const int k = h->gfx_slot;
+    h->gfx_slot ^= 1;
+    // a staging buffer is reused every second export: its previous copy must have left before the kernel overwrites it
+    if (h->gfx_inflight[k]) FSIM_CUDA(h, cudaStreamWaitEvent(h->stream, h->gfx_copied[k], 0));
+    if (!(h->gfx_async[k] && h->gfx_async_cap[k] >= h->np)) {
+        if (h->gfx_inflight[k]) FSIM_CUDA(h, cudaEventSynchronize(h->gfx_copied[k]));
+        cudaFree(h->gfx_async[k]);
+        h->gfx_async[k] = nullptr;
+        h->gfx_async_cap[k] = h->cap;
+        FSIM_CUDA(h, cudaMalloc((void**)&h->gfx_async[k], sizeof(FsimParticleGfx) * (size_t)(h->cap > 0 ? h->cap : 1)));
     }
-    TRY(k_export_gfx(h, h->gfx));
-    FSIM_CUDA(h, cudaEventRecord(h->gfx_ready, h->stream));
-    FSIM_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->gfx_ready, 0));
-    FSIM_CUDA(h, cudaMemcpyAsync(out, h->gfx, sizeof(FsimParticleGfx) * m, cudaMemcpyDeviceToHost, h->copy_stream));
-    FSIM_CUDA(h, cudaEventRecord(h->gfx_copied, h->copy_stream));
-    h->gfx_inflight = true;
+    TRY(k_export_gfx(h, h->gfx_async[k]));
+    FSIM_CUDA(h, cudaEventRecord(h->gfx_ready[k], h->stream));
+    FSIM_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->gfx_ready[k], 0));
+    FSIM_CUDA(h, cudaMemcpyAsync(out, h->gfx_async[k], sizeof(FsimParticleGfx) * m, cudaMemcpyDeviceToHost, h->copy_stream));
+    FSIM_CUDA(h, cudaEventRecord(h->gfx_copied[k], h->copy_stream));
+    h->gfx_inflight[k] = true;
     return FSIM_OK;
 }
 
 int fsim_export_gfx_wait(fsim_t* h) {
     BIND(h);
-    if (h->gfx_inflight) {
-        FSIM_CUDA(h, cudaEventSynchronize(h->gfx_copied));
-        h->gfx_inflight = false;
+    for (int k = 0; k < 2; k++)
+        if (h->gfx_inflight[k]) {
+            FSIM_CUDA(h, cudaEventSynchronize(h->gfx_copied[k]));
+            h->gfx_inflight[k] = false;
+        }
+    return FSIM_OK;
+}
+
+int fsim_export_gfx_wait_previous(fsim_t* h) {
+    BIND(h);
+    const int k = h->gfx_slot;  // the slot of the export before the most recent one
+    if (h->gfx_inflight[k]) {
+        FSIM_CUDA(h, cudaEventSynchronize(h->gfx_copied[k]));
+        h->gfx_inflight[k] = false;
     }
     return FSIM_OK;
 }

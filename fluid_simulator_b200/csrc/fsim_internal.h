@@ -98,13 +98,19 @@ struct fsim {
     uint32_t next_id;         // next persistent particle id to hand out
     FsimParticleGfx* gfx;     // device buffer of the gfx export, [gfx_cap]
     int64_t gfx_cap;
-    cudaStream_t copy_stream;  // D2H of the async gfx export
-    cudaEvent_t gfx_ready, gfx_copied;
-    bool gfx_inflight;
+    // async gfx export: two device staging buffers so that the export kernel of step k+1 never waits for the D2H copy of step k
+    cudaStream_t copy_stream;
+    FsimParticleGfx* gfx_async[2];
+    int64_t gfx_async_cap[2];
+    cudaEvent_t gfx_ready[2], gfx_copied[2];
+    bool gfx_inflight[2];
+    int gfx_slot;              // slot the next async export uses
     uint32_t *key, *rank;     // [cap+1] each
     uint8_t* kill;            // [cap] sink-capture flags written by the advect kernel
     bool kill_pending;        // kill[] holds flags the next sort must honour
     bool sorted;  // particles are in cell-binned order consistent with cell_start
+    bool lazy_g2p;     // fsim_step defers its G2P into the next step's fused G2P + advect kernel (FSIM_NO_LAZY_G2P=1: off)
+    bool g2p_pending;  // the particle velocities still lack the G2P of the last step (u / u2 hold its grid)
     bool binned;  // key / rank / cnt are current for the particle arrays (the fused advect kernel produced them)
 
     // grid
@@ -206,7 +212,7 @@ struct KScope {
 
 // ---- kernels' host launchers (one per stage file) ----------------------------------------------------
 int k_upload_obstacles(fsim* h);
-int k_advect(fsim* h, double dt, bool do_advect, bool do_pushout, bool do_stop, bool do_bin = false);
+int k_advect(fsim* h, double dt, bool do_advect, bool do_pushout, bool do_stop, bool do_bin = false, bool fuse_g2p = false);
 int k_sort(fsim* h);
 int k_push_apart(fsim* h);  // key/count -> scan -> reorder; updates np when particles were removed
 int k_p2g(fsim* h);

@@ -588,28 +588,26 @@ __device__ void t_prolong_jacobi(const Lv& L, const Lv& C, const float* b, const
     }
 }
 
-__global__ void __launch_bounds__(TAIL_THREADS, 1) mg_tail_kernel(TailArgs a) {
-    __shared__ float xs[2][COARSE_MAX];
-    if (a.sc->done) return;  // uniform over the cluster
-    cg::cluster_group cluster = cg::this_cluster();
-    const int t0 = (int)cluster.block_rank() * TAIL_THREADS + threadIdx.x;
-    const int nt = (int)cluster.num_blocks() * TAIL_THREADS;
+// V(2,2) sub-cycle over levels lv[0..n-1] by a group of CTAs whose threads are numbered t0 (of nt) and which meet at
+// bar(); the coarsest level is iterated by the group's first CTA (lead) in shared memory.  The result ends in lv[0].xa.
+template <class Bar>
+__device__ __forceinline__ void tail_cycle(const TailLevel* lv, int n, bool zero_guess, int t0, int nt, bool lead, float (*xs)[COARSE_MAX], Bar& bar) {
     // down
-    for (int i = 0; i + 1 < a.n; i++) {
-        const TailLevel& T = a.lv[i];
-        if (i == 0 && !a.zero_guess) {
-            t_jacobi(T.L, T.b, T.xa, T.xb, t0, nt, OM_A); cluster.sync();
-            t_jacobi(T.L, T.b, T.xb, T.xa, t0, nt, OM_B); cluster.sync();
+    for (int i = 0; i + 1 < n; i++) {
+        const TailLevel& T = lv[i];
+        if (i == 0 && !zero_guess) {
+            t_jacobi(T.L, T.b, T.xa, T.xb, t0, nt, OM_A); bar();
+            t_jacobi(T.L, T.b, T.xb, T.xa, t0, nt, OM_B); bar();
         } else {
-            t_pre2(T.L, T.b, T.xa, t0, nt); cluster.sync();
+            t_pre2(T.L, T.b, T.xa, t0, nt); bar();
         }
-        t_restrict(T.L, a.lv[i + 1].L, T.b, T.xa, a.lv[i + 1].b, t0, nt); cluster.sync();
+        t_restrict(T.L, lv[i + 1].L, T.b, T.xa, lv[i + 1].b, t0, nt); bar();
     }
-    // coarsest level: CTA 0, damped Jacobi in shared memory (zero guess unless it is the only level of a revisit)
+    // coarsest level: damped Jacobi in shared memory (zero guess unless it is the only level of a revisit)
     {
-        const TailLevel& T = a.lv[a.n - 1];
+        const TailLevel& T = lv[n - 1];
         const Lv& L = T.L;
-        if (cluster.block_rank() == 0) {
+        if (lead) {
             const int c = threadIdx.x;
             const int nc = L.gx * L.gy * L.gz;
             const bool in = c < nc;
@@ -624,7 +622,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) mg_tail_kernel(TailArgs a) {
                 for (int k = 0; k < 6; k++)
                     if (!(w[k] > 0.f) || nb[k] < 0 || nb[k] >= nc) { w[k] = 0.f; nb[k] = c; }
             }
-            xs[0][c] = (in && a.n == 1 && !a.zero_guess) ? T.xa[c] : 0.f;
+            xs[0][c] = (in && n == 1 && !zero_guess) ? T.xa[c] : 0.f;
             __syncthreads();
             int cur = 0;
             for (int s = 0; s < COARSE_SWEEPS; s++) {
@@ -641,15 +639,25 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) mg_tail_kernel(TailArgs a) {
             }
             if (in) T.xa[c] = xs[cur][c];
         }
-        cluster.sync();
+        bar();
     }
     // up
-    for (int i = a.n - 2; i >= 0; i--) {
-        const TailLevel& T = a.lv[i];
-        t_prolong_jacobi(T.L, a.lv[i + 1].L, T.b, T.xa, a.lv[i + 1].xa, T.xb, t0, nt); cluster.sync();
+    for (int i = n - 2; i >= 0; i--) {
+        const TailLevel& T = lv[i];
+        t_prolong_jacobi(T.L, lv[i + 1].L, T.b, T.xa, lv[i + 1].xa, T.xb, t0, nt); bar();
         t_jacobi(T.L, T.b, T.xb, T.xa, t0, nt, OM_A);
-        if (i > 0) cluster.sync();
+        if (i > 0) bar();
     }
+}
+
+__global__ void __launch_bounds__(TAIL_THREADS, 1) mg_tail_kernel(TailArgs a) {
+    __shared__ float xs[2][COARSE_MAX];
+    if (a.sc->done) return;  // uniform over the cluster
+    cg::cluster_group cluster = cg::this_cluster();
+    const int t0 = (int)cluster.block_rank() * TAIL_THREADS + threadIdx.x;
+    const int nt = (int)cluster.num_blocks() * TAIL_THREADS;
+    auto bar = [&]() { cluster.sync(); };
+    tail_cycle(a.lv, a.n, a.zero_guess != 0, t0, nt, cluster.block_rank() == 0, xs, bar);
 }
 
 Lv view(const fsim* h, const MgLevel* m, int level) {

@@ -52,7 +52,7 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
 // One staggered face pass, AXIS = 0,1,2: 2 nodes along AXIS (the pair a packed FFMA2 works on), 3 along the other two
 // dimensions B < C.  Per particle and node pair: weights += (wA0, wA1) * wB*wC ; values += (wA0*val0, wA1*val1) * wB*wC,
 // val_n = v + c[AXIS] . (face_n - particle) (APIC, simulator.cpp:327-328) or v (PIC / FLIP, :324).
-template <int AXIS>
+template <int AXIS, bool APIC>
 __device__ __forceinline__ void p2g_face_pass(const P2GArgs& a, float* s_val, float* s_w, bool active, int x, int y, int z,
                                               uint32_t start, uint32_t n, int lane, int wy, int wz) {
     constexpr int B = AXIS == 0 ? 1 : 0, C = AXIS == 2 ? 1 : 2;
@@ -78,7 +78,7 @@ __device__ __forceinline__ void p2g_face_pass(const P2GArgs& a, float* s_val, fl
             const float v = __ldg(vel + p);
             float2 wav = make_float2(wA.x * v, wA.y * v), P = make_float2(0.f, 0.f);
             float cB = 0.f, cC = 0.f;
-            if (a.apic) {
+            if (APIC) {
                 const float cA = __ldg(a.c[3 * AXIS + AXIS] + p) * hh[AXIS];
                 cB = __ldg(a.c[3 * AXIS + B] + p) * hh[B];
                 cC = __ldg(a.c[3 * AXIS + C] + p) * hh[C];
@@ -92,7 +92,7 @@ __device__ __forceinline__ void p2g_face_pass(const P2GArgs& a, float* s_val, fl
                     const float2 w2 = make_float2(wbc, wbc);
                     aw[c][b] = ffma2(wA, w2, aw[c][b]);
                     float2 tv = wav;
-                    if (a.apic) {
+                    if (APIC) {
                         const float base = v + cB * ((float)b - 0.5f - f[B]) + cC * ((float)c - 0.5f - f[C]);
                         tv = ffma2(wA, make_float2(base, base), P);
                     }
@@ -165,6 +165,7 @@ __device__ __forceinline__ void p2g_density_pass(const P2GArgs& a, float* s_w, b
         }
 }
 
+template <bool APIC>
 __global__ void __launch_bounds__(NTHREADS, 2) p2g_kernel(P2GArgs a) {
     __shared__ float s[7][SN];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -184,9 +185,9 @@ __global__ void __launch_bounds__(NTHREADS, 2) p2g_kernel(P2GArgs a) {
     __syncthreads();
 
     const bool active = n > 0;
-    p2g_face_pass<0>(a, s[0], s[3], active, x, y, z, start, n, lane, wy, wz);
-    p2g_face_pass<1>(a, s[1], s[4], active, x, y, z, start, n, lane, wy, wz);
-    p2g_face_pass<2>(a, s[2], s[5], active, x, y, z, start, n, lane, wy, wz);
+    p2g_face_pass<0, APIC>(a, s[0], s[3], active, x, y, z, start, n, lane, wy, wz);
+    p2g_face_pass<1, APIC>(a, s[1], s[4], active, x, y, z, start, n, lane, wy, wz);
+    p2g_face_pass<2, APIC>(a, s[2], s[5], active, x, y, z, start, n, lane, wy, wz);
     p2g_density_pass(a, s[6], active, x, y, z, start, n, lane, wy, wz);
 
     // flush tile + halo: one RED per touched node and channel (x fastest => coalesced)
@@ -233,7 +234,11 @@ int k_p2g(fsim* h) {
     a.dens = h->dens;
     a.apic = (h->par.transfer_type == FSIM_TRANSFER_APIC) && h->have_c;
     dim3 grid(div_up(g.gx, TX), div_up(g.gy, TY), div_up(g.gz, TZ));
-    { KScope ks(h, K_P2G); p2g_kernel<<<grid, NTHREADS, 0, h->stream>>>(a); }
+    {
+        KScope ks(h, K_P2G);
+        if (a.apic) p2g_kernel<true><<<grid, NTHREADS, 0, h->stream>>>(a);
+        else p2g_kernel<false><<<grid, NTHREADS, 0, h->stream>>>(a);
+    }
     FSIM_CHECK_LAUNCH(h);
     return FSIM_OK;
 }

@@ -12,6 +12,7 @@
 #include <cmath>
 
 #include "fsim_internal.h"
+#include "g2p_core.cuh"
 
 #define INVALID_KEY 0xFFFFFFFFu
 
@@ -53,15 +54,10 @@ struct AdvectArgs {
 
 __device__ __forceinline__ uint32_t cell_key(const GridDims& g, float x, float y, float z);
 
-__global__ void __launch_bounds__(256, 4) advect_kernel(AdvectArgs a) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = i < a.n;
-    if (!live && !a.do_bin) return;  // with fused binning whole warps stay for the __match_any_sync below
-    D3 pos = mk(0, 0, 0), v = mk(0, 0, 0);
-    if (live) { pos = mk(a.px[i], a.py[i], a.pz[i]); v = mk(a.vx[i], a.vy[i], a.vz[i]); }
+// one particle through advectParticles + pushParticlesOutOfObstacles + stopParticles; returns true if a sink captured it
+__device__ __forceinline__ bool advect_particle(const AdvectArgs& a, D3& pos, D3& v) {
     bool killed = false;
-
-    if (a.do_advect && live) {
+    if (a.do_advect) {
         const double dt = a.dt, pr = a.pr;
         double t = 0;
         int run = 0;
@@ -163,7 +159,7 @@ __global__ void __launch_bounds__(256, 4) advect_kernel(AdvectArgs a) {
         pos.z = clampd(pos.z, a.lo.z, a.hi.z);
     }
 
-    if (a.do_pushout && !killed && live) {  // simulator.cpp:253-312; obstacles in list order, per particle independent
+    if (a.do_pushout && !killed) {  // simulator.cpp:253-312; obstacles in list order, per particle independent
         const double pr = a.pr;
         for (int k = 0; k < a.nobs; k++) {
             const DevObstacle& ob = a.obs[k];
@@ -202,25 +198,107 @@ __global__ void __launch_bounds__(256, 4) advect_kernel(AdvectArgs a) {
     }
     if (a.do_stop) v = mk(0, 0, 0);
 
+    return killed;
+}
+
+// key / rank / histogram of the stored (fp32-rounded) position; every lane of the warp must call this (lanes without a
+// particle pass live = false)
+__device__ __forceinline__ void bin_particle(const AdvectArgs& a, int64_t i, bool live, bool killed, float fx, float fy, float fz) {
+    uint32_t k = INVALID_KEY;
+    if (live && !killed) k = cell_key(a.g, fx, fy, fz);
+    const unsigned peers = __match_any_sync(0xffffffffu, k);
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(peers) - 1;
+    uint32_t base = 0;
+    if (lane == leader && k != INVALID_KEY) base = atomicAdd(&a.cnt[k], (uint32_t)__popc(peers));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (live) {
+        a.key[i] = k;
+        a.rank[i] = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+    }
+}
+
+__global__ void __launch_bounds__(256, 4) advect_kernel(AdvectArgs a) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < a.n;
+    if (!live && !a.do_bin) return;  // with fused binning whole warps stay for the __match_any_sync
+    D3 pos = mk(0, 0, 0), v = mk(0, 0, 0);
+    bool killed = false;
+    if (live) {
+        pos = mk(a.px[i], a.py[i], a.pz[i]);
+        v = mk(a.vx[i], a.vy[i], a.vz[i]);
+        killed = advect_particle(a, pos, v);
+    }
     const float fx = (float)pos.x, fy = (float)pos.y, fz = (float)pos.z;
     if (live) {
         a.px[i] = fx; a.py[i] = fy; a.pz[i] = fz;
         a.vx[i] = (float)v.x; a.vy[i] = (float)v.y; a.vz[i] = (float)v.z;
         if (a.kill && a.do_advect) a.kill[i] = killed ? 1 : 0;
     }
-    if (a.do_bin) {  // same as bin_kernel, on the stored (fp32-rounded) position
-        uint32_t k = INVALID_KEY;
-        if (live && !killed) k = cell_key(a.g, fx, fy, fz);
-        const unsigned peers = __match_any_sync(0xffffffffu, k);
-        const int lane = threadIdx.x & 31;
-        const int leader = __ffs(peers) - 1;
-        uint32_t base = 0;
-        if (lane == leader && k != INVALID_KEY) base = atomicAdd(&a.cnt[k], (uint32_t)__popc(peers));
-        base = __shfl_sync(0xffffffffu, base, leader);
+    if (a.do_bin) bin_particle(a, i, live, killed, fx, fy, fz);
+}
+
+// Fused G2P (of the step that just ended) + advect + push-out + bin (of the step that starts): fsim_step defers the
+// gather so that the particle state makes one HBM round trip instead of two.  Tile / gather code: g2p_core.cuh.  The
+// loop over the tile's particles has a CTA-uniform trip count (bin_particle needs whole warps).
+constexpr int GA_THREADS = 256;
+struct GaLoad { uint32_t p; bool live; float x, y, z, vx, vy, vz; };
+__device__ __forceinline__ GaLoad ga_load(const g2p::Args& ga, const uint32_t* row_beg, const uint32_t* row_pre, uint32_t j, uint32_t total) {
+    GaLoad L;
+    L.live = j < total;
+    L.p = 0; L.x = L.y = L.z = L.vx = L.vy = L.vz = 0.f;
+    if (L.live) {
+        int r = 0;
+#pragma unroll
+        for (int step = g2p::ROWS / 2; step > 0; step >>= 1)
+            if (row_pre[r + step] <= j) r += step;
+        L.p = row_beg[r] + (j - row_pre[r]);
+        L.x = ga.px[L.p]; L.y = ga.py[L.p]; L.z = ga.pz[L.p];
+        if (ga.kb != 0.f) { L.vx = ga.vx[L.p]; L.vy = ga.vy[L.p]; L.vz = ga.vz[L.p]; }
+    }
+    return L;
+}
+
+// 6 CTAs / SM (40 registers, the rare obstacle / wall paths spill): measured best of 3..8 -- the kernel is latency-bound and
+// wants resident warps more than it minds the spills; prefetching the next particle into registers was slower.
+__global__ void __launch_bounds__(GA_THREADS, 6) g2p_advect_kernel(g2p::Args ga, AdvectArgs a) {
+    using namespace g2p;
+    __shared__ float s[3][SN];
+    __shared__ uint32_t row_beg[ROWS], row_end[ROWS], row_pre[ROWS + 1];
+    const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY, z0 = blockIdx.z * TZ;
+    tile_rows(ga, x0, y0, z0, row_beg, row_end);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t acc = 0;
+        for (int r = 0; r < ROWS; r++) { row_pre[r] = acc; acc += row_end[r] - row_beg[r]; }
+        row_pre[ROWS] = acc;
+    }
+    __syncthreads();
+    const uint32_t total = row_pre[ROWS];
+    if (total == 0) return;
+    stage_tile(ga, s, x0, y0, z0, GA_THREADS);
+    __syncthreads();
+    for (uint32_t base = 0; base < total; base += GA_THREADS) {
+        const GaLoad cur = ga_load(ga, row_beg, row_pre, base + threadIdx.x, total);
+        const uint32_t p = cur.p;
+        const bool live = cur.live;
+        D3 pos = mk(0, 0, 0), v = mk(0, 0, 0);
+        bool killed = false;
         if (live) {
-            a.key[i] = k;
-            a.rank[i] = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+            const float vold[3] = {cur.vx, cur.vy, cur.vz};
+            float vnew[3];
+            gather(ga, s, x0, y0, z0, p, cur.x, cur.y, cur.z, vold, vnew);
+            pos = mk(cur.x, cur.y, cur.z);
+            v = mk(vnew[0], vnew[1], vnew[2]);
+            killed = advect_particle(a, pos, v);
         }
+        const float fx = (float)pos.x, fy = (float)pos.y, fz = (float)pos.z;
+        if (live) {
+            a.px[p] = fx; a.py[p] = fy; a.pz[p] = fz;
+            a.vx[p] = (float)v.x; a.vy[p] = (float)v.y; a.vz[p] = (float)v.z;
+            if (a.kill && a.do_advect) a.kill[p] = killed ? 1 : 0;
+        }
+        bin_particle(a, p, live, killed, fx, fy, fz);
     }
 }
 
@@ -346,15 +424,24 @@ struct ReorderArgs {
     int64_t n;
 };
 
+// All channel loads are issued before the first scattered store (source and destination sets never alias, but the
+// compiler cannot know): one DRAM round trip per thread instead of one per channel.
+template <int NCH>
 __global__ void __launch_bounds__(256) reorder_kernel(ReorderArgs a) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n) return;
-    const uint32_t k = a.key[i];
+    const uint32_t k = __ldg(a.key + i);
+    const uint32_t r = __ldg(a.rank + i);
+    float v[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; c++) v[c] = __ldg(a.src[c] + i);
+    uint32_t id = 0;
+    if (a.src_id) id = __ldg(a.src_id + i);
     if (k == INVALID_KEY) return;
-    const uint32_t d = a.cell_start[k] + a.rank[i];
-#pragma unroll 6
-    for (int c = 0; c < a.nch; c++) a.dst[c][d] = a.src[c][i];
-    if (a.src_id) a.dst_id[d] = a.src_id[i];
+    const uint32_t d = __ldg(a.cell_start + k) + r;
+#pragma unroll
+    for (int c = 0; c < NCH; c++) a.dst[c][d] = v[c];
+    if (a.src_id) a.dst_id[d] = id;
 }
 
 // ---- push-apart (HashedParticles::pushParticlesApart, hashedParticles.cpp:64-107; SURVEY §8f "next #1") ----------
@@ -504,8 +591,9 @@ ReorderArgs reorder_args(fsim* h) {
 
 }  // namespace
 
-int k_advect(fsim* h, double dt, bool do_advect, bool do_pushout, bool do_stop, bool do_bin) {
+int k_advect(fsim* h, double dt, bool do_advect, bool do_pushout, bool do_stop, bool do_bin, bool fuse_g2p) {
     h->binned = false;
+    if (fuse_g2p) h->g2p_pending = false;
     if (h->np == 0) return FSIM_OK;
     AdvectArgs a;
     ParticleSet& p = h->ps[h->cur];
@@ -527,7 +615,17 @@ int k_advect(fsim* h, double dt, bool do_advect, bool do_pushout, bool do_stop, 
     a.kill = h->kill;
     a.do_bin = do_bin; a.g = h->g; a.cnt = h->cnt; a.key = h->key; a.rank = h->rank;
     if (do_bin) { KScope ks(h, K_MEMSET); FSIM_CUDA(h, cudaMemsetAsync(h->cnt, 0, sizeof(uint32_t) * h->g.nc, h->stream)); }
-    { KScope ks(h, K_ADVECT); advect_kernel<<<div_up(h->np, 256), 256, 0, h->stream>>>(a); }
+    if (fuse_g2p) {  // requires cell-binned particles (h->sorted) and do_bin
+        g2p::Args ga;
+        int rc = g2p_make_args(h, &ga);
+        if (rc) return rc;
+        dim3 grid(div_up(h->g.gx, g2p::TX), div_up(h->g.gy, g2p::TY), div_up(h->g.gz, g2p::TZ));
+        KScope ks(h, K_ADVECT);
+        g2p_advect_kernel<<<grid, GA_THREADS, 0, h->stream>>>(ga, a);
+    } else {
+        KScope ks(h, K_ADVECT);
+        advect_kernel<<<div_up(h->np, 256), 256, 0, h->stream>>>(a);
+    }
     FSIM_CHECK_LAUNCH(h);
     h->sorted = false;
     h->binned = do_bin;
@@ -549,7 +647,11 @@ int k_sort(fsim* h) {
     if (rc) return rc;
     if (h->np > 0) {
         ReorderArgs a = reorder_args(h);
-        { KScope ks(h, K_REORDER); reorder_kernel<<<div_up(h->np, 256), 256, 0, h->stream>>>(a); }
+        {
+            KScope ks(h, K_REORDER);
+            if (a.nch == 6) reorder_kernel<6><<<div_up(h->np, 256), 256, 0, h->stream>>>(a);
+            else reorder_kernel<15><<<div_up(h->np, 256), 256, 0, h->stream>>>(a);
+        }
         FSIM_CHECK_LAUNCH(h);
         h->cur ^= 1;
     }

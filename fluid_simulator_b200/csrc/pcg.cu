@@ -474,48 +474,53 @@ int k_project(fsim* h, double dt, int* iterations) {
     // one-thread kernel re-arms the condition from the done flag.  The host launches it once and never polls.
     bool graph = h->use_graph && h->prof_mask == 0;
     if (graph && !h->pcg_graph && !h->pcg_graph_failed) {
-        cudaGraph_t gr = nullptr, body = nullptr;
-        cudaGraphConditionalHandle handle;
-        cudaGraphNode_t set_node, cond_node;
-        bool ok = cudaGraphCreate(&gr, 0) == cudaSuccess &&
-                  cudaGraphConditionalHandleCreate(&handle, gr, 1, cudaGraphCondAssignDefault) == cudaSuccess;
-        if (ok) {
-            void* kargs[2] = {(void*)&handle, (void*)&h->scal};
-            cudaKernelNodeParams kp = {};
-            kp.func = (void*)loop_condition_kernel;
-            kp.gridDim = dim3(1); kp.blockDim = dim3(1); kp.sharedMemBytes = 0; kp.kernelParams = kargs; kp.extra = nullptr;
-            ok = cudaGraphAddKernelNode(&set_node, gr, nullptr, 0, &kp) == cudaSuccess;
-        }
-        if (ok) {
-            cudaGraphNodeParams cp = {};
-            cp.type = cudaGraphNodeTypeConditional;
-            cp.conditional.handle = handle;
-            cp.conditional.type = cudaGraphCondTypeWhile;
-            cp.conditional.size = 1;
-            ok = cudaGraphAddNode(&cond_node, gr, &set_node, 1, &cp) == cudaSuccess;
-            if (ok) body = cp.conditional.phGraph_out[0];
-        }
-        if (ok) {
-            const int64_t l0 = h->launches;
-            int64_t c0[K_COUNT];
-            memcpy(c0, h->launch_n, sizeof(c0));
-            ok = cudaStreamBeginCaptureToGraph(h->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+        auto build = [&]() -> bool {
+            const int sticky0 = h->sticky;
+            cudaGraph_t gr = nullptr, body = nullptr;
+            cudaGraphConditionalHandle handle;
+            cudaGraphNode_t set_node, cond_node;
+            bool ok = cudaGraphCreate(&gr, 0) == cudaSuccess &&
+                      cudaGraphConditionalHandleCreate(&handle, gr, 1, cudaGraphCondAssignDefault) == cudaSuccess;
             if (ok) {
-                const int rc = enqueue_iteration(h, a, vec, use_mg, nbv);
-                loop_condition_kernel<<<1, 1, 0, h->stream>>>(handle, h->scal);
-                cudaGraph_t dummy = nullptr;
-                const cudaError_t e = cudaStreamEndCapture(h->stream, &dummy);
-                ok = rc == FSIM_OK && e == cudaSuccess;
+                void* kargs[2] = {(void*)&handle, (void*)&h->scal};
+                cudaKernelNodeParams kp = {};
+                kp.func = (void*)loop_condition_kernel;
+                kp.gridDim = dim3(1); kp.blockDim = dim3(1); kp.sharedMemBytes = 0; kp.kernelParams = kargs; kp.extra = nullptr;
+                ok = cudaGraphAddKernelNode(&set_node, gr, nullptr, 0, &kp) == cudaSuccess;
             }
-            h->pcg_graph_launches = (int)(h->launches - l0) + 1;
-            for (int k = 0; k < K_COUNT; k++) { h->pcg_graph_class[k] = (int)(h->launch_n[k] - c0[k]); h->launch_n[k] = c0[k]; }
-            h->launches = l0;  // capture does not execute
-        }
-        if (ok) ok = cudaGraphInstantiate(&h->pcg_graph, gr, 0) == cudaSuccess;
-        if (gr) cudaGraphDestroy(gr);
+            if (ok) {
+                cudaGraphNodeParams cp = {};
+                cp.type = cudaGraphNodeTypeConditional;
+                cp.conditional.handle = handle;
+                cp.conditional.type = cudaGraphCondTypeWhile;
+                cp.conditional.size = 1;
+                ok = cudaGraphAddNode(&cond_node, gr, &set_node, 1, &cp) == cudaSuccess;
+                if (ok) body = cp.conditional.phGraph_out[0];
+            }
+            if (ok) {
+                const int64_t l0 = h->launches;
+                int64_t c0[K_COUNT];
+                memcpy(c0, h->launch_n, sizeof(c0));
+                ok = cudaStreamBeginCaptureToGraph(h->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+                if (ok) {
+                    const int rc = enqueue_iteration(h, a, vec, use_mg, nbv);
+                    loop_condition_kernel<<<1, 1, 0, h->stream>>>(handle, h->scal);
+                    cudaGraph_t dummy = nullptr;
+                    const cudaError_t e = cudaStreamEndCapture(h->stream, &dummy);
+                    ok = rc == FSIM_OK && e == cudaSuccess;
+                }
+                h->pcg_graph_launches = (int)(h->launches - l0) + 1;
+                for (int k = 0; k < K_COUNT; k++) { h->pcg_graph_class[k] = (int)(h->launch_n[k] - c0[k]); h->launch_n[k] = c0[k]; }
+                h->launches = l0;  // capture does not execute
+            }
+            if (ok) ok = cudaGraphInstantiate(&h->pcg_graph, gr, 0) == cudaSuccess;
+            if (gr) cudaGraphDestroy(gr);
+            if (!ok) { h->pcg_graph = nullptr; cudaGetLastError(); h->sticky = sticky0; }
+            return ok;
+        };
+        bool ok = build();
         if (!ok) {  // older driver / unsupported node: fall back to enqueueing iterations from the host
-            const cudaError_t why = cudaGetLastError();
-            fprintf(stderr, "libfsim_b200: device-side PCG loop graph unavailable (%s); using the host-driven loop\n", cudaGetErrorString(why));
+            fprintf(stderr, "libfsim_b200: device-side PCG loop graph unavailable; using the host-driven loop\n");
             h->pcg_graph = nullptr;
             h->pcg_graph_failed = true;
         }

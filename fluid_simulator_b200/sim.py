@@ -78,6 +78,7 @@ def load_library():
         "fsim_export_gfx": (i32, [vp, vp, i64, P(i64)]),
         "fsim_export_gfx_async": (i32, [vp, vp, i64, P(i64)]),
         "fsim_export_gfx_wait": (i32, [vp]),
+        "fsim_export_gfx_wait_previous": (i32, [vp]),
         "fsim_get_step_durations": (i32, [vp, P(abi.Timings)]),
         "fsim_get_solve_info": (i32, [vp, P(abi.SolveInfo)]),
         "fsim_get_last_step_stats": (i32, [vp, P(dbl), P(i64)]),
@@ -264,6 +265,7 @@ class FluidSim:
         return int(n.value)
 
     def export_gfx_wait(self): self._ck(self.L.fsim_export_gfx_wait(self.h))
+    def export_gfx_wait_previous(self): self._ck(self.L.fsim_export_gfx_wait_previous(self.h))
 
     # --- introspection --------------------------------------------------------------------------
     def step_durations(self):

@@ -335,3 +335,66 @@ def test_cfg4_full_scale_source_sink_moving_box(gpu):
     lo, hi = 1.0 + 0.25 * 1.01 - 1e-4, n - (1.0 + 0.25 * 1.01) + 1e-4
     assert p.min() >= lo and p.max() <= hi
     diag(test="cfg4/192", counts=counts, stats=g.last_step_stats(), timings=g.step_durations())
+
+
+@pytest.mark.parametrize("transfer", [abi.FLIP, abi.APIC, abi.PIC])
+def test_deferred_g2p_matches_eager(gpu, transfer, monkeypatch):
+    """fsim_step defers its G2P into the next step's fused G2P + advect kernel.  The fused path must be invisible:
+    the same scene stepped with the deferral (default), with a forced flush after every step (download) and with the
+    deferral switched off (FSIM_NO_LAZY_G2P=1) ends in the same particle and grid state, obstacles included.  The
+    comparison is not bit-wise: the order of the particles inside a cell follows the order of the binning atomics, and
+    with it the fp32 summation order of the P2G scatter, from run to run of ANY of the three variants."""
+    n = 32
+    sc = scenes.dam_break_3d(n, transfer)
+    obstacles = [scenes.cfg3_box(n)]
+
+    def run(mode):
+        if mode == "eager":
+            monkeypatch.setenv("FSIM_NO_LAZY_G2P", "1")
+        else:
+            monkeypatch.delenv("FSIM_NO_LAZY_G2P", raising=False)
+        g = gpu(sc.dims, sc.resolution, sc.two_d, sc.particle_radius)
+        g.set_params(sc.params)
+        g.set_obstacles(obstacles)
+        g.upload_particles(sc.particles)
+        its = []
+        for _ in range(6):
+            its.append(g.step(sc.dt))
+            if mode == "flush":
+                g.download_particles()
+        out = (g.download_particles(), g.download_grid(abi.FIELD_V), g.download_grid(abi.FIELD_PRESSURE), its,
+               g.download_grid(abi.FIELD_TYPE))
+        g.close()
+        return out
+
+    ref = run("eager")
+    for mode in ("eager", "lazy", "flush"):  # eager twice: the run-to-run noise floor
+        got = run(mode)
+        res = {"pos": rel_l2(got[0][:, 0:3], ref[0][:, 0:3]), "vel": rel_l2(got[0][:, 3:6], ref[0][:, 3:6]),
+               "v": rel_l2(got[1], ref[1]), "p": rel_l2(got[2], ref[2]), "type_mismatch": int((got[4] != ref[4]).sum())}
+        diag(test=f"deferred_g2p/{transfer}/{mode}", its=got[3], its_ref=ref[3], **res)
+        assert max(abs(a - b) for a, b in zip(got[3], ref[3])) <= 1
+        assert res["type_mismatch"] == 0
+        assert res["pos"] <= 1e-6 and res["vel"] <= TOL and res["v"] <= TOL and res["p"] <= TOL, f"{mode}: {res}"
+
+
+def test_async_gfx_export_matches_sync(gpu):
+    """fsim_export_gfx_async / _wait_previous / _wait (two staging slots) deliver exactly what fsim_export_gfx does."""
+    import torch
+    n = 32
+    sc = scenes.dam_break_3d(n, abi.FLIP)
+    g = gpu(sc.dims, sc.resolution, sc.two_d, sc.particle_radius)
+    g.set_params(sc.params)
+    g.upload_particles(sc.particles)
+    npart = sc.n_particles
+    bufs = [torch.zeros((npart, 5), dtype=torch.float32).pin_memory() for _ in range(2)]
+    want = []
+    for i in range(4):
+        g.step(sc.dt)
+        assert g.export_gfx_async_ptr(bufs[i % 2].data_ptr(), npart) == npart
+        g.export_gfx_wait_previous()
+        if i > 0:
+            assert np.array_equal(bufs[(i - 1) % 2].numpy(), want[i - 1]), f"async export {i - 1} differs"
+        want.append(g.export_gfx(by_id=False))
+    g.export_gfx_wait()
+    assert np.array_equal(bufs[3 % 2].numpy(), want[3])
