@@ -49,11 +49,20 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
     return d;
 }
 
+// Where a cell's particles are read from.  STAGED kernels copy the tile's particle runs into shared memory with coalesced
+// loads first (everything in flight at once); the per-cell walk then reads shared memory.  Index i of the staged run lives
+// at i + i/8: neighbouring cells start ~8 particles apart, which would put all lanes of a warp on 4 banks.
+struct Src {
+    const float *sx, *sy, *sz, *sv;  // staged copies (shared memory), valid for particle t < ns of this cell
+    uint32_t s0, ns;                 // staged index of the cell's first particle; how many of its particles are staged
+};
+__device__ __forceinline__ uint32_t swz(uint32_t i) { return i + (i >> 3); }
+
 // One staggered face pass, AXIS = 0,1,2: 2 nodes along AXIS (the pair a packed FFMA2 works on), 3 along the other two
 // dimensions B < C.  Per particle and node pair: weights += (wA0, wA1) * wB*wC ; values += (wA0*val0, wA1*val1) * wB*wC,
 // val_n = v + c[AXIS] . (face_n - particle) (APIC, simulator.cpp:327-328) or v (PIC / FLIP, :324).
-template <int AXIS, bool APIC>
-__device__ __forceinline__ void p2g_face_pass(const P2GArgs& a, float* s_val, float* s_w, bool active, int x, int y, int z,
+template <int AXIS, bool APIC, bool STAGED>
+__device__ __forceinline__ void p2g_face_pass(const P2GArgs& a, const Src& src, float* s_val, float* s_w, bool active, int x, int y, int z,
                                               uint32_t start, uint32_t n, int lane, int wy, int wz) {
     constexpr int B = AXIS == 0 ? 1 : 0, C = AXIS == 2 ? 1 : 2;
     float2 aw[3][3], av[3][3];  // [c][b]
@@ -65,17 +74,15 @@ __device__ __forceinline__ void p2g_face_pass(const P2GArgs& a, float* s_val, fl
     if (active) {
         const float* vel = AXIS == 0 ? a.vx : (AXIS == 1 ? a.vy : a.vz);
         const float hh[3] = {a.g.hx, a.g.hy, a.g.hz};
-        for (uint32_t t = 0; t < n; t++) {
-            const uint32_t p = start + t;
+        auto body = [&](float X, float Y, float Z, float v, uint32_t p) {
             float f[3];
-            f[0] = fmaf(__ldg(a.px + p), a.g.ihx, -(float)x);  // single rounding
-            f[1] = fmaf(__ldg(a.py + p), a.g.ihy, -(float)y);
-            f[2] = fmaf(__ldg(a.pz + p), a.g.ihz, -(float)z);
+            f[0] = fmaf(X, a.g.ihx, -(float)x);  // single rounding
+            f[1] = fmaf(Y, a.g.ihy, -(float)y);
+            f[2] = fmaf(Z, a.g.ihz, -(float)z);
             const float2 wA = make_float2(1.f - f[AXIS], f[AXIS]);
             float wB[3], wC[3];
             centred_w(f[B], wB);
             centred_w(f[C], wC);
-            const float v = __ldg(vel + p);
             float2 wav = make_float2(wA.x * v, wA.y * v), P = make_float2(0.f, 0.f);
             float cB = 0.f, cC = 0.f;
             if (APIC) {
@@ -98,6 +105,16 @@ __device__ __forceinline__ void p2g_face_pass(const P2GArgs& a, float* s_val, fl
                     }
                     av[c][b] = ffma2(tv, w2, av[c][b]);
                 }
+        };
+        uint32_t t = 0;
+        if (STAGED)
+            for (; t < src.ns; t++) {
+                const uint32_t j = swz(src.s0 + t);
+                body(src.sx[j], src.sy[j], src.sz[j], src.sv[j], start + t);
+            }
+        for (; t < n; t++) {
+            const uint32_t p = start + t;
+            body(__ldg(a.px + p), __ldg(a.py + p), __ldg(a.pz + p), __ldg(vel + p), p);
         }
     }
     // fold: phases over (k, j), lanes along x.  (i,j,k) -> (pair half, b, c) depends on which dimension is staggered.
@@ -123,7 +140,8 @@ __device__ __forceinline__ void p2g_face_pass(const P2GArgs& a, float* s_val, fl
 }
 
 // cell-centred density pass (avgPNum, simulator.cpp:362-366): 3x3x3 nodes, weights only; x nodes packed as (0,1),(2,-)
-__device__ __forceinline__ void p2g_density_pass(const P2GArgs& a, float* s_w, bool active, int x, int y, int z, uint32_t start,
+template <bool STAGED>
+__device__ __forceinline__ void p2g_density_pass(const P2GArgs& a, const Src& src, float* s_w, bool active, int x, int y, int z, uint32_t start,
                                                  uint32_t n, int lane, int wy, int wz) {
     float2 aw[3][3][2];
 #pragma unroll
@@ -131,11 +149,10 @@ __device__ __forceinline__ void p2g_density_pass(const P2GArgs& a, float* s_w, b
 #pragma unroll
         for (int j = 0; j < 3; j++) { aw[k][j][0] = make_float2(0.f, 0.f); aw[k][j][1] = make_float2(0.f, 0.f); }
     if (active) {
-        for (uint32_t t = 0; t < n; t++) {
-            const uint32_t p = start + t;
-            const float fx = fmaf(__ldg(a.px + p), a.g.ihx, -(float)x);
-            const float fy = fmaf(__ldg(a.py + p), a.g.ihy, -(float)y);
-            const float fz = fmaf(__ldg(a.pz + p), a.g.ihz, -(float)z);
+        auto body = [&](float X, float Y, float Z) {
+            const float fx = fmaf(X, a.g.ihx, -(float)x);
+            const float fy = fmaf(Y, a.g.ihy, -(float)y);
+            const float fz = fmaf(Z, a.g.ihz, -(float)z);
             float wx[3], wy_[3], wz_[3];
             centred_w(fx, wx); centred_w(fy, wy_); centred_w(fz, wz_);
             const float2 wx01 = make_float2(wx[0], wx[1]), wx2 = make_float2(wx[2], 0.f);
@@ -148,6 +165,16 @@ __device__ __forceinline__ void p2g_density_pass(const P2GArgs& a, float* s_w, b
                     aw[k][j][0] = ffma2(wx01, w2, aw[k][j][0]);
                     aw[k][j][1] = ffma2(wx2, w2, aw[k][j][1]);
                 }
+        };
+        uint32_t t = 0;
+        if (STAGED)
+            for (; t < src.ns; t++) {
+                const uint32_t j = swz(src.s0 + t);
+                body(src.sx[j], src.sy[j], src.sz[j]);
+            }
+        for (; t < n; t++) {
+            const uint32_t p = start + t;
+            body(__ldg(a.px + p), __ldg(a.py + p), __ldg(a.pz + p));
         }
     }
 #pragma unroll
@@ -165,9 +192,58 @@ __device__ __forceinline__ void p2g_density_pass(const P2GArgs& a, float* s_w, b
         }
 }
 
+// ---- the kernel -----------------------------------------------------------------------------------------------------
+// Read straight from global memory, the per-cell walk fetches particle p = start + t at stride ~8 floats across the lanes, so every warp-wide load
+// touches 32 sectors that are only consumed over the next 8 iterations; with two CTAs per SM the 2 x 4 arrays x 16 KB
+// in flight no longer fit L1 (ncu: 74 % hit rate, long-scoreboard the top stall; 1.72 ms, APIC 3.6 ms).  So every warp
+// copies its own row's particle run into shared memory with coalesced loads (positions once, one velocity component per pass;
+// 1.54 ms, APIC 2.1 ms) and the walk reads
+// conflict-free shared memory; the accumulator tile shrinks to the two channels of the running pass and is flushed
+// after every pass.  Particles beyond the staging capacity (tiles denser than 8 per cell) are read from global memory.
+constexpr int CAP = 4096;               // staged particles per tile
+constexpr int CAPP = CAP + CAP / 8;     // with the bank padding of swz()
+constexpr size_t STAGED_SMEM = (size_t)(2 * SN + 4 * CAPP) * sizeof(float);
+
+// a warp copies its own row's particle run (NA arrays at once) into the staged slots [off, off + len)
+template <int NA>
+__device__ __forceinline__ void stage_row(float* const (&dst)[NA], const float* const (&src)[NA], uint32_t beg, uint32_t off, uint32_t len, int lane) {
+#pragma unroll 4
+    for (uint32_t k = lane; k < len; k += 32) {
+        const uint32_t j = swz(off + k);
+        float v[NA];
+#pragma unroll
+        for (int q = 0; q < NA; q++) v[q] = __ldg(src[q] + beg + k);
+#pragma unroll
+        for (int q = 0; q < NA; q++) dst[q][j] = v[q];
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ void flush_pass(const P2GArgs& a, float* s_val, float* s_w, float* g_val, float* g_w, int x0, int y0, int z0) {
+    for (int i = threadIdx.x; i < SN; i += NTHREADS) {
+        const float w = s_w[i];
+        if (w != 0.f) {
+            const int sx = i % SX, sy = (i / SX) % SY, sz = i / (SX * SY);
+            const int gx = x0 - 1 + sx, gy = y0 - 1 + sy, gz = z0 - 1 + sz;
+            if (gx >= 0 && gy >= 0 && gz >= 0 && gx < a.g.gx && gy < a.g.gy && gz < a.g.gz) {
+                const int64_t c = ((int64_t)gz * a.g.gy + gy) * a.g.gx + gx;
+                atomicAdd(g_w + c, w);
+                if (g_val) atomicAdd(g_val + c, s_val[i]);
+            }
+            s_w[i] = 0.f;
+            s_val[i] = 0.f;
+        }
+    }
+    __syncthreads();
+}
+
 template <bool APIC>
 __global__ void __launch_bounds__(NTHREADS, 2) p2g_kernel(P2GArgs a) {
-    __shared__ float s[7][SN];
+    extern __shared__ float dyn[];
+    __shared__ uint32_t row_beg[TY * TZ], row_off[TY * TZ + 1];
+    float* s_val = dyn;
+    float* s_w = dyn + SN;
+    float* sp = dyn + 2 * SN;  // x | y | z | v, CAPP floats each
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int wy = warp % TY, wz = warp / TY;
     const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY, z0 = blockIdx.z * TZ;
@@ -181,32 +257,45 @@ __global__ void __launch_bounds__(NTHREADS, 2) p2g_kernel(P2GArgs a) {
     }
     if (!__syncthreads_or(n > 0)) return;  // empty tile: nothing to scatter
 
-    for (int i = threadIdx.x; i < 7 * SN; i += NTHREADS) (&s[0][0])[i] = 0.f;
+    // the warp's row of cells is one contiguous particle run [beg, end)
+    {
+        const int last = min(31, a.g.gx - 1 - x0);
+        uint32_t beg = __shfl_sync(0xffffffffu, start, 0), end = __shfl_sync(0xffffffffu, start + n, last);
+        if (!(y < a.g.gy && z < a.g.gz)) beg = end = 0;
+        if (lane == 0) { row_beg[warp] = beg; row_off[warp + 1] = end - beg; }
+    }
+    for (int i = threadIdx.x; i < 2 * SN; i += NTHREADS) dyn[i] = 0.f;
     __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t acc = 0;
+        for (int r = 0; r < TY * TZ; r++) { const uint32_t len = row_off[r + 1]; row_off[r] = acc; acc += len; }
+        row_off[TY * TZ] = acc;
+    }
+    __syncthreads();
+    const uint32_t r_beg = row_beg[warp], r_off = row_off[warp];
+    const uint32_t r_len = min(row_off[warp + 1], (uint32_t)CAP) - min(r_off, (uint32_t)CAP);  // staged part of the warp's row
+    Src src;
+    src.sx = sp; src.sy = sp + CAPP; src.sz = sp + 2 * CAPP; src.sv = sp + 3 * CAPP;
+    src.s0 = row_off[warp] + (start - row_beg[warp]);
+    src.ns = n == 0 ? 0u : (src.s0 >= (uint32_t)CAP ? 0u : min(n, (uint32_t)CAP - src.s0));
+    {
+        float* const d4[4] = {sp, sp + CAPP, sp + 2 * CAPP, sp + 3 * CAPP};
+        const float* const g4[4] = {a.px, a.py, a.pz, a.vx};
+        stage_row<4>(d4, g4, r_beg, r_off, r_len, lane);
+    }
+    float* const d1[1] = {sp + 3 * CAPP};
 
     const bool active = n > 0;
-    p2g_face_pass<0, APIC>(a, s[0], s[3], active, x, y, z, start, n, lane, wy, wz);
-    p2g_face_pass<1, APIC>(a, s[1], s[4], active, x, y, z, start, n, lane, wy, wz);
-    p2g_face_pass<2, APIC>(a, s[2], s[5], active, x, y, z, start, n, lane, wy, wz);
-    p2g_density_pass(a, s[6], active, x, y, z, start, n, lane, wy, wz);
-
-    // flush tile + halo: one RED per touched node and channel (x fastest => coalesced)
-    for (int i = threadIdx.x; i < SN; i += NTHREADS) {
-        const int sx = i % SX, sy = (i / SX) % SY, sz = i / (SX * SY);
-        const int gx = x0 - 1 + sx, gy = y0 - 1 + sy, gz = z0 - 1 + sz;
-        if (gx < 0 || gy < 0 || gz < 0 || gx >= a.g.gx || gy >= a.g.gy || gz >= a.g.gz) continue;
-        const int64_t c = ((int64_t)gz * a.g.gy + gy) * a.g.gx + gx;
-#pragma unroll
-        for (int ax = 0; ax < 3; ax++) {
-            const float w = s[3 + ax][i];
-            if (w != 0.f) {
-                atomicAdd(a.wu[ax] + c, w);
-                atomicAdd(a.su[ax] + c, s[ax][i]);
-            }
-        }
-        const float d = s[6][i];
-        if (d != 0.f) atomicAdd(a.dens + c, d);
-    }
+    p2g_face_pass<0, APIC, true>(a, src, s_val, s_w, active, x, y, z, start, n, lane, wy, wz);
+    { const float* const g1[1] = {a.vy}; stage_row<1>(d1, g1, r_beg, r_off, r_len, lane); }  // every thread is past its vx reads (the fold ends with a barrier)
+    flush_pass(a, s_val, s_w, a.su[0], a.wu[0], x0, y0, z0);
+    p2g_face_pass<1, APIC, true>(a, src, s_val, s_w, active, x, y, z, start, n, lane, wy, wz);
+    { const float* const g1[1] = {a.vz}; stage_row<1>(d1, g1, r_beg, r_off, r_len, lane); }
+    flush_pass(a, s_val, s_w, a.su[1], a.wu[1], x0, y0, z0);
+    p2g_face_pass<2, APIC, true>(a, src, s_val, s_w, active, x, y, z, start, n, lane, wy, wz);
+    flush_pass(a, s_val, s_w, a.su[2], a.wu[2], x0, y0, z0);
+    p2g_density_pass<true>(a, src, s_w, active, x, y, z, start, n, lane, wy, wz);
+    flush_pass(a, s_val, s_w, nullptr, a.dens, x0, y0, z0);
 }
 
 }  // namespace
@@ -236,8 +325,13 @@ int k_p2g(fsim* h) {
     dim3 grid(div_up(g.gx, TX), div_up(g.gy, TY), div_up(g.gz, TZ));
     {
         KScope ks(h, K_P2G);
-        if (a.apic) p2g_kernel<true><<<grid, NTHREADS, 0, h->stream>>>(a);
-        else p2g_kernel<false><<<grid, NTHREADS, 0, h->stream>>>(a);
+        if (a.apic) {
+            FSIM_CUDA(h, cudaFuncSetAttribute(p2g_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STAGED_SMEM));
+            p2g_kernel<true><<<grid, NTHREADS, STAGED_SMEM, h->stream>>>(a);
+        } else {
+            FSIM_CUDA(h, cudaFuncSetAttribute(p2g_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STAGED_SMEM));
+            p2g_kernel<false><<<grid, NTHREADS, STAGED_SMEM, h->stream>>>(a);
+        }
     }
     FSIM_CHECK_LAUNCH(h);
     return FSIM_OK;

@@ -398,3 +398,34 @@ def test_async_gfx_export_matches_sync(gpu):
         want.append(g.export_gfx(by_id=False))
     g.export_gfx_wait()
     assert np.array_equal(bufs[3 % 2].numpy(), want[3])
+
+
+@pytest.mark.parametrize("transfer", [abi.FLIP, abi.APIC])
+def test_p2g_dense_tiles_beyond_staging_capacity(gpu, oracle_lib, transfer):
+    """The P2G kernel stages up to 4096 particles of a 32x4x4-cell tile in shared memory and reads the rest from global
+    memory.  A block seeded four times over (32 particles per cell, 16 K per full tile) exercises both sources, the
+    switch in the middle of a cell included, against the oracle: P2G sums, classification and one full step."""
+    n = 40  # x rows longer than one tile, ragged in y / z
+    sc = scenes.dam_break_3d(n, transfer, ny=12, nz=10, tol=1e-9)
+    rng = np.random.default_rng(11)
+    layers = []
+    for k in range(4):
+        p = sc.particles.copy()
+        p[:, 0:3] += rng.uniform(-0.12, 0.12, size=(p.shape[0], 3))
+        p[:, 0:3] = p[:, 0:3].astype(np.float32)
+        p[:, 3:6] = rng.normal(0, 1.0, size=(p.shape[0], 3)).astype(np.float32)
+        if transfer == abi.APIC:
+            p[:, 6:15] = rng.normal(0, 0.3, size=(p.shape[0], 9)).astype(np.float32)
+        layers.append(p)
+    parts = np.concatenate(layers)
+    g, o = make_pair(gpu, sc, oracle_lib, particles=parts)
+    assert np.array_equal(g.download_particle_cells(), o.download_particle_cells())
+    g.stage_p2g(); o.stage_p2g()
+    cnt = g.download_grid(abi.FIELD_PCOUNT)
+    assert np.array_equal(cnt, o.download_grid(abi.FIELD_PCOUNT)) and cnt.max() >= 24
+    compare_state(f"dense/{transfer}/p2g_wsum", g, o, [(abi.FIELD_WSUM, "wsum")], particles=False)
+    g.stage_classify(sc.dt); o.stage_classify(sc.dt)
+    compare_state(f"dense/{transfer}/classify", g, o, NO_P, particles=False)
+    g2, o2 = make_pair(gpu, sc, oracle_lib, particles=parts)
+    g2.step(sc.dt); o2.step(sc.dt)
+    compare_state(f"dense/{transfer}/step", g2, o2, ALL, apic=transfer == abi.APIC)
