@@ -249,6 +249,7 @@ __global__ void __launch_bounds__(PT) spmv_kernel(PcgArgs a) {
 }
 
 // same as spmv_kernel<true> with four cells per thread and trip (gx % 4 == 0): 13 independent loads in flight per thread
+// (issuing all neighbour loads unconditionally, in parallel with the code load, was measured slower: +50 % traffic over AIR)
 __global__ void __launch_bounds__(PT, 4) spmv4_kernel(PcgArgs a) {
     if (a.sc->done) return;
     double acc[1] = {0.0};
@@ -257,20 +258,21 @@ __global__ void __launch_bounds__(PT, 4) spmv4_kernel(PcgArgs a) {
     const int64_t cend = min((int64_t)(blockIdx.x + 1) * CHUNK, a.g.nc);
     for (int64_t c = (int64_t)blockIdx.x * CHUNK + (int64_t)threadIdx.x * 4; c < cend; c += PT * 4) {
         const ushort4 t = *reinterpret_cast<const ushort4*>(a.code + c);
-        const unsigned cd[4] = {t.x, t.y, t.z, t.w};
-        const unsigned any = cd[0] | cd[1] | cd[2] | cd[3];
-        if (!(any & CODE_ACTIVE)) continue;
         double sc[4], ym[4] = {0, 0, 0, 0}, yp[4] = {0, 0, 0, 0}, zm[4] = {0, 0, 0, 0}, zp[4] = {0, 0, 0, 0};
+        double xl = 0.0, xr = 0.0;
         auto ld = [&](double* dst, const double* src) {
             const double2 u = *reinterpret_cast<const double2*>(src), v = *reinterpret_cast<const double2*>(src + 2);
             dst[0] = u.x; dst[1] = u.y; dst[2] = v.x; dst[3] = v.y;
         };
+        const unsigned cd[4] = {t.x, t.y, t.z, t.w};
+        const unsigned any = cd[0] | cd[1] | cd[2] | cd[3];
+        if (!(any & CODE_ACTIVE)) continue;
         ld(sc, a.s + c);
         if (any & 4u) ld(ym, a.s + c - sy);
         if (any & 8u) ld(yp, a.s + c + sy);
         if (any & 16u) ld(zm, a.s + c - sz);
         if (any & 32u) ld(zp, a.s + c + sz);
-        const double xl = (cd[0] & 1u) ? a.s[c - 1] : 0.0, xr = (cd[3] & 2u) ? a.s[c + 4] : 0.0;
+        xl = (cd[0] & 1u) ? a.s[c - 1] : 0.0; xr = (cd[3] & 2u) ? a.s[c + 4] : 0.0;
         double q[4] = {0, 0, 0, 0};
 #pragma unroll
         for (int i = 0; i < 4; i++)
