@@ -119,7 +119,8 @@ struct fsim {
     uint8_t* flags;
     uint16_t* code;                        // stencil codes of the current solve
     float *u[3], *u2[3], *wsum[3], *dens;  // u: post-P2G v / accumulators; u2: working v2
-    double *p, *rhs, *r, *s, *q, *z;       // pressure + PCG vectors (fp64)
+    double *p, *rhs, *r, *q, *z;           // pressure + PCG vectors (fp64)
+    float* s;                              // PCG search direction (fp32 storage, see pcg.cu)
     float* mg_z32;                         // result of the last multigrid cycle (fp32, 0 outside WATER)
     bool use_mg;                           // multigrid (default) or diagonal preconditioner (FSIM_PRECOND=jacobi)
     double mg_inv_scale;                   // 1 / (dt / (rho h^2)): the hierarchy works on the integer-weight Laplacian

@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(256) mg_jacobi4_kernel(Lv L, PcgScalars* __res
 //   alpha = sigma / s.q ; p += alpha s ; r -= alpha q ; ||r||_inf ; b = r / scale ; x1 = omega b / diag
 constexpr int UF_CHUNK = 8192;
 __global__ void __launch_bounds__(256) mg_update_first4_kernel(Lv L, int64_t nc, PcgScalars* sc, PcgHostStatus* status, double* __restrict__ p,
-                                                               const double* __restrict__ sv, double* __restrict__ r,
+                                                               const float* __restrict__ sv, double* __restrict__ r,
                                                                const double* __restrict__ q, float* __restrict__ b, float* __restrict__ xout,
                                                                double* partials, unsigned int* counter) {
     if (sc->done) return;
@@ -328,11 +328,15 @@ __global__ void __launch_bounds__(256) mg_update_first4_kernel(Lv L, int64_t nc,
             const unsigned cd[4] = {t.x, t.y, t.z, t.w};
             if (!((cd[0] | cd[1] | cd[2] | cd[3]) & CODE_ACTIVE)) continue;
             double pp[4], ss[4], rr[4], qq[4];
+            {
+                const float4 sf = *reinterpret_cast<const float4*>(sv + c);
+                ss[0] = (double)sf.x; ss[1] = (double)sf.y; ss[2] = (double)sf.z; ss[3] = (double)sf.w;
+            }
 #pragma unroll
             for (int h2 = 0; h2 < 2; h2++) {
-                const double2 a0 = *reinterpret_cast<const double2*>(p + c + 2 * h2), a1 = *reinterpret_cast<const double2*>(sv + c + 2 * h2);
+                const double2 a0 = *reinterpret_cast<const double2*>(p + c + 2 * h2);
                 const double2 a2 = *reinterpret_cast<const double2*>(r + c + 2 * h2), a3 = *reinterpret_cast<const double2*>(q + c + 2 * h2);
-                pp[2 * h2] = a0.x; pp[2 * h2 + 1] = a0.y; ss[2 * h2] = a1.x; ss[2 * h2 + 1] = a1.y;
+                pp[2 * h2] = a0.x; pp[2 * h2 + 1] = a0.y;
                 rr[2 * h2] = a2.x; rr[2 * h2 + 1] = a2.y; qq[2 * h2] = a3.x; qq[2 * h2 + 1] = a3.y;
             }
             F4 bb = zero4(), xo = zero4();

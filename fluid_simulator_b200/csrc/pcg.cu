@@ -35,7 +35,8 @@ struct PcgArgs {
     uint16_t* code;
     const float* u2[3];
     const float* dens;
-    double *p, *rhs, *r, *s, *q, *z;
+    double *p, *rhs, *r, *q, *z;
+    float* s;  // search direction, stored in fp32: A s and p += alpha s both use the stored value, so r = b - A p keeps holding to fp64 rounding
     float* p_prev;     // last step's converged pressure (fp32 copy) for the extrapolated warm start
     const float* z32;  // multigrid result (fp32) when the multigrid preconditioner is active, else nullptr
     PcgScalars* sc;
@@ -173,7 +174,7 @@ __global__ void __launch_bounds__(PT) start_kernel(PcgArgs a) {
             acc[0] += z * r;
         }
         if (JACOBI) a.z[c] = z;
-        a.s[c] = z;
+        a.s[c] = (float)z;
     }
     double out[1];
     if (grid_reduce<1, 0>(acc, a.partials, a.counter, out)) a.sc->sigma = out[0];
@@ -192,14 +193,15 @@ __global__ void __launch_bounds__(PT) spmv_kernel(PcgArgs a) {
             const ushort2 cd = *reinterpret_cast<const ushort2*>(a.code + c);
             const unsigned c0 = cd.x, c1 = cd.y;
             if ((c0 | c1) & CODE_ACTIVE) {
-                const double2 sc = *reinterpret_cast<const double2*>(a.s + c);
+                auto ld2 = [&](const float* src) { const float2 v = *reinterpret_cast<const float2*>(src); return make_double2((double)v.x, (double)v.y); };
+                const double2 sc = ld2(a.s + c);
                 const unsigned any = c0 | c1;
                 double2 ym = {0, 0}, yp = {0, 0}, zm = {0, 0}, zp = {0, 0};
-                if (any & 4u) ym = *reinterpret_cast<const double2*>(a.s + c - sy);
-                if (any & 8u) yp = *reinterpret_cast<const double2*>(a.s + c + sy);
-                if (any & 16u) zm = *reinterpret_cast<const double2*>(a.s + c - sz);
-                if (any & 32u) zp = *reinterpret_cast<const double2*>(a.s + c + sz);
-                const double xl = (c0 & 1u) ? a.s[c - 1] : 0.0, xr = (c1 & 2u) ? a.s[c + 2] : 0.0;
+                if (any & 4u) ym = ld2(a.s + c - sy);
+                if (any & 8u) yp = ld2(a.s + c + sy);
+                if (any & 16u) zm = ld2(a.s + c - sz);
+                if (any & 32u) zp = ld2(a.s + c + sz);
+                const double xl = (c0 & 1u) ? (double)a.s[c - 1] : 0.0, xr = (c1 & 2u) ? (double)a.s[c + 2] : 0.0;
                 double2 q = {0, 0};
                 if (c0 & CODE_ACTIVE) {
                     double n = xl;
@@ -231,14 +233,14 @@ __global__ void __launch_bounds__(PT) spmv_kernel(PcgArgs a) {
             if (cc >= a.g.nc) break;
             const unsigned cd = a.code[cc];
             if (!(cd & CODE_ACTIVE)) continue;
-            const double sc = a.s[cc];
+            const double sc = (double)a.s[cc];
             double n = 0.0;
-            if (cd & 1u) n += a.s[cc - 1];
-            if (cd & 2u) n += a.s[cc + 1];
-            if (cd & 4u) n += a.s[cc - sy];
-            if (cd & 8u) n += a.s[cc + sy];
-            if (cd & 16u) n += a.s[cc - sz];
-            if (cd & 32u) n += a.s[cc + sz];
+            if (cd & 1u) n += (double)a.s[cc - 1];
+            if (cd & 2u) n += (double)a.s[cc + 1];
+            if (cd & 4u) n += (double)a.s[cc - sy];
+            if (cd & 8u) n += (double)a.s[cc + sy];
+            if (cd & 16u) n += (double)a.s[cc - sz];
+            if (cd & 32u) n += (double)a.s[cc + sz];
             const double q = scale * ((double)code_ns(cd) * sc - n);
             a.q[cc] = q;
             acc[0] += sc * q;
@@ -260,9 +262,9 @@ __global__ void __launch_bounds__(PT, 4) spmv4_kernel(PcgArgs a) {
         const ushort4 t = *reinterpret_cast<const ushort4*>(a.code + c);
         double sc[4], ym[4] = {0, 0, 0, 0}, yp[4] = {0, 0, 0, 0}, zm[4] = {0, 0, 0, 0}, zp[4] = {0, 0, 0, 0};
         double xl = 0.0, xr = 0.0;
-        auto ld = [&](double* dst, const double* src) {
-            const double2 u = *reinterpret_cast<const double2*>(src), v = *reinterpret_cast<const double2*>(src + 2);
-            dst[0] = u.x; dst[1] = u.y; dst[2] = v.x; dst[3] = v.y;
+        auto ld = [&](double* dst, const float* src) {
+            const float4 u = *reinterpret_cast<const float4*>(src);
+            dst[0] = (double)u.x; dst[1] = (double)u.y; dst[2] = (double)u.z; dst[3] = (double)u.w;
         };
         const unsigned cd[4] = {t.x, t.y, t.z, t.w};
         const unsigned any = cd[0] | cd[1] | cd[2] | cd[3];
@@ -272,7 +274,7 @@ __global__ void __launch_bounds__(PT, 4) spmv4_kernel(PcgArgs a) {
         if (any & 8u) ld(yp, a.s + c + sy);
         if (any & 16u) ld(zm, a.s + c - sz);
         if (any & 32u) ld(zp, a.s + c + sz);
-        xl = (cd[0] & 1u) ? a.s[c - 1] : 0.0; xr = (cd[3] & 2u) ? a.s[c + 4] : 0.0;
+        xl = (cd[0] & 1u) ? (double)a.s[c - 1] : 0.0; xr = (cd[3] & 2u) ? (double)a.s[c + 4] : 0.0;
         double q[4] = {0, 0, 0, 0};
 #pragma unroll
         for (int i = 0; i < 4; i++)
@@ -310,7 +312,7 @@ __global__ void __launch_bounds__(PT) update_kernel(PcgArgs a) {
             if (c >= a.g.nc) break;
             const unsigned code = a.code[c];
             if (!(code & CODE_ACTIVE)) continue;
-            a.p[c] += alpha * a.s[c];
+            a.p[c] += alpha * (double)a.s[c];
             const double r = a.r[c] - alpha * a.q[c];
             a.r[c] = r;
             acc[1] = fmax(acc[1], fabs(r));
@@ -368,7 +370,7 @@ __global__ void __launch_bounds__(PT) direction_kernel(PcgArgs a) {
         const int64_t c = c0 + k;
         if (c >= a.g.nc) break;
         if (!(a.code[c] & CODE_ACTIVE)) continue;
-        a.s[c] = a.s[c] * beta + (a.z32 ? (double)a.z32[c] : a.z[c]);
+        a.s[c] = (float)((double)a.s[c] * beta + (a.z32 ? (double)a.z32[c] : a.z[c]));
     }
 }
 // loop condition of the device-side WHILE graph: keep iterating until an update kernel has set the done flag
