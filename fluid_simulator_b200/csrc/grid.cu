@@ -33,15 +33,28 @@ __device__ __forceinline__ unsigned obstacle_mask(const DevObstacle* obs, int no
     return m;
 }
 
+// one thread per cell on a (32,4,2) block / 3-D grid: (x, y, z) come straight from the block and thread indices
+// (a flat index would cost two 64-bit divisions per thread, which made these short kernels issue-bound)
+constexpr int CBX = 32, CBY = 4, CBZ = 2;
+__device__ __forceinline__ bool cell_xyz(const GridDims& g, int& x, int& y, int& z, int64_t& c) {
+    x = blockIdx.x * CBX + threadIdx.x;
+    y = blockIdx.y * CBY + threadIdx.y;
+    z = blockIdx.z * CBZ + threadIdx.z;
+    c = ((int64_t)z * g.gy + y) * g.gx + x;
+    return x < g.gx && y < g.gy && z < g.gz;
+}
+inline dim3 cell_grid(const GridDims& g) { return dim3(div_up(g.gx, CBX), div_up(g.gy, CBY), div_up(g.gz, CBZ)); }
+inline dim3 cell_block() { return dim3(CBX, CBY, CBZ); }
+
 __device__ __forceinline__ bool is_border(const GridDims& g, int x, int y, int z, int top_solid) {
     return x == 0 || x == g.gx - 1 || y == 0 || (top_solid && y == g.gy - 1) || z == 0 || z == g.gz - 1;
 }
 
 __global__ void __launch_bounds__(256) classify_kernel(GridDims g, const uint32_t* __restrict__ cnt, const DevObstacle* obs,
                                                         int nobs, int top_solid, uint8_t* __restrict__ flags) {
-    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= g.nc) return;
-    const int x = (int)(c % g.gx), y = (int)((c / g.gx) % g.gy), z = (int)(c / ((int64_t)g.gx * g.gy));
+    int x, y, z;
+    int64_t c;
+    if (!cell_xyz(g, x, y, z, c)) return;
     const bool has = cnt[c] > 0;
     int type = has ? FSIM_CELL_WATER : FSIM_CELL_AIR;
     if (nobs > 0 && obstacle_mask(obs, nobs, x, y, z)) type = FSIM_CELL_SOLID;
@@ -83,9 +96,9 @@ __device__ __forceinline__ int face_obstacle(unsigned mA, unsigned mB, bool hasA
 
 __global__ void __launch_bounds__(256) finalize_kernel(FinalizeArgs a) {
     const GridDims& g = a.g;
-    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= g.nc) return;
-    const int x = (int)(c % g.gx), y = (int)((c / g.gx) % g.gy), z = (int)(c / ((int64_t)g.gx * g.gy));
+    int x, y, z;
+    int64_t c;
+    if (!cell_xyz(g, x, y, z, c)) return;
     const uint8_t f0 = a.flags[c];
     const int t0 = f0 & FL_TYPE_MASK;
     const int nx[3] = {x + 1, x, x}, ny[3] = {y, y + 1, y}, nz[3] = {z, z, z + 1};
@@ -133,9 +146,9 @@ struct ApplyArgs {
 
 __global__ void __launch_bounds__(256) pressure_apply_kernel(ApplyArgs a) {
     const GridDims& g = a.g;
-    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= g.nc) return;
-    const int x = (int)(c % g.gx), y = (int)((c / g.gx) % g.gy), z = (int)(c / ((int64_t)g.gx * g.gy));
+    int x, y, z;
+    int64_t c;
+    if (!cell_xyz(g, x, y, z, c)) return;
     const int t0 = a.flags[c] & FL_TYPE_MASK;
     if (t0 == FSIM_CELL_SOLID) return;
     const double p0 = (t0 == FSIM_CELL_WATER) ? a.p[c] : 0.0;
@@ -162,12 +175,12 @@ struct ExtrapArgs {
 
 __global__ void __launch_bounds__(256) extrapolate_kernel(ExtrapArgs a) {
     const GridDims& g = a.g;
-    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= g.nc) return;
+    int x, y, z;
+    int64_t c;
+    if (!cell_xyz(g, x, y, z, c)) return;
     const uint8_t f0 = a.flags[c];
     const int valid0 = (f0 & FL_VALID_MASK) >> FL_VALID_SHIFT;
     if (valid0 <= a.it) return;
-    const int x = (int)(c % g.gx), y = (int)((c / g.gx) % g.gy), z = (int)(c / ((int64_t)g.gx * g.gy));
     int cntv = 0;
     float s0 = 0.f, s1 = 0.f, s2 = 0.f;
     // neighbour order of the reference: -x,+x,-y,+y,-z,+z (macGrid.cpp:313-324)
@@ -206,9 +219,9 @@ struct BasicArgs {
 
 __global__ void __launch_bounds__(256) basic_sor_kernel(BasicArgs a) {
     const GridDims& g = a.g;
-    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= g.nc) return;
-    const int x = (int)(c % g.gx), y = (int)((c / g.gx) % g.gy), z = (int)(c / ((int64_t)g.gx * g.gy));
+    int x, y, z;
+    int64_t c;
+    if (!cell_xyz(g, x, y, z, c)) return;
     if (((x + y + z) & 1) != a.parity) return;
     if (x < 1 || y < 1 || z < 1 || x >= g.gx - 1 || y >= g.gy - 1 || z >= g.gz - 1) return;
     if ((a.flags[c] & FL_TYPE_MASK) != FSIM_CELL_WATER) return;
@@ -291,14 +304,14 @@ __global__ void __launch_bounds__(256) grid_upload_kernel(UpArgs a) {
 
 int k_classify(fsim* h, double dt) {
     const GridDims& g = h->g;
-    { KScope ks(h, K_CLASSIFY); classify_kernel<<<div_up(g.nc, 256), 256, 0, h->stream>>>(g, h->cnt, h->d_obs, h->nobs, h->par.top_solid, h->flags); }
+    { KScope ks(h, K_CLASSIFY); classify_kernel<<<cell_grid(h->g), cell_block(), 0, h->stream>>>(g, h->cnt, h->d_obs, h->nobs, h->par.top_solid, h->flags); }
     FinalizeArgs a;
     a.g = g; a.flags = h->flags;
     for (int ax = 0; ax < 3; ax++) { a.u[ax] = h->u[ax]; a.u2[ax] = h->u2[ax]; a.wsum[ax] = h->wsum[ax]; }
     a.obs = h->d_obs; a.nobs = h->nobs; a.top_solid = h->par.top_solid; a.post_only = 0;
     // config.gravity is a float, dt a double: gravityEnabled ? gravity * dt : 0 (simulator.cpp:85)
     a.gdt = h->par.gravity_enabled ? (float)((double)h->par.gravity * dt) : 0.f;
-    { KScope ks(h, K_FINALIZE); finalize_kernel<<<div_up(g.nc, 256), 256, 0, h->stream>>>(a); }
+    { KScope ks(h, K_FINALIZE); finalize_kernel<<<cell_grid(h->g), cell_block(), 0, h->stream>>>(a); }
     FSIM_CHECK_LAUNCH(h);
     return FSIM_OK;
 }
@@ -311,7 +324,7 @@ int k_post_p2g_only(fsim* h, double gravity_increment) {
     for (int ax = 0; ax < 3; ax++) { a.u[ax] = h->u[ax]; a.u2[ax] = h->u2[ax]; a.wsum[ax] = h->wsum[ax]; }
     a.obs = h->d_obs; a.nobs = 0; a.top_solid = h->par.top_solid; a.post_only = 1;
     a.gdt = (float)gravity_increment;
-    { KScope ks(h, K_FINALIZE); finalize_kernel<<<div_up(g.nc, 256), 256, 0, h->stream>>>(a); }
+    { KScope ks(h, K_FINALIZE); finalize_kernel<<<cell_grid(h->g), cell_block(), 0, h->stream>>>(a); }
     FSIM_CHECK_LAUNCH(h);
     return FSIM_OK;
 }
@@ -322,7 +335,7 @@ int k_pressure_apply(fsim* h, double dt) {
     a.g = g; a.flags = h->flags; a.p = h->p;
     for (int ax = 0; ax < 3; ax++) a.u2[ax] = h->u2[ax];
     a.scale = dt / (h->par.fluid_density * h->info.cell_d[0]);
-    { KScope ks(h, K_APPLY); pressure_apply_kernel<<<div_up(g.nc, 256), 256, 0, h->stream>>>(a); }
+    { KScope ks(h, K_APPLY); pressure_apply_kernel<<<cell_grid(h->g), cell_block(), 0, h->stream>>>(a); }
     FSIM_CHECK_LAUNCH(h);
     return FSIM_OK;
 }
@@ -338,7 +351,7 @@ int k_project_basic(fsim* h, int* iterations) {
         for (int colour = 1; colour >= 0; colour--) {  // odd cells first (z starts at 1 + (x+y)%2), then even
             a.parity = colour;
             KScope ks(h, K_APPLY);
-            basic_sor_kernel<<<div_up(g.nc, 256), 256, 0, h->stream>>>(a);
+            basic_sor_kernel<<<cell_grid(h->g), cell_block(), 0, h->stream>>>(a);
         }
     FSIM_CHECK_LAUNCH(h);
     h->solve.iterations = n; h->solve.early_out = 0; h->solve.rhs_sumsq = 0; h->solve.residual_max = 0; h->solve.fluid_cells = 0;
@@ -356,7 +369,7 @@ int k_extrapolate(fsim* h) {
     for (int it = 0; it < 2; it++) {
         a.it = it;
         KScope ks(h, K_EXTRAP);
-        extrapolate_kernel<<<div_up(g.nc, 256), 256, 0, h->stream>>>(a);
+        extrapolate_kernel<<<cell_grid(h->g), cell_block(), 0, h->stream>>>(a);
     }
     FSIM_CHECK_LAUNCH(h);
     return FSIM_OK;
