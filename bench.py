@@ -99,6 +99,8 @@ def run_reference(args):
     if refsim.available():
         sc = scenes.dam_break_3d(n, abi.FLIP)
         sim = refsim.RefSim(sc.dims, sc.resolution, sc.two_d, sc.particle_radius)
+        # all host threads this process may use (torchrun exports OMP_NUM_THREADS=1: override it for the reference arm)
+        sim.set_omp_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
         cores = sim.omp_threads()
     else:  # the compiled reference always travels with the repo; the plain-C restatement is the documented stand-in
         from oracle.oracle import OracleSim
