@@ -3,7 +3,7 @@
 // simulator.cpp:314-333, 362-366).
 //
 // Design: particles are cell-binned, so the scatter is tile-local.  One CTA owns a
-// 32x4x4 tile of cells, one THREAD owns one cell and walks that cell's particles sequentially.  All
+// 32x4x2 tile of cells (4 CTAs / SM; 32x4x4 with 2 CTAs / SM was 4-6 % slower: more warps per barrier), one THREAD owns one cell and walks that cell's particles sequentially.  All
 // particles of a cell touch the same 2x3x3 (staggered axis) / 3x3x3 (cell-centred) node neighbourhood,
 // so the thread accumulates the whole neighbourhood in REGISTERS with packed fp32x2 FMAs (FFMA2; hat weights are
 // exactly 0 outside the 2x2x2 bracket the reference picks, macGrid.cpp:142-148) and only then folds it into a shared-memory
@@ -15,7 +15,7 @@
 
 namespace {
 
-constexpr int TX = 32, TY = 4, TZ = 4;
+constexpr int TX = 32, TY = 4, TZ = 2;
 constexpr int SX = TX + 2, SY = TY + 2, SZ = TZ + 2;
 constexpr int SN = SX * SY * SZ;  // nodes per channel in the shared tile
 constexpr int NTHREADS = TX * TY * TZ;
@@ -200,7 +200,7 @@ __device__ __forceinline__ void p2g_density_pass(const P2GArgs& a, const Src& sr
 // 1.54 ms, APIC 2.1 ms) and the walk reads
 // conflict-free shared memory; the accumulator tile shrinks to the two channels of the running pass and is flushed
 // after every pass.  Particles beyond the staging capacity (tiles denser than 8 per cell) are read from global memory.
-constexpr int CAP = 4096;               // staged particles per tile
+constexpr int CAP = 2048;               // staged particles per tile (8 per cell)
 constexpr int CAPP = CAP + CAP / 8;     // with the bank padding of swz()
 constexpr size_t STAGED_SMEM = (size_t)(2 * SN + 4 * CAPP) * sizeof(float);
 
@@ -240,7 +240,7 @@ __device__ __forceinline__ void flush_pass(const P2GArgs& a, float* s_val, float
 }
 
 template <bool APIC>
-__global__ void __launch_bounds__(NTHREADS, 2) p2g_kernel(P2GArgs a) {
+__global__ void __launch_bounds__(NTHREADS, 4) p2g_kernel(P2GArgs a) {
     extern __shared__ float dyn[];
     __shared__ uint32_t row_beg[TY * TZ], row_off[TY * TZ + 1];
     float* s_val = dyn;
