@@ -292,7 +292,7 @@ int fsim_create(const FsimGridDesc* desc, fsim_t** out) {
     { const char* e = getenv("FSIM_NO_GRAPH"); h->use_graph = !(e && e[0] == '1'); }
     { const char* e = getenv("FSIM_NO_WARM_START"); h->warm_start = !(e && e[0] == '1'); }
     { const char* e = getenv("FSIM_WARM_EXTRAPOLATE"); h->warm_extrapolate = !(e && e[0] == '0'); }
-    h->warm_history = 0; h->p_prev = nullptr;
+    h->warm_history = 0; h->p_prev = nullptr; h->mg_tail_cluster = 0;
     h->status_host = nullptr; h->status_dev = nullptr;
     { const char* e = getenv("FSIM_PRECOND"); h->use_mg = !(e && strcmp(e, "jacobi") == 0); }
     memset(h->prof_ms, 0, sizeof(h->prof_ms)); memset(h->prof_n, 0, sizeof(h->prof_n)); memset(h->launch_n, 0, sizeof(h->launch_n));

@@ -126,6 +126,7 @@ struct fsim {
     double mg_inv_scale;                   // 1 / (dt / (rho h^2)): the hierarchy works on the integer-weight Laplacian
     std::vector<MgLevel*> mg;
     int mg_tail_first;                     // levels >= this run inside the single-cluster tail kernel
+    int mg_tail_cluster;                   // CTAs of that cluster (0: not probed yet)
     PcgScalars* scal;                      // device
     PcgScalars* scal_host;                 // pinned
     PcgHostStatus* status_host;            // pinned + mapped

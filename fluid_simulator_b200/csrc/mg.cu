@@ -38,7 +38,7 @@ constexpr float OM_A = 1.389f, OM_B = 0.5617f;   // 2-step Chebyshev weights for
 constexpr float OVER = 1.8f;
 constexpr int PRE = 2, POST = 2;
 constexpr int W_FIRST = 2, W_LAST = 2; // levels W_FIRST..W_LAST are visited twice per visit of their parent
-constexpr int COARSE_SWEEPS = 30;
+constexpr int COARSE_SWEEPS = 30;    // damped Jacobi sweeps on the coarsest level (12 is 0.05 ms/step cheaper at 256^3 but costs iterations elsewhere: 128^3 cold 8 -> 10)
 constexpr int COARSE_MAX = 1024;     // the coarsest level fits one CTA
 
 struct Lv {  // kernel view of a level
@@ -500,12 +500,13 @@ __global__ void __launch_bounds__(256) mg_buildn_kernel(Lv L, Lv C, float* __res
 
 // ---- the small end of the hierarchy in ONE launch -----------------------------------------------------------------
 // Levels with <= TAIL_MAX_CELLS cells are latency-bound (a separate launch per sweep costs more than the sweep), so one
-// thread-block cluster runs their whole V(2,2) sub-cycle: all CTAs stride over the cells of a level, phases are separated
+// thread-block cluster (16 CTAs = 16 K threads) runs their whole V(2,2) sub-cycle: all CTAs stride over the cells of a level, phases are separated
 // by cluster barriers (release/acquire at cluster scope; data is exchanged through global memory, i.e. L2), and the
 // coarsest level is iterated by CTA 0 in shared memory.
 constexpr int TAIL_MAX_CELLS = 40000;
 constexpr int TAIL_MAX_LEVELS = 8;
-constexpr int TAIL_CLUSTER = 8;
+constexpr int TAIL_CLUSTER = 16;     // non-portable cluster size (one GPC); 8 is used when 16 cannot be scheduled
+constexpr int TAIL_CLUSTER_PORTABLE = 8;
 constexpr int TAIL_THREADS = 1024;
 
 struct TailLevel { Lv L; float *xa, *xb, *b; };
@@ -712,12 +713,27 @@ int cycle(fsim* h, int l, bool zero_guess, float** result, bool first_done = fal
         ta.sc = sc;
         ta.zero_guess = zero_guess ? 1 : 0;
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(TAIL_CLUSTER);
+        if (h->mg_tail_cluster == 0) {  // first use: can a 16-CTA cluster of 1024-thread CTAs be co-scheduled on this device?
+            h->mg_tail_cluster = TAIL_CLUSTER_PORTABLE;
+            if (cudaFuncSetAttribute(mg_tail_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+                cudaLaunchConfig_t q = {};
+                q.gridDim = dim3(TAIL_CLUSTER); q.blockDim = dim3(TAIL_THREADS);
+                cudaLaunchAttribute qa[1];
+                qa[0].id = cudaLaunchAttributeClusterDimension;
+                qa[0].val.clusterDim.x = TAIL_CLUSTER; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+                q.attrs = qa; q.numAttrs = 1;
+                int nclusters = 0;
+                if (cudaOccupancyMaxActiveClusters(&nclusters, mg_tail_kernel, &q) == cudaSuccess && nclusters >= 1) h->mg_tail_cluster = TAIL_CLUSTER;
+            }
+            cudaGetLastError();
+        }
+        const int tail_cluster = h->mg_tail_cluster;
+        cfg.gridDim = dim3(tail_cluster);
         cfg.blockDim = dim3(TAIL_THREADS);
         cfg.stream = h->stream;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = TAIL_CLUSTER; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        at[0].val.clusterDim.x = tail_cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
         KScope ks(h, K_MG2);
         FSIM_CUDA(h, cudaLaunchKernelEx(&cfg, mg_tail_kernel, ta));
