@@ -319,11 +319,14 @@ int fsim_create(const FsimGridDesc* desc, fsim_t** out) {
     A(dev_alloc(h, &h->scan_block, (size_t)((std::max<int64_t>(g.nc, int64_t(1) << 31)) / 4096 + 2)));
     h->stage = nullptr; h->stage_bytes = STAGE_BYTES;
     if (!rc && cudaMalloc(&h->stage, h->stage_bytes) != cudaSuccess) rc = fsim_fail(h, FSIM_ERR_CUDA, "staging alloc failed");
-    h->scal_host = nullptr;
+    h->scal_host = nullptr; h->result_host = nullptr; h->result_dev = nullptr;
     if (!rc && cudaMallocHost((void**)&h->scal_host, sizeof(PcgScalars)) != cudaSuccess) rc = fsim_fail(h, FSIM_ERR_CUDA, "pinned alloc failed");
     if (!rc && (cudaHostAlloc((void**)&h->status_host, sizeof(PcgHostStatus), cudaHostAllocMapped) != cudaSuccess ||
                 cudaHostGetDevicePointer((void**)&h->status_dev, (void*)h->status_host, 0) != cudaSuccess))
         rc = fsim_fail(h, FSIM_ERR_CUDA, "mapped status alloc failed");
+    if (!rc && (cudaHostAlloc((void**)&h->result_host, sizeof(PcgScalars), cudaHostAllocMapped) != cudaSuccess ||
+                cudaHostGetDevicePointer((void**)&h->result_dev, (void*)h->result_host, 0) != cudaSuccess))
+        rc = fsim_fail(h, FSIM_ERR_CUDA, "mapped result alloc failed");
     if (!rc) { h->status_host->done = 0; h->status_host->it_done = 0; }
     for (int i = 0; i < 16 && !rc; i++)
         if (cudaEventCreate(&h->ev[i]) != cudaSuccess) rc = fsim_fail(h, FSIM_ERR_CUDA, "event create failed");
@@ -367,6 +370,7 @@ int fsim_destroy(fsim_t* h) {
     for (const ProfRec& r : h->prof_recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     for (cudaEvent_t e : h->prof_free) cudaEventDestroy(e);
     if (h->scal_host) cudaFreeHost(h->scal_host);
+    if (h->result_host) cudaFreeHost(h->result_host);
     if (h->status_host) cudaFreeHost((void*)h->status_host);
     if (h->pcg_graph) cudaGraphExecDestroy(h->pcg_graph);
     for (int i = 0; i < 16; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);

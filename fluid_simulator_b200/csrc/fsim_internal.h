@@ -128,7 +128,9 @@ struct fsim {
     int mg_tail_first;                     // levels >= this run inside the single-cluster tail kernel
     int mg_tail_cluster;                   // CTAs of that cluster (0: not probed yet)
     PcgScalars* scal;                      // device
-    PcgScalars* scal_host;                 // pinned
+    PcgScalars* scal_host;                 // pinned (parameter upload)
+    PcgScalars* result_host;               // pinned + mapped: the solve's scalars, written by publish_kernel
+    PcgScalars* result_dev;                // device alias of result_host
     PcgHostStatus* status_host;            // pinned + mapped
     PcgHostStatus* status_dev;             // device alias of status_host
     cudaGraphExec_t pcg_graph;             // device-side WHILE loop around one PCG iteration (SpMV, update, multigrid cycle, direction)
