@@ -15,6 +15,7 @@
 //    MIC(0) needs 80..155.
 //  * fp32 throughout (it only has to be an approximate inverse); the CG recurrence around it is fp64 (pcg.cu).
 // Level-0 kernels process 4 cells per thread (float4 / ushort4); small levels run in one thread-block-cluster launch.
+#include <algorithm>
 #include <cooperative_groups.h>
 
 #include "fsim_internal.h"
@@ -275,15 +276,10 @@ __global__ void __launch_bounds__(256) mg_first4_kernel(Lv L, const double* __re
     }
 }
 
-// DOT: the last sweep of the cycle also accumulates sigma' = z.r = scale * z.b (fp64 accumulation; saves a pass over z and r.
-// The fp32 rounding of r inside b perturbs sigma' by ~1e-8 relative: it only enters alpha and beta, never p or r)
-template <bool DOT>
 __global__ void __launch_bounds__(256) mg_jacobi4_kernel(Lv L, PcgScalars* __restrict__ sc, const float* __restrict__ b, const float* __restrict__ xin,
-                                                         float* __restrict__ xout, const double* __restrict__ r64, double* partials,
-                                                         unsigned int* counter, float om) {
+                                                         float* __restrict__ xout, float om) {
     if (sc->done) return;
     int64_t c; unsigned cd[4];
-    double acc[1] = {0.0};
     if (group_of(L, c, cd) && ((cd[0] | cd[1] | cd[2] | cd[3]) & CODE_ACTIVE)) {
         F4 xo = zero4();
         const Stencil4 s = load_stencil4(L, xin, c, cd);
@@ -296,17 +292,42 @@ __global__ void __launch_bounds__(256) mg_jacobi4_kernel(Lv L, PcgScalars* __res
                 xo.v[i] = d > 0.f ? xi + om * (bb.v[i] - (d * xi - off4(s, i, cd[i]))) / d : 0.f;
             }
         st4(xout + c, xo);
-        if (DOT) {  // b = fp32(r / scale) is already in registers: 8 B/cell less than re-reading the fp64 residual
+    }
+}
+
+// The last sweep of the cycle also accumulates sigma' = z.r = scale * z.b (fp64 accumulation; saves a pass over z and r.
+// The fp32 rounding of r inside b perturbs sigma' by ~1e-8 relative: it only enters alpha and beta, never p or r).
+// Persistent form: ~8 CTAs per SM walk the (32,4,2)-thread tiles of the grid, so the grid-wide reduction sees ~1.2 K
+// partials instead of 16 K -- with one CTA per tile its fence + arrival atomic per CTA cost 30 us on top of the 37 us sweep.
+__global__ void __launch_bounds__(256) mg_jacobi4_dot_kernel(Lv L, PcgScalars* __restrict__ sc, const float* __restrict__ b, const float* __restrict__ xin,
+                                                             float* __restrict__ xout, double* partials, unsigned int* counter, float om,
+                                                             int ntx, int nty, int ntiles) {
+    if (sc->done) return;
+    double acc[1] = {0.0};
+    const int tx = threadIdx.x & 31, ty = (threadIdx.x >> 5) & 3, tz = threadIdx.x >> 7;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int bx = t % ntx, by = (t / ntx) % nty, bz = t / (ntx * nty);
+        const int x = (bx * 32 + tx) * 4, y = by * 4 + ty, z = bz * 2 + tz;
+        if (x >= L.gx || y >= L.gy || z >= L.gz) continue;
+        const int64_t c = ((int64_t)z * L.gy + y) * L.gx + x;
+        const ushort4 tc = *reinterpret_cast<const ushort4*>(L.code + c);
+        const unsigned cd[4] = {tc.x, tc.y, tc.z, tc.w};
+        if (!((cd[0] | cd[1] | cd[2] | cd[3]) & CODE_ACTIVE)) continue;
+        F4 xo = zero4();
+        const Stencil4 s = load_stencil4(L, xin, c, cd);
+        const F4 bb = ld4(b + c);
 #pragma unroll
-            for (int i = 0; i < 4; i++)
-                if (cd[i] & CODE_ACTIVE) acc[0] += (double)xo.v[i] * (double)bb.v[i];
-        }
+        for (int i = 0; i < 4; i++)
+            if (cd[i] & CODE_ACTIVE) {
+                const float d = (float)((cd[i] >> 6) & 7u);
+                const float xi = s.c.v[i];
+                xo.v[i] = d > 0.f ? xi + om * (bb.v[i] - (d * xi - off4(s, i, cd[i]))) / d : 0.f;
+                acc[0] += (double)xo.v[i] * (double)bb.v[i];
+            }
+        st4(xout + c, xo);
     }
-    if (DOT) {
-        double out[1];
-        const unsigned bid = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
-        if (grid_reduce<1, 0>(acc, partials, counter, out, bid, gridDim.x * gridDim.y * gridDim.z)) sc->sigma_new = out[0] * sc->scale;
-    }
+    double out[1];
+    if (grid_reduce<1, 0>(acc, partials, counter, out)) sc->sigma_new = out[0] * sc->scale;
 }
 
 // CG update fused with the first smoothing sweep of the next cycle (level 0, linear chunks of 4-cell groups):
@@ -756,7 +777,7 @@ int cycle(fsim* h, int l, bool zero_guess, float** result, bool first_done = fal
                 else mg_first_kernel<false><<<grid_of(m, blk), blk, 0, h->stream>>>(L, nullptr, sc, m->b, cur);
             } else {
                 const float om = s == 0 ? OM_A : OM_B;
-                if (v4) mg_jacobi4_kernel<false><<<grd4, blk4, 0, h->stream>>>(L, h->scal, m->b, cur, oth, nullptr, nullptr, nullptr, om);
+                if (v4) mg_jacobi4_kernel<<<grd4, blk4, 0, h->stream>>>(L, h->scal, m->b, cur, oth, om);
                 else if (fine) mg_jacobi_kernel<true><<<grid_of(m, blk), blk, 0, h->stream>>>(L, sc, m->b, cur, oth, om);
                 else mg_jacobi_kernel<false><<<grid_of(m, blk), blk, 0, h->stream>>>(L, sc, m->b, cur, oth, om);
                 float* t = cur; cur = oth; oth = t;
@@ -786,9 +807,11 @@ int cycle(fsim* h, int l, bool zero_guess, float** result, bool first_done = fal
         { float* t = cur; cur = oth; oth = t; }
         for (int s = 1; s < POST; s++) {
             const float om = OM_A;  // post-sweeps run the pre-sweep weights in reverse order (B in the fused prolongation sweep, then A)
-            if (v4 && with_dot && s == POST - 1)
-                mg_jacobi4_kernel<true><<<grd4, blk4, 0, h->stream>>>(L, h->scal, m->b, cur, oth, h->r, h->partials, h->red_counter, om);
-            else if (v4) mg_jacobi4_kernel<false><<<grd4, blk4, 0, h->stream>>>(L, h->scal, m->b, cur, oth, nullptr, nullptr, nullptr, om);
+            if (v4 && with_dot && s == POST - 1) {
+                const int ntiles = (int)(grd4.x * grd4.y * grd4.z);
+                mg_jacobi4_dot_kernel<<<std::min(ntiles, h->sm_count * 8), 256, 0, h->stream>>>(L, h->scal, m->b, cur, oth, h->partials, h->red_counter, om,
+                                                                                               (int)grd4.x, (int)grd4.y, ntiles);
+            } else if (v4) mg_jacobi4_kernel<<<grd4, blk4, 0, h->stream>>>(L, h->scal, m->b, cur, oth, om);
             else if (fine) mg_jacobi_kernel<true><<<grid_of(m, blk), blk, 0, h->stream>>>(L, sc, m->b, cur, oth, om);
             else mg_jacobi_kernel<false><<<grid_of(m, blk), blk, 0, h->stream>>>(L, sc, m->b, cur, oth, om);
             float* t = cur; cur = oth; oth = t;

@@ -447,7 +447,6 @@ int k_project(fsim* h, double dt, int* iterations) {
     a.warm = (h->warm_start && h->pressure_valid) ? (h->warm_extrapolate && h->warm_history >= 2 ? 2 : 1) : 0;
     a.p_prev = h->warm_extrapolate ? h->p_prev : nullptr;
     a.z32 = nullptr;
-    const int nb1 = div_up(g.nc, PT);        // one cell per thread
     const int nbv = div_up(g.nc, CHUNK);     // chunked kernels
     const bool vec = (g.gx % 2 == 0) && (g.nc % 2 == 0);
     const bool use_mg = mg_enabled(h);
@@ -464,7 +463,7 @@ int k_project(fsim* h, double dt, int* iterations) {
     h->status_host->it_done = 0;
     FSIM_CUDA(h, cudaMemcpyAsync(h->scal, sh, sizeof(PcgScalars), cudaMemcpyHostToDevice, h->stream));
 
-    { KScope ks(h, K_RHS); rhs_kernel<<<nb1, PT, 0, h->stream>>>(a); }
+    { KScope ks(h, K_RHS); rhs_kernel<<<div_up(g.nc, PT), PT, 0, h->stream>>>(a); }  // one cell per thread (a chunked loop was 25 % slower)
     if (a.warm) { KScope ks(h, K_RHS); residual_kernel<<<nbv, PT, 0, h->stream>>>(a); }
     if (use_mg) {
         int rc = mg_build(h);
