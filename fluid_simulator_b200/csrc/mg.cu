@@ -120,29 +120,31 @@ __global__ void __launch_bounds__(256) mg_jacobi_kernel(Lv L, const PcgScalars* 
 }
 
 // two pre-smoothing sweeps from a zero guess in one pass (coarse levels): x1 = omega b / d needs no neighbours, so
-// x2 = x1 + omega (b - A x1) / d only reads b and d at the 7 stencil points
+// x2 = x1 + omega (b - A x1) / d only reads b and d at the 7 stencil points.  All 20 loads are issued at once (the arrays
+// are padded by a plane of zeros, a zero weight masks an absent neighbour): one L2 round trip instead of three dependent
+// ones -- these levels are pure latency.
+template <class I>
+__device__ __forceinline__ float pre2_value(const Lv& L, const float* __restrict__ b, I c) {
+    const I nb[6] = {c - 1, c + 1, c - L.sy, c + L.sy, c - L.sz, c + L.sz};
+    const float w[6] = {L.wx[c - 1], L.wx[c], L.wy[c - L.sy], L.wy[c], L.wz[c - L.sz], L.wz[c]};
+    const float d = L.diag[c], bb = b[c];
+    float dn[6], bn[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) { dn[k] = L.diag[nb[k]]; bn[k] = b[nb[k]]; }
+    float off = 0.f;
+#pragma unroll
+    for (int k = 0; k < 6; k++)
+        if (w[k] > 0.f && dn[k] > 0.f) off += w[k] * (OM_A * bn[k] / dn[k]);
+    if (!(d > 0.f)) return 0.f;
+    const float xi = OM_A * bb / d;
+    return xi + OM_B * (bb - (d * xi - off)) / d;
+}
 __global__ void __launch_bounds__(256) mg_pre2_kernel(Lv L, const PcgScalars* __restrict__ sc, const float* __restrict__ b,
                                                       float* __restrict__ xout) {
     if (sc->done) return;
     int x, y, z; int64_t c;
     if (!cell_of(L, x, y, z, c)) return;
-    const float d = L.diag[c];
-    float v = 0.f;
-    if (d > 0.f) {
-        auto x1 = [&](int64_t cn) -> float { const float dn = L.diag[cn]; return dn > 0.f ? OM_A * b[cn] / dn : 0.f; };
-        const float w0 = L.wx[c - 1], w1 = L.wx[c], w2 = L.wy[c - L.sy], w3 = L.wy[c], w4 = L.wz[c - L.sz], w5 = L.wz[c];
-        float off = 0.f;
-        if (w0 > 0.f) off += w0 * x1(c - 1);
-        if (w1 > 0.f) off += w1 * x1(c + 1);
-        if (w2 > 0.f) off += w2 * x1(c - L.sy);
-        if (w3 > 0.f) off += w3 * x1(c + L.sy);
-        if (w4 > 0.f) off += w4 * x1(c - L.sz);
-        if (w5 > 0.f) off += w5 * x1(c + L.sz);
-        const float bb = b[c];
-        const float xi = OM_A * bb / d;
-        v = xi + OM_B * (bb - (d * xi - off)) / d;
-    }
-    xout[c] = v;
+    xout[c] = pre2_value(L, b, c);
 }
 
 // coarse right-hand side: b_c(I) = sum over the 2x2x2 children of (b - A x)   (restriction = P^T)
@@ -168,6 +170,32 @@ __global__ void __launch_bounds__(256) mg_restrict_kernel(Lv L, Lv C, const PcgS
                 s += b[c] - (d * xf[c] - off);
             }
     bc[cc] = s;
+}
+
+// the same restriction for the stored-operator levels with one FINE cell per thread (see t_restrict below): eight lanes per
+// coarse cell, three shuffles
+__global__ void __launch_bounds__(256) mg_restrict8_kernel(Lv L, Lv C, const PcgScalars* __restrict__ sc, const float* __restrict__ b,
+                                                            const float* __restrict__ xf, float* __restrict__ bc, int ncc) {
+    if (sc->done) return;
+    const int g = blockIdx.x * 256 + threadIdx.x;
+    const int cc = g >> 3, sub = g & 7;
+    float r = 0.f;
+    if (cc < ncc) {
+        const int X = cc % C.gx, Y = (cc / C.gx) % C.gy, Z = cc / (C.gx * C.gy);
+        const int x = 2 * X + (sub & 1), y = 2 * Y + ((sub >> 1) & 1), z = 2 * Z + (sub >> 2);
+        if (x < L.gx && y < L.gy && z < L.gz) {
+            const int64_t c = ((int64_t)z * L.gy + y) * L.gx + x;
+            if (active<false>(L, c)) {
+                float off;
+                const float d = row<false>(L, c, xf, &off);
+                r = b[c] - (d * xf[c] - off);
+            }
+        }
+    }
+    r += __shfl_xor_sync(0xffffffffu, r, 1);
+    r += __shfl_xor_sync(0xffffffffu, r, 2);
+    r += __shfl_xor_sync(0xffffffffu, r, 4);
+    if (sub == 0 && cc < ncc) bc[cc] = r;
 }
 
 // prolongation + over-corrected update fused with the first post-smoothing sweep:
@@ -554,62 +582,51 @@ __device__ void t_jacobi(const Lv& L, const float* b, const float* xin, float* x
 }
 __device__ void t_pre2(const Lv& L, const float* b, float* xout, int t0, int nt) {
     const int nc = L.gx * L.gy * L.gz;
-    for (int c = t0; c < nc; c += nt) {
-        const float d = L.diag[c];
-        float v = 0.f;
-        if (d > 0.f) {
-            const int nb[6] = {c - 1, c + 1, c - L.sy, c + L.sy, c - L.sz, c + L.sz};
-            const float w[6] = {L.wx[c - 1], L.wx[c], L.wy[c - L.sy], L.wy[c], L.wz[c - L.sz], L.wz[c]};
-            float off = 0.f;
-#pragma unroll
-            for (int k = 0; k < 6; k++)
-                if (w[k] > 0.f) { const float dn = L.diag[nb[k]]; if (dn > 0.f) off += w[k] * OM_A * b[nb[k]] / dn; }
-            const float bb = b[c], xi = OM_A * bb / d;
-            v = xi + OM_B * (bb - (d * xi - off)) / d;
-        }
-        xout[c] = v;
-    }
+    for (int c = t0; c < nc; c += nt) xout[c] = pre2_value(L, b, c);
+}
+// restriction with one FINE cell per thread: lanes 8k..8k+7 hold the 2x2x2 children of one coarse cell and fold their
+// residuals with three shuffles -- a thread per coarse cell walks its eight children one dependent L2 round trip after the
+// other, which made this the longest stage of the tail (measured 10-11 K cycles per call, now ~3 K)
+__device__ __forceinline__ float child_residual(const Lv& L, const Lv& C, const float* b, const float* xf, int cc, int sub) {
+    const int X = cc % C.gx, Y = (cc / C.gx) % C.gy, Z = cc / (C.gx * C.gy);
+    const int x = 2 * X + (sub & 1), y = 2 * Y + ((sub >> 1) & 1), z = 2 * Z + (sub >> 2);
+    if (x >= L.gx || y >= L.gy || z >= L.gz) return 0.f;
+    const int c = (z * L.gy + y) * L.gx + x;
+    float off;
+    const float d = t_row(L, c, xf, &off);
+    return d > 0.f ? b[c] - (d * xf[c] - off) : 0.f;
 }
 __device__ void t_restrict(const Lv& L, const Lv& C, const float* b, const float* xf, float* bc, int t0, int nt) {
     const int ncc = C.gx * C.gy * C.gz;
-    for (int cc = t0; cc < ncc; cc += nt) {
-        const int X = cc % C.gx, Y = (cc / C.gx) % C.gy, Z = cc / (C.gx * C.gy);
-        float s = 0.f;
-        for (int k = 0; k < 2; k++)
-            for (int j = 0; j < 2; j++)
-                for (int i = 0; i < 2; i++) {
-                    const int x = 2 * X + i, y = 2 * Y + j, z = 2 * Z + k;
-                    if (x >= L.gx || y >= L.gy || z >= L.gz) continue;
-                    const int c = (z * L.gy + y) * L.gx + x;
-                    float off;
-                    const float d = t_row(L, c, xf, &off);
-                    if (d > 0.f) s += b[c] - (d * xf[c] - off);
-                }
-        bc[cc] = s;
+    const int n8 = (ncc * 8 + 31) & ~31;  // whole warps take part in the shuffles
+    for (int g = t0; g < n8; g += nt) {
+        const int cc = g >> 3;
+        float r = cc < ncc ? child_residual(L, C, b, xf, cc, g & 7) : 0.f;
+        r += __shfl_xor_sync(0xffffffffu, r, 1);
+        r += __shfl_xor_sync(0xffffffffu, r, 2);
+        r += __shfl_xor_sync(0xffffffffu, r, 4);
+        if ((g & 7) == 0 && cc < ncc) bc[cc] = r;
     }
 }
 __device__ void t_prolong_jacobi(const Lv& L, const Lv& C, const float* b, const float* xin, const float* ec, float* xout, int t0, int nt) {
     const int nc = L.gx * L.gy * L.gz;
     for (int c = t0; c < nc; c += nt) {
-        const float d = L.diag[c];
-        float v = 0.f;
-        if (d > 0.f) {
-            const int x = c % L.gx, y = (c / L.gx) % L.gy, z = c / (L.gx * L.gy);
-            auto xc = [&](int xx, int yy, int zz, int cn) -> float {
-                return xin[cn] + OVER * ec[((zz >> 1) * C.gy + (yy >> 1)) * C.gx + (xx >> 1)];
-            };
-            const float w0 = L.wx[c - 1], w1 = L.wx[c], w2 = L.wy[c - L.sy], w3 = L.wy[c], w4 = L.wz[c - L.sz], w5 = L.wz[c];
-            float off = 0.f;
-            if (w0 > 0.f) off += w0 * xc(x - 1, y, z, c - 1);
-            if (w1 > 0.f) off += w1 * xc(x + 1, y, z, c + 1);
-            if (w2 > 0.f) off += w2 * xc(x, y - 1, z, c - L.sy);
-            if (w3 > 0.f) off += w3 * xc(x, y + 1, z, c + L.sy);
-            if (w4 > 0.f) off += w4 * xc(x, y, z - 1, c - L.sz);
-            if (w5 > 0.f) off += w5 * xc(x, y, z + 1, c + L.sz);
-            const float xi = xc(x, y, z, c);
-            v = xi + OM_B * (b[c] - (d * xi - off)) / d;
-        }
-        xout[c] = v;
+        const int x = c % L.gx, y = (c / L.gx) % L.gy, z = c / (L.gx * L.gy);
+        // every load up front (clamped coarse coordinates keep the addresses valid; zero weights mask what is not there)
+        const int cn[7] = {c, c - 1, c + 1, c - L.sy, c + L.sy, c - L.sz, c + L.sz};
+        const int xs[7] = {x, max(x - 1, 0), min(x + 1, L.gx - 1), x, x, x, x};
+        const int ys[7] = {y, y, y, max(y - 1, 0), min(y + 1, L.gy - 1), y, y};
+        const int zs[7] = {z, z, z, z, z, max(z - 1, 0), min(z + 1, L.gz - 1)};
+        const float w[7] = {0.f, L.wx[c - 1], L.wx[c], L.wy[c - L.sy], L.wy[c], L.wz[c - L.sz], L.wz[c]};
+        const float d = L.diag[c], bb = b[c];
+        float xc[7];
+#pragma unroll
+        for (int k = 0; k < 7; k++) xc[k] = xin[cn[k]] + OVER * ec[((zs[k] >> 1) * C.gy + (ys[k] >> 1)) * C.gx + (xs[k] >> 1)];
+        float off = 0.f;
+#pragma unroll
+        for (int k = 1; k < 7; k++)
+            if (w[k] > 0.f) off += w[k] * xc[k];
+        xout[c] = d > 0.f ? xc[0] + OM_B * (bb - (d * xc[0] - off)) / d : 0.f;
     }
 }
 
@@ -788,7 +805,8 @@ int cycle(fsim* h, int l, bool zero_guess, float** result, bool first_done = fal
         KScope ks(h, kid);
         if (v4) mg_restrict4_kernel<<<dim3(div_up(mc->gx, 2 * 32), div_up(mc->gy, 4), div_up(mc->gz, 2)), blk4, 0, h->stream>>>(L, C, sc, m->b, cur, mc->b);
         else if (fine) mg_restrict_kernel<true><<<grid_of(mc, blk), blk, 0, h->stream>>>(L, C, sc, m->b, cur, mc->b);
-        else mg_restrict_kernel<false><<<grid_of(mc, blk), blk, 0, h->stream>>>(L, C, sc, m->b, cur, mc->b);
+        else if (mc->nc > 100000) mg_restrict_kernel<false><<<grid_of(mc, blk), blk, 0, h->stream>>>(L, C, sc, m->b, cur, mc->b);  // enough threads as it is
+        else mg_restrict8_kernel<<<div_up(mc->nc * 8, 256), 256, 0, h->stream>>>(L, C, sc, m->b, cur, mc->b, (int)mc->nc);
     }
     float* ec = nullptr;
     const int visits = (l + 1 >= W_FIRST && l + 1 <= W_LAST && l + 1 < (int)h->mg.size() - 1) ? 2 : 1;
