@@ -207,13 +207,13 @@ __global__ void __launch_bounds__(256) mg_prolong_jacobi_kernel(Lv L, Lv C, cons
     int x, y, z; int64_t c;
     if (!cell_of(L, x, y, z, c)) return;
     float v = 0.f;
-    if (active<FINE>(L, c)) {
-        auto xc = [&](int xx, int yy, int zz, int64_t cn) -> float {
-            const int64_t pc = ((int64_t)(zz >> 1) * C.gy + (yy >> 1)) * C.gx + (xx >> 1);
-            return xin[cn] + OVER * ec[pc];
-        };
-        float d, off = 0.f;
-        if (FINE) {
+    auto xc = [&](int xx, int yy, int zz, int64_t cn) -> float {
+        const int64_t pc = ((int64_t)(zz >> 1) * C.gy + (yy >> 1)) * C.gx + (xx >> 1);
+        return xin[cn] + OVER * ec[pc];
+    };
+    if (FINE) {
+        if (active<FINE>(L, c)) {
+            float off = 0.f;
             const unsigned cd = L.code[c];
             if (cd & 1u) off += xc(x - 1, y, z, c - 1);
             if (cd & 2u) off += xc(x + 1, y, z, c + 1);
@@ -221,19 +221,24 @@ __global__ void __launch_bounds__(256) mg_prolong_jacobi_kernel(Lv L, Lv C, cons
             if (cd & 8u) off += xc(x, y + 1, z, c + L.sy);
             if (cd & 16u) off += xc(x, y, z - 1, c - L.sz);
             if (cd & 32u) off += xc(x, y, z + 1, c + L.sz);
-            d = (float)((cd >> 6) & 7u);
-        } else {
-            d = L.diag[c];
-            const float w0 = L.wx[c - 1], w1 = L.wx[c], w2 = L.wy[c - L.sy], w3 = L.wy[c], w4 = L.wz[c - L.sz], w5 = L.wz[c];
+            const float d = (float)((cd >> 6) & 7u);
+            const float xi = xc(x, y, z, c);
+            v = d > 0.f ? xi + OM_B * (b[c] - (d * xi - off)) / d : 0.f;
+        }
+    } else {
+        // first batch: everything that does not depend on the weights (the arrays are padded: all addresses valid)
+        const float d = L.diag[c], bb = b[c], xi = xc(x, y, z, c);
+        const float w0 = L.wx[c - 1], w1 = L.wx[c], w2 = L.wy[c - L.sy], w3 = L.wy[c], w4 = L.wz[c - L.sz], w5 = L.wz[c];
+        if (d > 0.f) {
+            float off = 0.f;
             if (w0 > 0.f) off += w0 * xc(x - 1, y, z, c - 1);
             if (w1 > 0.f) off += w1 * xc(x + 1, y, z, c + 1);
             if (w2 > 0.f) off += w2 * xc(x, y - 1, z, c - L.sy);
             if (w3 > 0.f) off += w3 * xc(x, y + 1, z, c + L.sy);
             if (w4 > 0.f) off += w4 * xc(x, y, z - 1, c - L.sz);
             if (w5 > 0.f) off += w5 * xc(x, y, z + 1, c + L.sz);
+            v = xi + OM_B * (bb - (d * xi - off)) / d;
         }
-        const float xi = xc(x, y, z, c);
-        v = d > 0.f ? xi + OM_B * (b[c] - (d * xi - off)) / d : 0.f;
     }
     xout[c] = v;
 }
