@@ -118,6 +118,10 @@ struct fsim {
     uint32_t* scan_block;        // scan scratch
     uint8_t* flags;
     uint16_t* code;                        // stencil codes of the current solve
+    void* hot;                             // one allocation: [codes | level-0 multigrid rhs], the solver's L2-persisting window
+    size_t hot_bytes, hot_code_bytes;
+    float* mg_b0;                          // level-0 multigrid right-hand side (inside hot)
+    bool l2_persist;                       // FSIM_L2_PERSIST=0 switches the L2 persistence window on the codes off
     float *u[3], *u2[3], *wsum[3], *dens;  // u: post-P2G v / accumulators; u2: working v2
     double *p, *rhs, *r, *q, *z;           // pressure + PCG vectors (fp64)
     float* s;                              // PCG search direction (fp32 storage, see pcg.cu)

@@ -727,6 +727,7 @@ int alloc_level(fsim* h, MgLevel* m, bool fine) {
         m->base[k] = nullptr;
         *dst[k] = nullptr;
         if (fine && k < 4) continue;  // level 0 is matrix-free
+        if (fine && k == 6) { *dst[k] = h->mg_b0; continue; }  // lives next to the codes (fsim_create)
         FSIM_CUDA(h, cudaMalloc((void**)&m->base[k], n * sizeof(float)));
         FSIM_CUDA(h, cudaMemsetAsync(m->base[k], 0, n * sizeof(float), h->stream));
         *dst[k] = m->base[k] + m->pad;
