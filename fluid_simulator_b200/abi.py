@@ -5,7 +5,7 @@ compiled reference (oracle/refsim.py), which deliberately reuses the same POD st
 """
 import ctypes as C
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_COMM = 0, 1, 2, 3, 4
 PIC, FLIP, APIC = 0, 1, 2
@@ -25,6 +25,17 @@ class GridDesc(C.Structure):
 class GridInfo(C.Structure):
     _fields_ = [("cell_d", C.c_double * 3), ("cell_d_inv", C.c_double * 3), ("grid_size", C.c_int32 * 3),
                 ("two_d", C.c_int32), ("dimensions", C.c_double * 3), ("cell_count", C.c_int64)]
+
+
+class SlabInfo(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("nranks", C.c_int32), ("z_offset", C.c_int32), ("gz_local", C.c_int32),
+                ("own_lo", C.c_int32), ("own_hi", C.c_int32), ("reserved", C.c_int32 * 2)]
+
+
+class DistExport(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("nranks", C.c_int32), ("device", C.c_int32), ("ipc_missing", C.c_int32),
+                ("pid", C.c_int64), ("zown0", C.c_int32), ("zown1", C.c_int32), ("gz_local", C.c_int32),
+                ("z_offset", C.c_int32), ("raw", C.c_uint64 * 16), ("ipc", (C.c_uint8 * 64) * 16)]
 
 
 class Params(C.Structure):

@@ -1,0 +1,593 @@
+// dist.cu -- z-slab decomposition of the hot path over NVLink peer memory.
+//
+// One handle (= one process, one GPU) holds the global planes [zoff, zoff + gz) of the grid: the planes it owns plus one
+// ghost plane towards each z-neighbour.  Positions stay global, so every particle-side expression is the one the
+// single-GPU path evaluates.  All inter-GPU traffic is hand-written loads / stores on peer memory (cudaIpc mappings of
+// the neighbours' arrays, or plain peer pointers when the handles live in one process):
+//   * halo_kernel       two-sided handshake + pull of the neighbours' boundary planes into the local ghost planes
+//                       (epochs live in device memory, so the kernel replays unchanged inside the PCG loop graph);
+//   * allreduce_kernel  every rank pushes its partial reduction into a slot of every rank, then sums the slots in rank
+//                       order: deterministic, bit-identical on all ranks, ~one NVLink round trip; it then takes the PCG
+//                       decision (pcg_finish.cuh) that the last block takes in the single-GPU path;
+//   * mig_send / mig_recv  particles whose cell left the owned planes are pushed into the neighbour's receive buffer and
+//                       binned there before the sort.
+// Every wait is bounded (FSIM_DIST_TIMEOUT_MS, default 20 s): a lost peer becomes FSIM_ERR_COMM, never a hung GPU.
+#include <unistd.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "fsim_internal.h"
+#include "pcg_finish.cuh"
+
+#define DIST_MAX_RANKS 16
+#define DIST_NARR 16
+#define DIST_NCH 15  // particle channels of the widest (APIC) layout
+
+enum { ARR_U = 0, ARR_U2 = 3, ARR_W = 6, ARR_DENS = 9, ARR_CNT = 10, ARR_FLAGS = 11, ARR_P = 12, ARR_S = 13, ARR_COMM = 14, ARR_RECV = 15 };
+
+struct DistSlot { double v[4]; uint32_t epoch; uint32_t pad[7]; };
+
+struct DistComm {
+    // written by the z-neighbours ([0]: by the lower one, [1]: by the upper one)
+    uint32_t arrive[2], done[2];
+    uint32_t mig_epoch[2], mig_count[2];
+    // written by every rank: slot[parity][source rank]
+    DistSlot slot[2][DIST_MAX_RANKS];
+    // local
+    uint32_t halo_epoch, ar_epoch, mig_ep, blocks_done, mig_blocks_done;
+    uint32_t error;   // 1 wait timed out, 2 emigrant list full, 3 immigrant outside the owned planes
+    uint32_t n_src;   // particles the next reorder reads: locals + immigrants
+    uint32_t pad0;
+    unsigned long long timeout_ns;
+};
+
+struct DistState {
+    int rank, nranks;
+    int own_lo, own_hi;  // global planes owned
+    DistComm* comm;
+    uint32_t* err_host;  // pinned + mapped
+    uint32_t* err_dev;
+    MigDev* mig;
+    uint32_t* mig_idx[2];
+    int64_t mig_cap;
+    float* recv;         // [2 sides][DIST_NCH + 1 (ids)][mig_cap]
+    float* stage;        // P2G staging: [2 sides][2 (ghost, boundary)][7 channels][plane]
+    void* local_arr[DIST_NARR];
+    void* peer_arr[2][DIST_NARR];
+    DistComm* peer_comm[2];
+    int peer_ghost[2], peer_bnd[2];  // the neighbour's ghost plane towards us / its boundary plane (its local indices)
+    DistComm* all_comm[DIST_MAX_RANKS];
+    bool connected, nsrc_valid;
+    std::vector<void*> ipc_opened;
+};
+
+namespace {
+
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint4 ld_peer_u4(const void* p) {  // never served from a stale L1 line
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long now_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// spin until *flag >= ep (epochs only grow); bounded: on time-out the error word is set and every later wait returns at once
+__device__ bool wait_ge(const uint32_t* flag, uint32_t ep, DistComm* c, uint32_t* err_host) {
+    if (*(volatile uint32_t*)&c->error == 1u) return false;
+    const unsigned long long t0 = now_ns();
+    while ((int32_t)(ld_acquire_sys(flag) - ep) < 0) {
+        if (now_ns() - t0 > c->timeout_ns) {
+            *(volatile uint32_t*)&c->error = 1u;
+            *(volatile uint32_t*)err_host = 1u;
+            __threadfence_system();
+            return false;
+        }
+        __nanosleep(64);
+    }
+    return true;
+}
+
+struct HaloCopy { void* dst; const void* src; uint32_t bytes; int side; };
+struct HaloArgs {
+    DistComm* comm;
+    DistComm* peer[2];
+    uint32_t* err_host;
+    const PcgScalars* sc;  // non-null inside the PCG loop: skip once the solve is done (the flag is the same on all ranks)
+    int ncopy;
+    HaloCopy cp[32];
+};
+
+__global__ void __launch_bounds__(256) halo_kernel(const __grid_constant__ HaloArgs a) {
+    if (a.sc && a.sc->done) return;
+    DistComm* c = a.comm;
+    __shared__ uint32_t ep_s;
+    if (threadIdx.x == 0) {
+        const uint32_t ep = *(volatile uint32_t*)&c->halo_epoch + 1u;  // advanced by the last block on its way out
+        ep_s = ep;
+        if (blockIdx.x == 0) {  // everything this rank launched before is complete: its planes are final, its ghosts free
+            __threadfence_system();
+            for (int side = 0; side < 2; side++)
+                if (a.peer[side]) st_release_sys(&a.peer[side]->arrive[1 - side], ep);
+        }
+        for (int side = 0; side < 2; side++)
+            if (a.peer[side]) wait_ge(&c->arrive[side], ep, c, a.err_host);
+    }
+    __syncthreads();
+    const uint32_t ep = ep_s;
+    const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, gsz = (size_t)gridDim.x * blockDim.x;
+    for (int k = 0; k < a.ncopy; k++) {
+        const HaloCopy& cp = a.cp[k];
+        if (!a.peer[cp.side]) continue;
+        if ((((size_t)cp.dst | (size_t)cp.src | (size_t)cp.bytes) & 15) == 0) {
+            const size_t n = cp.bytes >> 4;
+            for (size_t i = gtid; i < n; i += gsz) reinterpret_cast<uint4*>(cp.dst)[i] = ld_peer_u4(reinterpret_cast<const uint4*>(cp.src) + i);
+        } else {
+            for (size_t i = gtid; i < cp.bytes; i += gsz) reinterpret_cast<uint8_t*>(cp.dst)[i] = reinterpret_cast<const volatile uint8_t*>(cp.src)[i];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const uint32_t old = atomicAdd(&c->blocks_done, 1u);
+        if (old == gridDim.x - 1) {  // last block: tell the neighbours we are done reading their planes, wait for the same
+            c->blocks_done = 0;
+            __threadfence_system();
+            for (int side = 0; side < 2; side++)
+                if (a.peer[side]) st_release_sys(&a.peer[side]->done[1 - side], ep);
+            for (int side = 0; side < 2; side++)
+                if (a.peer[side]) wait_ge(&c->done[side], ep, c, a.err_host);
+            c->halo_epoch = ep;
+            __threadfence();
+        }
+    }
+}
+
+// P2G ghost-plane sum: boundary plane += what the neighbour scattered into its ghost plane; ghost plane += the neighbour's
+// own boundary plane (fp32 addition commutes, so both ranks hold bit-identical totals)
+struct HaloAddArgs {
+    float* dst[2][2][7];        // [side][0: my boundary plane, 1: my ghost plane][channel]
+    const float* stg[2][2][7];  // [side][0: neighbour's ghost plane, 1: neighbour's boundary plane][channel]
+    int has[2];
+    int plane;
+};
+__global__ void __launch_bounds__(256) halo_add_kernel(const __grid_constant__ HaloAddArgs a) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.plane) return;
+    const int side = blockIdx.y >> 1, which = blockIdx.y & 1;
+    if (!a.has[side]) return;
+#pragma unroll
+    for (int ch = 0; ch < 7; ch++) a.dst[side][which][ch][i] += a.stg[side][which][ch][i];
+}
+
+struct ArArgs {
+    DistComm* comm;
+    DistComm* all[DIST_MAX_RANKS];
+    uint32_t* err_host;
+    PcgScalars* sc;
+    PcgHostStatus* status;
+    int rank, nranks, kind, check_done;
+};
+
+__global__ void __launch_bounds__(32) allreduce_kernel(const __grid_constant__ ArArgs a) {
+    if (a.check_done && a.sc->done) return;
+    DistComm* c = a.comm;
+    const int lane = threadIdx.x;
+    const uint32_t ep = *(volatile uint32_t*)&c->ar_epoch + 1u;
+    const int par = ep & 1u;
+    __shared__ double sv[DIST_MAX_RANKS][4];
+    if (lane < a.nranks) {
+        DistSlot* s = &a.all[lane]->slot[par][a.rank];
+        volatile double* v = s->v;
+        v[0] = a.sc->loc[0]; v[1] = a.sc->loc[1]; v[2] = a.sc->loc[2]; v[3] = a.sc->loc[3];
+        __threadfence_system();
+        st_release_sys(&s->epoch, ep);
+        DistSlot* m = &c->slot[par][lane];
+        wait_ge(&m->epoch, ep, c, a.err_host);
+        volatile double* w = m->v;
+        sv[lane][0] = w[0]; sv[lane][1] = w[1]; sv[lane][2] = w[2]; sv[lane][3] = w[3];
+    }
+    __syncwarp();
+    if (lane == 0) {
+        double s0 = 0.0, s1 = 0.0, mx = 0.0, s3 = 0.0;
+        for (int r = 0; r < a.nranks; r++) { s0 += sv[r][0]; s1 += sv[r][1]; mx = fmax(mx, sv[r][2]); s3 += sv[r][3]; }
+        PcgScalars* sc = a.sc;
+        switch (a.kind) {
+            case AR_RHS: pcg_finish_rhs(sc, a.status, s0, s3); break;
+            case AR_RESIDUAL: pcg_finish_residual(sc, a.status, mx); break;
+            case AR_START: sc->sigma = s0; break;
+            case AR_SPMV: sc->sq = s0; break;
+            case AR_UPDATE: pcg_finish_update(sc, a.status, 0.0, mx); break;
+            case AR_UPDATE_JACOBI: pcg_finish_update(sc, a.status, s0, mx); break;
+            case AR_DOTZR: sc->sigma_new = s0; break;
+        }
+        sc->loc[0] = sc->loc[1] = sc->loc[2] = sc->loc[3] = 0.0;
+        c->ar_epoch = ep;
+        __threadfence();
+    }
+}
+
+struct MigSendArgs {
+    DistComm* comm;
+    DistComm* peer[2];
+    MigDev* mig;
+    const float* src[DIST_NCH];
+    const uint32_t* src_id;
+    int nch;
+    float* peer_recv[2];  // the receive area of neighbour `dir` that belongs to us (its side 1 - dir)
+    int64_t cap;
+};
+
+__global__ void __launch_bounds__(256) mig_send_kernel(const __grid_constant__ MigSendArgs a) {
+    const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, gsz = (size_t)gridDim.x * blockDim.x;
+    for (int dir = 0; dir < 2; dir++) {
+        if (!a.peer[dir]) continue;
+        const uint32_t n = min(a.mig->count[dir], a.mig->cap);
+        float* out = a.peer_recv[dir];
+        for (size_t j = gtid; j < n; j += gsz) {
+            const uint32_t i = a.mig->idx[dir][j];
+            for (int ch = 0; ch < a.nch; ch++) out[(size_t)ch * a.cap + j] = a.src[ch][i];
+            reinterpret_cast<uint32_t*>(out)[(size_t)DIST_NCH * a.cap + j] = a.src_id ? a.src_id[i] : 0u;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        DistComm* c = a.comm;
+        const uint32_t old = atomicAdd(&c->mig_blocks_done, 1u);
+        if (old == gridDim.x - 1) {
+            c->mig_blocks_done = 0;
+            const uint32_t ep = c->mig_ep + 1u;
+            for (int dir = 0; dir < 2; dir++) {
+                if (!a.peer[dir]) continue;
+                *(volatile uint32_t*)&a.peer[dir]->mig_count[1 - dir] = min(a.mig->count[dir], a.mig->cap);
+                __threadfence_system();
+                st_release_sys(&a.peer[dir]->mig_epoch[1 - dir], ep);
+            }
+            if (a.mig->overflow) { *(volatile uint32_t*)&c->error = 2u; }
+            c->mig_ep = ep;
+            __threadfence();
+        }
+    }
+}
+
+struct MigRecvArgs {
+    DistComm* comm;
+    int has[2];
+    uint32_t* err_host;
+    MigDev* mig;
+    const float* recv;  // [2][DIST_NCH + 1][cap]
+    int64_t cap;
+    float* dst[DIST_NCH];
+    uint32_t* dst_id;
+    int nch;
+    int64_t np;  // immigrants are appended behind the locals
+    GridDims g;
+    uint32_t *cnt, *key, *rank;
+};
+
+__global__ void __launch_bounds__(256) mig_recv_kernel(const __grid_constant__ MigRecvArgs a) {
+    DistComm* c = a.comm;
+    if (threadIdx.x == 0) {
+        const uint32_t ep = c->mig_ep;  // advanced by this step's mig_send_kernel
+        for (int side = 0; side < 2; side++)
+            if (a.has[side]) wait_ge(&c->mig_epoch[side], ep, c, a.err_host);
+    }
+    __syncthreads();
+    const uint32_t n0 = a.has[0] ? *(volatile uint32_t*)&c->mig_count[0] : 0u, n1 = a.has[1] ? *(volatile uint32_t*)&c->mig_count[1] : 0u;
+    const uint32_t total = n0 + n1;
+    const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, gsz = (size_t)gridDim.x * blockDim.x;
+    const GridDims& g = a.g;
+    for (size_t j = gtid; j < total; j += gsz) {
+        const int side = j < n0 ? 0 : 1;
+        const size_t jj = side ? j - n0 : j;
+        const float* in = a.recv + (size_t)side * (DIST_NCH + 1) * a.cap;
+        const size_t d = (size_t)a.np + j;
+        float x = 0.f, y = 0.f, z = 0.f;
+        for (int ch = 0; ch < a.nch; ch++) {
+            const float v = in[(size_t)ch * a.cap + jj];
+            a.dst[ch][d] = v;
+            if (ch == 0) x = v; else if (ch == 1) y = v; else if (ch == 2) z = v;
+        }
+        if (a.dst_id) a.dst_id[d] = reinterpret_cast<const uint32_t*>(in)[(size_t)DIST_NCH * a.cap + jj];
+        // same key expression as the advect kernels (particles.cu cell_key)
+        int ix = (int)((double)x * g.dihx), iy = (int)((double)y * g.dihy), iz = (int)((double)z * g.dihz) - g.zoff;
+        ix = min(max(ix, 0), g.gx - 1); iy = min(max(iy, 0), g.gy - 1);
+        if (iz < g.zown0 || iz >= g.zown1) {  // crossed a whole slab in one step: not supported, flagged
+            *(volatile uint32_t*)&c->error = 3u;
+            *(volatile uint32_t*)a.err_host = 3u;
+            iz = min(max(iz, g.zown0), g.zown1 - 1);
+        }
+        const uint32_t k = (uint32_t)((iz * g.gy + iy) * g.gx + ix);
+        a.key[d] = k;
+        a.rank[d] = atomicAdd(&a.cnt[k], 1u);
+    }
+    if (gtid == 0) {
+        c->n_src = (uint32_t)a.np + total;
+        if (*(volatile uint32_t*)&c->error == 2u) *(volatile uint32_t*)a.err_host = 2u;
+        a.mig->count[0] = 0; a.mig->count[1] = 0; a.mig->overflow = 0;
+    }
+}
+
+template <typename T>
+int dalloc(fsim* h, T** p, size_t n) {
+    *p = nullptr;
+    FSIM_CUDA(h, cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T)));
+    FSIM_CUDA(h, cudaMemsetAsync(*p, 0, std::max<size_t>(n, 1) * sizeof(T), h->stream));
+    return FSIM_OK;
+}
+
+size_t elem_size(int arr) { return arr == ARR_FLAGS ? 1 : (arr == ARR_P ? 8 : 4); }
+
+int check_err(fsim* h) {
+    DistState* d = h->dist;
+    const uint32_t e = *(volatile uint32_t*)d->err_host;
+    if (!e) return FSIM_OK;
+    h->sticky = FSIM_ERR_COMM;
+    return fsim_fail(h, FSIM_ERR_COMM, e == 1 ? "slab exchange timed out waiting for a neighbour (rank %d of %d)"
+                                      : e == 2 ? "emigrant list overflow (rank %d of %d): more particles crossed a slab boundary in one step than the list holds"
+                                               : "a particle crossed a whole slab in one step (rank %d of %d)", d->rank, d->nranks);
+}
+
+}  // namespace
+
+MigDev* dist_mig_dev(const fsim* h) { return h->dist ? h->dist->mig : nullptr; }
+int64_t dist_mig_capacity(const fsim* h) { return h->dist ? h->dist->mig_cap : 0; }
+const uint32_t* dist_nsrc_dev(fsim* h) {
+    DistState* d = h->dist;
+    if (!d || !d->nsrc_valid) return nullptr;
+    d->nsrc_valid = false;
+    return &d->comm->n_src;
+}
+
+void dist_rank(const fsim* h, int* rank, int* nranks) { if (h->dist) { *rank = h->dist->rank; *nranks = h->dist->nranks; } }
+
+int dist_check(fsim* h) { return (h->dist && h->dist->connected) ? check_err(h) : FSIM_OK; }
+
+// the slab geometry of rank r of n over gzg global planes
+void dist_partition(int gzg, int rank, int nranks, int* own_lo, int* own_hi, int* zoff, int* gz_local) {
+    const int lo = (int)((int64_t)gzg * rank / nranks), hi = (int)((int64_t)gzg * (rank + 1) / nranks);
+    const int z0 = std::max(lo - 1, 0), z1 = std::min(hi + 1, gzg);
+    *own_lo = lo; *own_hi = hi; *zoff = z0; *gz_local = z1 - z0;
+}
+
+int dist_init(fsim* h, int rank, int nranks, int own_lo, int own_hi) {
+    DistState* d = new DistState();  // value-initialised: every POD member is zero
+    h->dist = d;
+    d->rank = rank; d->nranks = nranks; d->own_lo = own_lo; d->own_hi = own_hi;
+    const GridDims& g = h->g;
+    int rc = dalloc(h, &d->comm, 1);
+    if (rc) return rc;
+    DistComm c0;
+    memset(&c0, 0, sizeof(c0));
+    const char* e = getenv("FSIM_DIST_TIMEOUT_MS");
+    c0.timeout_ns = (unsigned long long)(e ? atoll(e) : 20000) * 1000000ull;
+    FSIM_CUDA(h, cudaMemcpyAsync(d->comm, &c0, sizeof(c0), cudaMemcpyHostToDevice, h->stream));
+    FSIM_CUDA(h, cudaStreamSynchronize(h->stream));
+    FSIM_CUDA(h, cudaHostAlloc((void**)&d->err_host, sizeof(uint32_t), cudaHostAllocMapped));
+    *d->err_host = 0;
+    FSIM_CUDA(h, cudaHostGetDevicePointer((void**)&d->err_dev, d->err_host, 0));
+    // up to two planes of 8 particles per cell may change owner in one step before the lists overflow (FSIM_DIST_MIG_CAP overrides)
+    const char* mc = getenv("FSIM_DIST_MIG_CAP");
+    d->mig_cap = mc ? atoll(mc) : std::max<int64_t>(4096, (int64_t)g.gx * g.gy * 16);
+    for (int k = 0; k < 2; k++) if ((rc = dalloc(h, &d->mig_idx[k], (size_t)d->mig_cap))) return rc;
+    if ((rc = dalloc(h, &d->mig, 1))) return rc;
+    MigDev m;
+    memset(&m, 0, sizeof(m));
+    m.cap = (uint32_t)d->mig_cap; m.idx[0] = d->mig_idx[0]; m.idx[1] = d->mig_idx[1]; m.own_lo = own_lo; m.own_hi = own_hi;
+    FSIM_CUDA(h, cudaMemcpyAsync(d->mig, &m, sizeof(m), cudaMemcpyHostToDevice, h->stream));
+    FSIM_CUDA(h, cudaStreamSynchronize(h->stream));
+    if ((rc = dalloc(h, &d->recv, (size_t)2 * (DIST_NCH + 1) * d->mig_cap))) return rc;
+    if ((rc = dalloc(h, &d->stage, (size_t)2 * 2 * 7 * g.sz))) return rc;
+    for (int a = 0; a < 3; a++) { d->local_arr[ARR_U + a] = h->u[a]; d->local_arr[ARR_U2 + a] = h->u2[a]; d->local_arr[ARR_W + a] = h->wsum[a]; }
+    d->local_arr[ARR_DENS] = h->dens; d->local_arr[ARR_CNT] = h->cnt; d->local_arr[ARR_FLAGS] = h->flags;
+    d->local_arr[ARR_P] = h->p; d->local_arr[ARR_S] = h->s; d->local_arr[ARR_COMM] = d->comm; d->local_arr[ARR_RECV] = d->recv;
+    d->all_comm[rank] = d->comm;
+    return FSIM_OK;
+}
+
+void dist_free(fsim* h) {
+    DistState* d = h->dist;
+    if (!d) return;
+    for (void* p : d->ipc_opened) cudaIpcCloseMemHandle(p);
+    cudaFree(d->comm); cudaFree(d->mig); cudaFree(d->mig_idx[0]); cudaFree(d->mig_idx[1]); cudaFree(d->recv); cudaFree(d->stage);
+    if (d->err_host) cudaFreeHost(d->err_host);
+    delete d;
+    h->dist = nullptr;
+}
+
+int dist_export(fsim* h, FsimDistExport* out) {
+    DistState* d = h->dist;
+    memset(out, 0, sizeof(*out));
+    out->rank = d->rank; out->nranks = d->nranks; out->device = h->device; out->pid = (int64_t)getpid();
+    out->zown0 = h->g.zown0; out->zown1 = h->g.zown1; out->gz_local = h->g.gz; out->z_offset = h->g.zoff;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+    for (int k = 0; k < DIST_NARR; k++) {
+        out->raw[k] = (uint64_t)(uintptr_t)d->local_arr[k];
+        cudaIpcMemHandle_t hd;
+        const cudaError_t e = cudaIpcGetMemHandle(&hd, d->local_arr[k]);
+        if (e == cudaSuccess) memcpy(out->ipc[k], &hd, 64);
+        else { cudaGetLastError(); out->ipc_missing = 1; }  // same-process connections do not need it
+    }
+    return FSIM_OK;
+}
+
+int dist_connect(fsim* h, const FsimDistExport* all, int n) {
+    DistState* d = h->dist;
+    if (n != d->nranks) return fsim_fail(h, FSIM_ERR_INVALID, "expected %d exports, got %d", d->nranks, n);
+    const int64_t pid = (int64_t)getpid();
+    auto map = [&](const FsimDistExport& ex, int arr, void** out) -> int {
+        if (ex.pid == pid) {  // same process: plain pointers (peer access when the handle lives on another device)
+            if (ex.device != h->device) {
+                const cudaError_t e = cudaDeviceEnablePeerAccess(ex.device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                    return fsim_fail(h, FSIM_ERR_COMM, "cudaDeviceEnablePeerAccess(%d): %s", ex.device, cudaGetErrorString(e));
+                cudaGetLastError();
+            }
+            *out = (void*)(uintptr_t)ex.raw[arr];
+            return FSIM_OK;
+        }
+        if (ex.ipc_missing) return fsim_fail(h, FSIM_ERR_COMM, "rank %d exported no IPC handles", ex.rank);
+        cudaIpcMemHandle_t hd;
+        memcpy(&hd, ex.ipc[arr], 64);
+        const cudaError_t e = cudaIpcOpenMemHandle(out, hd, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) return fsim_fail(h, FSIM_ERR_COMM, "cudaIpcOpenMemHandle(rank %d, array %d): %s", ex.rank, arr, cudaGetErrorString(e));
+        d->ipc_opened.push_back(*out);
+        return FSIM_OK;
+    };
+    for (int r = 0; r < n; r++) {
+        const FsimDistExport& ex = all[r];
+        if (ex.rank != r || ex.nranks != n) return fsim_fail(h, FSIM_ERR_INVALID, "export %d is from rank %d of %d", r, ex.rank, ex.nranks);
+        if (r == d->rank) continue;
+        const int side = r == d->rank - 1 ? 0 : (r == d->rank + 1 ? 1 : -1);
+        if (side >= 0) {
+            for (int k = 0; k < DIST_NARR; k++) { int rc = map(ex, k, &d->peer_arr[side][k]); if (rc) return rc; }
+            d->peer_comm[side] = (DistComm*)d->peer_arr[side][ARR_COMM];
+            d->all_comm[r] = d->peer_comm[side];
+            // the lower neighbour's ghost plane towards us is its plane zown1, its boundary plane zown1 - 1; the upper one's: zown0 - 1, zown0
+            d->peer_ghost[side] = side == 0 ? ex.zown1 : ex.zown0 - 1;
+            d->peer_bnd[side] = side == 0 ? ex.zown1 - 1 : ex.zown0;
+        } else {
+            void* p = nullptr;
+            int rc = map(ex, ARR_COMM, &p);
+            if (rc) return rc;
+            d->all_comm[r] = (DistComm*)p;
+        }
+    }
+    d->connected = true;
+    return FSIM_OK;
+}
+
+int dist_halo(fsim* h, int what, bool in_pcg_loop) {
+    DistState* d = h->dist;
+    if (!d || !d->connected) return fsim_fail(h, FSIM_ERR_COMM, "slab handle is not connected to its neighbours (fsim_dist_connect)");
+    const GridDims& g = h->g;
+    HaloArgs a;
+    memset(&a, 0, sizeof(a));
+    a.comm = d->comm; a.peer[0] = d->peer_comm[0]; a.peer[1] = d->peer_comm[1]; a.err_host = d->err_dev;
+    a.sc = in_pcg_loop ? h->scal : nullptr;
+    const size_t plane = (size_t)g.sz;
+    const int my_ghost[2] = {g.zown0 - 1, g.zown1}, my_bnd[2] = {g.zown0, g.zown1 - 1};
+    auto pull = [&](int arr) {  // my ghost plane <- the neighbour's boundary plane
+        const size_t es = elem_size(arr);
+        for (int side = 0; side < 2; side++) {
+            if (!d->peer_comm[side]) continue;
+            HaloCopy& c = a.cp[a.ncopy++];
+            c.dst = (char*)d->local_arr[arr] + (size_t)my_ghost[side] * plane * es;
+            c.src = (const char*)d->peer_arr[side][arr] + (size_t)d->peer_bnd[side] * plane * es;
+            c.bytes = (uint32_t)(plane * es);
+            c.side = side;
+        }
+    };
+    size_t bytes = 0;
+    switch (what) {
+        case HALO_P: pull(ARR_P); break;
+        case HALO_S: pull(ARR_S); break;
+        case HALO_U2: for (int ax = 0; ax < 3; ax++) pull(ARR_U2 + ax); break;
+        case HALO_U2_FLAGS: for (int ax = 0; ax < 3; ax++) pull(ARR_U2 + ax); pull(ARR_FLAGS); break;
+        case HALO_P2G: {
+            pull(ARR_CNT);
+            const int chan[7] = {ARR_U, ARR_U + 1, ARR_U + 2, ARR_W, ARR_W + 1, ARR_W + 2, ARR_DENS};
+            for (int side = 0; side < 2; side++) {
+                if (!d->peer_comm[side]) continue;
+                for (int which = 0; which < 2; which++)  // 0: the neighbour's ghost plane (its scatter into my boundary plane), 1: its boundary plane
+                    for (int ch = 0; ch < 7; ch++) {
+                        HaloCopy& c = a.cp[a.ncopy++];
+                        c.dst = d->stage + ((size_t)(side * 2 + which) * 7 + ch) * plane;
+                        c.src = (const float*)d->peer_arr[side][chan[ch]] + (size_t)(which == 0 ? d->peer_ghost[side] : d->peer_bnd[side]) * plane;
+                        c.bytes = (uint32_t)(plane * sizeof(float));
+                        c.side = side;
+                    }
+            }
+            break;
+        }
+        default: return fsim_fail(h, FSIM_ERR_INVALID, "unknown halo %d", what);
+    }
+    for (int k = 0; k < a.ncopy; k++) bytes += a.cp[k].bytes;
+    const int blocks = (int)std::min<size_t>(128, std::max<size_t>(4, bytes / (16 * 256 * 4)));
+    { KScope ks(h, K_HALO); halo_kernel<<<blocks, 256, 0, h->stream>>>(a); }
+    if (what == HALO_P2G) {
+        HaloAddArgs b;
+        memset(&b, 0, sizeof(b));
+        const int chan[7] = {ARR_U, ARR_U + 1, ARR_U + 2, ARR_W, ARR_W + 1, ARR_W + 2, ARR_DENS};
+        for (int side = 0; side < 2; side++) {
+            b.has[side] = d->peer_comm[side] != nullptr;
+            for (int ch = 0; ch < 7; ch++) {
+                float* base = (float*)d->local_arr[chan[ch]];
+                b.dst[side][0][ch] = base + (size_t)my_bnd[side] * plane;
+                b.dst[side][1][ch] = base + (size_t)(b.has[side] ? my_ghost[side] : my_bnd[side]) * plane;
+                b.stg[side][0][ch] = d->stage + ((size_t)(side * 2 + 0) * 7 + ch) * plane;
+                b.stg[side][1][ch] = d->stage + ((size_t)(side * 2 + 1) * 7 + ch) * plane;
+            }
+        }
+        b.plane = (int)plane;
+        KScope ks(h, K_HALO);
+        halo_add_kernel<<<dim3(div_up(plane, 256), 4), 256, 0, h->stream>>>(b);
+    }
+    FSIM_CHECK_LAUNCH(h);
+    return FSIM_OK;
+}
+
+int dist_allreduce(fsim* h, int kind, bool in_pcg_loop) {
+    DistState* d = h->dist;
+    if (!d || !d->connected) return fsim_fail(h, FSIM_ERR_COMM, "slab handle is not connected to its neighbours (fsim_dist_connect)");
+    ArArgs a;
+    memset(&a, 0, sizeof(a));
+    a.comm = d->comm;
+    for (int r = 0; r < d->nranks; r++) a.all[r] = d->all_comm[r];
+    a.err_host = d->err_dev; a.sc = h->scal; a.status = h->status_dev;
+    a.rank = d->rank; a.nranks = d->nranks; a.kind = kind; a.check_done = in_pcg_loop ? 1 : 0;
+    { KScope ks(h, K_ALLREDUCE); allreduce_kernel<<<1, 32, 0, h->stream>>>(a); }
+    FSIM_CHECK_LAUNCH(h);
+    return FSIM_OK;
+}
+
+int fsim_ensure_capacity(fsim* h, int64_t n);  // fsim_api.cu
+
+int dist_migrate(fsim* h) {
+    DistState* d = h->dist;
+    if (!d || !d->connected) return fsim_fail(h, FSIM_ERR_COMM, "slab handle is not connected to its neighbours (fsim_dist_connect)");
+    int rc = fsim_ensure_capacity(h, h->np + 2 * d->mig_cap);
+    if (rc) return rc;
+    const ParticleSet& p = h->ps[h->cur];
+    const int nch = h->have_c ? 15 : 6;
+    MigSendArgs s;
+    memset(&s, 0, sizeof(s));
+    s.comm = d->comm; s.peer[0] = d->peer_comm[0]; s.peer[1] = d->peer_comm[1]; s.mig = d->mig;
+    for (int c = 0; c < 3; c++) { s.src[c] = p.pos[c]; s.src[3 + c] = p.vel[c]; }
+    for (int c = 0; c < 9; c++) s.src[6 + c] = p.c[c];
+    s.src_id = h->track_ids ? p.id : nullptr;
+    s.nch = nch; s.cap = d->mig_cap;
+    for (int dir = 0; dir < 2; dir++)
+        if (d->peer_comm[dir]) s.peer_recv[dir] = (float*)d->peer_arr[dir][ARR_RECV] + (size_t)(1 - dir) * (DIST_NCH + 1) * d->mig_cap;
+    MigRecvArgs r;
+    memset(&r, 0, sizeof(r));
+    r.comm = d->comm; r.has[0] = d->peer_comm[0] != nullptr; r.has[1] = d->peer_comm[1] != nullptr; r.err_host = d->err_dev; r.mig = d->mig;
+    r.recv = d->recv; r.cap = d->mig_cap;
+    for (int c = 0; c < 3; c++) { r.dst[c] = p.pos[c]; r.dst[3 + c] = p.vel[c]; }
+    for (int c = 0; c < 9; c++) r.dst[6 + c] = p.c[c];
+    r.dst_id = h->track_ids ? p.id : nullptr;
+    r.nch = nch; r.np = h->np; r.g = h->g; r.cnt = h->cnt; r.key = h->key; r.rank = h->rank;
+    {
+        KScope ks(h, K_MIGRATE, 2);
+        mig_send_kernel<<<32, 256, 0, h->stream>>>(s);
+        mig_recv_kernel<<<32, 256, 0, h->stream>>>(r);
+    }
+    FSIM_CHECK_LAUNCH(h);
+    d->nsrc_valid = true;
+    h->kill_pending = true;  // the particle count changes: k_sort reads the new total back
+    return FSIM_OK;
+}

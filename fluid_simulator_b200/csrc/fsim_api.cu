@@ -98,6 +98,10 @@ int ensure_capacity(fsim* h, int64_t n) {
     return FSIM_OK;
 }
 
+}  // namespace
+int fsim_ensure_capacity(fsim* h, int64_t n) { return ensure_capacity(h, n); }
+namespace {
+
 int ensure_c(fsim* h) {  // APIC affine matrices are allocated the first time they are needed
     if (h->have_c) return FSIM_OK;
     for (int k = 0; k < 2; k++)
@@ -212,8 +216,9 @@ int fsim_abi_version(void) { return FSIM_ABI_VERSION; }
 
 const char* fsim_last_error(const fsim_t* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
-int fsim_create(const FsimGridDesc* desc, fsim_t** out) {
+static int create_impl(const FsimGridDesc* desc, int rank, int nranks, fsim_t** out) {
     if (!desc || !out) return fsim_fail(nullptr, FSIM_ERR_INVALID, "null argument");
+    if (nranks < 1 || nranks > 16 || rank < 0 || rank >= nranks) return fsim_fail(nullptr, FSIM_ERR_INVALID, "bad rank %d of %d", rank, nranks);
     *out = nullptr;
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -260,6 +265,18 @@ int fsim_create(const FsimGridDesc* desc, fsim_t** out) {
     GridDims& g = h->g;
     g.gx = gi.grid_size[0]; g.gy = gi.grid_size[1]; g.gz = gi.grid_size[2];
     g.sy = g.gx; g.sz = g.gx * g.gy; g.nc = gi.cell_count;
+    g.zoff = 0; g.gzg = g.gz; g.zown0 = 0; g.zown1 = g.gz;
+    int own_lo = 0, own_hi = g.gz;
+    if (nranks > 1) {  // z-slab: this handle stores the planes it owns + one ghost plane towards each neighbour
+        if (twoD || g.gzg < 2 * nranks) {
+            delete h;
+            return fsim_fail(nullptr, FSIM_ERR_INVALID, "cannot cut %d z-planes%s into %d slabs", g.gzg, twoD ? " (2D)" : "", nranks);
+        }
+        int zoff, gzl;
+        dist_partition(g.gzg, rank, nranks, &own_lo, &own_hi, &zoff, &gzl);
+        g.zoff = zoff; g.gz = gzl; g.zown0 = own_lo - zoff; g.zown1 = own_hi - zoff;
+        g.nc = (int64_t)g.gx * g.gy * g.gz;
+    }
     g.dhx = gi.cell_d[0]; g.dhy = gi.cell_d[1]; g.dhz = gi.cell_d[2];
     g.dihx = gi.cell_d_inv[0]; g.dihy = gi.cell_d_inv[1]; g.dihz = gi.cell_d_inv[2];
     g.hx = (float)g.dhx; g.hy = (float)g.dhy; g.hz = (float)g.dhz;
@@ -294,6 +311,7 @@ int fsim_create(const FsimGridDesc* desc, fsim_t** out) {
     { const char* e = getenv("FSIM_WARM_EXTRAPOLATE"); h->warm_extrapolate = !(e && e[0] == '0'); }
     h->warm_history = 0; h->p_prev = nullptr; h->mg_tail_cluster = 0;
     h->status_host = nullptr; h->status_dev = nullptr;
+    h->dist = nullptr; h->code_mg = nullptr;
     { const char* e = getenv("FSIM_PRECOND"); h->use_mg = !(e && strcmp(e, "jacobi") == 0); }
     memset(h->prof_ms, 0, sizeof(h->prof_ms)); memset(h->prof_n, 0, sizeof(h->prof_n)); memset(h->launch_n, 0, sizeof(h->launch_n));
 
@@ -330,6 +348,7 @@ int fsim_create(const FsimGridDesc* desc, fsim_t** out) {
         }
         cudaGetLastError();
     }
+    if (nranks > 1) A(dev_alloc(h, &h->code_mg, g.nc + 8)); else h->code_mg = h->code;
     for (int a = 0; a < 3; a++) { A(dev_alloc(h, &h->u[a], g.nc)); A(dev_alloc(h, &h->u2[a], g.nc)); A(dev_alloc(h, &h->wsum[a], g.nc)); }
     A(dev_alloc(h, &h->dens, g.nc));
     A(dev_alloc(h, &h->p, g.nc)); A(dev_alloc(h, &h->rhs, g.nc)); A(dev_alloc(h, &h->r, g.nc));
@@ -357,7 +376,8 @@ int fsim_create(const FsimGridDesc* desc, fsim_t** out) {
     if (!rc) { h->status_host->done = 0; h->status_host->it_done = 0; }
     for (int i = 0; i < 16 && !rc; i++)
         if (cudaEventCreate(&h->ev[i]) != cudaSuccess) rc = fsim_fail(h, FSIM_ERR_CUDA, "event create failed");
-    if (!rc && cap0 > 0) rc = ensure_capacity(h, cap0);
+    if (!rc && nranks > 1) rc = dist_init(h, rank, nranks, own_lo, own_hi);
+    if (!rc && cap0 > 0) rc = ensure_capacity(h, cap0 + (h->dist ? 2 * dist_mig_capacity(h) : 0));
     if (!rc) {
         // MacGrid ctor leaves every cell AIR with the solid border shell (macGrid.cpp:15-16)
         rc = k_upload_obstacles(h);
@@ -374,10 +394,49 @@ int fsim_create(const FsimGridDesc* desc, fsim_t** out) {
     return FSIM_OK;
 }
 
+int fsim_create(const FsimGridDesc* desc, fsim_t** out) { return create_impl(desc, 0, 1, out); }
+int fsim_create_slab(const FsimGridDesc* desc, int rank, int nranks, fsim_t** out) { return create_impl(desc, rank, nranks, out); }
+
+int fsim_slab_partition(int global_gz, int rank, int nranks, FsimSlabInfo* out) {
+    if (!out || nranks < 1 || rank < 0 || rank >= nranks || global_gz < 1) return FSIM_ERR_INVALID;
+    memset(out, 0, sizeof(*out));
+    int lo, hi, zoff, gzl;
+    dist_partition(global_gz, rank, nranks, &lo, &hi, &zoff, &gzl);
+    if (nranks == 1) { lo = 0; hi = global_gz; zoff = 0; gzl = global_gz; }
+    out->rank = rank; out->nranks = nranks; out->z_offset = zoff; out->gz_local = gzl; out->own_lo = lo; out->own_hi = hi;
+    return FSIM_OK;
+}
+
+int fsim_get_slab_info(const fsim_t* h, FsimSlabInfo* out) {
+    if (!h || !out) return FSIM_ERR_INVALID;
+    memset(out, 0, sizeof(*out));
+    out->rank = 0; out->nranks = 1;
+    dist_rank(h, &out->rank, &out->nranks);
+    out->z_offset = h->g.zoff; out->gz_local = h->g.gz; out->own_lo = h->g.zoff + h->g.zown0; out->own_hi = h->g.zoff + h->g.zown1;
+    return FSIM_OK;
+}
+
+int fsim_dist_export(fsim_t* h, FsimDistExport* out) {
+    BIND(h);
+    if (!out) return fsim_fail(h, FSIM_ERR_INVALID, "null export");
+    if (!h->dist) return fsim_fail(h, FSIM_ERR_INVALID, "not a slab handle (fsim_create_slab with nranks > 1)");
+    FSIM_CUDA(h, cudaStreamSynchronize(h->stream));
+    return dist_export(h, out);
+}
+
+int fsim_dist_connect(fsim_t* h, const FsimDistExport* all, int n) {
+    BIND(h);
+    if (!all) return fsim_fail(h, FSIM_ERR_INVALID, "null exports");
+    if (!h->dist) return fsim_fail(h, FSIM_ERR_INVALID, "not a slab handle (fsim_create_slab with nranks > 1)");
+    return dist_connect(h, all, n);
+}
+
 int fsim_destroy(fsim_t* h) {
     if (!h) return FSIM_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    dist_free(h);
+    if (h->code_mg && h->code_mg != h->code) cudaFree(h->code_mg);
     mg_free(h);
     free_particle_set(h->ps[0]);
     free_particle_set(h->ps[1]);
@@ -527,6 +586,15 @@ int fsim_download_particle_ids(fsim_t* h, uint32_t* out, int64_t cap) {
     return FSIM_OK;
 }
 
+int fsim_upload_particle_ids(fsim_t* h, const uint32_t* ids, int64_t n) {
+    BIND(h);
+    if (!h->track_ids) return fsim_fail(h, FSIM_ERR_INVALID, "id tracking is off");
+    if (n != h->np || (n > 0 && !ids)) return fsim_fail(h, FSIM_ERR_INVALID, "expected %lld ids", (long long)h->np);
+    if (n > 0) FSIM_CUDA(h, cudaMemcpyAsync(h->ps[h->cur].id, ids, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, h->stream));
+    FSIM_CUDA(h, cudaStreamSynchronize(h->stream));
+    return FSIM_OK;
+}
+
 int fsim_set_id_tracking(fsim_t* h, int on) {
     BIND(h);
     if (on && !h->track_ids) {
@@ -637,8 +705,48 @@ int fsim_stage_extrapolate(fsim_t* h) { BIND_FLUSH(h); return k_extrapolate(h); 
 int fsim_stage_g2p(fsim_t* h) { BIND_FLUSH(h); TRY(ensure_sorted(h)); return k_g2p(h); }
 
 // Simulator::simulate (simulator.cpp:51-100)
+// the same step on one z-slab of the grid (dist.cu): collective over the ranks
+static int step_slab(fsim* h, double dt, int* pcg_iterations) {
+    TRY(dist_check(h));
+    if (h->par.spawning_enabled || h->par.push_apart_enabled)
+        return fsim_fail(h, FSIM_ERR_INVALID, "particle spawning and push-apart are not available on slab handles");
+    if (h->par.solver_type != FSIM_SOLVER_BRIDSON) return fsim_fail(h, FSIM_ERR_INVALID, "slab handles run the PCG projection only");
+    fold_timings(h);
+    const int64_t l0 = h->launches;
+    FSIM_CUDA(h, cudaEventRecord(h->ev[0], h->stream));
+    const bool fuse = h->g2p_pending && h->sorted && h->np > 0;
+    if (!fuse) TRY(flush_g2p(h));
+    TRY(k_advect(h, dt, true, true, h->par.stop_particles != 0, /*do_bin=*/true, fuse));
+    if (h->np > 0 && !h->binned) return fsim_fail(h, FSIM_ERR_INVALID, "slab step: particles were not binned");
+    h->push_timed = false;
+    TRY(dist_migrate(h));  // emigrants -> neighbours; immigrants appended behind the locals and binned
+    FSIM_CUDA(h, cudaEventRecord(h->ev[1], h->stream));
+    TRY(k_sort(h));        // also reads the new particle count back
+    FSIM_CUDA(h, cudaEventRecord(h->ev[2], h->stream));
+    TRY(k_p2g(h));
+    TRY(dist_halo(h, HALO_P2G, false));  // ghost-plane sums of the 7 scatter channels + the neighbours' particle counts
+    FSIM_CUDA(h, cudaEventRecord(h->ev[3], h->stream));
+    TRY(k_classify(h, dt));
+    FSIM_CUDA(h, cudaEventRecord(h->ev[4], h->stream));
+    int its = 0;
+    TRY(k_project(h, dt, &its));  // halos of the search direction / pressure and the all-rank reductions inside
+    FSIM_CUDA(h, cudaEventRecord(h->ev[5], h->stream));
+    TRY(dist_halo(h, HALO_U2, false));
+    TRY(k_extrapolate(h));        // exchanges u2 + validity between and after its two sweeps
+    FSIM_CUDA(h, cudaEventRecord(h->ev[6], h->stream));
+    if (h->lazy_g2p) h->g2p_pending = true;
+    else TRY(k_g2p(h));
+    FSIM_CUDA(h, cudaEventRecord(h->ev[7], h->stream));
+    FSIM_CUDA(h, cudaEventRecord(h->ev[8], h->stream));
+    h->ev_valid = true;
+    h->last_step_launches = h->launches - l0;
+    if (pcg_iterations) *pcg_iterations = its;
+    return FSIM_OK;
+}
+
 int fsim_step(fsim_t* h, double dt, int* pcg_iterations) {
     BIND(h);
+    if (h->dist) return step_slab(h, dt, pcg_iterations);
     fold_timings(h);
     const int64_t l0 = h->launches;
     FSIM_CUDA(h, cudaEventRecord(h->ev[0], h->stream));
@@ -829,7 +937,7 @@ int fsim_get_last_step_stats(const fsim_t* hc, double* device_ms, int64_t* kerne
 
 static const char* const kKernelNames[K_COUNT] = {"advect", "bin", "scan", "reorder", "p2g", "classify", "finalize", "rhs",
                                                     "pcg_init", "spmv", "pcg_update", "pcg_direction", "mg", "mg_level1", "mg_coarse", "pressure_apply",
-                                                    "extrapolate", "g2p", "gfx", "memset", "push_apart"};
+                                                    "extrapolate", "g2p", "gfx", "memset", "push_apart", "halo", "allreduce", "migrate"};
 
 int fsim_kernel_class_count(void) { return K_COUNT; }
 const char* fsim_kernel_class_name(int kid) { return (kid >= 0 && kid < K_COUNT) ? kKernelNames[kid] : ""; }
@@ -879,6 +987,7 @@ int fsim_timer_elapsed_ms(fsim_t* h, int slot_begin, int slot_end, double* ms) {
 int fsim_synchronize(fsim_t* h) {
     BIND(h);
     FSIM_CUDA(h, cudaStreamSynchronize(h->stream));
+    TRY(dist_check(h));
     return FSIM_OK;
 }
 

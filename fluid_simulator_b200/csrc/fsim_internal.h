@@ -35,6 +35,9 @@ struct GridDims {
     float ihx, ihy, ihz;  // cellDInv
     double dhx, dhy, dhz, dihx, dihy, dihz;
     int twoD;
+    // z-slab decomposition (dist.cu): this handle holds global planes [zoff, zoff + gz) of a grid with gzg planes and owns
+    // local planes [zown0, zown1); the others are ghost planes.  Single-GPU handles: zoff = 0, gzg = gz, zown = [0, gz).
+    int zoff, gzg, zown0, zown1;
 };
 
 // obstacle as the kernels see it (constant memory); integer raster bounds are computed on the host with the
@@ -58,6 +61,8 @@ struct ParticleSet {
 struct PcgScalars {  // device-resident scalars of the solve (kernels read their parameters here so that the captured
                      // CUDA graph of one PCG iteration never has to be re-instantiated)
     double sigma, sigma_new, sq, rmax, rhs_sumsq, r0max;
+    double loc[4];                  // slab mode: this rank's reduction results ([0],[1],[3] summed, [2] maxed over the ranks)
+    int dist;                       // slab mode: reductions are finished by dist_allreduce_kernel (dist.cu)
     double scale, inv_scale, tol;   // dt/(rho h^2), its inverse, residualTolerance
     int max_it, it;                 // iteration cap, index of the iteration in flight
     int iterations, done, early_out, nan_break;
@@ -69,11 +74,20 @@ struct PcgHostStatus {  // pinned, device-mapped: written by the device, polled 
 };
 
 struct MgLevel;
+struct DistState;  // dist.cu
+// slab mode: emigrant lists filled by the binning code of the advect kernels (particles.cu), consumed by dist.cu
+struct MigDev {
+    uint32_t count[2];   // particles leaving towards the lower / upper z-neighbour this step
+    uint32_t overflow;   // emigrants dropped because a list was full (reported as FSIM_ERR_COMM)
+    uint32_t cap;        // entries per list
+    uint32_t* idx[2];    // their indices in the current particle set
+    int own_lo, own_hi;  // global z-planes this rank owns: [own_lo, own_hi)
+};
 
 // kernel classes for launch counting and the optional per-launch CUDA-event profiling (fsim_profile_*)
 enum KernelId {
     K_ADVECT = 0, K_BIN, K_SCAN, K_REORDER, K_P2G, K_CLASSIFY, K_FINALIZE, K_RHS, K_PCG_INIT, K_SPMV, K_UPDATE,
-    K_DIRECTION, K_MG, K_MG1, K_MG2, K_APPLY, K_EXTRAP, K_G2P, K_GFX, K_MEMSET, K_PUSH, K_COUNT
+    K_DIRECTION, K_MG, K_MG1, K_MG2, K_APPLY, K_EXTRAP, K_G2P, K_GFX, K_MEMSET, K_PUSH, K_HALO, K_ALLREDUCE, K_MIGRATE, K_COUNT
 };
 struct ProfRec { int kid; cudaEvent_t e0, e1; };
 
@@ -173,6 +187,10 @@ struct fsim {
     int64_t prof_n[K_COUNT];
     int64_t launch_n[K_COUNT];
 
+    // z-slab multi-GPU state (nullptr for a single-GPU handle)
+    DistState* dist;
+    uint16_t* code_mg;  // stencil codes the multigrid preconditioner sees (slab mode: links into ghost planes cut); == code otherwise
+
     // error
     mutable std::string err;
     int sticky;
@@ -243,3 +261,21 @@ int k_iota_ids(fsim* h, int64_t first, int64_t n, uint32_t base);
 int k_compact_remove(fsim* h, const int32_t* dev_sorted_ids, int64_t n);
 int mg_build(fsim* h);
 void mg_free(fsim* h);
+
+// ---- z-slab decomposition over peer memory (dist.cu) ----------------------------------------------------
+enum { AR_RHS = 0, AR_RESIDUAL, AR_START, AR_SPMV, AR_UPDATE, AR_UPDATE_JACOBI, AR_DOTZR };
+enum { HALO_P2G = 0, HALO_P, HALO_S, HALO_U2, HALO_U2_FLAGS };
+int dist_halo(fsim* h, int what, bool in_pcg_loop);      // ghost-plane exchange with both z-neighbours (pull over peer memory)
+int dist_allreduce(fsim* h, int kind, bool in_pcg_loop);  // finishes a PCG reduction across the ranks
+int dist_migrate(fsim* h);                                // emigrants -> neighbours, immigrants appended + binned
+void dist_free(fsim* h);
+void dist_partition(int gzg, int rank, int nranks, int* own_lo, int* own_hi, int* zoff, int* gz_local);
+int dist_init(fsim* h, int rank, int nranks, int own_lo, int own_hi);
+int dist_export(fsim* h, FsimDistExport* out);
+int dist_connect(fsim* h, const FsimDistExport* all, int n);
+void dist_rank(const fsim* h, int* rank, int* nranks);
+int dist_check(fsim* h);  // FSIM_ERR_COMM once an exchange timed out / a migration list overflowed
+int fsim_ensure_capacity(fsim* h, int64_t n);  // fsim_api.cu
+MigDev* dist_mig_dev(const fsim* h);
+const uint32_t* dist_nsrc_dev(fsim* h);                   // device count of source particles for the reorder (locals + immigrants); valid once after dist_migrate
+int64_t dist_mig_capacity(const fsim* h);

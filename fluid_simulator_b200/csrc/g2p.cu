@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(256) gfx_kernel(GridDims g, const float* px, c
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float x = px[i], y = py[i], z = pz[i];
-    const float qx = x * g.ihx - 0.5f, qy = y * g.ihy - 0.5f, qz = z * g.ihz - 0.5f;
+    const float qx = x * g.ihx - 0.5f, qy = y * g.ihy - 0.5f, qz = z * g.ihz - 0.5f - (float)g.zoff;
     int ix = (int)floorf(qx), iy = (int)floorf(qy), iz = (int)floorf(qz);
     ix = max(0, min(ix, g.gx - 2)); iy = max(0, min(iy, g.gy - 2)); iz = max(0, min(iz, g.gz - 2));
     const float wx1 = qx - ix, wy1 = qy - iy, wz1 = qz - iz;

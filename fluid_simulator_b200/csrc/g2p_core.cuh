@@ -86,7 +86,7 @@ __device__ __forceinline__ void gather(const Args& a, const float (*s)[SN], int 
     const bool apic = a.transfer == FSIM_TRANSFER_APIC;
     const int naxis = g.twoD ? 2 : 3;  // 2D: v.z = 0 and c[2] untouched (simulator.cpp:382-385)
     // node-index-space origin of the tile: staggered dim: face i sits at i+1 => q = p/h - 1 ; centred: q = p/h - 0.5
-    const float ox = (float)(x0 - 1), oy = (float)(y0 - 1), oz = (float)(z0 - 1);
+    const float ox = (float)(x0 - 1), oy = (float)(y0 - 1), oz = (float)(z0 - 1 + g.zoff);  // positions are global, the tile is local
     const float gxp = x * g.ihx, gyp = y * g.ihy, gzp = z * g.ihz;
     vnew[0] = vnew[1] = vnew[2] = 0.f;
     for (int ax = 0; ax < naxis; ax++) {

@@ -47,7 +47,7 @@ inline dim3 cell_grid(const GridDims& g) { return dim3(div_up(g.gx, CBX), div_up
 inline dim3 cell_block() { return dim3(CBX, CBY, CBZ); }
 
 __device__ __forceinline__ bool is_border(const GridDims& g, int x, int y, int z, int top_solid) {
-    return x == 0 || x == g.gx - 1 || y == 0 || (top_solid && y == g.gy - 1) || z == 0 || z == g.gz - 1;
+    return x == 0 || x == g.gx - 1 || y == 0 || (top_solid && y == g.gy - 1) || z + g.zoff == 0 || z + g.zoff == g.gzg - 1;
 }
 
 __global__ void __launch_bounds__(256) classify_kernel(GridDims g, const uint32_t* __restrict__ cnt, const DevObstacle* obs,
@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(256) classify_kernel(GridDims g, const uint32_
     if (!cell_xyz(g, x, y, z, c)) return;
     const bool has = cnt[c] > 0;
     int type = has ? FSIM_CELL_WATER : FSIM_CELL_AIR;
-    if (nobs > 0 && obstacle_mask(obs, nobs, x, y, z)) type = FSIM_CELL_SOLID;
+    if (nobs > 0 && obstacle_mask(obs, nobs, x, y, z + g.zoff)) type = FSIM_CELL_SOLID;
     if (is_border(g, x, y, z, top_solid)) type = FSIM_CELL_SOLID;
     const int valid = (type == FSIM_CELL_WATER) ? 0 : 3;
     flags[c] = (uint8_t)(type | (has ? FL_HASPART : 0) | (valid << FL_VALID_SHIFT));
@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(FinalizeArgs a) {
     const int t0 = f0 & FL_TYPE_MASK;
     const int nx[3] = {x + 1, x, x}, ny[3] = {y, y + 1, y}, nz[3] = {z, z, z + 1};
     unsigned m0 = 0;
-    if (a.nobs > 0) m0 = obstacle_mask(a.obs, a.nobs, x, y, z);
+    if (a.nobs > 0) m0 = obstacle_mask(a.obs, a.nobs, x, y, z + g.zoff);
 #pragma unroll
     for (int ax = 0; ax < 3; ax++) {
         float val = a.u[ax][c];
@@ -116,13 +116,13 @@ __global__ void __launch_bounds__(256) finalize_kernel(FinalizeArgs a) {
         uint8_t f1 = 0;
         if (nb_ok) { f1 = a.flags[cidx(g, nx[ax], ny[ax], nz[ax])]; t1 = f1 & FL_TYPE_MASK; }
         if (a.nobs > 0 && nb_ok && !a.post_only) {
-            const unsigned m1 = obstacle_mask(a.obs, a.nobs, nx[ax], ny[ax], nz[ax]);
+            const unsigned m1 = obstacle_mask(a.obs, a.nobs, nx[ax], ny[ax], nz[ax] + g.zoff);
             const int k = face_obstacle(m0, m1, (f0 & FL_HASPART) != 0, (f1 & FL_HASPART) != 0);
             if (k >= 0) val = (float)a.obs[k].speed[ax];
         }
         // border shell: wall-normal face next to a WATER interior cell is zeroed (macGrid.cpp:80-104)
-        const int pos_ax = ax == 0 ? x : (ax == 1 ? y : z);
-        const int gsz = ax == 0 ? g.gx : (ax == 1 ? g.gy : g.gz);
+        const int pos_ax = ax == 0 ? x : (ax == 1 ? y : z + g.zoff);
+        const int gsz = ax == 0 ? g.gx : (ax == 1 ? g.gy : g.gzg);
         if (!a.post_only) {
             if (pos_ax == 0 && t1 == FSIM_CELL_WATER) val = 0.f;
             if (pos_ax == gsz - 2 && t0 == FSIM_CELL_WATER && (ax != 1 || a.top_solid)) val = 0.f;
@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(256) basic_sor_kernel(BasicArgs a) {
     int64_t c;
     if (!cell_xyz(g, x, y, z, c)) return;
     if (((x + y + z) & 1) != a.parity) return;
-    if (x < 1 || y < 1 || z < 1 || x >= g.gx - 1 || y >= g.gy - 1 || z >= g.gz - 1) return;
+    if (x < 1 || y < 1 || z < 1 || x >= g.gx - 1 || y >= g.gy - 1 || z >= g.gz - 1) return;  // (single-GPU only)
     if ((a.flags[c] & FL_TYPE_MASK) != FSIM_CELL_WATER) return;
     const int s1 = (a.flags[c + g.sz] & FL_TYPE_MASK) != FSIM_CELL_SOLID, s2 = (a.flags[c - g.sz] & FL_TYPE_MASK) != FSIM_CELL_SOLID;
     const int s3 = (a.flags[c + g.sy] & FL_TYPE_MASK) != FSIM_CELL_SOLID, s4 = (a.flags[c - g.sy] & FL_TYPE_MASK) != FSIM_CELL_SOLID;
@@ -368,8 +368,9 @@ int k_extrapolate(fsim* h) {
     for (int ax = 0; ax < 3; ax++) a.u2[ax] = h->u2[ax];
     for (int it = 0; it < 2; it++) {
         a.it = it;
-        KScope ks(h, K_EXTRAP);
-        extrapolate_kernel<<<cell_grid(h->g), cell_block(), 0, h->stream>>>(a);
+        { KScope ks(h, K_EXTRAP); extrapolate_kernel<<<cell_grid(h->g), cell_block(), 0, h->stream>>>(a); }
+        // slab mode: a sweep reads the validity and velocities the neighbours wrote in the previous one
+        if (h->dist) { int rc = dist_halo(h, HALO_U2_FLAGS, false); if (rc) return rc; }
     }
     FSIM_CHECK_LAUNCH(h);
     return FSIM_OK;

@@ -496,7 +496,7 @@ __global__ void __launch_bounds__(256) mg_prolong_jacobi4_kernel(Lv L, Lv C, con
     }
 }
 
-// Galerkin operator of level 1 from the cell flags: face weight = # WATER-WATER fine connections across the coarse
+// Galerkin operator of level 1 from the stencil codes: face weight = # WATER-WATER fine connections across the coarse
 // face; diagonal = # connections from WATER children to non-solid cells outside the aggregate
 __global__ void __launch_bounds__(256) mg_build1_kernel(Lv L, Lv C, float* __restrict__ wx, float* __restrict__ wy,
                                                          float* __restrict__ wz, float* __restrict__ diag) {
@@ -509,17 +509,18 @@ __global__ void __launch_bounds__(256) mg_build1_kernel(Lv L, Lv C, float* __res
                 const int x = 2 * X + i, y = 2 * Y + j, z = 2 * Z + k;
                 if (x >= L.gx || y >= L.gy || z >= L.gz) continue;
                 const int64_t c = ((int64_t)z * L.gy + y) * L.gx + x;
-                if ((L.flags[c] & FL_TYPE_MASK) != FSIM_CELL_WATER) continue;  // WATER => interior => neighbours exist
+                // from the stencil code (bits 0-5: linked WATER neighbours, bits 6-8: # non-solid neighbours); in slab mode
+                // the links into ghost planes are cut in these codes, so such a neighbour counts on the diagonal only
+                const unsigned cd = L.code[c];
+                if (!(cd & CODE_ACTIVE)) continue;
                 const int loc[3] = {i, j, k};
-                const int64_t st[3] = {1, L.sy, L.sz};
+                d += (float)((cd >> 6) & 7u);
 #pragma unroll
                 for (int a = 0; a < 3; a++) {
-                    const int tm = L.flags[c - st[a]] & FL_TYPE_MASK, tp = L.flags[c + st[a]] & FL_TYPE_MASK;
-                    // - neighbour: inside the aggregate iff loc == 1
-                    if (tm != FSIM_CELL_SOLID && !(loc[a] == 1 && tm == FSIM_CELL_WATER)) d += 1.f;
-                    // + neighbour: inside the aggregate iff loc == 0
-                    if (tp != FSIM_CELL_SOLID && !(loc[a] == 0 && tp == FSIM_CELL_WATER)) d += 1.f;
-                    if (loc[a] == 1 && tp == FSIM_CELL_WATER) w[a] += 1.f;
+                    const bool wm = (cd >> (2 * a)) & 1u, wp = (cd >> (2 * a + 1)) & 1u;
+                    if (loc[a] == 1 && wm) d -= 1.f;  // - neighbour is a WATER sibling inside the aggregate
+                    if (loc[a] == 0 && wp) d -= 1.f;  // + neighbour is a WATER sibling inside the aggregate
+                    if (loc[a] == 1 && wp) w[a] += 1.f;
                 }
             }
     wx[cc] = w[0]; wy[cc] = w[1]; wz[cc] = w[2]; diag[cc] = d;
@@ -712,7 +713,7 @@ Lv view(const fsim* h, const MgLevel* m, int level) {
     v.gx = m->gx; v.gy = m->gy; v.gz = m->gz; v.sy = m->sy; v.sz = m->sz;
     v.wx = m->wx; v.wy = m->wy; v.wz = m->wz; v.diag = m->diag;
     v.flags = level == 0 ? h->flags : nullptr;
-    v.code = level == 0 ? h->code : nullptr;
+    v.code = level == 0 ? h->code_mg : nullptr;
     return v;
 }
 
@@ -888,7 +889,7 @@ int mg_build(fsim* h) {
 }
 
 // the fused paths need the float4 level-0 kernels
-bool mg_can_fuse(const fsim* h) { return h->use_mg && !h->mg.empty() && h->mg[0]->gx % 4 == 0 && h->g.nc % 4 == 0; }
+bool mg_can_fuse(const fsim* h) { return h->use_mg && !h->dist && !h->mg.empty() && h->mg[0]->gx % 4 == 0 && h->g.nc % 4 == 0; }
 
 // CG update (p, r, ||r||_inf, convergence flags) fused with the first smoothing sweep of the cycle that follows
 int mg_update_first(fsim* h) {

@@ -78,7 +78,7 @@ __device__ __forceinline__ void p2g_face_pass(const P2GArgs& a, const Src& src, 
             float f[3];
             f[0] = fmaf(X, a.g.ihx, -(float)x);  // single rounding
             f[1] = fmaf(Y, a.g.ihy, -(float)y);
-            f[2] = fmaf(Z, a.g.ihz, -(float)z);
+            f[2] = fmaf(Z, a.g.ihz, -(float)(z + a.g.zoff));
             const float2 wA = make_float2(1.f - f[AXIS], f[AXIS]);
             float wB[3], wC[3];
             centred_w(f[B], wB);
@@ -152,7 +152,7 @@ __device__ __forceinline__ void p2g_density_pass(const P2GArgs& a, const Src& sr
         auto body = [&](float X, float Y, float Z) {
             const float fx = fmaf(X, a.g.ihx, -(float)x);
             const float fy = fmaf(Y, a.g.ihy, -(float)y);
-            const float fz = fmaf(Z, a.g.ihz, -(float)z);
+            const float fz = fmaf(Z, a.g.ihz, -(float)(z + a.g.zoff));
             float wx[3], wy_[3], wz_[3];
             centred_w(fx, wx); centred_w(fy, wy_); centred_w(fz, wz_);
             const float2 wx01 = make_float2(wx[0], wx[1]), wx2 = make_float2(wx[2], 0.f);
@@ -313,7 +313,7 @@ int k_p2g(fsim* h) {
         }
         FSIM_CUDA(h, cudaMemsetAsync(h->dens, 0, sizeof(float) * g.nc, h->stream));
     }
-    if (h->np == 0) return FSIM_OK;
+    if (h->np == 0) return FSIM_OK;  // (slab mode: np is current here, k_sort read it back)
     P2GArgs a;
     a.g = g;
     const ParticleSet& p = h->ps[h->cur];

@@ -50,6 +50,7 @@ struct AdvectArgs {
     int do_bin;
     GridDims g;
     uint32_t *cnt, *key, *rank;
+    MigDev* mig;  // slab mode: particles whose cell left the owned z-range are listed here instead of being binned
 };
 
 __device__ __forceinline__ uint32_t cell_key(const GridDims& g, float x, float y, float z);
@@ -207,7 +208,19 @@ __device__ __forceinline__ bool advect_particle(const AdvectArgs& a, D3& pos, D3
 // particle pass live = false)
 __device__ __forceinline__ void bin_particle(const AdvectArgs& a, int64_t i, bool live, bool killed, float fx, float fy, float fz) {
     uint32_t k = INVALID_KEY;
-    if (live && !killed) k = cell_key(a.g, fx, fy, fz);
+    if (live && !killed) {
+        k = cell_key(a.g, fx, fy, fz);
+        if (a.mig) {  // slab mode: same index expression as cell_key, on the global grid
+            const int izg = min(max((int)((double)fz * a.g.dihz), 0), a.g.gzg - 1);
+            const int dir = izg < a.mig->own_lo ? 0 : (izg >= a.mig->own_hi ? 1 : -1);
+            if (dir >= 0) {
+                k = INVALID_KEY;
+                const uint32_t slot = atomicAdd(&a.mig->count[dir], 1u);
+                if (slot < a.mig->cap) a.mig->idx[dir][slot] = (uint32_t)i;
+                else atomicAdd(&a.mig->overflow, 1u);
+            }
+        }
+    }
     const unsigned peers = __match_any_sync(0xffffffffu, k);
     const int lane = threadIdx.x & 31;
     const int leader = __ffs(peers) - 1;
@@ -303,7 +316,7 @@ __global__ void __launch_bounds__(GA_THREADS, 6) g2p_advect_kernel(const __grid_
 // particle -> device cell key; the index is ivec3(pos * cellDInv) evaluated in fp64 on the stored fp32 position,
 // exactly what the reference computes on the same coordinates (simulator.cpp:358-359).
 __device__ __forceinline__ uint32_t cell_key(const GridDims& g, float x, float y, float z) {
-    int ix = (int)((double)x * g.dihx), iy = (int)((double)y * g.dihy), iz = (int)((double)z * g.dihz);
+    int ix = (int)((double)x * g.dihx), iy = (int)((double)y * g.dihy), iz = (int)((double)z * g.dihz) - g.zoff;
     ix = min(max(ix, 0), g.gx - 1); iy = min(max(iy, 0), g.gy - 1); iz = min(max(iz, 0), g.gz - 1);
     return (uint32_t)((iz * g.gy + iy) * g.gx + ix);
 }
@@ -420,6 +433,7 @@ struct ReorderArgs {
     int nch;
     const uint32_t *key, *rank, *cell_start;
     int64_t n;
+    const uint32_t* n_dev;  // slab mode: the source count (locals + immigrants) is only known on the device
 };
 
 // All channel loads are issued before the first scattered store (source and destination sets never alias, but the
@@ -427,7 +441,7 @@ struct ReorderArgs {
 template <int NCH>
 __global__ void __launch_bounds__(256) reorder_kernel(ReorderArgs a) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.n) return;
+    if (i >= (a.n_dev ? (int64_t)*a.n_dev : a.n)) return;
     const uint32_t k = __ldg(a.key + i);
     const uint32_t r = __ldg(a.rank + i);
     float v[NCH];
@@ -467,7 +481,7 @@ __global__ void __launch_bounds__(256) push_apart_kernel(PushApartArgs a) {
     const GridDims& g = a.g;
     const float x = a.px[i], y = a.py[i], z = a.pz[i];
     const int cx = min(max((int)((double)x * g.dihx), 0), g.gx - 1), cy = min(max((int)((double)y * g.dihy), 0), g.gy - 1),
-              cz = min(max((int)((double)z * g.dihz), 0), g.gz - 1);
+              cz = min(max((int)((double)z * g.dihz) - g.zoff, 0), g.gz - 1);
     float dx = 0.f, dy = 0.f, dz = 0.f;
     const int x0 = max(cx - a.R, 0), x1 = min(cx + a.R, g.gx - 1);
     for (int zz = max(cz - a.R, 0); zz <= min(cz + a.R, g.gz - 1); zz++)
@@ -535,7 +549,7 @@ __global__ void particle_cells_kernel(GridDims g, const float* px, const float* 
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int ix = (int)((double)px[i] * g.dihx), iy = (int)((double)py[i] * g.dihy), iz = (int)((double)pz[i] * g.dihz);
-    out[i] = ix * g.gy * g.gz + iy * g.gz + iz;
+    out[i] = ix * g.gy * g.gzg + iy * g.gzg + iz;  // global reference-order index
 }
 // stable compaction by sorted id list (HashedParticles::removeParticles, hashedParticles.cpp:158-172):
 // marks, then the generic bin/scan/reorder machinery is not used here because the order must be preserved.
@@ -583,7 +597,7 @@ ReorderArgs reorder_args(fsim* h) {
     for (int c = 0; c < 15; c++) { a.src[c] = s.ch[c]; a.dst[c] = d.ch[c]; }
     a.src_id = h->track_ids ? h->ps[h->cur].id : nullptr;
     a.dst_id = h->track_ids ? h->ps[h->cur ^ 1].id : nullptr;
-    a.key = h->key; a.rank = h->rank; a.cell_start = h->cell_start; a.n = h->np;
+    a.key = h->key; a.rank = h->rank; a.cell_start = h->cell_start; a.n = h->np; a.n_dev = nullptr;
     return a;
 }
 
@@ -592,6 +606,13 @@ ReorderArgs reorder_args(fsim* h) {
 int k_advect(fsim* h, double dt, bool do_advect, bool do_pushout, bool do_stop, bool do_bin, bool fuse_g2p) {
     h->binned = false;
     if (fuse_g2p) h->g2p_pending = false;
+    if (h->np == 0 && h->dist && do_bin) {  // an empty slab still takes part in the migration: its histogram must be zero
+        KScope ks(h, K_MEMSET);
+        FSIM_CUDA(h, cudaMemsetAsync(h->cnt, 0, sizeof(uint32_t) * h->g.nc, h->stream));
+        h->sorted = false;
+        h->binned = true;
+        return FSIM_OK;
+    }
     if (h->np == 0) return FSIM_OK;
     AdvectArgs a;
     ParticleSet& p = h->ps[h->cur];
@@ -612,6 +633,7 @@ int k_advect(fsim* h, double dt, bool do_advect, bool do_pushout, bool do_stop, 
     a.obs = h->d_obs;
     a.kill = h->kill;
     a.do_bin = do_bin; a.g = h->g; a.cnt = h->cnt; a.key = h->key; a.rank = h->rank;
+    a.mig = (h->dist && do_bin) ? dist_mig_dev(h) : nullptr;
     if (do_bin) { KScope ks(h, K_MEMSET); FSIM_CUDA(h, cudaMemsetAsync(h->cnt, 0, sizeof(uint32_t) * h->g.nc, h->stream)); }
     if (fuse_g2p) {  // requires cell-binned particles (h->sorted) and do_bin
         g2p::Args ga;
@@ -643,12 +665,15 @@ int k_sort(fsim* h) {
     FSIM_CHECK_LAUNCH(h);
     int rc = exclusive_scan(h, h->cnt, g.nc, h->cell_start);
     if (rc) return rc;
-    if (h->np > 0) {
+    const uint32_t* nsrc = h->dist ? dist_nsrc_dev(h) : nullptr;  // non-null right after dist_migrate (one-shot)
+    if (h->np > 0 || nsrc) {
         ReorderArgs a = reorder_args(h);
+        int64_t nthreads = h->np;
+        if (nsrc) { a.n_dev = nsrc; nthreads = h->np + 2 * dist_mig_capacity(h); }  // immigrants sit behind the locals
         {
             KScope ks(h, K_REORDER);
-            if (a.nch == 6) reorder_kernel<6><<<div_up(h->np, 256), 256, 0, h->stream>>>(a);
-            else reorder_kernel<15><<<div_up(h->np, 256), 256, 0, h->stream>>>(a);
+            if (a.nch == 6) reorder_kernel<6><<<div_up(nthreads, 256), 256, 0, h->stream>>>(a);
+            else reorder_kernel<15><<<div_up(nthreads, 256), 256, 0, h->stream>>>(a);
         }
         FSIM_CHECK_LAUNCH(h);
         h->cur ^= 1;

@@ -17,6 +17,7 @@
 
 #include "fsim_internal.h"
 #include "reduce.cuh"
+#include "pcg_finish.cuh"
 
 int mg_apply(fsim* h, bool first_done, bool with_dot);  // z = M^-1 r   (mg.cu)
 int mg_update_first(fsim* h);
@@ -33,6 +34,7 @@ struct PcgArgs {
     GridDims g;
     const uint8_t* flags;
     uint16_t* code;
+    uint16_t* code_mg;  // slab mode: the codes the multigrid sees (links into ghost planes cut); nullptr otherwise
     const float* u2[3];
     const float* dens;
     double *p, *rhs, *r, *q, *z;
@@ -65,7 +67,9 @@ __global__ void __launch_bounds__(PT) rhs_kernel(PcgArgs a) {
     if (c < a.g.nc) {
         double rhs = 0.0;
         unsigned code = 0;
-        if ((a.flags[c] & FL_TYPE_MASK) == FSIM_CELL_WATER) {  // WATER cells are interior: all six neighbours exist
+        const int zc = (int)c / a.g.sz;
+        const bool owned = zc >= a.g.zown0 && zc < a.g.zown1;  // slab mode: ghost planes never become active
+        if (owned && (a.flags[c] & FL_TYPE_MASK) == FSIM_CELL_WATER) {  // WATER cells are interior: all six neighbours exist
             const int64_t nb[6] = {c - 1, c + 1, c - a.g.sy, c + a.g.sy, c - a.g.sz, c + a.g.sz};
             unsigned wm = 0, ns = 0;
 #pragma unroll
@@ -82,6 +86,12 @@ __global__ void __launch_bounds__(PT) rhs_kernel(PcgArgs a) {
             acc[1] = 1.0;
         }
         a.code[c] = (uint16_t)code;
+        if (a.code_mg) {
+            unsigned cm = code;
+            if (zc - 1 < a.g.zown0) cm &= ~16u;
+            if (zc + 1 >= a.g.zown1) cm &= ~32u;
+            a.code_mg[c] = (uint16_t)cm;
+        }
         a.rhs[c] = rhs;
         if (!a.warm) { a.r[c] = rhs; a.p[c] = 0.0; if (a.p_prev) a.p_prev[c] = 0.f; }
         else {
@@ -99,18 +109,8 @@ __global__ void __launch_bounds__(PT) rhs_kernel(PcgArgs a) {
     }
     double out[2];
     if (grid_reduce<2, 0>(acc, a.partials, a.counter, out)) {
-        a.sc->rhs_sumsq = out[0];
-        a.sc->fluid_cells = (long long)(out[1] + 0.5);
-        a.sc->early_out = out[0] < 1e-7;
-        a.sc->done = a.sc->early_out;
-        a.sc->iterations = 0;
-        a.sc->nan_break = 0;
-        a.sc->rmax = 0.0;
-        a.sc->sigma = 0.0;
-        a.sc->it = 0;
-        a.status->done = a.sc->done;
-        a.status->it_done = 0;
-        __threadfence_system();
+        if (a.sc->dist) { a.sc->loc[0] = out[0]; a.sc->loc[3] = out[1]; a.sc->done = 0; }
+        else pcg_finish_rhs(a.sc, a.status, out[0], out[1]);
     }
 }
 
@@ -141,13 +141,8 @@ __global__ void __launch_bounds__(PT) residual_kernel(PcgArgs a) {
     }
     double out[1];
     if (grid_reduce<0, 1>(acc, a.partials, a.counter, out)) {
-        a.sc->r0max = out[0];
-        if (out[0] < a.sc->tol) {  // last step's pressure already satisfies the tolerance
-            a.sc->done = 1;
-            a.sc->rmax = out[0];
-            a.status->done = 1;
-            __threadfence_system();
-        }
+        if (a.sc->dist) a.sc->loc[2] = out[0];
+        else pcg_finish_residual(a.sc, a.status, out[0]);
     }
 }
 
@@ -177,7 +172,7 @@ __global__ void __launch_bounds__(PT) start_kernel(PcgArgs a) {
         a.s[c] = (float)z;
     }
     double out[1];
-    if (grid_reduce<1, 0>(acc, a.partials, a.counter, out)) a.sc->sigma = out[0];
+    if (grid_reduce<1, 0>(acc, a.partials, a.counter, out)) { if (a.sc->dist) a.sc->loc[0] = out[0]; else a.sc->sigma = out[0]; }
 }
 
 // q = A s fused with s.q  (applyAMatrix :165-198 + dotProduct :200-214); VEC: 16-byte loads, two cells per thread
@@ -247,7 +242,7 @@ __global__ void __launch_bounds__(PT) spmv_kernel(PcgArgs a) {
         }
     }
     double out[1];
-    if (grid_reduce<1, 0>(acc, a.partials, a.counter, out)) a.sc->sq = out[0];
+    if (grid_reduce<1, 0>(acc, a.partials, a.counter, out)) { if (a.sc->dist) a.sc->loc[0] = out[0]; else a.sc->sq = out[0]; }
 }
 
 // same as spmv_kernel<true> with four cells per thread and trip (gx % 4 == 0): 13 independent loads in flight per thread
@@ -293,7 +288,7 @@ __global__ void __launch_bounds__(PT, 4) spmv4_kernel(PcgArgs a) {
         *reinterpret_cast<double2*>(a.q + c + 2) = make_double2(q[2], q[3]);
     }
     double out[1];
-    if (grid_reduce<1, 0>(acc, a.partials, a.counter, out)) a.sc->sq = out[0];
+    if (grid_reduce<1, 0>(acc, a.partials, a.counter, out)) { if (a.sc->dist) a.sc->loc[0] = out[0]; else a.sc->sq = out[0]; }
 }
 
 // alpha = sigma / s.q ; p += alpha s ; r -= alpha q ; ||r||_inf ; (JACOBI: z = r / A_ii ; sigma' = z.r)   (:270-284)
@@ -325,23 +320,8 @@ __global__ void __launch_bounds__(PT) update_kernel(PcgArgs a) {
     }
     double out[2];
     if (grid_reduce<1, 1>(acc, a.partials, a.counter, out)) {
-        const int it = a.sc->it;
-        if (bad) {
-            a.sc->nan_break = 1;
-            a.sc->done = 1;
-            a.sc->iterations = it;
-        } else {
-            a.sc->rmax = out[1];
-            a.sc->sigma_new = out[0];
-            if (out[1] < a.sc->tol) {  // converged inside iteration `it` => the reference returns it (:280-281, 292)
-                a.sc->done = 1;
-                a.sc->iterations = it;
-            } else if (it + 1 >= a.sc->max_it) {
-                a.sc->done = 2;  // iteration cap; the direction update is skipped like the loop exit would
-                a.sc->iterations = a.sc->max_it;
-            }
-        }
-        if (a.sc->done) { a.status->done = a.sc->done; __threadfence_system(); }
+        if (a.sc->dist) { a.sc->loc[0] = out[0]; a.sc->loc[2] = out[1]; }
+        else pcg_finish_update(a.sc, a.status, out[0], out[1]);
     }
 }
 
@@ -357,7 +337,7 @@ __global__ void __launch_bounds__(PT) dot_zr_kernel(PcgArgs a) {
         if (a.code[c] & CODE_ACTIVE) acc[0] += (double)a.z32[c] * a.r[c];
     }
     double out[1];
-    if (grid_reduce<1, 0>(acc, a.partials, a.counter, out)) a.sc->sigma_new = out[0];
+    if (grid_reduce<1, 0>(acc, a.partials, a.counter, out)) { if (a.sc->dist) a.sc->loc[0] = out[0]; else a.sc->sigma_new = out[0]; }
 }
 
 // beta = sigma'/sigma ; s = z + beta s   (:284-289); sigma <- sigma' is published by sigma_kernel afterwards
@@ -398,12 +378,16 @@ __global__ void sigma_kernel(PcgScalars* sc, PcgHostStatus* status) {
 
 // one PCG iteration: SpMV -> update -> (multigrid cycle -> z.r | fused diagonal) -> direction -> close
 static int enqueue_iteration(fsim* h, const PcgArgs& a, bool vec, bool use_mg, int nbv) {
+    const bool dist = h->dist != nullptr;
+    auto AR = [&](int kind) { return dist ? dist_allreduce(h, kind, true) : FSIM_OK; };
+    if (dist) { int rc = dist_halo(h, HALO_S, true); if (rc) return rc; }  // ghost planes of the search direction
     {
         KScope ks(h, K_SPMV);
         if (vec && a.g.gx % 4 == 0 && a.g.nc % 4 == 0) spmv4_kernel<<<nbv, PT, 0, h->stream>>>(a);
         else if (vec) spmv_kernel<true><<<nbv, PT, 0, h->stream>>>(a);
         else spmv_kernel<false><<<nbv, PT, 0, h->stream>>>(a);
     }
+    { int rc = AR(AR_SPMV); if (rc) return rc; }
     if (use_mg && mg_can_fuse(h)) {
         // update fused with the cycle's first sweep, z.r fused with its last sweep: 2 passes and 2 launches fewer
         int rc = mg_update_first(h);
@@ -413,14 +397,18 @@ static int enqueue_iteration(fsim* h, const PcgArgs& a, bool vec, bool use_mg, i
         if (a.z32 != h->mg_z32) return fsim_fail(h, FSIM_ERR_INVALID, "multigrid result buffer moved between cycles");
     } else if (use_mg) {
         { KScope ks(h, K_UPDATE); update_kernel<false><<<nbv, PT, 0, h->stream>>>(a); }
-        int rc = mg_apply(h, false, false);
+        int rc = AR(AR_UPDATE);
+        if (rc) return rc;
+        rc = mg_apply(h, false, false);
         if (rc) return rc;
         if (a.z32 != h->mg_z32) return fsim_fail(h, FSIM_ERR_INVALID, "multigrid result buffer moved between cycles");
-        KScope ks(h, K_UPDATE);
-        dot_zr_kernel<<<nbv, PT, 0, h->stream>>>(a);
+        { KScope ks(h, K_UPDATE); dot_zr_kernel<<<nbv, PT, 0, h->stream>>>(a); }
+        rc = AR(AR_DOTZR);
+        if (rc) return rc;
     } else {
-        KScope ks(h, K_UPDATE);
-        update_kernel<true><<<nbv, PT, 0, h->stream>>>(a);
+        { KScope ks(h, K_UPDATE); update_kernel<true><<<nbv, PT, 0, h->stream>>>(a); }
+        int rc = AR(AR_UPDATE_JACOBI);
+        if (rc) return rc;
     }
     {
         KScope ks(h, K_DIRECTION, 2);
@@ -434,7 +422,7 @@ int k_project(fsim* h, double dt, int* iterations) {
     if (h->par.solver_type == FSIM_SOLVER_BASIC) return k_project_basic(h, iterations);
     const GridDims& g = h->g;
     PcgArgs a;
-    a.g = g; a.flags = h->flags; a.code = h->code;
+    a.g = g; a.flags = h->flags; a.code = h->code; a.code_mg = h->code_mg != h->code ? h->code_mg : nullptr;
     for (int ax = 0; ax < 3; ax++) a.u2[ax] = h->u2[ax];
     a.dens = h->dens;
     a.p = h->p; a.rhs = h->rhs; a.r = h->r; a.s = h->s; a.q = h->q; a.z = h->z;
@@ -459,24 +447,31 @@ int k_project(fsim* h, double dt, int* iterations) {
     sh->inv_scale = 1.0 / sh->scale;
     sh->tol = h->par.residual_tolerance;
     sh->max_it = max_it;
+    sh->dist = h->dist ? 1 : 0;
     h->status_host->done = 0;
     h->status_host->it_done = 0;
     FSIM_CUDA(h, cudaMemcpyAsync(h->scal, sh, sizeof(PcgScalars), cudaMemcpyHostToDevice, h->stream));
 
+    const bool dist = h->dist != nullptr;
     { KScope ks(h, K_RHS); rhs_kernel<<<div_up(g.nc, PT), PT, 0, h->stream>>>(a); }  // one cell per thread (a chunked loop was 25 % slower)
-    if (a.warm) { KScope ks(h, K_RHS); residual_kernel<<<nbv, PT, 0, h->stream>>>(a); }
+    if (dist) { int rc = dist_allreduce(h, AR_RHS, false); if (rc) return rc; }
+    if (a.warm) {
+        if (dist) { int rc = dist_halo(h, HALO_P, true); if (rc) return rc; }  // the initial guess of the neighbours' boundary planes
+        { KScope ks(h, K_RHS); residual_kernel<<<nbv, PT, 0, h->stream>>>(a); }
+        if (dist) { int rc = dist_allreduce(h, AR_RESIDUAL, true); if (rc) return rc; }
+    }
     if (use_mg) {
         int rc = mg_build(h);
         if (rc) return rc;
         rc = mg_apply(h, false, false);
         if (rc) return rc;
         a.z32 = h->mg_z32;
-        KScope ks(h, K_PCG_INIT);
-        start_kernel<false><<<nbv, PT, 0, h->stream>>>(a);
+        { KScope ks(h, K_PCG_INIT); start_kernel<false><<<nbv, PT, 0, h->stream>>>(a); }
     } else {
         KScope ks(h, K_PCG_INIT);
         start_kernel<true><<<nbv, PT, 0, h->stream>>>(a);
     }
+    if (dist) { int rc = dist_allreduce(h, AR_START, true); if (rc) return rc; }
     FSIM_CHECK_LAUNCH(h);
 
     // The whole PCG loop runs on the device: a CUDA graph whose body (one iteration, captured once -- every argument is a
@@ -568,6 +563,9 @@ int k_project(fsim* h, double dt, int* iterations) {
     if (iterations) *iterations = h->solve.iterations;
     h->pressure_valid = !s.early_out;
     h->warm_history = s.early_out ? 0 : h->warm_history + 1;
-    if (!s.early_out) return k_pressure_apply(h, dt);  // the early-out returns before applying anything (:257-258)
+    if (!s.early_out) {  // the early-out returns before applying anything (:257-258)
+        if (dist) { int rc = dist_halo(h, HALO_P, false); if (rc) return rc; }  // pressure of the neighbours' boundary planes
+        return k_pressure_apply(h, dt);
+    }
     return FSIM_OK;
 }

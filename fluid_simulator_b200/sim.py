@@ -48,6 +48,12 @@ def load_library():
         "fsim_create": (i32, [P(abi.GridDesc), P(vp)]),
         "fsim_destroy": (i32, [vp]),
         "fsim_get_grid_info": (i32, [vp, P(abi.GridInfo)]),
+        "fsim_create_slab": (i32, [P(abi.GridDesc), i32, i32, P(vp)]),
+        "fsim_get_slab_info": (i32, [vp, P(abi.SlabInfo)]),
+        "fsim_dist_export": (i32, [vp, P(abi.DistExport)]),
+        "fsim_dist_connect": (i32, [vp, P(abi.DistExport), i32]),
+        "fsim_slab_partition": (i32, [i32, i32, i32, P(abi.SlabInfo)]),
+        "fsim_upload_particle_ids": (i32, [vp, vp, i64]),
         "fsim_set_params": (i32, [vp, P(abi.Params)]),
         "fsim_set_obstacles": (i32, [vp, P(abi.Obstacle), i32]),
         "fsim_get_obstacles": (i32, [vp, P(abi.Obstacle), i32, P(i32)]),
@@ -103,7 +109,7 @@ def load_library():
 class FluidSim:
     """B200 Simulator: BridsonSolverGrid + HashedParticles + Simulator behind the fsim C ABI."""
 
-    def __init__(self, dims, resolution=1.0, two_d=False, particle_radius=0.25, capacity=0, device=0, **_):
+    def __init__(self, dims, resolution=1.0, two_d=False, particle_radius=0.25, capacity=0, device=0, rank=0, nranks=1, **_):
         self.L = load_library()
         d = abi.GridDesc()
         d.target_dims[:] = dims
@@ -113,7 +119,10 @@ class FluidSim:
         d.particle_capacity = int(capacity)
         d.device = int(device)
         self.h = C.c_void_p()
-        rc = self.L.fsim_create(C.byref(d), C.byref(self.h))
+        if nranks > 1:  # one z-slab of the grid (fluid_simulator_b200.slab drives the group)
+            rc = self.L.fsim_create_slab(C.byref(d), int(rank), int(nranks), C.byref(self.h))
+        else:
+            rc = self.L.fsim_create(C.byref(d), C.byref(self.h))
         if rc:
             msg = self.L.fsim_last_error(None).decode()
             self.h = None
@@ -122,6 +131,13 @@ class FluidSim:
         self._ck(self.L.fsim_get_grid_info(self.h, C.byref(self.info)))
         self.grid_size = tuple(self.info.grid_size)
         self.nc = int(self.info.cell_count)
+        self.slab = abi.SlabInfo()
+        self._ck(self.L.fsim_get_slab_info(self.h, C.byref(self.slab)))
+        if nranks > 1:  # grid transfers move the local block: the owned planes + one ghost plane per neighbour
+            self.local_grid_size = (self.grid_size[0], self.grid_size[1], int(self.slab.gz_local))
+            self.nc = self.local_grid_size[0] * self.local_grid_size[1] * self.local_grid_size[2]
+        else:
+            self.local_grid_size = self.grid_size
 
     def _ck(self, rc):
         if rc:
@@ -137,6 +153,20 @@ class FluidSim:
             self.close()
         except Exception:
             pass
+
+    # --- z-slab group membership (include/fsim.h "z-slab decomposition") ----------------------------
+    def dist_export(self):
+        ex = abi.DistExport()
+        self._ck(self.L.fsim_dist_export(self.h, C.byref(ex)))
+        return ex
+
+    def dist_connect(self, exports):
+        arr = (abi.DistExport * len(exports))(*exports)
+        self._ck(self.L.fsim_dist_connect(self.h, arr, len(exports)))
+
+    def upload_particle_ids(self, ids):
+        a = np.ascontiguousarray(ids, dtype=np.uint32)
+        self._ck(self.L.fsim_upload_particle_ids(self.h, a.ctypes.data, a.shape[0]))
 
     # --- configuration (simulator->config = ..., simulator->obstacles = ...) ---------------------
     def set_params(self, params):
@@ -289,6 +319,10 @@ class FluidSim:
         return float(ms.value), int(n.value)
 
     def synchronize(self): self._ck(self.L.fsim_synchronize(self.h))
+
+    def synchronize_quiet(self):
+        if getattr(self, "h", None):
+            self.L.fsim_synchronize(self.h)
 
     def set_id_tracking(self, on): self._ck(self.L.fsim_set_id_tracking(self.h, int(on)))
 
