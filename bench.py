@@ -136,6 +136,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--obstacle-box", action="store_true", help="add the static box of SURVEY cfg 3 (size (24,96,N) at (0.7N,48,0.5N))")
+    ap.add_argument("--shard", default=os.environ.get("FSIM_BENCH_SHARD", "slab"), choices=["slab", "replicas"],
+                    help="N > 1: 'slab' cuts ONE N^3 domain into z-slabs (strong scaling; halos, migration and reductions over NVLink peer "
+                         "memory), 'replicas' runs an independent domain per GPU (weak scaling, no data-path exchange)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -165,19 +168,39 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback")
+    # FSIM_BENCH_SAME_DEVICE=1 (debugging on a one-GPU box): all ranks share cuda:0 and the plumbing runs over gloo
+    same_dev = os.environ.get("FSIM_BENCH_SAME_DEVICE") == "1"
+    if same_dev:
+        local_rank = 0
+    red_dev = "cpu" if same_dev else "cuda"
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        if same_dev:
+            dist.init_process_group("gloo")
+        else:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     transfer = {"PIC": abi.PIC, "FLIP": abi.FLIP, "APIC": abi.APIC}[args.transfer]
     n = args.grid
-    # weak scaling over ranks: every rank advances its own N^3 dam break (independent replicas of the workload);
-    # z-slab sharding of ONE domain with NCCL halos is the next step
     t_gen = time.perf_counter()
     from fluid_simulator_b200 import dist as fdist
-    pos = scenes.block_positions_f32(1, n // 2, 1, n - 1, 1, n - 1, seed=fdist.replica_seed(scenes.SEED, rank))
-    np_local = pos.shape[0]
-    sim = FluidSim((float(n),) * 3, 1.0, False, 0.25, capacity=np_local, device=local_rank)
+    from fluid_simulator_b200 import slab as fslab
+    slab_mode = world > 1 and args.shard == "slab"
+    if slab_mode:
+        # strong scaling: ONE N^3 dam break cut into z-slabs; every rank builds the part of the dam block that
+        # lies in the planes it owns (the jitter keeps a particle inside its cell, so ownership holds by construction)
+        lo, hi, zoff, gzl = fslab.partition(n, world)[rank]
+        pos = scenes.block_positions_f32(1, n // 2, 1, n - 1, max(lo, 1), min(hi, n - 1), seed=fdist.replica_seed(scenes.SEED, rank))
+        np_local = pos.shape[0]
+        sim = FluidSim((float(n),) * 3, 1.0, False, 0.25, capacity=int(np_local * 1.25) + 1024, device=local_rank, rank=rank, nranks=world)
+        fslab.connect_torch(sim, dist)
+        nc_local = n * n * gzl
+    else:
+        # weak scaling: every rank advances its own N^3 dam break (independent replicas of the workload)
+        pos = scenes.block_positions_f32(1, n // 2, 1, n - 1, 1, n - 1, seed=fdist.replica_seed(scenes.SEED, rank))
+        np_local = pos.shape[0]
+        sim = FluidSim((float(n),) * 3, 1.0, False, 0.25, capacity=np_local, device=local_rank)
+        nc_local = n ** 3
     sim.set_id_tracking(False)  # ids are test support; the hot path does not carry them
     sim.set_params(scene_params(n, transfer))
     if args.obstacle_box:
@@ -222,14 +245,15 @@ def main():
     prof = sim.profile_read(reset=True)
     sim.profile_enable([])
     kernel_ms = {k: {"ms_per_step": round(v[0] / prof_steps, 4), "launches_per_step": v[2] / prof_steps} for k, v in prof.items() if v[2]}
-    dominant = max(prof, key=lambda k: prof[k][0])
+    dominant = max((k for k in prof if k not in ("halo", "allreduce", "migrate")), key=lambda k: prof[k][0])  # exchange kernels mostly wait
     launches = sum(v[2] for v in counts.values())
     info = sim.solve_info()
     nf = int(info.fluid_cells)
+    nf_local = nf // world if slab_mode else nf  # the solve reports the all-rank count
     timings = sim.timings()
 
-    total_units, dev_ms_max, value = fdist.aggregate(dist, "cuda", np_local * args.steps, dev_ms, world)
-    total_particles = np_local * world
+    total_units, dev_ms_max, value = fdist.aggregate(dist, red_dev, np_local * args.steps, dev_ms, world)
+    total_particles = int(round(total_units / args.steps))
 
     # ---- end-to-end through the C ABI with host buffers: per step set_params + set_obstacles (H2D) + simulate + the
     # manager's gfx export into pinned host memory (D2H 20 B/particle), what simulationThreadWorker does per iteration
@@ -237,10 +261,11 @@ def main():
     if not args.no_e2e:
         # two pinned host buffers: the D2H copy of step k overlaps the simulation of step k+1 (the consumer of this data,
         # the render thread, is asynchronous in the reference as well); every buffer is complete before it is reused
-        gfx = [torch.empty((np_local, 5), dtype=torch.float32, pin_memory=True) for _ in range(2)]
+        gfx_cap = int(np_local * 1.25) + 1024 if slab_mode else np_local  # slab ranks gain and lose particles
+        gfx = [torch.empty((gfx_cap, 5), dtype=torch.float32, pin_memory=True) for _ in range(2)]
         params = scene_params(n, transfer)
         k = max(2, args.steps)  # same step count as the device-resident measurement (pipeline fill and drain are inside the timed region)
-        sim.set_params(params); sim.set_obstacles([]); sim.step(DT); sim.export_gfx_async_ptr(gfx[0].data_ptr(), np_local)
+        sim.set_params(params); sim.set_obstacles([]); sim.step(DT); sim.export_gfx_async_ptr(gfx[0].data_ptr(), gfx_cap)
         sim.export_gfx_wait()
         barrier()
         t0 = time.perf_counter()
@@ -248,12 +273,12 @@ def main():
             sim.set_params(params)
             sim.set_obstacles([scenes.cfg3_box(n)] if args.obstacle_box else [])
             sim.step(DT)
-            sim.export_gfx_async_ptr(gfx[i % 2].data_ptr(), np_local)
+            sim.export_gfx_async_ptr(gfx[i % 2].data_ptr(), gfx_cap)
             sim.export_gfx_wait_previous()            # buffer (i-1)%2 has landed and may be consumed
         sim.export_gfx_wait()
         barrier()
         el = time.perf_counter() - t0
-        t = torch.tensor([el], dtype=torch.float64, device="cuda")
+        t = torch.tensor([el], dtype=torch.float64, device=red_dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e = {"value": total_particles * k / float(t.item()), "unit": UNIT, "steps": k,
@@ -271,14 +296,14 @@ def main():
     its_mean = float(np.mean(step_its))
     # per-launch algorithmic bytes of the dominant kernel class
     pb = {abi.PIC: 24, abi.FLIP: 24, abi.APIC: 60}[transfer]
-    nc = n ** 3
+    nc = nc_local
     alg = {"advect": np_local * 2 * pb,                      # pass A: read + write pos, vel (+C)
            "p2g": np_local * pb + nc * (8 + 28),             # particles in, bin table, 7 accumulator channels out
            "g2p": np_local * (36 if transfer == abi.FLIP else pb + (12 if transfer == abi.PIC else 48)) + nc * (24 if transfer == abi.FLIP else 12),
            "reorder": np_local * (2 * pb + 8), "bin": np_local * 20,   # sort passes: implementation overhead, listed with their own minimal traffic
-           "spmv": nf * 16 + nc * 2, "pcg_update": nf * 56 + nc * 2, "pcg_direction": nf * 20 + nc * 2,
-           "mg": nf * 15 + nc * 2,                          # average level-0 multigrid kernel (jacobi 14, restrict 10, prolong 14, jacobi+dot 22 B)
-           "mg_level1": (nc // 8) * 28, "finalize": nc * 53, "extrapolate": nc * 25, "classify": nc * 5, "rhs": nc * 17 + nf * 28}
+           "spmv": nf_local * 16 + nc * 2, "pcg_update": nf_local * 56 + nc * 2, "pcg_direction": nf_local * 20 + nc * 2,
+           "mg": nf_local * 15 + nc * 2,                          # average level-0 multigrid kernel (jacobi 14, restrict 10, prolong 14, jacobi+dot 22 B)
+           "mg_level1": (nc // 8) * 28, "finalize": nc * 53, "extrapolate": nc * 25, "classify": nc * 5, "rhs": nc * 17 + nf_local * 28}
     if not prof.get("g2p", (0, 0, 0))[2]:  # the G2P ran inside the fused G2P + advect + bin kernel: its grid reads and key/rank writes join that pass
         alg["advect"] += nc * (24 if transfer == abi.FLIP else 12) + np_local * ((36 if transfer == abi.APIC else 0) + 8)
     traffic_path = os.path.join(ROOT, "profiles", "r1_dram_traffic_256_flip.json")
@@ -293,15 +318,22 @@ def main():
                     "traffic": traffic, "peak_source": peak_src, "avg_launch_ms": dom_ms / dom_n, "launches_timed": dom_n,
                     "algorithmic_bytes_per_launch": alg[dominant], "share_of_step": (dom_ms / prof_steps) / sum(v[0] / prof_steps for v in prof.values()),
                     "timed_in": f"{prof_steps} event-bracketed steps right after the timed region"}
-    b_step = np_local * B_PARTICLE[transfer] + n ** 3 * B_CELL + its_mean * nf * B_IT
-    step_frac = b_step / (dev_ms_max / args.steps * 1e-3) / 1e9 / peak
+    if slab_mode:  # one domain over all GPUs (fluid_cells is the all-rank count); the roof is N x the single-GPU peak
+        b_step = total_particles * B_PARTICLE[transfer] + n ** 3 * B_CELL + its_mean * nf * B_IT
+        step_frac = b_step / (dev_ms_max / args.steps * 1e-3) / 1e9 / (peak * world)
+    else:
+        b_step = np_local * B_PARTICLE[transfer] + n ** 3 * B_CELL + its_mean * nf * B_IT
+        step_frac = b_step / (dev_ms_max / args.steps * 1e-3) / 1e9 / peak
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "strong" if slab_mode else "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"3D {args.transfer} dam break {n}^3 (SURVEY §8d cfg 3 headline variant), {np_local} particles per GPU, "
-                                   f"8 per fluid cell, dt {DT}, PCG tol 1e-6", "grid": [n, n, n], "particles_per_gpu": np_local,
-                       "fluid_cells": nf, "pcg_iterations_mean": its_mean, "parallelism": f"replicas x{world}" if world > 1 else "single GPU",
+            "config": {"workload": f"3D {args.transfer} dam break {n}^3 (SURVEY §8d cfg 3 headline variant), "
+                                   + (f"{total_particles} particles in ONE domain cut into {world} z-slabs, " if slab_mode else f"{np_local} particles per GPU, ")
+                                   + f"8 per fluid cell, dt {DT}, PCG tol 1e-6", "grid": [n, n, n], "particles_per_gpu": np_local,
+                       "particles_total": total_particles, "fluid_cells": nf, "pcg_iterations_mean": its_mean,
+                       "parallelism": (f"z-slabs x{world} (ghost planes, particle migration and PCG reductions over NVLink peer memory)" if slab_mode
+                                       else (f"replicas x{world}" if world > 1 else "single GPU")),
                        "l2": "inputs larger than L2 (particle + grid state >> 126 MB), no flush needed"},
             "wall_ms_per_step": 1e3 * wall / args.steps, "clocks": clocks, "gpu_launches": int(launches),
             "step_hbm_frac": step_frac, "step_algorithmic_bytes": b_step,

@@ -36,8 +36,9 @@ struct DistComm {
     uint32_t mig_epoch[2], mig_count[2];
     // written by every rank: slot[parity][source rank]
     DistSlot slot[2][DIST_MAX_RANKS];
+    uint32_t arrive_all[DIST_MAX_RANKS], done_all[DIST_MAX_RANKS];  // all-rank handshake of the solver-input gather
     // local
-    uint32_t halo_epoch, ar_epoch, mig_ep, blocks_done, mig_blocks_done;
+    uint32_t halo_epoch, ar_epoch, mig_ep, blocks_done, mig_blocks_done, gather_epoch, gather_blocks_done, pad1;
     uint32_t error;   // 1 wait timed out, 2 emigrant list full, 3 immigrant outside the owned planes
     uint32_t n_src;   // particles the next reorder reads: locals + immigrants
     uint32_t pad0;
@@ -60,6 +61,8 @@ struct DistState {
     DistComm* peer_comm[2];
     int peer_ghost[2], peer_bnd[2];  // the neighbour's ghost plane towards us / its boundary plane (its local indices)
     DistComm* all_comm[DIST_MAX_RANKS];
+    void* all_arr[DIST_MAX_RANKS][DIST_NARR];     // every rank's arrays (the gather pulls the planes each rank owns)
+    int all_zown0[DIST_MAX_RANKS], all_zown1[DIST_MAX_RANKS], all_zoff[DIST_MAX_RANKS];
     bool connected, nsrc_valid;
     std::vector<void*> ipc_opened;
 };
@@ -86,13 +89,18 @@ __device__ __forceinline__ unsigned long long now_ns() {
 }
 
 // spin until *flag >= ep (epochs only grow); bounded: on time-out the error word is set and every later wait returns at once
-__device__ bool wait_ge(const uint32_t* flag, uint32_t ep, DistComm* c, uint32_t* err_host) {
+// (err_host[1..3] record which wait gave up: 1 halo arrive, 2 halo done, 3 all-rank reduction, 4 migration; the epoch; the flag)
+__device__ bool wait_ge(const uint32_t* flag, uint32_t ep, DistComm* c, uint32_t* err_host, uint32_t where) {
     if (*(volatile uint32_t*)&c->error == 1u) return false;
     const unsigned long long t0 = now_ns();
     while ((int32_t)(ld_acquire_sys(flag) - ep) < 0) {
         if (now_ns() - t0 > c->timeout_ns) {
+            if (atomicCAS(&c->error, 0u, 1u) == 0u) {
+                volatile uint32_t* eh = err_host;
+                eh[1] = where; eh[2] = ep; eh[3] = ld_acquire_sys(flag);
+                eh[0] = 1u;
+            }
             *(volatile uint32_t*)&c->error = 1u;
-            *(volatile uint32_t*)err_host = 1u;
             __threadfence_system();
             return false;
         }
@@ -124,7 +132,7 @@ __global__ void __launch_bounds__(256) halo_kernel(const __grid_constant__ HaloA
                 if (a.peer[side]) st_release_sys(&a.peer[side]->arrive[1 - side], ep);
         }
         for (int side = 0; side < 2; side++)
-            if (a.peer[side]) wait_ge(&c->arrive[side], ep, c, a.err_host);
+            if (a.peer[side]) wait_ge(&c->arrive[side], ep, c, a.err_host, 0x10u + side);
     }
     __syncthreads();
     const uint32_t ep = ep_s;
@@ -149,7 +157,7 @@ __global__ void __launch_bounds__(256) halo_kernel(const __grid_constant__ HaloA
             for (int side = 0; side < 2; side++)
                 if (a.peer[side]) st_release_sys(&a.peer[side]->done[1 - side], ep);
             for (int side = 0; side < 2; side++)
-                if (a.peer[side]) wait_ge(&c->done[side], ep, c, a.err_host);
+                if (a.peer[side]) wait_ge(&c->done[side], ep, c, a.err_host, 0x20u + side);
             c->halo_epoch = ep;
             __threadfence();
         }
@@ -196,7 +204,7 @@ __global__ void __launch_bounds__(32) allreduce_kernel(const __grid_constant__ A
         __threadfence_system();
         st_release_sys(&s->epoch, ep);
         DistSlot* m = &c->slot[par][lane];
-        wait_ge(&m->epoch, ep, c, a.err_host);
+        wait_ge(&m->epoch, ep, c, a.err_host, 0x300u + (a.kind << 4) + lane);
         volatile double* w = m->v;
         sv[lane][0] = w[0]; sv[lane][1] = w[1]; sv[lane][2] = w[2]; sv[lane][3] = w[3];
     }
@@ -284,7 +292,7 @@ __global__ void __launch_bounds__(256) mig_recv_kernel(const __grid_constant__ M
     if (threadIdx.x == 0) {
         const uint32_t ep = c->mig_ep;  // advanced by this step's mig_send_kernel
         for (int side = 0; side < 2; side++)
-            if (a.has[side]) wait_ge(&c->mig_epoch[side], ep, c, a.err_host);
+            if (a.has[side]) wait_ge(&c->mig_epoch[side], ep, c, a.err_host, 0x40u + side);
     }
     __syncthreads();
     const uint32_t n0 = a.has[0] ? *(volatile uint32_t*)&c->mig_count[0] : 0u, n1 = a.has[1] ? *(volatile uint32_t*)&c->mig_count[1] : 0u;
@@ -322,6 +330,66 @@ __global__ void __launch_bounds__(256) mig_recv_kernel(const __grid_constant__ M
     }
 }
 
+// All-rank gather of the solver inputs (replicated projection): after an all-to-all handshake every rank pulls, from every
+// other rank, the planes that rank owns of flags / v2 / avgPNum into its full-grid arrays; a second handshake keeps the
+// sources untouched until everybody has read them.
+struct GatherCopy { void* dst; const void* src; size_t bytes; };
+struct GatherArgs {
+    DistComm* comm;
+    DistComm* all[DIST_MAX_RANKS];
+    uint32_t* err_host;
+    int rank, nranks, ncopy;
+    GatherCopy cp[DIST_MAX_RANKS * 5];
+};
+
+__global__ void __launch_bounds__(256) gather_kernel(const __grid_constant__ GatherArgs a) {
+    DistComm* c = a.comm;
+    __shared__ uint32_t ep_s;
+    if (threadIdx.x == 0) ep_s = *(volatile uint32_t*)&c->gather_epoch + 1u;
+    __syncthreads();
+    const uint32_t ep = ep_s;
+    if (threadIdx.x < a.nranks && threadIdx.x != a.rank) {
+        const int r = threadIdx.x;
+        if (blockIdx.x == 0) { __threadfence_system(); st_release_sys(&a.all[r]->arrive_all[a.rank], ep); }
+        wait_ge(&c->arrive_all[r], ep, c, a.err_host, 0x50u + r);
+    }
+    __syncthreads();
+    const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, gsz = (size_t)gridDim.x * blockDim.x;
+    for (int k = 0; k < a.ncopy; k++) {
+        const GatherCopy& cp = a.cp[k];
+        if ((((size_t)cp.dst | (size_t)cp.src | cp.bytes) & 15) == 0) {
+            const size_t n = cp.bytes >> 4;
+            const uint4* src = reinterpret_cast<const uint4*>(cp.src);
+            uint4* dst = reinterpret_cast<uint4*>(cp.dst);
+            size_t i = gtid;
+            for (; i + 3 * gsz < n; i += 4 * gsz) {  // four loads in flight per thread: the pull is NVLink-latency bound
+                const uint4 v0 = ld_peer_u4(src + i), v1 = ld_peer_u4(src + i + gsz), v2 = ld_peer_u4(src + i + 2 * gsz), v3 = ld_peer_u4(src + i + 3 * gsz);
+                dst[i] = v0; dst[i + gsz] = v1; dst[i + 2 * gsz] = v2; dst[i + 3 * gsz] = v3;
+            }
+            for (; i < n; i += gsz) dst[i] = ld_peer_u4(src + i);
+        } else {
+            for (size_t i = gtid; i < cp.bytes; i += gsz) reinterpret_cast<uint8_t*>(cp.dst)[i] = reinterpret_cast<const volatile uint8_t*>(cp.src)[i];
+        }
+    }
+    __syncthreads();
+    __shared__ int last_s;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        last_s = atomicAdd(&c->gather_blocks_done, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last_s) {  // last block: nobody may overwrite its planes before every rank has read them
+        if (threadIdx.x < a.nranks && threadIdx.x != a.rank) {
+            const int r = threadIdx.x;
+            __threadfence_system();
+            st_release_sys(&a.all[r]->done_all[a.rank], ep);
+            wait_ge(&c->done_all[r], ep, c, a.err_host, 0x60u + r);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) { c->gather_blocks_done = 0; c->gather_epoch = ep; __threadfence(); }
+    }
+}
+
 template <typename T>
 int dalloc(fsim* h, T** p, size_t n) {
     *p = nullptr;
@@ -337,6 +405,10 @@ int check_err(fsim* h) {
     const uint32_t e = *(volatile uint32_t*)d->err_host;
     if (!e) return FSIM_OK;
     h->sticky = FSIM_ERR_COMM;
+    const uint32_t* eh = d->err_host;
+    if (e == 1)
+        return fsim_fail(h, FSIM_ERR_COMM, "slab exchange timed out waiting for a neighbour (rank %d of %d; wait 0x%x, epoch %u, flag %u)", d->rank,
+                         d->nranks, eh[1], eh[2], eh[3]);
     return fsim_fail(h, FSIM_ERR_COMM, e == 1 ? "slab exchange timed out waiting for a neighbour (rank %d of %d)"
                                       : e == 2 ? "emigrant list overflow (rank %d of %d): more particles crossed a slab boundary in one step than the list holds"
                                                : "a particle crossed a whole slab in one step (rank %d of %d)", d->rank, d->nranks);
@@ -377,8 +449,8 @@ int dist_init(fsim* h, int rank, int nranks, int own_lo, int own_hi) {
     c0.timeout_ns = (unsigned long long)(e ? atoll(e) : 20000) * 1000000ull;
     FSIM_CUDA(h, cudaMemcpyAsync(d->comm, &c0, sizeof(c0), cudaMemcpyHostToDevice, h->stream));
     FSIM_CUDA(h, cudaStreamSynchronize(h->stream));
-    FSIM_CUDA(h, cudaHostAlloc((void**)&d->err_host, sizeof(uint32_t), cudaHostAllocMapped));
-    *d->err_host = 0;
+    FSIM_CUDA(h, cudaHostAlloc((void**)&d->err_host, 4 * sizeof(uint32_t), cudaHostAllocMapped));
+    memset(d->err_host, 0, 4 * sizeof(uint32_t));
     FSIM_CUDA(h, cudaHostGetDevicePointer((void**)&d->err_dev, d->err_host, 0));
     // up to two planes of 8 particles per cell may change owner in one step before the lists overflow (FSIM_DIST_MIG_CAP overrides)
     const char* mc = getenv("FSIM_DIST_MIG_CAP");
@@ -451,20 +523,24 @@ int dist_connect(fsim* h, const FsimDistExport* all, int n) {
     for (int r = 0; r < n; r++) {
         const FsimDistExport& ex = all[r];
         if (ex.rank != r || ex.nranks != n) return fsim_fail(h, FSIM_ERR_INVALID, "export %d is from rank %d of %d", r, ex.rank, ex.nranks);
-        if (r == d->rank) continue;
+        d->all_zown0[r] = ex.zown0; d->all_zown1[r] = ex.zown1; d->all_zoff[r] = ex.z_offset;
+        if (r == d->rank) {
+            for (int k = 0; k < DIST_NARR; k++) d->all_arr[r][k] = d->local_arr[k];
+            continue;
+        }
         const int side = r == d->rank - 1 ? 0 : (r == d->rank + 1 ? 1 : -1);
+        for (int k = 0; k < DIST_NARR; k++) {
+            if (k == ARR_RECV && side < 0) continue;  // only neighbours push particles
+            int rc = map(ex, k, &d->all_arr[r][k]);
+            if (rc) return rc;
+        }
+        d->all_comm[r] = (DistComm*)d->all_arr[r][ARR_COMM];
         if (side >= 0) {
-            for (int k = 0; k < DIST_NARR; k++) { int rc = map(ex, k, &d->peer_arr[side][k]); if (rc) return rc; }
-            d->peer_comm[side] = (DistComm*)d->peer_arr[side][ARR_COMM];
-            d->all_comm[r] = d->peer_comm[side];
+            for (int k = 0; k < DIST_NARR; k++) d->peer_arr[side][k] = d->all_arr[r][k];
+            d->peer_comm[side] = d->all_comm[r];
             // the lower neighbour's ghost plane towards us is its plane zown1, its boundary plane zown1 - 1; the upper one's: zown0 - 1, zown0
             d->peer_ghost[side] = side == 0 ? ex.zown1 : ex.zown0 - 1;
             d->peer_bnd[side] = side == 0 ? ex.zown1 - 1 : ex.zown0;
-        } else {
-            void* p = nullptr;
-            int rc = map(ex, ARR_COMM, &p);
-            if (rc) return rc;
-            d->all_comm[r] = (DistComm*)p;
         }
     }
     d->connected = true;
@@ -555,13 +631,43 @@ int dist_allreduce(fsim* h, int kind, bool in_pcg_loop) {
     return FSIM_OK;
 }
 
+int dist_gather_solver_inputs(fsim* h) {
+    DistState* d = h->dist;
+    fsim* hs = h->solver;
+    if (!d || !d->connected || !hs) return fsim_fail(h, FSIM_ERR_COMM, "slab handle is not connected to its neighbours (fsim_dist_connect)");
+    GatherArgs a;
+    memset(&a, 0, sizeof(a));
+    a.comm = d->comm; a.err_host = d->err_dev; a.rank = d->rank; a.nranks = d->nranks;
+    for (int r = 0; r < d->nranks; r++) a.all[r] = d->all_comm[r];
+    const size_t plane = (size_t)h->g.sz;
+    const int arr[5] = {ARR_FLAGS, ARR_U2, ARR_U2 + 1, ARR_U2 + 2, ARR_DENS};
+    void* dst[5] = {hs->flags, hs->u2[0], hs->u2[1], hs->u2[2], hs->dens};
+    size_t bytes = 0;
+    for (int r = 0; r < d->nranks; r++) {
+        const int own_lo = d->all_zoff[r] + d->all_zown0[r], planes = d->all_zown1[r] - d->all_zown0[r];
+        for (int k = 0; k < 5; k++) {
+            const size_t es = elem_size(arr[k]);
+            GatherCopy& c = a.cp[a.ncopy++];
+            c.dst = (char*)dst[k] + (size_t)own_lo * plane * es;
+            c.src = (const char*)d->all_arr[r][arr[k]] + (size_t)d->all_zown0[r] * plane * es;
+            c.bytes = (size_t)planes * plane * es;
+            bytes += c.bytes;
+        }
+    }
+    int blocks = (int)std::min<size_t>((size_t)h->sm_count * 4, std::max<size_t>(4, bytes / (16 * 256 * 8)));
+    // several ranks sharing ONE device (tests): all their spinning gather blocks must be resident at the same time
+    if (const char* e = getenv("FSIM_DIST_GATHER_BLOCKS")) blocks = std::max(1, std::min(blocks, atoi(e)));
+    { KScope ks(h, K_HALO); gather_kernel<<<blocks, 256, 0, h->stream>>>(a); }
+    FSIM_CHECK_LAUNCH(h);
+    return FSIM_OK;
+}
+
 int fsim_ensure_capacity(fsim* h, int64_t n);  // fsim_api.cu
 
 int dist_migrate(fsim* h) {
     DistState* d = h->dist;
     if (!d || !d->connected) return fsim_fail(h, FSIM_ERR_COMM, "slab handle is not connected to its neighbours (fsim_dist_connect)");
-    int rc = fsim_ensure_capacity(h, h->np + 2 * d->mig_cap);
-    if (rc) return rc;
+    if (h->cap < h->np + 2 * d->mig_cap) return fsim_fail(h, FSIM_ERR_NOMEM, "no room for immigrants (capacity %lld, %lld particles)", (long long)h->cap, (long long)h->np);
     const ParticleSet& p = h->ps[h->cur];
     const int nch = h->have_c ? 15 : 6;
     MigSendArgs s;

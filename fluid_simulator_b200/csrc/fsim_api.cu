@@ -66,6 +66,7 @@ void free_particle_set(ParticleSet& s) {
 }
 
 int ensure_capacity(fsim* h, int64_t n) {
+    if (h->dist) n += 2 * dist_mig_capacity(h);  // slab mode: immigrants are appended behind the locals before the sort
     if (n <= h->cap) return FSIM_OK;
     int64_t ncap = h->cap > 0 ? h->cap : 1024;
     while (ncap < n) ncap += ncap / 2 + 1024;
@@ -311,7 +312,7 @@ static int create_impl(const FsimGridDesc* desc, int rank, int nranks, fsim_t** 
     { const char* e = getenv("FSIM_WARM_EXTRAPOLATE"); h->warm_extrapolate = !(e && e[0] == '0'); }
     h->warm_history = 0; h->p_prev = nullptr; h->mg_tail_cluster = 0;
     h->status_host = nullptr; h->status_dev = nullptr;
-    h->dist = nullptr; h->code_mg = nullptr;
+    h->dist = nullptr; h->code_mg = nullptr; h->solver = nullptr; h->stream_shared = false; h->skip_apply = false;
     { const char* e = getenv("FSIM_PRECOND"); h->use_mg = !(e && strcmp(e, "jacobi") == 0); }
     memset(h->prof_ms, 0, sizeof(h->prof_ms)); memset(h->prof_n, 0, sizeof(h->prof_n)); memset(h->launch_n, 0, sizeof(h->launch_n));
 
@@ -377,7 +378,41 @@ static int create_impl(const FsimGridDesc* desc, int rank, int nranks, fsim_t** 
     for (int i = 0; i < 16 && !rc; i++)
         if (cudaEventCreate(&h->ev[i]) != cudaSuccess) rc = fsim_fail(h, FSIM_ERR_CUDA, "event create failed");
     if (!rc && nranks > 1) rc = dist_init(h, rank, nranks, own_lo, own_hi);
-    if (!rc && cap0 > 0) rc = ensure_capacity(h, cap0 + (h->dist ? 2 * dist_mig_capacity(h) : 0));
+    if (!rc && nranks > 1) {
+        // Projection of a slab handle: by default every rank solves the FULL pressure system redundantly on a
+        // full-grid context fed by an all-rank gather of flags / v2 / avgPNum -- same multigrid, same iteration counts and the
+        // same pressure as the single-GPU path.  FSIM_SLAB_SOLVER=distributed keeps the solve on the slab instead (halo of the
+        // search direction, all-rank reductions, block-local multigrid: 3-4x the iterations, measured).
+        const char* e = getenv("FSIM_SLAB_SOLVER");
+        if (!(e && e[0] == 'd')) {
+            FsimGridDesc d2 = *desc;
+            d2.particle_capacity = 0;
+            fsim* hs = nullptr;
+            rc = create_impl(&d2, 0, 1, &hs);
+            if (rc) h->err = g_create_error;
+            else {
+                cudaSetDevice(h->device);
+                cudaStreamSynchronize(hs->stream);
+                cudaStreamDestroy(hs->stream);
+                hs->stream = h->stream; hs->stream_shared = true; hs->skip_apply = true;
+                h->solver = hs;
+                // the L2 persistence window of this stream follows the codes the solver actually reads
+                const size_t capb = std::min((size_t)40 << 20, (size_t)prop.persistingL2CacheMaxSize);
+                if (hs->l2_persist && capb > 0 && hs->hot_code_bytes <= (size_t)prop.accessPolicyMaxWindowSize) {
+                    cudaStreamAttrValue v;
+                    memset(&v, 0, sizeof(v));
+                    v.accessPolicyWindow.base_ptr = hs->code;
+                    v.accessPolicyWindow.num_bytes = hs->hot_code_bytes;
+                    v.accessPolicyWindow.hitRatio = hs->hot_code_bytes <= capb ? 1.0f : (float)((double)capb / (double)hs->hot_code_bytes);
+                    v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+                    v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+                    cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &v);
+                    cudaGetLastError();
+                }
+            }
+        }
+    }
+    if (!rc && cap0 > 0) rc = ensure_capacity(h, cap0);
     if (!rc) {
         // MacGrid ctor leaves every cell AIR with the solid border shell (macGrid.cpp:15-16)
         rc = k_upload_obstacles(h);
@@ -435,6 +470,7 @@ int fsim_destroy(fsim_t* h) {
     if (!h) return FSIM_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    if (h->solver) { fsim_destroy(h->solver); h->solver = nullptr; }
     dist_free(h);
     if (h->code_mg && h->code_mg != h->code) cudaFree(h->code_mg);
     mg_free(h);
@@ -460,7 +496,7 @@ int fsim_destroy(fsim_t* h) {
     if (h->status_host) cudaFreeHost((void*)h->status_host);
     if (h->pcg_graph) cudaGraphExecDestroy(h->pcg_graph);
     for (int i = 0; i < 16; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
-    cudaStreamDestroy(h->stream);
+    if (!h->stream_shared) cudaStreamDestroy(h->stream);
     delete h;
     return FSIM_OK;
 }
@@ -714,6 +750,7 @@ static int step_slab(fsim* h, double dt, int* pcg_iterations) {
     fold_timings(h);
     const int64_t l0 = h->launches;
     FSIM_CUDA(h, cudaEventRecord(h->ev[0], h->stream));
+    TRY(ensure_capacity(h, h->np));  // room for this step's immigrants; must happen before the advect kernel bins
     const bool fuse = h->g2p_pending && h->sorted && h->np > 0;
     if (!fuse) TRY(flush_g2p(h));
     TRY(k_advect(h, dt, true, true, h->par.stop_particles != 0, /*do_bin=*/true, fuse));
@@ -729,7 +766,29 @@ static int step_slab(fsim* h, double dt, int* pcg_iterations) {
     TRY(k_classify(h, dt));
     FSIM_CUDA(h, cudaEventRecord(h->ev[4], h->stream));
     int its = 0;
-    TRY(k_project(h, dt, &its));  // halos of the search direction / pressure and the all-rank reductions inside
+    if (h->solver) {
+        // replicated projection: gather every rank's planes of the solver inputs, solve the whole system here, keep our planes
+        fsim* hs = h->solver;
+        TRY(dist_gather_solver_inputs(h));
+        hs->par = h->par;
+        hs->prof_mask = h->prof_mask;
+        const int64_t ls0 = hs->launches;
+        int64_t c0[K_COUNT];
+        memcpy(c0, hs->launch_n, sizeof(c0));
+        const int rc = k_project(hs, dt, &its);
+        if (rc) { h->err = hs->err; if (hs->sticky) h->sticky = hs->sticky; return rc; }
+        h->launches += hs->launches - ls0;
+        for (int k = 0; k < K_COUNT; k++) h->launch_n[k] += hs->launch_n[k] - c0[k];
+        for (const ProfRec& r : hs->prof_recs) h->prof_recs.push_back(r);  // event pairs of the profiled launches
+        hs->prof_recs.clear();
+        h->solve = hs->solve;
+        const size_t plane = (size_t)h->g.sz;
+        FSIM_CUDA(h, cudaMemcpyAsync(h->p, hs->p + (size_t)h->g.zoff * plane, sizeof(double) * plane * h->g.gz, cudaMemcpyDeviceToDevice, h->stream));
+        FSIM_CUDA(h, cudaMemcpyAsync(h->rhs, hs->rhs + (size_t)h->g.zoff * plane, sizeof(double) * plane * h->g.gz, cudaMemcpyDeviceToDevice, h->stream));
+        if (!hs->solve.early_out) TRY(k_pressure_apply(h, dt));  // ghost planes included: the pressure around them is known
+    } else {
+        TRY(k_project(h, dt, &its));  // halos of the search direction / pressure and the all-rank reductions inside
+    }
     FSIM_CUDA(h, cudaEventRecord(h->ev[5], h->stream));
     TRY(dist_halo(h, HALO_U2, false));
     TRY(k_extrapolate(h));        // exchanges u2 + validity between and after its two sweeps

@@ -189,6 +189,9 @@ struct fsim {
 
     // z-slab multi-GPU state (nullptr for a single-GPU handle)
     DistState* dist;
+    fsim* solver;        // slab mode, replicated projection: a full-grid solver context sharing this handle's stream (nullptr otherwise)
+    bool stream_shared;  // this handle is such a context: its stream belongs to the slab handle
+    bool skip_apply;     // ... and k_project leaves the pressure gradient to the slab handle
     uint16_t* code_mg;  // stencil codes the multigrid preconditioner sees (slab mode: links into ghost planes cut); == code otherwise
 
     // error
@@ -267,7 +270,8 @@ enum { AR_RHS = 0, AR_RESIDUAL, AR_START, AR_SPMV, AR_UPDATE, AR_UPDATE_JACOBI, 
 enum { HALO_P2G = 0, HALO_P, HALO_S, HALO_U2, HALO_U2_FLAGS };
 int dist_halo(fsim* h, int what, bool in_pcg_loop);      // ghost-plane exchange with both z-neighbours (pull over peer memory)
 int dist_allreduce(fsim* h, int kind, bool in_pcg_loop);  // finishes a PCG reduction across the ranks
-int dist_migrate(fsim* h);                                // emigrants -> neighbours, immigrants appended + binned
+int dist_migrate(fsim* h);
+int dist_gather_solver_inputs(fsim* h);                  // all ranks' owned planes of flags / v2 / avgPNum -> the full-grid solver context                                // emigrants -> neighbours, immigrants appended + binned
 void dist_free(fsim* h);
 void dist_partition(int gzg, int rank, int nranks, int* own_lo, int* own_hi, int* zoff, int* gz_local);
 int dist_init(fsim* h, int rank, int nranks, int own_lo, int own_hi);

@@ -771,6 +771,8 @@ int cycle(fsim* h, int l, bool zero_guess, float** result, bool first_done = fal
                 if (cudaOccupancyMaxActiveClusters(&nclusters, mg_tail_kernel, &q) == cudaSuccess && nclusters >= 1) h->mg_tail_cluster = TAIL_CLUSTER;
             }
             cudaGetLastError();
+            // FSIM_MG_TAIL_CLUSTER=<1..16>: several slab handles sharing ONE device (tests) must not need a whole GPC each
+            if (const char* e = getenv("FSIM_MG_TAIL_CLUSTER")) { const int v = atoi(e); if (v >= 1 && v <= h->mg_tail_cluster) h->mg_tail_cluster = v; }
         }
         const int tail_cluster = h->mg_tail_cluster;
         cfg.gridDim = dim3(tail_cluster);

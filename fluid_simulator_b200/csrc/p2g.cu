@@ -326,14 +326,17 @@ int k_p2g(fsim* h) {
     a.apic = (h->par.transfer_type == FSIM_TRANSFER_APIC) && h->have_c;
     dim3 grid(div_up(g.gx, TX), div_up(g.gy, TY), div_up(g.gz, TZ));
     {
-        KScope ks(h, K_P2G);
-        if (a.apic) {
-            FSIM_CUDA(h, cudaFuncSetAttribute(p2g_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STAGED_SMEM));
-            p2g_kernel<true><<<grid, NTHREADS, STAGED_SMEM, h->stream>>>(a);
-        } else {
-            FSIM_CUDA(h, cudaFuncSetAttribute(p2g_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STAGED_SMEM));
-            p2g_kernel<false><<<grid, NTHREADS, STAGED_SMEM, h->stream>>>(a);
+        // the opt-in shared-memory size is a per-device function attribute: set it once per device, not per launch
+        static bool attr_set[2][64] = {};
+        const int dev = h->device & 63;
+        if (!attr_set[a.apic ? 1 : 0][dev]) {
+            if (a.apic) FSIM_CUDA(h, cudaFuncSetAttribute(p2g_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STAGED_SMEM));
+            else FSIM_CUDA(h, cudaFuncSetAttribute(p2g_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STAGED_SMEM));
+            attr_set[a.apic ? 1 : 0][dev] = true;
         }
+        KScope ks(h, K_P2G);
+        if (a.apic) p2g_kernel<true><<<grid, NTHREADS, STAGED_SMEM, h->stream>>>(a);
+        else p2g_kernel<false><<<grid, NTHREADS, STAGED_SMEM, h->stream>>>(a);
     }
     FSIM_CHECK_LAUNCH(h);
     return FSIM_OK;

@@ -48,6 +48,7 @@ struct PcgArgs {
     double inv_h;           // 1/h
     double avg_pressure, pressure_k;
     int pressure_enabled, warm;
+    int cut_neumann;  // slab mode: how code_mg treats a cut link
 };
 
 // iteration space of the chunked kernels: block b owns cells [b*CHUNK, (b+1)*CHUNK), a thread visits CV cells per trip
@@ -87,9 +88,12 @@ __global__ void __launch_bounds__(PT) rhs_kernel(PcgArgs a) {
         }
         a.code[c] = (uint16_t)code;
         if (a.code_mg) {
+            // the preconditioner is block-local: a link into a ghost plane is cut, either leaving the neighbour on the diagonal
+            // (Dirichlet: the exact diagonal block of A) or dropping it from the diagonal as well (Neumann: A = M + a positive
+            // semi-definite interface term); which one converges faster is measured, not assumed (FSIM_SLAB_CUT)
             unsigned cm = code;
-            if (zc - 1 < a.g.zown0) cm &= ~16u;
-            if (zc + 1 >= a.g.zown1) cm &= ~32u;
+            if (zc - 1 < a.g.zown0 && (cm & 16u)) { cm &= ~16u; if (a.cut_neumann) cm -= 1u << 6; }
+            if (zc + 1 >= a.g.zown1 && (cm & 32u)) { cm &= ~32u; if (a.cut_neumann) cm -= 1u << 6; }
             a.code_mg[c] = (uint16_t)cm;
         }
         a.rhs[c] = rhs;
@@ -434,6 +438,7 @@ int k_project(fsim* h, double dt, int* iterations) {
     a.pressure_enabled = h->par.pressure_enabled;
     a.warm = (h->warm_start && h->pressure_valid) ? (h->warm_extrapolate && h->warm_history >= 2 ? 2 : 1) : 0;
     a.p_prev = h->warm_extrapolate ? h->p_prev : nullptr;
+    { const char* e = getenv("FSIM_SLAB_CUT"); a.cut_neumann = (e && e[0] == 'n') ? 1 : 0; }
     a.z32 = nullptr;
     const int nbv = div_up(g.nc, CHUNK);     // chunked kernels
     const bool vec = (g.gx % 2 == 0) && (g.nc % 2 == 0);
@@ -564,6 +569,7 @@ int k_project(fsim* h, double dt, int* iterations) {
     h->pressure_valid = !s.early_out;
     h->warm_history = s.early_out ? 0 : h->warm_history + 1;
     if (!s.early_out) {  // the early-out returns before applying anything (:257-258)
+        if (h->skip_apply) return FSIM_OK;  // full-grid solver context of a slab handle: the slab applies its own part
         if (dist) { int rc = dist_halo(h, HALO_P, false); if (rc) return rc; }  // pressure of the neighbours' boundary planes
         return k_pressure_apply(h, dt);
     }

@@ -11,8 +11,7 @@ peer memory inside the library.  This module is the host-side plumbing the libra
 * `partition(...)` / `owner_of(...)` / `stitch(...)`  pure numpy helpers (which planes a rank owns, which rank owns a
                                particle, how local blocks become the global grid) -- covered by CPU tests.
 """
-import ctypes as C
-import threading
+import os
 from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
@@ -69,9 +68,18 @@ class SlabGroup:
     rank must be inside it at the same time).  Interface mirrors FluidSim where the tests need it."""
 
     def __init__(self, nranks, dims, resolution=1.0, two_d=False, particle_radius=0.25, capacity=0, devices=None, **_):
+        if os.environ.get("CUDA_MODULE_LOADING", "").upper() != "EAGER":
+            # a rank's exchange kernel spins until its neighbour's kernel runs; with lazy loading the neighbour's first launch of
+            # a kernel waits for the device to go idle first -> both wait for ever (only when ranks share a process)
+            raise RuntimeError("SlabGroup needs CUDA_MODULE_LOADING=EAGER in the environment before CUDA is initialised")
         load_library()
         self.n = int(nranks)
         devices = list(devices) if devices is not None else [0] * self.n
+        if len(set(devices)) < len(devices):
+            # ranks share a device: kernels of different ranks must be able to co-reside while they wait for each other, so
+            # none of them may need a whole GPC (multigrid tail cluster) or most of the SMs (gather blocks) for itself
+            os.environ.setdefault("FSIM_MG_TAIL_CLUSTER", "2")
+            os.environ.setdefault("FSIM_DIST_GATHER_BLOCKS", "16")
         self.sims = [FluidSim(dims, resolution, two_d, particle_radius, capacity=capacity, device=devices[r], rank=r, nranks=self.n)
                      for r in range(self.n)]
         s0 = self.sims[0]
@@ -124,6 +132,8 @@ class SlabGroup:
 
     def step(self, dt):
         its = self._all(lambda r, s: s.step(dt))
+        if len(set(its)) != 1:
+            self.synchronize()  # a timed-out exchange surfaces here as FsimError(ERR_COMM) with the wait that gave up
         assert len(set(its)) == 1, f"ranks disagree on the PCG iteration count: {its}"
         return its[0]
 
