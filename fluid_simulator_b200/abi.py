@@ -5,7 +5,7 @@ compiled reference (oracle/refsim.py), which deliberately reuses the same POD st
 """
 import ctypes as C
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_COMM = 0, 1, 2, 3, 4
 PIC, FLIP, APIC = 0, 1, 2
@@ -35,7 +35,7 @@ class SlabInfo(C.Structure):
 class DistExport(C.Structure):
     _fields_ = [("rank", C.c_int32), ("nranks", C.c_int32), ("device", C.c_int32), ("ipc_missing", C.c_int32),
                 ("pid", C.c_int64), ("zown0", C.c_int32), ("zown1", C.c_int32), ("gz_local", C.c_int32),
-                ("z_offset", C.c_int32), ("raw", C.c_uint64 * 16), ("ipc", (C.c_uint8 * 64) * 16)]
+                ("z_offset", C.c_int32), ("raw", C.c_uint64 * 24), ("offset", C.c_uint64 * 24), ("ipc", (C.c_uint8 * 64) * 24)]
 
 
 class Params(C.Structure):

@@ -23,10 +23,12 @@
 #include "pcg_finish.cuh"
 
 #define DIST_MAX_RANKS 16
-#define DIST_NARR 16
+#define DIST_NARR 24
 #define DIST_NCH 15  // particle channels of the widest (APIC) layout
 
-enum { ARR_U = 0, ARR_U2 = 3, ARR_W = 6, ARR_DENS = 9, ARR_CNT = 10, ARR_FLAGS = 11, ARR_P = 12, ARR_S = 13, ARR_COMM = 14, ARR_RECV = 15 };
+enum { ARR_U = 0, ARR_U2 = 3, ARR_W = 6, ARR_DENS = 9, ARR_CNT = 10, ARR_FLAGS = 11, ARR_P = 12, ARR_S = 13, ARR_COMM = 14, ARR_RECV = 15,
+       // arrays of the full-grid solver context (hybrid projection): same global plane index on every rank
+       ARR_HS_S = 16, ARR_HS_P = 17, ARR_HS_XA = 18, ARR_HS_XB = 19, ARR_HS_B1 = 20 };
 
 struct DistSlot { double v[4]; uint32_t epoch; uint32_t pad[7]; };
 
@@ -56,7 +58,8 @@ struct DistState {
     int64_t mig_cap;
     float* recv;         // [2 sides][DIST_NCH + 1 (ids)][mig_cap]
     float* stage;        // P2G staging: [2 sides][2 (ghost, boundary)][7 channels][plane]
-    void* local_arr[DIST_NARR];
+    void* local_arr[DIST_NARR];       // allocation bases
+    size_t local_off[DIST_NARR];      // byte offset of the array inside its allocation
     void* peer_arr[2][DIST_NARR];
     DistComm* peer_comm[2];
     int peer_ghost[2], peer_bnd[2];  // the neighbour's ghost plane towards us / its boundary plane (its local indices)
@@ -338,11 +341,13 @@ struct GatherArgs {
     DistComm* comm;
     DistComm* all[DIST_MAX_RANKS];
     uint32_t* err_host;
+    const PcgScalars* sc;  // non-null inside the PCG loop: skip once the solve is done
     int rank, nranks, ncopy;
     GatherCopy cp[DIST_MAX_RANKS * 5];
 };
 
 __global__ void __launch_bounds__(256) gather_kernel(const __grid_constant__ GatherArgs a) {
+    if (a.sc && a.sc->done) return;
     DistComm* c = a.comm;
     __shared__ uint32_t ep_s;
     if (threadIdx.x == 0) ep_s = *(volatile uint32_t*)&c->gather_epoch + 1u;
@@ -416,6 +421,8 @@ int check_err(fsim* h) {
 
 }  // namespace
 
+static DistState* dist_of(const fsim* h) { return h->dist ? h->dist : (h->parent ? h->parent->dist : nullptr); }
+
 MigDev* dist_mig_dev(const fsim* h) { return h->dist ? h->dist->mig : nullptr; }
 int64_t dist_mig_capacity(const fsim* h) { return h->dist ? h->dist->mig_cap : 0; }
 const uint32_t* dist_nsrc_dev(fsim* h) {
@@ -431,7 +438,10 @@ int dist_check(fsim* h) { return (h->dist && h->dist->connected) ? check_err(h) 
 
 // the slab geometry of rank r of n over gzg global planes
 void dist_partition(int gzg, int rank, int nranks, int* own_lo, int* own_hi, int* zoff, int* gz_local) {
-    const int lo = (int)((int64_t)gzg * rank / nranks), hi = (int)((int64_t)gzg * (rank + 1) / nranks);
+    // slab boundaries are even planes: the 2x2x2 aggregates of the multigrid never straddle two ranks
+    const int half = gzg / 2;
+    const int lo = rank == 0 ? 0 : 2 * (int)((int64_t)half * rank / nranks);
+    const int hi = rank == nranks - 1 ? gzg : 2 * (int)((int64_t)half * (rank + 1) / nranks);
     const int z0 = std::max(lo - 1, 0), z1 = std::min(hi + 1, gzg);
     *own_lo = lo; *own_hi = hi; *zoff = z0; *gz_local = z1 - z0;
 }
@@ -488,7 +498,9 @@ int dist_export(fsim* h, FsimDistExport* out) {
     out->zown0 = h->g.zown0; out->zown1 = h->g.zown1; out->gz_local = h->g.gz; out->z_offset = h->g.zoff;
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
     for (int k = 0; k < DIST_NARR; k++) {
+        if (!d->local_arr[k]) continue;
         out->raw[k] = (uint64_t)(uintptr_t)d->local_arr[k];
+        out->offset[k] = (uint64_t)d->local_off[k];
         cudaIpcMemHandle_t hd;
         const cudaError_t e = cudaIpcGetMemHandle(&hd, d->local_arr[k]);
         if (e == cudaSuccess) memcpy(out->ipc[k], &hd, 64);
@@ -501,7 +513,7 @@ int dist_connect(fsim* h, const FsimDistExport* all, int n) {
     DistState* d = h->dist;
     if (n != d->nranks) return fsim_fail(h, FSIM_ERR_INVALID, "expected %d exports, got %d", d->nranks, n);
     const int64_t pid = (int64_t)getpid();
-    auto map = [&](const FsimDistExport& ex, int arr, void** out) -> int {
+    auto map_base = [&](const FsimDistExport& ex, int arr, void** out) -> int {
         if (ex.pid == pid) {  // same process: plain pointers (peer access when the handle lives on another device)
             if (ex.device != h->device) {
                 const cudaError_t e = cudaDeviceEnablePeerAccess(ex.device, 0);
@@ -520,12 +532,20 @@ int dist_connect(fsim* h, const FsimDistExport* all, int n) {
         d->ipc_opened.push_back(*out);
         return FSIM_OK;
     };
+    auto map = [&](const FsimDistExport& ex, int arr, void** out) -> int {
+        *out = nullptr;
+        if (!ex.raw[arr]) return FSIM_OK;  // not published by that rank (e.g. no hybrid solver context)
+        int rc = map_base(ex, arr, out);
+        if (rc) return rc;
+        *out = (char*)*out + ex.offset[arr];
+        return FSIM_OK;
+    };
     for (int r = 0; r < n; r++) {
         const FsimDistExport& ex = all[r];
         if (ex.rank != r || ex.nranks != n) return fsim_fail(h, FSIM_ERR_INVALID, "export %d is from rank %d of %d", r, ex.rank, ex.nranks);
         d->all_zown0[r] = ex.zown0; d->all_zown1[r] = ex.zown1; d->all_zoff[r] = ex.z_offset;
         if (r == d->rank) {
-            for (int k = 0; k < DIST_NARR; k++) d->all_arr[r][k] = d->local_arr[k];
+            for (int k = 0; k < DIST_NARR; k++) d->all_arr[r][k] = d->local_arr[k] ? (char*)d->local_arr[k] + d->local_off[k] : nullptr;
             continue;
         }
         const int side = r == d->rank - 1 ? 0 : (r == d->rank + 1 ? 1 : -1);
@@ -618,7 +638,7 @@ int dist_halo(fsim* h, int what, bool in_pcg_loop) {
 }
 
 int dist_allreduce(fsim* h, int kind, bool in_pcg_loop) {
-    DistState* d = h->dist;
+    DistState* d = dist_of(h);
     if (!d || !d->connected) return fsim_fail(h, FSIM_ERR_COMM, "slab handle is not connected to its neighbours (fsim_dist_connect)");
     ArArgs a;
     memset(&a, 0, sizeof(a));
@@ -659,6 +679,85 @@ int dist_gather_solver_inputs(fsim* h) {
     if (const char* e = getenv("FSIM_DIST_GATHER_BLOCKS")) blocks = std::max(1, std::min(blocks, atoi(e)));
     { KScope ks(h, K_HALO); gather_kernel<<<blocks, 256, 0, h->stream>>>(a); }
     FSIM_CHECK_LAUNCH(h);
+    return FSIM_OK;
+}
+
+// ---- hybrid projection: the solver context stores every array at global plane indices, so a neighbour's plane z lives at
+// the same offset in the neighbour's array -------------------------------------------------------------------------------
+int dist_register_solver(fsim* h) {
+    DistState* d = h->dist;
+    fsim* hs = h->solver;
+    if (!d || !hs) return FSIM_OK;
+    d->local_arr[ARR_HS_S] = hs->s; d->local_arr[ARR_HS_P] = hs->p;
+    float* base = nullptr;
+    size_t pad = 0;
+    mg_level_array(hs, 0, 0, &base, &pad); d->local_arr[ARR_HS_XA] = base; d->local_off[ARR_HS_XA] = pad * sizeof(float);
+    mg_level_array(hs, 0, 1, &base, &pad); d->local_arr[ARR_HS_XB] = base; d->local_off[ARR_HS_XB] = pad * sizeof(float);
+    mg_level_array(hs, 1, 2, &base, &pad); d->local_arr[ARR_HS_B1] = base; d->local_off[ARR_HS_B1] = pad * sizeof(float);
+    return FSIM_OK;
+}
+
+int dist_halo_sym(fsim* hs, int which, const void* ptr, bool in_pcg_loop) {
+    DistState* d = dist_of(hs);
+    if (!d || !d->connected) return fsim_fail(hs, FSIM_ERR_COMM, "slab handle is not connected to its neighbours (fsim_dist_connect)");
+    int arr = which == SYM_S ? ARR_HS_S : (which == SYM_P ? ARR_HS_P : -1);
+    if (which == SYM_X) {  // the multigrid ping-pongs between two level-0 arrays
+        const void* xa = (char*)d->local_arr[ARR_HS_XA] + d->local_off[ARR_HS_XA];
+        const void* xb = (char*)d->local_arr[ARR_HS_XB] + d->local_off[ARR_HS_XB];
+        arr = ptr == xa ? ARR_HS_XA : (ptr == xb ? ARR_HS_XB : -1);
+    }
+    if (arr < 0) return fsim_fail(hs, FSIM_ERR_INVALID, "halo of an array that is not published");
+    const size_t es = arr == ARR_HS_P ? 8 : 4, plane = (size_t)hs->g.sz;
+    HaloArgs a;
+    memset(&a, 0, sizeof(a));
+    a.comm = d->comm; a.peer[0] = d->peer_comm[0]; a.peer[1] = d->peer_comm[1]; a.err_host = d->err_dev;
+    a.sc = in_pcg_loop ? hs->scal : nullptr;
+    const int zpl[2] = {d->own_lo - 1, d->own_hi};  // the planes just outside the owned range
+    char* mine = (char*)d->local_arr[arr] + d->local_off[arr];
+    for (int side = 0; side < 2; side++) {
+        if (!d->peer_comm[side]) continue;
+        if (!d->peer_arr[side][arr]) return fsim_fail(hs, FSIM_ERR_COMM, "neighbour did not publish its solver arrays (mixed FSIM_SLAB_SOLVER settings?)");
+        HaloCopy& c = a.cp[a.ncopy++];
+        c.dst = mine + (size_t)zpl[side] * plane * es;
+        c.src = (const char*)d->peer_arr[side][arr] + (size_t)zpl[side] * plane * es;
+        c.bytes = (uint32_t)(plane * es);
+        c.side = side;
+    }
+    size_t bytes = 0;
+    for (int k = 0; k < a.ncopy; k++) bytes += a.cp[k].bytes;
+    const int blocks = (int)std::min<size_t>(128, std::max<size_t>(4, bytes / (16 * 256 * 4)));
+    { KScope ks(hs, K_HALO); halo_kernel<<<blocks, 256, 0, hs->stream>>>(a); }
+    FSIM_CHECK_LAUNCH(hs);
+    return FSIM_OK;
+}
+
+int dist_gather_coarse(fsim* hs, bool in_pcg_loop) {
+    DistState* d = dist_of(hs);
+    if (!d || !d->connected) return fsim_fail(hs, FSIM_ERR_COMM, "slab handle is not connected to its neighbours (fsim_dist_connect)");
+    GatherArgs a;
+    memset(&a, 0, sizeof(a));
+    a.comm = d->comm; a.err_host = d->err_dev; a.rank = d->rank; a.nranks = d->nranks;
+    a.sc = in_pcg_loop ? hs->scal : nullptr;
+    for (int r = 0; r < d->nranks; r++) a.all[r] = d->all_comm[r];
+    // level 1 has (gx+1)/2 x (gy+1)/2 cells per plane; rank r owns the coarse planes [own_lo_r / 2, own_hi_r / 2) (boundaries are even)
+    const size_t cplane = (size_t)((hs->g.gx + 1) / 2) * ((hs->g.gy + 1) / 2);
+    char* mine = (char*)d->local_arr[ARR_HS_B1] + d->local_off[ARR_HS_B1];
+    size_t bytes = 0;
+    for (int r = 0; r < d->nranks; r++) {
+        if (r == d->rank) continue;
+        if (!d->all_arr[r][ARR_HS_B1]) return fsim_fail(hs, FSIM_ERR_COMM, "rank %d did not publish its solver arrays", r);
+        const int lo = d->all_zoff[r] + d->all_zown0[r], hi = d->all_zoff[r] + d->all_zown1[r];
+        const int clo = lo / 2, chi = r == d->nranks - 1 ? (hs->g.gz + 1) / 2 : hi / 2;
+        GatherCopy& c = a.cp[a.ncopy++];
+        c.dst = mine + (size_t)clo * cplane * sizeof(float);
+        c.src = (const char*)d->all_arr[r][ARR_HS_B1] + (size_t)clo * cplane * sizeof(float);
+        c.bytes = (size_t)(chi - clo) * cplane * sizeof(float);
+        bytes += c.bytes;
+    }
+    int blocks = (int)std::min<size_t>((size_t)hs->sm_count * 2, std::max<size_t>(4, bytes / (16 * 256 * 4)));
+    if (const char* e = getenv("FSIM_DIST_GATHER_BLOCKS")) blocks = std::max(1, std::min(blocks, atoi(e)));
+    { KScope ks(hs, K_HALO); gather_kernel<<<blocks, 256, 0, hs->stream>>>(a); }
+    FSIM_CHECK_LAUNCH(hs);
     return FSIM_OK;
 }
 

@@ -313,6 +313,7 @@ static int create_impl(const FsimGridDesc* desc, int rank, int nranks, fsim_t** 
     h->warm_history = 0; h->p_prev = nullptr; h->mg_tail_cluster = 0;
     h->status_host = nullptr; h->status_dev = nullptr;
     h->dist = nullptr; h->code_mg = nullptr; h->solver = nullptr; h->stream_shared = false; h->skip_apply = false;
+    h->parent = nullptr; h->hybrid = 0; h->code_full = nullptr;
     { const char* e = getenv("FSIM_PRECOND"); h->use_mg = !(e && strcmp(e, "jacobi") == 0); }
     memset(h->prof_ms, 0, sizeof(h->prof_ms)); memset(h->prof_n, 0, sizeof(h->prof_n)); memset(h->launch_n, 0, sizeof(h->launch_n));
 
@@ -384,6 +385,7 @@ static int create_impl(const FsimGridDesc* desc, int rank, int nranks, fsim_t** 
         // same pressure as the single-GPU path.  FSIM_SLAB_SOLVER=distributed keeps the solve on the slab instead (halo of the
         // search direction, all-rank reductions, block-local multigrid: 3-4x the iterations, measured).
         const char* e = getenv("FSIM_SLAB_SOLVER");
+        const bool hybrid = !(e && e[0] == 'r');  // default: hybrid
         if (!(e && e[0] == 'd')) {
             FsimGridDesc d2 = *desc;
             d2.particle_capacity = 0;
@@ -395,7 +397,19 @@ static int create_impl(const FsimGridDesc* desc, int rank, int nranks, fsim_t** 
                 cudaStreamSynchronize(hs->stream);
                 cudaStreamDestroy(hs->stream);
                 hs->stream = h->stream; hs->stream_shared = true; hs->skip_apply = true;
+                hs->parent = h;
                 h->solver = hs;
+                if (hybrid) {
+                    // HYBRID projection: the CG vectors and the fine multigrid level only work on the planes this rank owns (ghost
+                    // planes of the search direction / iterate pulled from the neighbours, reductions over all ranks); the coarse
+                    // levels run replicated on the all-rank gather of the level-1 right-hand side.  Same operator, same cycle, same
+                    // iteration counts as one GPU.  FSIM_SLAB_SOLVER=replicated: every rank solves the whole system instead.
+                    hs->hybrid = 1;
+                    hs->g.zown0 = own_lo; hs->g.zown1 = own_hi;
+                    if (cudaMalloc((void**)&hs->code_full, (size_t)(hs->g.nc + 8) * sizeof(uint16_t)) != cudaSuccess) rc = fsim_fail(h, FSIM_ERR_CUDA, "solver code alloc failed");
+                    if (!rc) { cudaMemsetAsync(hs->code_full, 0, (size_t)(hs->g.nc + 8) * sizeof(uint16_t), h->stream); rc = mg_alloc(hs); if (rc) h->err = hs->err; }
+                    if (!rc) rc = dist_register_solver(h);
+                }
                 // the L2 persistence window of this stream follows the codes the solver actually reads
                 const size_t capb = std::min((size_t)40 << 20, (size_t)prop.persistingL2CacheMaxSize);
                 if (hs->l2_persist && capb > 0 && hs->hot_code_bytes <= (size_t)prop.accessPolicyMaxWindowSize) {
@@ -473,6 +487,7 @@ int fsim_destroy(fsim_t* h) {
     if (h->solver) { fsim_destroy(h->solver); h->solver = nullptr; }
     dist_free(h);
     if (h->code_mg && h->code_mg != h->code) cudaFree(h->code_mg);
+    cudaFree(h->code_full);
     mg_free(h);
     free_particle_set(h->ps[0]);
     free_particle_set(h->ps[1]);
@@ -782,6 +797,7 @@ static int step_slab(fsim* h, double dt, int* pcg_iterations) {
         for (const ProfRec& r : hs->prof_recs) h->prof_recs.push_back(r);  // event pairs of the profiled launches
         hs->prof_recs.clear();
         h->solve = hs->solve;
+        // (hybrid: hs->p holds this rank's planes and, after the last halo, the two planes around them -- exactly the local block)
         const size_t plane = (size_t)h->g.sz;
         FSIM_CUDA(h, cudaMemcpyAsync(h->p, hs->p + (size_t)h->g.zoff * plane, sizeof(double) * plane * h->g.gz, cudaMemcpyDeviceToDevice, h->stream));
         FSIM_CUDA(h, cudaMemcpyAsync(h->rhs, hs->rhs + (size_t)h->g.zoff * plane, sizeof(double) * plane * h->g.gz, cudaMemcpyDeviceToDevice, h->stream));

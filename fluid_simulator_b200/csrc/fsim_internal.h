@@ -192,6 +192,10 @@ struct fsim {
     fsim* solver;        // slab mode, replicated projection: a full-grid solver context sharing this handle's stream (nullptr otherwise)
     bool stream_shared;  // this handle is such a context: its stream belongs to the slab handle
     bool skip_apply;     // ... and k_project leaves the pressure gradient to the slab handle
+    fsim* parent;        // ... the slab handle it belongs to
+    int hybrid;          // ... 1: fine level and CG vectors restricted to the planes this rank owns (halos + all-rank reductions),
+                         //        coarse multigrid levels replicated; 0: the whole solve is replicated
+    uint16_t* code_full; // hybrid: stencil codes of ALL fluid cells (the coarse operators are global); h->code is owned-only
     uint16_t* code_mg;  // stencil codes the multigrid preconditioner sees (slab mode: links into ghost planes cut); == code otherwise
 
     // error
@@ -271,7 +275,14 @@ enum { HALO_P2G = 0, HALO_P, HALO_S, HALO_U2, HALO_U2_FLAGS };
 int dist_halo(fsim* h, int what, bool in_pcg_loop);      // ghost-plane exchange with both z-neighbours (pull over peer memory)
 int dist_allreduce(fsim* h, int kind, bool in_pcg_loop);  // finishes a PCG reduction across the ranks
 int dist_migrate(fsim* h);
-int dist_gather_solver_inputs(fsim* h);                  // all ranks' owned planes of flags / v2 / avgPNum -> the full-grid solver context                                // emigrants -> neighbours, immigrants appended + binned
+int dist_gather_solver_inputs(fsim* h);
+// hybrid projection (solver context hs of a slab handle): arrays live at global plane indices on every rank
+enum { SYM_S = 0, SYM_P, SYM_X };
+int dist_halo_sym(fsim* hs, int which, const void* ptr, bool in_pcg_loop);  // planes own_lo-1 / own_hi <- the neighbours' same planes
+int dist_gather_coarse(fsim* hs, bool in_pcg_loop);                          // level-1 right-hand side: every rank's coarse planes
+int dist_register_solver(fsim* h);                                           // publishes the solver context's exchanged arrays
+int mg_alloc(fsim* h);
+float* mg_level_array(fsim* h, int level, int which, float** base, size_t* pad);  // which: 0 xa, 1 xb, 2 b                  // all ranks' owned planes of flags / v2 / avgPNum -> the full-grid solver context                                // emigrants -> neighbours, immigrants appended + binned
 void dist_free(fsim* h);
 void dist_partition(int gzg, int rank, int nranks, int* own_lo, int* own_hi, int* zoff, int* gz_local);
 int dist_init(fsim* h, int rank, int nranks, int own_lo, int own_hi);

@@ -803,6 +803,7 @@ int cycle(fsim* h, int l, bool zero_guess, float** result, bool first_done = fal
                 else mg_first_kernel<false><<<grid_of(m, blk), blk, 0, h->stream>>>(L, nullptr, sc, m->b, cur);
             } else {
                 const float om = s == 0 ? OM_A : OM_B;
+                if (fine && h->hybrid) { int rc = dist_halo_sym(h, SYM_X, cur, true); if (rc) return rc; }  // the neighbours' planes of the iterate
                 if (v4) mg_jacobi4_kernel<<<grd4, blk4, 0, h->stream>>>(L, h->scal, m->b, cur, oth, om);
                 else if (fine) mg_jacobi_kernel<true><<<grid_of(m, blk), blk, 0, h->stream>>>(L, sc, m->b, cur, oth, om);
                 else mg_jacobi_kernel<false><<<grid_of(m, blk), blk, 0, h->stream>>>(L, sc, m->b, cur, oth, om);
@@ -810,6 +811,7 @@ int cycle(fsim* h, int l, bool zero_guess, float** result, bool first_done = fal
             }
         }
     }
+    if (fine && h->hybrid) { int rc = dist_halo_sym(h, SYM_X, cur, true); if (rc) return rc; }
     {
         KScope ks(h, kid);
         if (v4) mg_restrict4_kernel<<<dim3(div_up(mc->gx, 2 * 32), div_up(mc->gy, 4), div_up(mc->gz, 2)), blk4, 0, h->stream>>>(L, C, sc, m->b, cur, mc->b);
@@ -817,6 +819,8 @@ int cycle(fsim* h, int l, bool zero_guess, float** result, bool first_done = fal
         else if (mc->nc > 100000) mg_restrict_kernel<false><<<grid_of(mc, blk), blk, 0, h->stream>>>(L, C, sc, m->b, cur, mc->b);  // enough threads as it is
         else mg_restrict8_kernel<<<div_up(mc->nc * 8, 256), 256, 0, h->stream>>>(L, C, sc, m->b, cur, mc->b, (int)mc->nc);
     }
+    // hybrid: every rank restricted the planes it owns; with all ranks' coarse planes gathered, levels >= 1 run replicated
+    if (fine && h->hybrid) { int rc = dist_gather_coarse(h, true); if (rc) return rc; }
     float* ec = nullptr;
     const int visits = (l + 1 >= W_FIRST && l + 1 <= W_LAST && l + 1 < (int)h->mg.size() - 1) ? 2 : 1;
     for (int v = 0; v < visits; v++) {
@@ -834,6 +838,7 @@ int cycle(fsim* h, int l, bool zero_guess, float** result, bool first_done = fal
         { float* t = cur; cur = oth; oth = t; }
         for (int s = 1; s < POST; s++) {
             const float om = OM_A;  // post-sweeps run the pre-sweep weights in reverse order (B in the fused prolongation sweep, then A)
+            if (fine && h->hybrid) { int rc = dist_halo_sym(h, SYM_X, cur, true); if (rc) return rc; }
             if (v4 && with_dot && s == POST - 1) {
                 const int ntiles = (int)(grd4.x * grd4.y * grd4.z);
                 mg_jacobi4_dot_kernel<<<std::min(ntiles, h->sm_count * 8), 256, 0, h->stream>>>(L, h->scal, m->b, cur, oth, h->partials, h->red_counter, om,
@@ -861,8 +866,19 @@ void mg_free(fsim* h) {
 }
 
 // (re)builds the Galerkin hierarchy for the current cell flags; arrays are allocated once per grid
-int mg_build(fsim* h) {
-    const dim3 blk(32, 4, 2);
+float* mg_level_array(fsim* h, int level, int which, float** base, size_t* pad) {
+    if (level >= (int)h->mg.size()) { if (base) *base = nullptr; if (pad) *pad = 0; return nullptr; }
+    MgLevel* m = h->mg[level];
+    float* p = which == 0 ? m->xa : (which == 1 ? m->xb : m->b);
+    // xa / xb may have been swapped since allocation: find the allocation that holds p
+    for (int k = 4; k < 7; k++)
+        if (m->base[k] && p == m->base[k] + m->pad) { if (base) *base = m->base[k]; if (pad) *pad = m->pad; return p; }
+    if (base) *base = p;
+    if (pad) *pad = 0;
+    return p;
+}
+
+int mg_alloc(fsim* h) {
     if (h->mg.empty()) {
         int gx = h->g.gx, gy = h->g.gy, gz = h->g.gz;
         for (int l = 0;; l++) {
@@ -880,10 +896,19 @@ int mg_build(fsim* h) {
         for (int l = 1; l < nl; l++)
             if (h->mg[l]->nc <= TAIL_MAX_CELLS && nl - l <= TAIL_MAX_LEVELS) { h->mg_tail_first = l; break; }
     }
+    return FSIM_OK;
+}
+
+int mg_build(fsim* h) {
+    const dim3 blk(32, 4, 2);
+    int rc0 = mg_alloc(h);
+    if (rc0) return rc0;
     for (size_t l = 1; l < h->mg.size(); l++) {
         MgLevel *f = h->mg[l - 1], *c = h->mg[l];
         KScope ks(h, K_MG);
-        if (l == 1) mg_build1_kernel<<<grid_of(c, blk), blk, 0, h->stream>>>(view(h, f, 0), view(h, c, 1), c->wx, c->wy, c->wz, c->diag);
+        Lv f0 = view(h, f, 0);
+        if (h->code_full) f0.code = h->code_full;  // hybrid: the coarse operators are global, h->code only marks this rank's planes
+        if (l == 1) mg_build1_kernel<<<grid_of(c, blk), blk, 0, h->stream>>>(f0, view(h, c, 1), c->wx, c->wy, c->wz, c->diag);
         else mg_buildn_kernel<<<grid_of(c, blk), blk, 0, h->stream>>>(view(h, f, (int)l - 1), view(h, c, (int)l), c->wx, c->wy, c->wz, c->diag);
     }
     FSIM_CHECK_LAUNCH(h);
@@ -891,7 +916,7 @@ int mg_build(fsim* h) {
 }
 
 // the fused paths need the float4 level-0 kernels
-bool mg_can_fuse(const fsim* h) { return h->use_mg && !h->dist && !h->mg.empty() && h->mg[0]->gx % 4 == 0 && h->g.nc % 4 == 0; }
+bool mg_can_fuse(const fsim* h) { return h->use_mg && !h->dist && !h->hybrid && !h->mg.empty() && h->mg[0]->gx % 4 == 0 && h->g.nc % 4 == 0; }
 
 // CG update (p, r, ||r||_inf, convergence flags) fused with the first smoothing sweep of the cycle that follows
 int mg_update_first(fsim* h) {

@@ -34,6 +34,7 @@ struct PcgArgs {
     GridDims g;
     const uint8_t* flags;
     uint16_t* code;
+    uint16_t* code_full;  // hybrid solver context: codes of ALL fluid cells (code is then owned-only); nullptr otherwise
     uint16_t* code_mg;  // slab mode: the codes the multigrid sees (links into ghost planes cut); nullptr otherwise
     const float* u2[3];
     const float* dens;
@@ -69,8 +70,9 @@ __global__ void __launch_bounds__(PT) rhs_kernel(PcgArgs a) {
         double rhs = 0.0;
         unsigned code = 0;
         const int zc = (int)c / a.g.sz;
-        const bool owned = zc >= a.g.zown0 && zc < a.g.zown1;  // slab mode: ghost planes never become active
-        if (owned && (a.flags[c] & FL_TYPE_MASK) == FSIM_CELL_WATER) {  // WATER cells are interior: all six neighbours exist
+        const bool owned = zc >= a.g.zown0 && zc < a.g.zown1;  // slab modes: only the planes this rank owns become active
+        unsigned full = 0;
+        if ((owned || a.code_full) && (a.flags[c] & FL_TYPE_MASK) == FSIM_CELL_WATER) {  // WATER cells are interior: all six neighbours exist
             const int64_t nb[6] = {c - 1, c + 1, c - a.g.sy, c + a.g.sy, c - a.g.sz, c + a.g.sz};
             unsigned wm = 0, ns = 0;
 #pragma unroll
@@ -79,18 +81,22 @@ __global__ void __launch_bounds__(PT) rhs_kernel(PcgArgs a) {
                 ns += (t != FSIM_CELL_SOLID);
                 wm |= (t == FSIM_CELL_WATER) ? (1u << k) : 0u;
             }
-            code = CODE_ACTIVE | (ns << 6) | wm;
-            const double div = ((double)a.u2[0][c] + (double)a.u2[1][c] + (double)a.u2[2][c]) - (double)a.u2[0][c - 1] -
-                               (double)a.u2[1][c - a.g.sy] - (double)a.u2[2][c - a.g.sz];
-            rhs = -a.inv_h * div + (a.pressure_enabled ? ((double)a.dens[c] - a.avg_pressure) * a.pressure_k : 0.0);
-            acc[0] = rhs * rhs;
-            acc[1] = 1.0;
+            full = CODE_ACTIVE | (ns << 6) | wm;
+            if (owned) {
+                code = full;
+                const double div = ((double)a.u2[0][c] + (double)a.u2[1][c] + (double)a.u2[2][c]) - (double)a.u2[0][c - 1] -
+                                   (double)a.u2[1][c - a.g.sy] - (double)a.u2[2][c - a.g.sz];
+                rhs = -a.inv_h * div + (a.pressure_enabled ? ((double)a.dens[c] - a.avg_pressure) * a.pressure_k : 0.0);
+                acc[0] = rhs * rhs;
+                acc[1] = 1.0;
+            }
         }
         a.code[c] = (uint16_t)code;
+        if (a.code_full) a.code_full[c] = (uint16_t)full;
         if (a.code_mg) {
             // the preconditioner is block-local: a link into a ghost plane is cut, either leaving the neighbour on the diagonal
             // (Dirichlet: the exact diagonal block of A) or dropping it from the diagonal as well (Neumann: A = M + a positive
-            // semi-definite interface term); which one converges faster is measured, not assumed (FSIM_SLAB_CUT)
+            // semi-definite interface term); measured: both need 3-5x the iterations of the global multigrid (FSIM_SLAB_CUT)
             unsigned cm = code;
             if (zc - 1 < a.g.zown0 && (cm & 16u)) { cm &= ~16u; if (a.cut_neumann) cm -= 1u << 6; }
             if (zc + 1 >= a.g.zown1 && (cm & 32u)) { cm &= ~32u; if (a.cut_neumann) cm -= 1u << 6; }
@@ -382,9 +388,11 @@ __global__ void sigma_kernel(PcgScalars* sc, PcgHostStatus* status) {
 
 // one PCG iteration: SpMV -> update -> (multigrid cycle -> z.r | fused diagonal) -> direction -> close
 static int enqueue_iteration(fsim* h, const PcgArgs& a, bool vec, bool use_mg, int nbv) {
-    const bool dist = h->dist != nullptr;
-    auto AR = [&](int kind) { return dist ? dist_allreduce(h, kind, true) : FSIM_OK; };
-    if (dist) { int rc = dist_halo(h, HALO_S, true); if (rc) return rc; }  // ghost planes of the search direction
+    const int mode = h->dist ? 1 : (h->hybrid ? 2 : 0);  // 1: slab-local solve, 2: full-grid context restricted to the owned planes
+    auto AR = [&](int kind) { return mode ? dist_allreduce(h, kind, true) : FSIM_OK; };
+    // the neighbours' boundary planes of the search direction
+    if (mode == 1) { int rc = dist_halo(h, HALO_S, true); if (rc) return rc; }
+    if (mode == 2) { int rc = dist_halo_sym(h, SYM_S, h->s, true); if (rc) return rc; }
     {
         KScope ks(h, K_SPMV);
         if (vec && a.g.gx % 4 == 0 && a.g.nc % 4 == 0) spmv4_kernel<<<nbv, PT, 0, h->stream>>>(a);
@@ -426,7 +434,7 @@ int k_project(fsim* h, double dt, int* iterations) {
     if (h->par.solver_type == FSIM_SOLVER_BASIC) return k_project_basic(h, iterations);
     const GridDims& g = h->g;
     PcgArgs a;
-    a.g = g; a.flags = h->flags; a.code = h->code; a.code_mg = h->code_mg != h->code ? h->code_mg : nullptr;
+    a.g = g; a.flags = h->flags; a.code = h->code; a.code_mg = h->code_mg != h->code ? h->code_mg : nullptr; a.code_full = h->code_full;
     for (int ax = 0; ax < 3; ax++) a.u2[ax] = h->u2[ax];
     a.dens = h->dens;
     a.p = h->p; a.rhs = h->rhs; a.r = h->r; a.s = h->s; a.q = h->q; a.z = h->z;
@@ -452,16 +460,19 @@ int k_project(fsim* h, double dt, int* iterations) {
     sh->inv_scale = 1.0 / sh->scale;
     sh->tol = h->par.residual_tolerance;
     sh->max_it = max_it;
-    sh->dist = h->dist ? 1 : 0;
+    sh->dist = (h->dist || h->hybrid) ? 1 : 0;
     h->status_host->done = 0;
     h->status_host->it_done = 0;
     FSIM_CUDA(h, cudaMemcpyAsync(h->scal, sh, sizeof(PcgScalars), cudaMemcpyHostToDevice, h->stream));
 
-    const bool dist = h->dist != nullptr;
+    const int mode = h->dist ? 1 : (h->hybrid ? 2 : 0);
+    const bool dist = mode != 0;
     { KScope ks(h, K_RHS); rhs_kernel<<<div_up(g.nc, PT), PT, 0, h->stream>>>(a); }  // one cell per thread (a chunked loop was 25 % slower)
     if (dist) { int rc = dist_allreduce(h, AR_RHS, false); if (rc) return rc; }
     if (a.warm) {
-        if (dist) { int rc = dist_halo(h, HALO_P, true); if (rc) return rc; }  // the initial guess of the neighbours' boundary planes
+        // the initial guess of the neighbours' boundary planes
+        if (mode == 1) { int rc = dist_halo(h, HALO_P, true); if (rc) return rc; }
+        if (mode == 2) { int rc = dist_halo_sym(h, SYM_P, h->p, true); if (rc) return rc; }
         { KScope ks(h, K_RHS); residual_kernel<<<nbv, PT, 0, h->stream>>>(a); }
         if (dist) { int rc = dist_allreduce(h, AR_RESIDUAL, true); if (rc) return rc; }
     }
@@ -569,8 +580,9 @@ int k_project(fsim* h, double dt, int* iterations) {
     h->pressure_valid = !s.early_out;
     h->warm_history = s.early_out ? 0 : h->warm_history + 1;
     if (!s.early_out) {  // the early-out returns before applying anything (:257-258)
+        if (mode == 2) { int rc = dist_halo_sym(h, SYM_P, h->p, false); if (rc) return rc; }  // pressure of the neighbours' boundary planes
         if (h->skip_apply) return FSIM_OK;  // full-grid solver context of a slab handle: the slab applies its own part
-        if (dist) { int rc = dist_halo(h, HALO_P, false); if (rc) return rc; }  // pressure of the neighbours' boundary planes
+        if (mode == 1) { int rc = dist_halo(h, HALO_P, false); if (rc) return rc; }
         return k_pressure_apply(h, dt);
     }
     return FSIM_OK;

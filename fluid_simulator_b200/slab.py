@@ -23,8 +23,11 @@ from .sim import FluidSim, load_library
 def partition(global_gz, nranks):
     """[(own_lo, own_hi, z_offset, gz_local)] per rank: same arithmetic as the library (fsim_slab_partition)."""
     out = []
+    half = global_gz // 2
     for r in range(nranks):
-        lo, hi = global_gz * r // nranks, global_gz * (r + 1) // nranks
+        # slab boundaries are even planes (the multigrid's 2x2x2 aggregates never straddle two ranks)
+        lo = 0 if r == 0 else 2 * (half * r // nranks)
+        hi = global_gz if r == nranks - 1 else 2 * (half * (r + 1) // nranks)
         if nranks == 1:
             out.append((0, global_gz, 0, global_gz))
             continue

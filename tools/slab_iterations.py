@@ -20,9 +20,8 @@ base = [one.step(sc.dt) for _ in range(steps)]
 one.close()
 print(json.dumps({"grid": n, "ranks": 1, "its": base}), flush=True)
 for r in ranks:
-    for cut in ("replicated", "dirichlet"):
-        os.environ["FSIM_SLAB_SOLVER"] = "replicated" if cut == "replicated" else "distributed"
-        os.environ["FSIM_SLAB_CUT"] = cut
+    for cut in ("hybrid", "replicated"):
+        os.environ["FSIM_SLAB_SOLVER"] = cut
         g = SlabGroup(r, sc.dims, sc.resolution, sc.two_d, sc.particle_radius, capacity=sc.n_particles)
         g.set_params(sc.params); g.set_obstacles([]); g.upload_particles(sc.particles)
         its = [g.step(sc.dt) for _ in range(steps)]
