@@ -39,8 +39,10 @@ struct DistComm {
     // written by every rank: slot[parity][source rank]
     DistSlot slot[2][DIST_MAX_RANKS];
     uint32_t arrive_all[DIST_MAX_RANKS], done_all[DIST_MAX_RANKS];  // all-rank handshake of the solver-input gather
+    uint32_t push_flag[2];                 // "your ghost plane holds my boundary plane of exchange #epoch" (push halos of the PCG loop)
+    uint32_t gpush_flag[DIST_MAX_RANKS];   // the same for the all-rank push of the coarse right-hand side
     // local
-    uint32_t halo_epoch, ar_epoch, mig_ep, blocks_done, mig_blocks_done, gather_epoch, gather_blocks_done, pad1;
+    uint32_t halo_epoch, ar_epoch, mig_ep, blocks_done, mig_blocks_done, gather_epoch, gather_blocks_done, push_epoch, push_blocks_done, gpush_epoch, gpush_blocks_done, pad1;
     uint32_t error;   // 1 wait timed out, 2 emigrant list full, 3 immigrant outside the owned planes
     uint32_t n_src;   // particles the next reorder reads: locals + immigrants
     uint32_t pad0;
@@ -165,6 +167,57 @@ __global__ void __launch_bounds__(256) halo_kernel(const __grid_constant__ HaloA
             __threadfence();
         }
     }
+}
+
+// Push form of the exchange, for the halos INSIDE the PCG loop (search direction, multigrid iterate, coarse right-hand side):
+// every rank stores its planes straight into the neighbours' arrays (posted NVLink writes, no read round trip) and raises a
+// flag; the kernel ends when the neighbours' flags have arrived.  No handshake guards the destination: between two uses of a
+// ghost plane the loop always passes an all-rank reduction or gather, so its previous reader has finished.
+struct PushCopy { void* dst; const void* src; size_t bytes; int to; };
+struct PushArgs {
+    DistComm* comm;
+    DistComm* peer[DIST_MAX_RANKS];  // halo: [0] lower, [1] upper neighbour; gather: every rank
+    uint32_t* err_host;
+    const PcgScalars* sc;
+    int npeer, self, all_ranks, ncopy;
+    PushCopy cp[DIST_MAX_RANKS];
+};
+
+__global__ void __launch_bounds__(256) push_kernel(const __grid_constant__ PushArgs a) {
+    if (a.sc && a.sc->done) return;
+    DistComm* c = a.comm;
+    const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, gsz = (size_t)gridDim.x * blockDim.x;
+    for (int k = 0; k < a.ncopy; k++) {
+        const PushCopy& cp = a.cp[k];
+        const size_t n = cp.bytes >> 4;  // planes are 16-byte multiples on this path (checked by the host)
+        const uint4* src = reinterpret_cast<const uint4*>(cp.src);
+        uint4* dst = reinterpret_cast<uint4*>(cp.dst);
+        for (size_t i = gtid; i < n; i += gsz) dst[i] = src[i];
+    }
+    __syncthreads();
+    __shared__ int last_s;
+    uint32_t* my_epoch = a.all_ranks ? &c->gpush_epoch : &c->push_epoch;
+    uint32_t* my_count = a.all_ranks ? &c->gpush_blocks_done : &c->push_blocks_done;
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        last_s = atomicAdd(my_count, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!last_s) return;
+    const uint32_t ep = *(volatile uint32_t*)my_epoch + 1u;
+    if (threadIdx.x < a.npeer && a.peer[threadIdx.x] && !(a.all_ranks && (int)threadIdx.x == a.self)) {
+        const int r = threadIdx.x;
+        __threadfence_system();
+        if (a.all_ranks) {
+            st_release_sys(&a.peer[r]->gpush_flag[a.self], ep);
+            wait_ge(&c->gpush_flag[r], ep, c, a.err_host, 0x70u + r);
+        } else {  // I am the upper neighbour of my lower neighbour: its flag [1], and the other way round
+            st_release_sys(&a.peer[r]->push_flag[1 - r], ep);
+            wait_ge(&c->push_flag[r], ep, c, a.err_host, 0x80u + r);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { *my_count = 0; *my_epoch = ep; __threadfence(); }
 }
 
 // P2G ghost-plane sum: boundary plane += what the neighbour scattered into its ghost plane; ghost plane += the neighbour's
@@ -697,6 +750,34 @@ int dist_register_solver(fsim* h) {
     return FSIM_OK;
 }
 
+static bool push_enabled() { const char* e = getenv("FSIM_SLAB_PUSH"); return !(e && e[0] == '0'); }
+
+// push form of dist_halo_sym / dist_gather_coarse (see push_kernel for when it is safe)
+static int halo_sym_push(fsim* hs, DistState* d, int arr, size_t es) {
+    const size_t plane = (size_t)hs->g.sz;
+    PushArgs a;
+    memset(&a, 0, sizeof(a));
+    a.comm = d->comm; a.peer[0] = d->peer_comm[0]; a.peer[1] = d->peer_comm[1]; a.err_host = d->err_dev; a.sc = hs->scal;
+    a.npeer = 2; a.self = d->rank; a.all_ranks = 0;
+    const int zpl[2] = {d->own_lo, d->own_hi - 1};  // my boundary planes: the lower one goes to the lower neighbour, ...
+    const char* mine = (const char*)d->local_arr[arr] + d->local_off[arr];
+    size_t bytes = 0;
+    for (int side = 0; side < 2; side++) {
+        if (!d->peer_comm[side]) continue;
+        if (!d->peer_arr[side][arr]) return fsim_fail(hs, FSIM_ERR_COMM, "neighbour did not publish its solver arrays (mixed FSIM_SLAB_SOLVER settings?)");
+        PushCopy& c = a.cp[a.ncopy++];
+        c.src = mine + (size_t)zpl[side] * plane * es;
+        c.dst = (char*)d->peer_arr[side][arr] + (size_t)zpl[side] * plane * es;  // same global plane index in the neighbour's array
+        c.bytes = plane * es;
+        c.to = side;
+        bytes += c.bytes;
+    }
+    const int blocks = (int)std::min<size_t>(128, std::max<size_t>(2, bytes / (16 * 256 * 2)));
+    { KScope ks(hs, K_HALO); push_kernel<<<blocks, 256, 0, hs->stream>>>(a); }
+    FSIM_CHECK_LAUNCH(hs);
+    return FSIM_OK;
+}
+
 int dist_halo_sym(fsim* hs, int which, const void* ptr, bool in_pcg_loop) {
     DistState* d = dist_of(hs);
     if (!d || !d->connected) return fsim_fail(hs, FSIM_ERR_COMM, "slab handle is not connected to its neighbours (fsim_dist_connect)");
@@ -708,6 +789,9 @@ int dist_halo_sym(fsim* hs, int which, const void* ptr, bool in_pcg_loop) {
     }
     if (arr < 0) return fsim_fail(hs, FSIM_ERR_INVALID, "halo of an array that is not published");
     const size_t es = arr == ARR_HS_P ? 8 : 4, plane = (size_t)hs->g.sz;
+    // in-loop halos of the search direction and of the float4 multigrid path (whose kernels never write a ghost plane) are pushed
+    if (in_pcg_loop && which != SYM_P && push_enabled() && (plane * es) % 16 == 0 && (which == SYM_S || hs->g.gx % 4 == 0))
+        return halo_sym_push(hs, d, arr, es);
     HaloArgs a;
     memset(&a, 0, sizeof(a));
     a.comm = d->comm; a.peer[0] = d->peer_comm[0]; a.peer[1] = d->peer_comm[1]; a.err_host = d->err_dev;
@@ -742,6 +826,30 @@ int dist_gather_coarse(fsim* hs, bool in_pcg_loop) {
     // level 1 has (gx+1)/2 x (gy+1)/2 cells per plane; rank r owns the coarse planes [own_lo_r / 2, own_hi_r / 2) (boundaries are even)
     const size_t cplane = (size_t)((hs->g.gx + 1) / 2) * ((hs->g.gy + 1) / 2);
     char* mine = (char*)d->local_arr[ARR_HS_B1] + d->local_off[ARR_HS_B1];
+    if (in_pcg_loop && push_enabled() && hs->g.gx % 4 == 0 && (cplane * sizeof(float)) % 16 == 0 && d->local_off[ARR_HS_B1] % 16 == 0) {
+        // push my coarse planes to every rank (the float4 restriction only writes the planes this rank owns)
+        PushArgs p;
+        memset(&p, 0, sizeof(p));
+        p.comm = d->comm; p.err_host = d->err_dev; p.sc = hs->scal; p.npeer = d->nranks; p.self = d->rank; p.all_ranks = 1;
+        const int clo = d->own_lo / 2, chi = d->rank == d->nranks - 1 ? (hs->g.gz + 1) / 2 : d->own_hi / 2;
+        size_t pbytes = 0;
+        for (int r = 0; r < d->nranks; r++) {
+            p.peer[r] = d->all_comm[r];
+            if (r == d->rank) continue;
+            if (!d->all_arr[r][ARR_HS_B1]) return fsim_fail(hs, FSIM_ERR_COMM, "rank %d did not publish its solver arrays", r);
+            PushCopy& c = p.cp[p.ncopy++];
+            c.src = mine + (size_t)clo * cplane * sizeof(float);
+            c.dst = (char*)d->all_arr[r][ARR_HS_B1] + (size_t)clo * cplane * sizeof(float);
+            c.bytes = (size_t)(chi - clo) * cplane * sizeof(float);
+            c.to = r;
+            pbytes += c.bytes;
+        }
+        int pblocks = (int)std::min<size_t>((size_t)hs->sm_count * 2, std::max<size_t>(2, pbytes / (16 * 256 * 4)));
+        if (const char* e = getenv("FSIM_DIST_GATHER_BLOCKS")) pblocks = std::max(1, std::min(pblocks, atoi(e)));
+        { KScope ks(hs, K_HALO); push_kernel<<<pblocks, 256, 0, hs->stream>>>(p); }
+        FSIM_CHECK_LAUNCH(hs);
+        return FSIM_OK;
+    }
     size_t bytes = 0;
     for (int r = 0; r < d->nranks; r++) {
         if (r == d->rank) continue;

@@ -429,11 +429,12 @@ __global__ void __launch_bounds__(256) mg_update_first4_kernel(Lv L, int64_t nc,
 
 // one thread = two coarse cells in x = a 4x2x2 block of fine cells
 __global__ void __launch_bounds__(256) mg_restrict4_kernel(Lv L, Lv C, const PcgScalars* __restrict__ sc, const float* __restrict__ b, const float* __restrict__ xf,
-                                                           float* __restrict__ bc) {
+                                                           float* __restrict__ bc, int cz0, int cz1) {
     if (sc->done) return;
     const int X = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
     const int Y = blockIdx.y * blockDim.y + threadIdx.y, Z = blockIdx.z * blockDim.z + threadIdx.z;
     if (X >= C.gx || Y >= C.gy || Z >= C.gz) return;
+    if (Z < cz0 || Z >= cz1) return;  // hybrid: the other coarse planes are written by the ranks that own them (pushed over NVLink)
     float s0 = 0.f, s1 = 0.f;
 #pragma unroll
     for (int k = 0; k < 2; k++)
@@ -812,9 +813,12 @@ int cycle(fsim* h, int l, bool zero_guess, float** result, bool first_done = fal
         }
     }
     if (fine && h->hybrid) { int rc = dist_halo_sym(h, SYM_X, cur, true); if (rc) return rc; }
+    // hybrid: the coarse planes whose children this rank owns (slab boundaries are even); otherwise all of them
+    const int cz0 = (fine && h->hybrid) ? h->g.zown0 / 2 : 0;
+    const int cz1 = (fine && h->hybrid && h->g.zown1 < h->g.gz) ? h->g.zown1 / 2 : (1 << 30);
     {
         KScope ks(h, kid);
-        if (v4) mg_restrict4_kernel<<<dim3(div_up(mc->gx, 2 * 32), div_up(mc->gy, 4), div_up(mc->gz, 2)), blk4, 0, h->stream>>>(L, C, sc, m->b, cur, mc->b);
+        if (v4) mg_restrict4_kernel<<<dim3(div_up(mc->gx, 2 * 32), div_up(mc->gy, 4), div_up(mc->gz, 2)), blk4, 0, h->stream>>>(L, C, sc, m->b, cur, mc->b, cz0, cz1);
         else if (fine) mg_restrict_kernel<true><<<grid_of(mc, blk), blk, 0, h->stream>>>(L, C, sc, m->b, cur, mc->b);
         else if (mc->nc > 100000) mg_restrict_kernel<false><<<grid_of(mc, blk), blk, 0, h->stream>>>(L, C, sc, m->b, cur, mc->b);  // enough threads as it is
         else mg_restrict8_kernel<<<div_up(mc->nc * 8, 256), 256, 0, h->stream>>>(L, C, sc, m->b, cur, mc->b, (int)mc->nc);

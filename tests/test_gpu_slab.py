@@ -73,10 +73,11 @@ def compare(tag, one, grp, tol=TOL, exact_flags=True, apic=False):
     return res
 
 
-@pytest.mark.parametrize("nranks,solver", [(2, "hybrid"), (3, "hybrid"), (4, "hybrid"), (3, "replicated"), (3, "distributed")])
+@pytest.mark.parametrize("nranks,solver", [(2, "hybrid"), (3, "hybrid"), (4, "hybrid"), (3, "hybrid-pull"), (3, "replicated"), (3, "distributed")])
 def test_slab_matches_single_flip(gpu, nranks, solver, monkeypatch):
     """3D FLIP dam break on a ragged grid; every step compared field by field with the single-handle run."""
-    monkeypatch.setenv("FSIM_SLAB_SOLVER", solver)
+    monkeypatch.setenv("FSIM_SLAB_SOLVER", solver.split("-")[0])
+    monkeypatch.setenv("FSIM_SLAB_PUSH", "0" if solver.endswith("-pull") else "1")  # in-loop halos: pushed (default) or pulled
     sc = scenes.dam_break_3d(24, abi.FLIP, ny=20, nz=26, tol=1e-9)
     one, grp = make_pair(gpu, sc, nranks)
     for st in range(3):
