@@ -175,6 +175,7 @@ def main():
     red_dev = "cpu" if same_dev else "cuda"
     torch.cuda.set_device(local_rank)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("FSIM_NCCL_DEBUG", "WARN")  # the image's default prints a version banner on stdout
         if same_dev:
             dist.init_process_group("gloo")
         else:
@@ -250,6 +251,7 @@ def main():
     info = sim.solve_info()
     nf = int(info.fluid_cells)
     nf_local = nf // world if slab_mode else nf  # the solve reports the all-rank count
+    solver_mode = (os.environ.get("FSIM_SLAB_SOLVER", "hybrid") if slab_mode else "single")
     timings = sim.timings()
 
     total_units, dev_ms_max, value = fdist.aggregate(dist, red_dev, np_local * args.steps, dev_ms, world)
@@ -297,6 +299,8 @@ def main():
     # per-launch algorithmic bytes of the dominant kernel class
     pb = {abi.PIC: 24, abi.FLIP: 24, abi.APIC: 60}[transfer]
     nc = nc_local
+    if slab_mode and solver_mode.startswith("r"):  # replicated projection: the solver kernels sweep the whole grid on every rank
+        nf_local = nf
     alg = {"advect": np_local * 2 * pb,                      # pass A: read + write pos, vel (+C)
            "p2g": np_local * pb + nc * (8 + 28),             # particles in, bin table, 7 accumulator channels out
            "g2p": np_local * (36 if transfer == abi.FLIP else pb + (12 if transfer == abi.PIC else 48)) + nc * (24 if transfer == abi.FLIP else 12),
@@ -332,7 +336,8 @@ def main():
                                    + (f"{total_particles} particles in ONE domain cut into {world} z-slabs, " if slab_mode else f"{np_local} particles per GPU, ")
                                    + f"8 per fluid cell, dt {DT}, PCG tol 1e-6", "grid": [n, n, n], "particles_per_gpu": np_local,
                        "particles_total": total_particles, "fluid_cells": nf, "pcg_iterations_mean": its_mean,
-                       "parallelism": (f"z-slabs x{world} (ghost planes, particle migration and PCG reductions over NVLink peer memory)" if slab_mode
+                       "slab_solver": solver_mode,
+                       "parallelism": (f"z-slabs x{world} (ghost planes, particle migration and PCG reductions over NVLink peer memory; projection: {solver_mode})" if slab_mode
                                        else (f"replicas x{world}" if world > 1 else "single GPU")),
                        "l2": "inputs larger than L2 (particle + grid state >> 126 MB), no flush needed"},
             "wall_ms_per_step": 1e3 * wall / args.steps, "clocks": clocks, "gpu_launches": int(launches),

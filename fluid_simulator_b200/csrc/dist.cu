@@ -716,9 +716,18 @@ int dist_gather_solver_inputs(fsim* h) {
     const int arr[5] = {ARR_FLAGS, ARR_U2, ARR_U2 + 1, ARR_U2 + 2, ARR_DENS};
     void* dst[5] = {hs->flags, hs->u2[0], hs->u2[1], hs->u2[2], hs->dens};
     size_t bytes = 0;
+    // hybrid: the right-hand side only exists on the owned planes, whose inputs (and the plane below) the slab already holds;
+    // only the cell types of the other ranks are needed (the coarse multigrid operators are global)
+    const int narr = hs->hybrid ? 1 : 5;
+    if (hs->hybrid) {
+        float* src4[4] = {h->u2[0], h->u2[1], h->u2[2], h->dens};
+        float* dst4[4] = {hs->u2[0], hs->u2[1], hs->u2[2], hs->dens};
+        for (int k = 0; k < 4; k++)
+            FSIM_CUDA(h, cudaMemcpyAsync(dst4[k] + (size_t)h->g.zoff * plane, src4[k], sizeof(float) * plane * h->g.gz, cudaMemcpyDeviceToDevice, h->stream));
+    }
     for (int r = 0; r < d->nranks; r++) {
         const int own_lo = d->all_zoff[r] + d->all_zown0[r], planes = d->all_zown1[r] - d->all_zown0[r];
-        for (int k = 0; k < 5; k++) {
+        for (int k = 0; k < narr; k++) {
             const size_t es = elem_size(arr[k]);
             GatherCopy& c = a.cp[a.ncopy++];
             c.dst = (char*)dst[k] + (size_t)own_lo * plane * es;

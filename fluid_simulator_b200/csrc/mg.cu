@@ -47,14 +47,15 @@ struct Lv {  // kernel view of a level
     const float *wx, *wy, *wz, *diag;
     const uint8_t* flags;   // level 0 only (hierarchy build)
     const uint16_t* code;   // level 0 only: stencil codes (fsim_internal.h CODE_ACTIVE)
+    int z0, z1;             // planes the per-cell kernels visit: [0, gz), or the planes this rank owns (hybrid slab projection, level 0)
 };
 
 __device__ __forceinline__ bool cell_of(const Lv& L, int& x, int& y, int& z, int64_t& c) {
     x = blockIdx.x * blockDim.x + threadIdx.x;
     y = blockIdx.y * blockDim.y + threadIdx.y;
-    z = blockIdx.z * blockDim.z + threadIdx.z;
+    z = blockIdx.z * blockDim.z + threadIdx.z + L.z0;
     c = ((int64_t)z * L.gy + y) * L.gx + x;
-    return x < L.gx && y < L.gy && z < L.gz;
+    return x < L.gx && y < L.gy && z < L.z1;
 }
 
 // (diagonal, sum of w_nbr * x_nbr) of row c.  FINE: from the cell flags (weights 1 to WATER neighbours, diagonal =
@@ -267,8 +268,8 @@ __device__ __forceinline__ float off4(const Stencil4& s, int i, unsigned cd) {
 }
 __device__ __forceinline__ bool group_of(const Lv& L, int64_t& c, unsigned cd[4]) {
     const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y, z = blockIdx.z * blockDim.z + threadIdx.z;
-    if (x >= L.gx || y >= L.gy || z >= L.gz) return false;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y, z = blockIdx.z * blockDim.z + threadIdx.z + L.z0;
+    if (x >= L.gx || y >= L.gy || z >= L.z1) return false;
     c = ((int64_t)z * L.gy + y) * L.gx + x;
     const ushort4 t = *reinterpret_cast<const ushort4*>(L.code + c);
     cd[0] = t.x; cd[1] = t.y; cd[2] = t.z; cd[3] = t.w;
@@ -432,9 +433,9 @@ __global__ void __launch_bounds__(256) mg_restrict4_kernel(Lv L, Lv C, const Pcg
                                                            float* __restrict__ bc, int cz0, int cz1) {
     if (sc->done) return;
     const int X = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
-    const int Y = blockIdx.y * blockDim.y + threadIdx.y, Z = blockIdx.z * blockDim.z + threadIdx.z;
+    const int Y = blockIdx.y * blockDim.y + threadIdx.y, Z = blockIdx.z * blockDim.z + threadIdx.z + cz0;
     if (X >= C.gx || Y >= C.gy || Z >= C.gz) return;
-    if (Z < cz0 || Z >= cz1) return;  // hybrid: the other coarse planes are written by the ranks that own them (pushed over NVLink)
+    if (Z >= cz1) return;  // hybrid: only the coarse planes [cz0, cz1) whose children this rank owns; the others are written by their owners (pushed over NVLink)
     float s0 = 0.f, s1 = 0.f;
 #pragma unroll
     for (int k = 0; k < 2; k++)
@@ -468,7 +469,7 @@ __global__ void __launch_bounds__(256) mg_prolong_jacobi4_kernel(Lv L, Lv C, con
     const unsigned any = cd[0] | cd[1] | cd[2] | cd[3];
     if (any & CODE_ACTIVE) {
         const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-        const int y = blockIdx.y * blockDim.y + threadIdx.y, z = blockIdx.z * blockDim.z + threadIdx.z;
+        const int y = blockIdx.y * blockDim.y + threadIdx.y, z = blockIdx.z * blockDim.z + threadIdx.z + L.z0;
         Stencil4 s = load_stencil4(L, xin, c, cd);
         // coarse corrections: the group's parents are (X0, X0+1) in row (y>>1, z>>1); neighbours use their own rows
         const int X0 = x >> 1;
@@ -715,6 +716,8 @@ Lv view(const fsim* h, const MgLevel* m, int level) {
     v.wx = m->wx; v.wy = m->wy; v.wz = m->wz; v.diag = m->diag;
     v.flags = level == 0 ? h->flags : nullptr;
     v.code = level == 0 ? h->code_mg : nullptr;
+    v.z0 = 0; v.z1 = m->gz;
+    if (level == 0 && h->hybrid) { v.z0 = h->g.zown0; v.z1 = h->g.zown1; }
     return v;
 }
 
@@ -747,7 +750,8 @@ int cycle(fsim* h, int l, bool zero_guess, float** result, bool first_done = fal
     const int kid = l == 0 ? K_MG : (l == 1 ? K_MG1 : K_MG2);
     const bool v4 = fine && (m->gx % 4 == 0);  // float4 path; then the coarse gx is even (float2 stores / loads)
     const dim3 blk4(32, 4, 2);
-    const dim3 grd4(div_up(m->gx, 4 * 32), div_up(m->gy, 4), div_up(m->gz, 2));
+    const dim3 grd4(div_up(m->gx, 4 * 32), div_up(m->gy, 4), div_up(L.z1 - L.z0, 2));
+    const dim3 grdL(div_up(m->gx, blk.x), div_up(m->gy, blk.y), div_up(L.z1 - L.z0, blk.z));  // per-cell kernels of this level
     if (l == h->mg_tail_first) {  // this level and everything below it: one cluster launch
         TailArgs ta;
         ta.n = (int)h->mg.size() - l;
@@ -793,21 +797,21 @@ int cycle(fsim* h, int l, bool zero_guess, float** result, bool first_done = fal
     float *cur = m->xa, *oth = m->xb;
     if (!fine && zero_guess && PRE == 2) {
         KScope ks(h, kid);
-        mg_pre2_kernel<<<grid_of(m, blk), blk, 0, h->stream>>>(L, sc, m->b, cur);
+        mg_pre2_kernel<<<grdL, blk, 0, h->stream>>>(L, sc, m->b, cur);
     } else {
         KScope ks(h, kid, PRE - ((zero_guess && first_done) ? 1 : 0));
         for (int s = 0; s < PRE; s++) {
             if (s == 0 && zero_guess && first_done) continue;  // x1 and b were written by the fused CG update
             if (s == 0 && zero_guess) {
                 if (v4) mg_first4_kernel<<<grd4, blk4, 0, h->stream>>>(L, h->r, sc, m->b, cur);
-                else if (fine) mg_first_kernel<true><<<grid_of(m, blk), blk, 0, h->stream>>>(L, h->r, sc, m->b, cur);
-                else mg_first_kernel<false><<<grid_of(m, blk), blk, 0, h->stream>>>(L, nullptr, sc, m->b, cur);
+                else if (fine) mg_first_kernel<true><<<grdL, blk, 0, h->stream>>>(L, h->r, sc, m->b, cur);
+                else mg_first_kernel<false><<<grdL, blk, 0, h->stream>>>(L, nullptr, sc, m->b, cur);
             } else {
                 const float om = s == 0 ? OM_A : OM_B;
                 if (fine && h->hybrid) { int rc = dist_halo_sym(h, SYM_X, cur, true); if (rc) return rc; }  // the neighbours' planes of the iterate
                 if (v4) mg_jacobi4_kernel<<<grd4, blk4, 0, h->stream>>>(L, h->scal, m->b, cur, oth, om);
-                else if (fine) mg_jacobi_kernel<true><<<grid_of(m, blk), blk, 0, h->stream>>>(L, sc, m->b, cur, oth, om);
-                else mg_jacobi_kernel<false><<<grid_of(m, blk), blk, 0, h->stream>>>(L, sc, m->b, cur, oth, om);
+                else if (fine) mg_jacobi_kernel<true><<<grdL, blk, 0, h->stream>>>(L, sc, m->b, cur, oth, om);
+                else mg_jacobi_kernel<false><<<grdL, blk, 0, h->stream>>>(L, sc, m->b, cur, oth, om);
                 float* t = cur; cur = oth; oth = t;
             }
         }
@@ -818,7 +822,7 @@ int cycle(fsim* h, int l, bool zero_guess, float** result, bool first_done = fal
     const int cz1 = (fine && h->hybrid && h->g.zown1 < h->g.gz) ? h->g.zown1 / 2 : (1 << 30);
     {
         KScope ks(h, kid);
-        if (v4) mg_restrict4_kernel<<<dim3(div_up(mc->gx, 2 * 32), div_up(mc->gy, 4), div_up(mc->gz, 2)), blk4, 0, h->stream>>>(L, C, sc, m->b, cur, mc->b, cz0, cz1);
+        if (v4) mg_restrict4_kernel<<<dim3(div_up(mc->gx, 2 * 32), div_up(mc->gy, 4), div_up(std::min(cz1, mc->gz) - cz0, 2)), blk4, 0, h->stream>>>(L, C, sc, m->b, cur, mc->b, cz0, cz1);
         else if (fine) mg_restrict_kernel<true><<<grid_of(mc, blk), blk, 0, h->stream>>>(L, C, sc, m->b, cur, mc->b);
         else if (mc->nc > 100000) mg_restrict_kernel<false><<<grid_of(mc, blk), blk, 0, h->stream>>>(L, C, sc, m->b, cur, mc->b);  // enough threads as it is
         else mg_restrict8_kernel<<<div_up(mc->nc * 8, 256), 256, 0, h->stream>>>(L, C, sc, m->b, cur, mc->b, (int)mc->nc);
@@ -837,8 +841,8 @@ int cycle(fsim* h, int l, bool zero_guess, float** result, bool first_done = fal
     {
         KScope ks(h, kid, POST);
         if (v4) mg_prolong_jacobi4_kernel<<<grd4, blk4, 0, h->stream>>>(L, C, sc, m->b, cur, mc->xa, oth);
-        else if (fine) mg_prolong_jacobi_kernel<true><<<grid_of(m, blk), blk, 0, h->stream>>>(L, C, sc, m->b, cur, mc->xa, oth);
-        else mg_prolong_jacobi_kernel<false><<<grid_of(m, blk), blk, 0, h->stream>>>(L, C, sc, m->b, cur, mc->xa, oth);
+        else if (fine) mg_prolong_jacobi_kernel<true><<<grdL, blk, 0, h->stream>>>(L, C, sc, m->b, cur, mc->xa, oth);
+        else mg_prolong_jacobi_kernel<false><<<grdL, blk, 0, h->stream>>>(L, C, sc, m->b, cur, mc->xa, oth);
         { float* t = cur; cur = oth; oth = t; }
         for (int s = 1; s < POST; s++) {
             const float om = OM_A;  // post-sweeps run the pre-sweep weights in reverse order (B in the fused prolongation sweep, then A)
@@ -848,8 +852,8 @@ int cycle(fsim* h, int l, bool zero_guess, float** result, bool first_done = fal
                 mg_jacobi4_dot_kernel<<<std::min(ntiles, h->sm_count * 8), 256, 0, h->stream>>>(L, h->scal, m->b, cur, oth, h->partials, h->red_counter, om,
                                                                                                (int)grd4.x, (int)grd4.y, ntiles);
             } else if (v4) mg_jacobi4_kernel<<<grd4, blk4, 0, h->stream>>>(L, h->scal, m->b, cur, oth, om);
-            else if (fine) mg_jacobi_kernel<true><<<grid_of(m, blk), blk, 0, h->stream>>>(L, sc, m->b, cur, oth, om);
-            else mg_jacobi_kernel<false><<<grid_of(m, blk), blk, 0, h->stream>>>(L, sc, m->b, cur, oth, om);
+            else if (fine) mg_jacobi_kernel<true><<<grdL, blk, 0, h->stream>>>(L, sc, m->b, cur, oth, om);
+            else mg_jacobi_kernel<false><<<grdL, blk, 0, h->stream>>>(L, sc, m->b, cur, oth, om);
             float* t = cur; cur = oth; oth = t;
         }
     }

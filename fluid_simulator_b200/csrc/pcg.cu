@@ -50,12 +50,14 @@ struct PcgArgs {
     double avg_pressure, pressure_k;
     int pressure_enabled, warm;
     int cut_neumann;  // slab mode: how code_mg treats a cut link
+    int64_t cb, ce;   // cell range of the chunked kernels
 };
 
 // iteration space of the chunked kernels: block b owns cells [b*CHUNK, (b+1)*CHUNK), a thread visits CV cells per trip
+// (a.cb, a.ce): the cell range the kernel visits -- the whole grid, or the planes this rank owns (hybrid slab projection)
 #define FOR_CHUNK(c0, nc)                                                                                      \
-    for (int64_t c0 = (int64_t)blockIdx.x * CHUNK + (int64_t)threadIdx.x * CV,                                  \
-                 cend__ = min((int64_t)(blockIdx.x + 1) * CHUNK, (int64_t)(nc));                                \
+    for (int64_t c0 = a.cb + (int64_t)blockIdx.x * CHUNK + (int64_t)threadIdx.x * CV,                           \
+                 cend__ = min(a.cb + (int64_t)(blockIdx.x + 1) * CHUNK, a.ce);                                  \
          c0 < cend__; c0 += PT * CV)
 
 // stencil code of a cell (calculateAMatrix, bridsonSolverGrid.cpp:40-77): bits 0-5 WATER neighbours (-x,+x,-y,+y,-z,+z),
@@ -262,8 +264,8 @@ __global__ void __launch_bounds__(PT, 4) spmv4_kernel(PcgArgs a) {
     double acc[1] = {0.0};
     const int64_t sy = a.g.sy, sz = a.g.sz;
     const double scale = a.sc->scale;
-    const int64_t cend = min((int64_t)(blockIdx.x + 1) * CHUNK, a.g.nc);
-    for (int64_t c = (int64_t)blockIdx.x * CHUNK + (int64_t)threadIdx.x * 4; c < cend; c += PT * 4) {
+    const int64_t cend = min(a.cb + (int64_t)(blockIdx.x + 1) * CHUNK, a.ce);
+    for (int64_t c = a.cb + (int64_t)blockIdx.x * CHUNK + (int64_t)threadIdx.x * 4; c < cend; c += PT * 4) {
         const ushort4 t = *reinterpret_cast<const ushort4*>(a.code + c);
         double sc[4], ym[4] = {0, 0, 0, 0}, yp[4] = {0, 0, 0, 0}, zm[4] = {0, 0, 0, 0}, zp[4] = {0, 0, 0, 0};
         double xl = 0.0, xr = 0.0;
@@ -448,7 +450,9 @@ int k_project(fsim* h, double dt, int* iterations) {
     a.p_prev = h->warm_extrapolate ? h->p_prev : nullptr;
     { const char* e = getenv("FSIM_SLAB_CUT"); a.cut_neumann = (e && e[0] == 'n') ? 1 : 0; }
     a.z32 = nullptr;
-    const int nbv = div_up(g.nc, CHUNK);     // chunked kernels
+    a.cb = h->hybrid ? (int64_t)g.zown0 * g.sz : 0;
+    a.ce = h->hybrid ? (int64_t)g.zown1 * g.sz : g.nc;
+    const int nbv = div_up(a.ce - a.cb, CHUNK);     // chunked kernels
     const bool vec = (g.gx % 2 == 0) && (g.nc % 2 == 0);
     const bool use_mg = mg_enabled(h);
     const int max_it = h->par.max_iterations;
