@@ -18,6 +18,8 @@
 #include <algorithm>
 #include <cooperative_groups.h>
 
+#include <memory>
+
 #include "fsim_internal.h"
 #include "reduce.cuh"
 
@@ -799,7 +801,7 @@ int cycle(fsim* h, int l, bool zero_guess, float** result, bool first_done = fal
         KScope ks(h, kid);
         mg_pre2_kernel<<<grdL, blk, 0, h->stream>>>(L, sc, m->b, cur);
     } else {
-        KScope ks(h, kid, PRE - ((zero_guess && first_done) ? 1 : 0));
+        std::unique_ptr<KScope> ks(new KScope(h, kid, PRE - ((zero_guess && first_done) ? 1 : 0)));
         for (int s = 0; s < PRE; s++) {
             if (s == 0 && zero_guess && first_done) continue;  // x1 and b were written by the fused CG update
             if (s == 0 && zero_guess) {
@@ -808,7 +810,12 @@ int cycle(fsim* h, int l, bool zero_guess, float** result, bool first_done = fal
                 else mg_first_kernel<false><<<grdL, blk, 0, h->stream>>>(L, nullptr, sc, m->b, cur);
             } else {
                 const float om = s == 0 ? OM_A : OM_B;
-                if (fine && h->hybrid) { int rc = dist_halo_sym(h, SYM_X, cur, true); if (rc) return rc; }  // the neighbours' planes of the iterate
+                if (fine && h->hybrid) {  // the neighbours' planes of the iterate (timed as an exchange, not as a sweep)
+                    ks.reset();
+                    int rc = dist_halo_sym(h, SYM_X, cur, true);
+                    if (rc) return rc;
+                    ks.reset(new KScope(h, kid, 0));
+                }
                 if (v4) mg_jacobi4_kernel<<<grd4, blk4, 0, h->stream>>>(L, h->scal, m->b, cur, oth, om);
                 else if (fine) mg_jacobi_kernel<true><<<grdL, blk, 0, h->stream>>>(L, sc, m->b, cur, oth, om);
                 else mg_jacobi_kernel<false><<<grdL, blk, 0, h->stream>>>(L, sc, m->b, cur, oth, om);
@@ -839,14 +846,19 @@ int cycle(fsim* h, int l, bool zero_guess, float** result, bool first_done = fal
         }
     }
     {
-        KScope ks(h, kid, POST);
+        std::unique_ptr<KScope> ks(new KScope(h, kid, POST));
         if (v4) mg_prolong_jacobi4_kernel<<<grd4, blk4, 0, h->stream>>>(L, C, sc, m->b, cur, mc->xa, oth);
         else if (fine) mg_prolong_jacobi_kernel<true><<<grdL, blk, 0, h->stream>>>(L, C, sc, m->b, cur, mc->xa, oth);
         else mg_prolong_jacobi_kernel<false><<<grdL, blk, 0, h->stream>>>(L, C, sc, m->b, cur, mc->xa, oth);
         { float* t = cur; cur = oth; oth = t; }
         for (int s = 1; s < POST; s++) {
             const float om = OM_A;  // post-sweeps run the pre-sweep weights in reverse order (B in the fused prolongation sweep, then A)
-            if (fine && h->hybrid) { int rc = dist_halo_sym(h, SYM_X, cur, true); if (rc) return rc; }
+            if (fine && h->hybrid) {
+                ks.reset();
+                int rc = dist_halo_sym(h, SYM_X, cur, true);
+                if (rc) return rc;
+                ks.reset(new KScope(h, kid, 0));
+            }
             if (v4 && with_dot && s == POST - 1) {
                 const int ntiles = (int)(grd4.x * grd4.y * grd4.z);
                 mg_jacobi4_dot_kernel<<<std::min(ntiles, h->sm_count * 8), 256, 0, h->stream>>>(L, h->scal, m->b, cur, oth, h->partials, h->red_counter, om,
