@@ -187,15 +187,36 @@ def main():
     from fluid_simulator_b200 import dist as fdist
     from fluid_simulator_b200 import slab as fslab
     slab_mode = world > 1 and args.shard == "slab"
+    slab_fallback = None
+    sim = None
     if slab_mode:
         # strong scaling: ONE N^3 dam break cut into z-slabs; every rank builds the part of the dam block that
         # lies in the planes it owns (the jitter keeps a particle inside its cell, so ownership holds by construction)
         lo, hi, zoff, gzl = fslab.partition(n, world)[rank]
         pos = scenes.block_positions_f32(1, n // 2, 1, n - 1, max(lo, 1), min(hi, n - 1), seed=fdist.replica_seed(scenes.SEED, rank))
         np_local = pos.shape[0]
-        sim = FluidSim((float(n),) * 3, 1.0, False, 0.25, capacity=int(np_local * 1.25) + 1024, device=local_rank, rank=rank, nranks=world)
-        fslab.connect_torch(sim, dist)
         nc_local = n * n * gzl
+        try:
+            sim = FluidSim((float(n),) * 3, 1.0, False, 0.25, capacity=int(np_local * 1.25) + 1024, device=local_rank, rank=rank, nranks=world)
+            ok = None
+        except Exception as ex:  # noqa: BLE001
+            ok = f"rank {rank}: {ex}"
+        oks = [None] * world
+        dist.all_gather_object(oks, ok)
+        if not any(oks):
+            try:
+                fslab.connect_torch(sim, dist)  # raises on every rank if any rank could not map its neighbours (e.g. no CUDA IPC)
+            except RuntimeError as ex:
+                oks = [str(ex)]
+        if any(oks):  # consistent on all ranks: fall back to independent replicas and say so
+            slab_fallback = "; ".join(o for o in oks if o)
+            slab_mode = False
+            if sim is not None:
+                sim.close()
+            sim = None
+            del pos
+    if slab_mode:
+        pass
     else:
         # weak scaling: every rank advances its own N^3 dam break (independent replicas of the workload)
         pos = scenes.block_positions_f32(1, n // 2, 1, n - 1, 1, n - 1, seed=fdist.replica_seed(scenes.SEED, rank))

@@ -1,9 +1,9 @@
-"""Multi-rank plumbing of the benchmark / drivers (torch.distributed; NCCL on GPUs, gloo in the CPU tests).
+"""Measurement protocol of the multi-rank benchmark (torch.distributed; NCCL on GPUs, gloo in the CPU tests).
 
-Round 1 runs the path as REPLICAS: every rank owns one full dam-break domain on its own GPU, there is no
-data-path collective; the only communication is the measurement protocol below (barrier, max-over-ranks of the device
-time, sum of the units processed).  The z-slab sharding of one domain (halo planes, particle migration, allreduced dot
-products) plugs in here in round 2.
+`bench.py --gpus N` either cuts ONE domain into z-slabs (fluid_simulator_b200.slab, csrc/dist.cu: ghost planes, particle
+migration and the PCG's reductions travel through NVLink peer memory inside the library) or, with `--shard replicas`, runs
+an independent domain per GPU.  In both modes torch.distributed only carries the protocol below: barrier, max-over-ranks
+of the device time, sum of the units processed.
 """
 import os
 

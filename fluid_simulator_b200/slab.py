@@ -62,8 +62,16 @@ def connect_torch(sim, dist):
     ex = sim.dist_export()
     blobs = [None] * dist.get_world_size()
     dist.all_gather_object(blobs, bytes(ex))
-    sim.dist_connect([abi.DistExport.from_buffer_copy(b) for b in blobs])
-    dist.barrier()
+    err = None
+    try:
+        sim.dist_connect([abi.DistExport.from_buffer_copy(b) for b in blobs])
+    except Exception as e:  # noqa: BLE001 -- e.g. CUDA IPC not permitted in this container
+        err = f"rank {dist.get_rank()}: {e}"
+    errs = [None] * dist.get_world_size()
+    dist.all_gather_object(errs, err)   # doubles as the barrier; every rank learns about every failure and raises together
+    bad = [e for e in errs if e]
+    if bad:
+        raise RuntimeError("slab connect failed: " + "; ".join(bad))
 
 
 class SlabGroup:

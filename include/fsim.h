@@ -210,9 +210,12 @@ FSIM_API int fsim_get_grid_info(const fsim_t* h, FsimGridInfo* out);
  * Particles uploaded to a rank must lie in the planes it owns (trunc(pos.z * cellDInv.z) in [own_lo, own_hi)).
  * Life cycle: every rank creates its handle -> fsim_dist_export -> the caller gathers all exports (any transport) ->
  * fsim_dist_connect -> a barrier of the caller -> fsim_step on all ranks (collective: same dt, params and obstacles on
- * every rank, one host thread or process per rank) -> a barrier -> fsim_destroy.  Spawning and push-apart are not
- * available on slab handles.  A peer that stops answering makes the step fail with FSIM_ERR_COMM after
- * FSIM_DIST_TIMEOUT_MS (default 20000). */
+ * every rank, one host thread or process per rank) -> a barrier -> fsim_destroy.  Spawning, push-apart and the
+ * BasicMacGrid solver are not available on slab handles.  A peer that stops answering makes the step fail with
+ * FSIM_ERR_COMM after FSIM_DIST_TIMEOUT_MS (default 20000).  The projection (bridsonSolverGrid.cpp:244-293) runs as
+ * FSIM_SLAB_SOLVER=hybrid (default: CG vectors and the fine multigrid level on the owned planes, coarse levels
+ * replicated), =replicated (every rank solves the whole system) or =distributed (slab-local solve, block-local
+ * multigrid); all ranks must use the same setting.  Slab boundaries are even planes. */
 FSIM_API int fsim_create_slab(const FsimGridDesc* desc, int rank, int nranks, fsim_t** out);
 FSIM_API int fsim_get_slab_info(const fsim_t* h, FsimSlabInfo* out);
 FSIM_API int fsim_dist_export(fsim_t* h, FsimDistExport* out);
