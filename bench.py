@@ -175,7 +175,11 @@ def main():
     red_dev = "cpu" if same_dev else "cuda"
     torch.cuda.set_device(local_rank)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("FSIM_NCCL_DEBUG", "WARN")  # the image's default prints a version banner on stdout
+        # NCCL_DEBUG at VERSION / WARN or above prints a version banner on stdout, in front of the JSON line
+        if "FSIM_NCCL_DEBUG" in os.environ:
+            os.environ["NCCL_DEBUG"] = os.environ["FSIM_NCCL_DEBUG"]
+        else:
+            os.environ.pop("NCCL_DEBUG", None)
         if same_dev:
             dist.init_process_group("gloo")
         else:
@@ -237,14 +241,16 @@ def main():
         if world > 1:
             dist.barrier()
 
+    # the clock sampler (nvidia-smi every 100 ms) runs from the warm-up on: at N = 8 the timed region is ~50 ms long
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     its = []
     for _ in range(args.warmup):
         its.append(sim.step(DT))
     sim.profile_read(reset=True)  # zero the launch counters
 
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    n_before = len(sampler.lines)
     sim.timer_record(0)
     t0 = time.perf_counter()
     step_its = []
@@ -254,8 +260,20 @@ def main():
     barrier()
     wall = time.perf_counter() - t0
     dev_ms = sim.timer_elapsed_ms(0, 1)
-    clocks = sampler.stop()
+    n_timed = len(sampler.lines) - n_before
     counts = sim.profile_read(reset=True)
+    # short run: keep the same load up until nvidia-smi has answered a few times (untimed; the decision and the number of
+    # extra steps are the same on every rank -- slab steps are collective)
+    need = torch.tensor([1.0 if len(sampler.lines) < 3 else 0.0], dtype=torch.float64, device=red_dev)
+    if world > 1:
+        dist.all_reduce(need, op=dist.ReduceOp.MAX)
+    if need.item() > 0:
+        for _ in range(40):
+            sim.step(DT)
+        sim.synchronize()
+        sim.profile_read(reset=True)
+    clocks = sampler.stop()
+    clocks["samples_in_timed_region"] = n_timed
     timings = sim.timings()
     # per-kernel-class durations: CUDA events around every launch on the launching stream, taken on two extra steps
     # right after the timed region (the timed steps replay the solver iteration as a CUDA graph, whose nodes cannot be
