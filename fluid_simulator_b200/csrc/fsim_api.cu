@@ -731,6 +731,8 @@ int fsim_stage_spawn(fsim_t* h, double dt) {
     return fsim_append_particles(h, fresh.data(), (int64_t)fresh.size() / 15);
 }
 
+static int project_slab(fsim* h, double dt, int* its_out);
+
 int fsim_stage_advect(fsim_t* h, double dt) {
     BIND_FLUSH(h);
     TRY(k_advect(h, dt, true, false, false));
@@ -751,11 +753,43 @@ int fsim_stage_p2g(fsim_t* h) {
 }
 int fsim_stage_classify(fsim_t* h, double dt) { BIND_FLUSH(h); TRY(ensure_sorted(h)); return k_classify(h, dt); }
 int fsim_stage_post_p2g_update(fsim_t* h, double gravity_increment) { BIND_FLUSH(h); return k_post_p2g_only(h, gravity_increment); }
-int fsim_stage_project(fsim_t* h, double dt, int* iterations) { BIND_FLUSH(h); return k_project(h, dt, iterations); }
+int fsim_stage_project(fsim_t* h, double dt, int* iterations) { BIND_FLUSH(h); return h->dist ? project_slab(h, dt, iterations) : k_project(h, dt, iterations); }
 int fsim_stage_extrapolate(fsim_t* h) { BIND_FLUSH(h); return k_extrapolate(h); }
 int fsim_stage_g2p(fsim_t* h) { BIND_FLUSH(h); TRY(ensure_sorted(h)); return k_g2p(h); }
 
 // Simulator::simulate (simulator.cpp:51-100)
+// BridsonSolverGrid::solveIncompressibility on a slab handle: hybrid / replicated run on the full-grid solver context
+// (DESIGN.md §7), distributed on the slab's own arrays
+static int project_slab(fsim* h, double dt, int* its_out) {
+    int its_local = 0;
+    if (!its_out) its_out = &its_local;
+    if (h->solver) {
+        // replicated projection: gather every rank's planes of the solver inputs, solve the whole system here, keep our planes
+        fsim* hs = h->solver;
+        TRY(dist_gather_solver_inputs(h));
+        hs->par = h->par;
+        hs->prof_mask = h->prof_mask;
+        const int64_t ls0 = hs->launches;
+        int64_t c0[K_COUNT];
+        memcpy(c0, hs->launch_n, sizeof(c0));
+        const int rc = k_project(hs, dt, its_out);
+        if (rc) { h->err = hs->err; if (hs->sticky) h->sticky = hs->sticky; return rc; }
+        h->launches += hs->launches - ls0;
+        for (int k = 0; k < K_COUNT; k++) h->launch_n[k] += hs->launch_n[k] - c0[k];
+        for (const ProfRec& r : hs->prof_recs) h->prof_recs.push_back(r);  // event pairs of the profiled launches
+        hs->prof_recs.clear();
+        h->solve = hs->solve;
+        // (hybrid: hs->p holds this rank's planes and, after the last halo, the two planes around them -- exactly the local block)
+        const size_t plane = (size_t)h->g.sz;
+        FSIM_CUDA(h, cudaMemcpyAsync(h->p, hs->p + (size_t)h->g.zoff * plane, sizeof(double) * plane * h->g.gz, cudaMemcpyDeviceToDevice, h->stream));
+        FSIM_CUDA(h, cudaMemcpyAsync(h->rhs, hs->rhs + (size_t)h->g.zoff * plane, sizeof(double) * plane * h->g.gz, cudaMemcpyDeviceToDevice, h->stream));
+        if (!hs->solve.early_out) TRY(k_pressure_apply(h, dt));  // ghost planes included: the pressure around them is known
+    } else {
+        TRY(k_project(h, dt, its_out));  // halos of the search direction / pressure and the all-rank reductions inside
+    }
+    return FSIM_OK;
+}
+
 // the same step on one z-slab of the grid (dist.cu): collective over the ranks
 static int step_slab(fsim* h, double dt, int* pcg_iterations) {
     TRY(dist_check(h));
@@ -781,30 +815,7 @@ static int step_slab(fsim* h, double dt, int* pcg_iterations) {
     TRY(k_classify(h, dt));
     FSIM_CUDA(h, cudaEventRecord(h->ev[4], h->stream));
     int its = 0;
-    if (h->solver) {
-        // replicated projection: gather every rank's planes of the solver inputs, solve the whole system here, keep our planes
-        fsim* hs = h->solver;
-        TRY(dist_gather_solver_inputs(h));
-        hs->par = h->par;
-        hs->prof_mask = h->prof_mask;
-        const int64_t ls0 = hs->launches;
-        int64_t c0[K_COUNT];
-        memcpy(c0, hs->launch_n, sizeof(c0));
-        const int rc = k_project(hs, dt, &its);
-        if (rc) { h->err = hs->err; if (hs->sticky) h->sticky = hs->sticky; return rc; }
-        h->launches += hs->launches - ls0;
-        for (int k = 0; k < K_COUNT; k++) h->launch_n[k] += hs->launch_n[k] - c0[k];
-        for (const ProfRec& r : hs->prof_recs) h->prof_recs.push_back(r);  // event pairs of the profiled launches
-        hs->prof_recs.clear();
-        h->solve = hs->solve;
-        // (hybrid: hs->p holds this rank's planes and, after the last halo, the two planes around them -- exactly the local block)
-        const size_t plane = (size_t)h->g.sz;
-        FSIM_CUDA(h, cudaMemcpyAsync(h->p, hs->p + (size_t)h->g.zoff * plane, sizeof(double) * plane * h->g.gz, cudaMemcpyDeviceToDevice, h->stream));
-        FSIM_CUDA(h, cudaMemcpyAsync(h->rhs, hs->rhs + (size_t)h->g.zoff * plane, sizeof(double) * plane * h->g.gz, cudaMemcpyDeviceToDevice, h->stream));
-        if (!hs->solve.early_out) TRY(k_pressure_apply(h, dt));  // ghost planes included: the pressure around them is known
-    } else {
-        TRY(k_project(h, dt, &its));  // halos of the search direction / pressure and the all-rank reductions inside
-    }
+    TRY(project_slab(h, dt, &its));
     FSIM_CUDA(h, cudaEventRecord(h->ev[5], h->stream));
     TRY(dist_halo(h, HALO_U2, false));
     TRY(k_extrapolate(h));        // exchanges u2 + validity between and after its two sweeps

@@ -176,6 +176,25 @@ class SlabGroup:
         g = stitch(blocks, self.parts, self.grid_size, trailing)
         return g.reshape((-1,) + trailing)
 
+    def upload_grid(self, field, arr):
+        """Global reference-order array -> every rank's local block (owned planes and ghost planes alike)."""
+        gx, gy, gz = self.grid_size
+        trailing = (3,) if field in (abi.FIELD_V, abi.FIELD_V2, abi.FIELD_WSUM) else ()
+        g = np.asarray(arr).reshape((gx, gy, gz) + trailing)
+        for s, (lo, hi, zoff, gzl) in zip(self.sims, self.parts):
+            s.upload_grid(field, np.ascontiguousarray(g[:, :, zoff:zoff + gzl]))
+
+    def post_p2g_update(self, gravity_increment):
+        for s in self.sims:
+            s.post_p2g_update(gravity_increment)
+
+    def stage_project(self, dt):
+        its = self._all(lambda r, s: s.stage_project(dt))
+        if len(set(its)) != 1:
+            self.synchronize()
+        assert len(set(its)) == 1, f"ranks disagree on the PCG iteration count: {its}"
+        return its[0]
+
     def download_grid_local(self, field, rank):
         self.synchronize()
         return self.sims[rank].download_grid(field)

@@ -176,6 +176,31 @@ def test_slab_projection_modes(gpu, solver, monkeypatch):
     one.close()
 
 
+@pytest.mark.parametrize("solver", ["hybrid", "replicated"])
+def test_slab_projection_only(gpu, solver, monkeypatch):
+    """SURVEY cfg 5 on slabs: uploaded cell types, hydrostatic start, one cold solve (fsim_stage_project on slab handles)."""
+    monkeypatch.setenv("FSIM_SLAB_SOLVER", solver)
+    monkeypatch.setenv("FSIM_NO_WARM_START", "1")
+    FluidSim, SlabGroup = gpu
+    n = 32
+    par = scenes.default_params(abi.FLIP, pressure_enabled=False, max_iterations=2000, tol=1e-9)
+    types = scenes.hydrostatic_types(n)
+    one = FluidSim((float(n),) * 3, 1.0, False, 0.25)
+    grp = SlabGroup(3, (float(n),) * 3, 1.0, False, 0.25)
+    for s in (one, grp):
+        s.set_params(par)
+        s.upload_grid(abi.FIELD_TYPE, types)
+        s.upload_grid(abi.FIELD_V, np.zeros((n ** 3, 3)))
+        s.post_p2g_update(-39.24 * 0.005)
+    i1, ig = one.stage_project(0.005), grp.stage_project(0.005)
+    ep = rel_l2(grp.download_grid(abi.FIELD_PRESSURE), one.download_grid(abi.FIELD_PRESSURE))
+    ev = rel_l2(grp.download_grid(abi.FIELD_V2), one.download_grid(abi.FIELD_V2))
+    diag(test=f"slab_projection_only_{solver}", its_single=i1, its_slab=ig, pressure=ep, v2=ev)
+    assert abs(i1 - ig) <= 1 and ep <= TOL and ev <= TOL
+    grp.close()
+    one.close()
+
+
 def test_slab_unsupported_and_errors(gpu):
     FluidSim, SlabGroup = gpu
     from fluid_simulator_b200.sim import FsimError
