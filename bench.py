@@ -241,6 +241,8 @@ def main():
         if world > 1:
             dist.barrier()
 
+    if world > 1:
+        dist.barrier()  # slab steps are collective: start them together (a rank still setting up would eat into the exchange time-out)
     # the clock sampler (nvidia-smi every 100 ms) runs from the warm-up on: at N = 8 the timed region is ~50 ms long
     sampler = ClockSampler(local_rank)
     sampler.start()

@@ -708,6 +708,7 @@ int fsim_download_particles_f32(fsim_t* h, float* pos, float* vel, float* c, int
 // the spawned set, is identical to the reference's (util/random.h:13-26)
 int fsim_stage_spawn(fsim_t* h, double dt) {
     BIND(h);
+    if (h->dist) return fsim_fail(h, FSIM_ERR_INVALID, "particle spawning is not available on a slab handle");
     std::vector<double> fresh;
     for (int k = 0; k < h->nobs; k++) {
         FsimObstacle& ob = h->obs[k];
@@ -733,28 +734,36 @@ int fsim_stage_spawn(fsim_t* h, double dt) {
 
 static int project_slab(fsim* h, double dt, int* its_out);
 
+#define NO_SLAB(h, what)                                                                                                   \
+    do {                                                                                                                   \
+        if ((h)->dist) return fsim_fail((h), FSIM_ERR_INVALID, what " is not available on a slab handle: its exchanges only run inside fsim_step"); \
+    } while (0)
+
 int fsim_stage_advect(fsim_t* h, double dt) {
     BIND_FLUSH(h);
+    NO_SLAB(h, "fsim_stage_advect");
     TRY(k_advect(h, dt, true, false, false));
     if (h->kill_pending) TRY(k_sort(h));  // removeParticles at the end of advectParticles (simulator.cpp:250)
     return FSIM_OK;
 }
 int fsim_stage_push_apart(fsim_t* h) {  /* updateParticleIntersectionHash + pushParticlesApart, simulator.cpp:61-64 */
     BIND_FLUSH(h);
+    NO_SLAB(h, "fsim_stage_push_apart");
     TRY(ensure_sorted(h));
     return k_push_apart(h);
 }
 int fsim_stage_push_out(fsim_t* h) { BIND_FLUSH(h); return k_advect(h, 0.0, false, true, false); }
 int fsim_stage_p2g(fsim_t* h) {
     BIND_FLUSH(h);
+    NO_SLAB(h, "fsim_stage_p2g");
     if (h->par.stop_particles) TRY(k_advect(h, 0.0, false, false, true));
     TRY(ensure_sorted(h));
     return k_p2g(h);
 }
-int fsim_stage_classify(fsim_t* h, double dt) { BIND_FLUSH(h); TRY(ensure_sorted(h)); return k_classify(h, dt); }
+int fsim_stage_classify(fsim_t* h, double dt) { BIND_FLUSH(h); NO_SLAB(h, "fsim_stage_classify"); TRY(ensure_sorted(h)); return k_classify(h, dt); }
 int fsim_stage_post_p2g_update(fsim_t* h, double gravity_increment) { BIND_FLUSH(h); return k_post_p2g_only(h, gravity_increment); }
 int fsim_stage_project(fsim_t* h, double dt, int* iterations) { BIND_FLUSH(h); return h->dist ? project_slab(h, dt, iterations) : k_project(h, dt, iterations); }
-int fsim_stage_extrapolate(fsim_t* h) { BIND_FLUSH(h); return k_extrapolate(h); }
+int fsim_stage_extrapolate(fsim_t* h) { BIND_FLUSH(h); NO_SLAB(h, "fsim_stage_extrapolate"); return k_extrapolate(h); }
 int fsim_stage_g2p(fsim_t* h) { BIND_FLUSH(h); TRY(ensure_sorted(h)); return k_g2p(h); }
 
 // Simulator::simulate (simulator.cpp:51-100)

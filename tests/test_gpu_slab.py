@@ -211,6 +211,10 @@ def test_slab_unsupported_and_errors(gpu):
     with pytest.raises(FsimError):  # not connected to its neighbour
         s.step(0.005)
     s.close()
+    s = FluidSim((16.0, 16.0, 16.0), 1.0, False, 0.25, rank=1, nranks=2)
+    with pytest.raises(FsimError):  # single stages would skip the exchanges: only fsim_step / fsim_stage_project run on slabs
+        s.stage_p2g()
+    s.close()
 
 
 def test_two_processes_ipc():
