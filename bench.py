@@ -49,7 +49,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "25"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except OSError:
@@ -58,6 +58,12 @@ class ClockSampler:
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
+
+    def wait_first(self, timeout=3.0):
+        """nvidia-smi needs a moment to start: wait for its first answer so that the timed region is covered."""
+        t0 = time.perf_counter()
+        while self.proc and not self.lines and time.perf_counter() - t0 < timeout:
+            time.sleep(0.01)
 
     def stop(self):
         if not self.proc:
@@ -243,9 +249,10 @@ def main():
 
     if world > 1:
         dist.barrier()  # slab steps are collective: start them together (a rank still setting up would eat into the exchange time-out)
-    # the clock sampler (nvidia-smi every 100 ms) runs from the warm-up on: at N = 8 the timed region is ~50 ms long
+    # the clock sampler (nvidia-smi every 25 ms) runs from the warm-up on: at N = 8 the timed region is ~50 ms long
     sampler = ClockSampler(local_rank)
     sampler.start()
+    sampler.wait_first()
     its = []
     for _ in range(args.warmup):
         its.append(sim.step(DT))
