@@ -10,7 +10,12 @@
 //                       order: deterministic, bit-identical on all ranks, ~one NVLink round trip; it then takes the PCG
 //                       decision (pcg_finish.cuh) that the last block takes in the single-GPU path;
 //   * mig_send / mig_recv  particles whose cell left the owned planes are pushed into the neighbour's receive buffer and
-//                       binned there before the sort.
+//                       binned there before the sort;
+//   * push_kernel       the in-loop exchanges of the hybrid projection (search direction, multigrid iterate, coarse
+//                       right-hand side): posted stores into the peers' arrays + a flag, no handshake (see the kernel);
+//   * gather_kernel     all-rank handshake + pull of the planes every rank owns (solver inputs, coarse right-hand side).
+// The projection of a slab handle runs on a full-grid solver context (fsim::solver) whose arrays sit at global plane
+// indices on every rank (DESIGN.md §7 "hybrid"): halos there need no index translation.
 // Every wait is bounded (FSIM_DIST_TIMEOUT_MS, default 20 s): a lost peer becomes FSIM_ERR_COMM, never a hung GPU.
 #include <unistd.h>
 

@@ -1,5 +1,6 @@
 """N>1 path on CPU: two gloo ranks run the benchmark's measurement protocol (replica seeds, barrier, max-over-ranks time,
-summed units) -- the only cross-rank logic of the round-1 multi-GPU mode (replicas)."""
+summed units) -- the cross-rank logic that lives in Python (the slab exchanges themselves are CUDA kernels,
+tests/test_gpu_slab.py, and their host-side arithmetic is covered by tests/test_slab_host.py)."""
 import os
 import socket
 
