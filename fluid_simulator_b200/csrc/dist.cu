@@ -472,9 +472,8 @@ int check_err(fsim* h) {
     if (e == 1)
         return fsim_fail(h, FSIM_ERR_COMM, "slab exchange timed out waiting for a neighbour (rank %d of %d; wait 0x%x, epoch %u, flag %u)", d->rank,
                          d->nranks, eh[1], eh[2], eh[3]);
-    return fsim_fail(h, FSIM_ERR_COMM, e == 1 ? "slab exchange timed out waiting for a neighbour (rank %d of %d)"
-                                      : e == 2 ? "emigrant list overflow (rank %d of %d): more particles crossed a slab boundary in one step than the list holds"
-                                               : "a particle crossed a whole slab in one step (rank %d of %d)", d->rank, d->nranks);
+    return fsim_fail(h, FSIM_ERR_COMM, e == 2 ? "emigrant list overflow (rank %d of %d): more particles crossed a slab boundary in one step than the list holds"
+                                              : "a particle crossed a whole slab in one step (rank %d of %d)", d->rank, d->nranks);
 }
 
 }  // namespace

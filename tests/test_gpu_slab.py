@@ -222,9 +222,13 @@ def test_two_processes_ipc():
     import torch
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
+    import socket
     env = dict(os.environ, FSIM_DIST_TIMEOUT_MS="60000")
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-           "--master-port", "29617", os.path.join(ROOT, "tests", "slab_worker.py")]
+           "--master-port", str(port), os.path.join(ROOT, "tests", "slab_worker.py")]
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
     sys.stdout.write(r.stdout[-4000:])
     sys.stderr.write(r.stderr[-4000:])
