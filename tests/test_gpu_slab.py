@@ -234,3 +234,18 @@ def test_two_processes_ipc():
     sys.stderr.write(r.stderr[-4000:])
     assert r.returncode == 0
     assert "SLAB_WORKER_OK" in r.stdout
+
+
+def test_cpp_host_drives_slabs():
+    """tests/cpp/slab_host.cpp: a C++ host (std::thread per rank) drives three slab handles through the plain C ABI and
+    compares them with a single handle (iteration counts, particle count, sum |v2|, sum p)."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    exe = os.path.join(ROOT, "tests", "cpp", "build", "slab_host")
+    if not os.path.exists(exe):
+        subprocess.check_call(["bash", os.path.join(ROOT, "tests", "cpp", "build_slab_host.sh")])
+    r = subprocess.run([exe, "3", "20", "3"], capture_output=True, text=True, timeout=300, env=dict(os.environ, FSIM_DIST_TIMEOUT_MS="20000"))
+    sys.stdout.write(r.stdout[-2000:])
+    sys.stderr.write(r.stderr[-2000:])
+    assert r.returncode == 0 and "SLAB_HOST_OK" in r.stdout

@@ -116,3 +116,9 @@ def test_export_exchange_over_gloo():
         seen = got[r]
         assert [(s[0], s[1], s[2], s[3]) for s in seen] == [(0, 2, 0x1000, 40), (1, 2, 0x2000, 41)]
         assert seen[0][4] != seen[1][4]      # two processes: the library will take the IPC path
+
+
+def test_cpp_slab_host_builds_against_c_abi():
+    """The C++ host of the z-slab ABI (tests/cpp/slab_host.cpp: std::thread per rank, plain fsim.h) compiles and links."""
+    subprocess.check_call(["bash", os.path.join(ROOT, "tests", "cpp", "build_slab_host.sh")])
+    assert os.path.exists(os.path.join(ROOT, "tests", "cpp", "build", "slab_host"))
