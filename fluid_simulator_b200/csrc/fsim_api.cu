@@ -313,7 +313,7 @@ static int create_impl(const FsimGridDesc* desc, int rank, int nranks, fsim_t** 
     h->warm_history = 0; h->p_prev = nullptr; h->mg_tail_cluster = 0;
     h->status_host = nullptr; h->status_dev = nullptr;
     h->dist = nullptr; h->code_mg = nullptr; h->solver = nullptr; h->stream_shared = false; h->skip_apply = false;
-    h->parent = nullptr; h->hybrid = 0; h->code_full = nullptr;
+    h->parent = nullptr; h->hybrid = 0; h->code_full = nullptr; h->slab_spawn_id = 0x80000000u;
     { const char* e = getenv("FSIM_PRECOND"); h->use_mg = !(e && strcmp(e, "jacobi") == 0); }
     memset(h->prof_ms, 0, sizeof(h->prof_ms)); memset(h->prof_n, 0, sizeof(h->prof_n)); memset(h->launch_n, 0, sizeof(h->launch_n));
 
@@ -708,7 +708,6 @@ int fsim_download_particles_f32(fsim_t* h, float* pos, float* vel, float* c, int
 // the spawned set, is identical to the reference's (util/random.h:13-26)
 int fsim_stage_spawn(fsim_t* h, double dt) {
     BIND(h);
-    if (h->dist) return fsim_fail(h, FSIM_ERR_INVALID, "particle spawning is not available on a slab handle");
     std::vector<double> fresh;
     for (int k = 0; k < h->nobs; k++) {
         FsimObstacle& ob = h->obs[k];
@@ -729,6 +728,30 @@ int fsim_stage_spawn(fsim_t* h, double dt) {
         }
     }
     if (fresh.empty()) return FSIM_OK;
+    if (h->dist) {
+        // slab handle (one PROCESS per rank, libc rand() seeded identically everywhere): every rank draws the whole spawn set
+        // -- so the rand() streams stay in step with the single-handle run -- and keeps the particles that start in its planes
+        // (same plane expression as the device binning); ids continue a sequence all ranks advance together
+        const int64_t total = (int64_t)fresh.size() / 15;
+        std::vector<double> mine;
+        std::vector<uint32_t> ids;
+        for (int64_t i = 0; i < total; i++) {
+            int iz = (int)((double)(float)fresh[15 * i + 2] * h->g.dihz);
+            iz = std::min(std::max(iz, 0), h->g.gzg - 1);
+            if (iz < h->g.zoff + h->g.zown0 || iz >= h->g.zoff + h->g.zown1) continue;
+            mine.insert(mine.end(), fresh.begin() + 15 * i, fresh.begin() + 15 * (i + 1));
+            ids.push_back(h->slab_spawn_id + (uint32_t)i);
+        }
+        h->slab_spawn_id += (uint32_t)total;
+        if (mine.empty()) return FSIM_OK;
+        const int64_t first = h->np;
+        TRY(fsim_append_particles(h, mine.data(), (int64_t)ids.size()));
+        if (h->track_ids) {
+            FSIM_CUDA(h, cudaMemcpyAsync(h->ps[h->cur].id + first, ids.data(), sizeof(uint32_t) * ids.size(), cudaMemcpyHostToDevice, h->stream));
+            FSIM_CUDA(h, cudaStreamSynchronize(h->stream));
+        }
+        return FSIM_OK;
+    }
     return fsim_append_particles(h, fresh.data(), (int64_t)fresh.size() / 15);
 }
 
@@ -802,12 +825,12 @@ static int project_slab(fsim* h, double dt, int* its_out) {
 // the same step on one z-slab of the grid (dist.cu): collective over the ranks
 static int step_slab(fsim* h, double dt, int* pcg_iterations) {
     TRY(dist_check(h));
-    if (h->par.spawning_enabled || h->par.push_apart_enabled)
-        return fsim_fail(h, FSIM_ERR_INVALID, "particle spawning and push-apart are not available on slab handles");
+    if (h->par.push_apart_enabled) return fsim_fail(h, FSIM_ERR_INVALID, "push-apart is not available on slab handles");
     if (h->par.solver_type != FSIM_SOLVER_BRIDSON) return fsim_fail(h, FSIM_ERR_INVALID, "slab handles run the PCG projection only");
     fold_timings(h);
     const int64_t l0 = h->launches;
     FSIM_CUDA(h, cudaEventRecord(h->ev[0], h->stream));
+    if (h->par.spawning_enabled) TRY(fsim_stage_spawn(h, dt));
     TRY(ensure_capacity(h, h->np));  // room for this step's immigrants; must happen before the advect kernel bins
     const bool fuse = h->g2p_pending && h->sorted && h->np > 0;
     if (!fuse) TRY(flush_g2p(h));

@@ -195,6 +195,7 @@ struct fsim {
     fsim* parent;        // ... the slab handle it belongs to
     int hybrid;          // ... 1: fine level and CG vectors restricted to the planes this rank owns (halos + all-rank reductions),
                          //        coarse multigrid levels replicated; 0: the whole solve is replicated
+    uint32_t slab_spawn_id;  // slab handles: next id of the spawn sequence that all ranks advance together
     uint16_t* code_full; // hybrid: stencil codes of ALL fluid cells (the coarse operators are global); h->code is owned-only
     uint16_t* code_mg;  // stencil codes the multigrid preconditioner sees (slab mode: links into ghost planes cut); == code otherwise
 
