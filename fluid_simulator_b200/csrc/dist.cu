@@ -177,7 +177,8 @@ __global__ void __launch_bounds__(256) halo_kernel(const __grid_constant__ HaloA
 // Push form of the exchange, for the halos INSIDE the PCG loop (search direction, multigrid iterate, coarse right-hand side):
 // every rank stores its planes straight into the neighbours' arrays (posted NVLink writes, no read round trip) and raises a
 // flag; the kernel ends when the neighbours' flags have arrived.  No handshake guards the destination: between two uses of a
-// ghost plane the loop always passes an all-rank reduction or gather, so its previous reader has finished.
+// ghost plane the loop always passes an all-rank reduction or gather, so its previous reader has finished (DESIGN.md §7;
+// the schedule is model-checked in tests/test_slab_protocol_model.py).
 struct PushCopy { void* dst; const void* src; size_t bytes; int to; };
 struct PushArgs {
     DistComm* comm;
