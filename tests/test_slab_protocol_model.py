@@ -130,3 +130,48 @@ def test_model_detects_a_race_when_nothing_orders_the_ranks():
             found = True
             break
     assert found
+
+
+# ---- allreduce_kernel: slot[parity][source rank] on every rank, double-buffered by the parity of the epoch -----------------
+def simulate_allreduce(nranks, rounds, seed, nbuf=2):
+    """Every rank: for ep = 1..rounds: store (value(rank, ep), ep) into slot[ep % nbuf][rank] of EVERY rank (one store at a
+    time, any interleaving), then wait until its own slots of that buffer all carry epoch >= ep, then read them.  Checks that
+    what is read is the value of exactly that epoch (i.e. nobody was able to overwrite a slot that was still to be read)."""
+    rng = random.Random(seed)
+    slots = [[[(None, 0)] * nranks for _ in range(nbuf)] for _ in range(nranks)]   # slots[owner][buffer][source] = (value, epoch)
+    ep = [1] * nranks
+    stage = [0] * nranks          # 0..nranks-1: next peer to store to; nranks: waiting
+    steps = 0
+    while any(e <= rounds for e in ep):
+        steps += 1
+        assert steps < 5_000_000
+        r = rng.randrange(nranks)
+        if ep[r] > rounds:
+            continue
+        e, b = ep[r], ep[r] % nbuf
+        if stage[r] < nranks:
+            slots[stage[r]][b][r] = ((r, e), e)
+            stage[r] += 1
+        elif all(slots[r][b][q][1] >= e for q in range(nranks)):
+            for q in range(nranks):
+                assert slots[r][b][q][0] == (q, e), f"rank {r} epoch {e}: slot of rank {q} holds {slots[r][b][q]}"
+            ep[r] += 1
+            stage[r] = 0
+    return steps
+
+
+@pytest.mark.parametrize("nranks", [2, 4, 8])
+def test_allreduce_double_buffering_is_enough(nranks):
+    for seed in range(40):
+        simulate_allreduce(nranks, rounds=12, seed=seed)
+
+
+def test_allreduce_model_catches_a_single_buffer():
+    found = False
+    for seed in range(200):
+        try:
+            simulate_allreduce(3, rounds=12, seed=seed, nbuf=1)
+        except AssertionError:
+            found = True
+            break
+    assert found
