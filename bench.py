@@ -362,7 +362,7 @@ def main():
         alg["advect"] += nc * (24 if transfer == abi.FLIP else 12) + np_local * ((36 if transfer == abi.APIC else 0) + 8)
     traffic_path = os.path.join(ROOT, "profiles", "r1_dram_traffic_256_flip.json")
     traffic = None
-    if n == 256 and transfer == abi.FLIP and os.path.exists(traffic_path):
+    if n == 256 and transfer == abi.FLIP and world == 1 and os.path.exists(traffic_path):  # ncu capture of the single-GPU launches
         traffic = json.load(open(traffic_path)).get(dominant)
     dom_ms, dom_n, _ = prof[dominant]
     roofline = None
