@@ -74,6 +74,7 @@ struct DistState {
     void* all_arr[DIST_MAX_RANKS][DIST_NARR];     // every rank's arrays (the gather pulls the planes each rank owns)
     int all_zown0[DIST_MAX_RANKS], all_zown1[DIST_MAX_RANKS], all_zoff[DIST_MAX_RANKS];
     bool connected, nsrc_valid;
+    bool peer_in_process;  // some other rank of the group lives in this process (they would share libc's rand() stream)
     std::vector<void*> ipc_opened;
 };
 
@@ -492,6 +493,8 @@ const uint32_t* dist_nsrc_dev(fsim* h) {
 
 void dist_rank(const fsim* h, int* rank, int* nranks) { if (h->dist) { *rank = h->dist->rank; *nranks = h->dist->nranks; } }
 
+bool dist_peer_in_process(const fsim* h) { return h->dist && h->dist->peer_in_process; }
+
 int dist_check(fsim* h) { return (h->dist && h->dist->connected) ? check_err(h) : FSIM_OK; }
 
 // the slab geometry of rank r of n over gzg global planes
@@ -606,6 +609,7 @@ int dist_connect(fsim* h, const FsimDistExport* all, int n) {
             for (int k = 0; k < DIST_NARR; k++) d->all_arr[r][k] = d->local_arr[k] ? (char*)d->local_arr[k] + d->local_off[k] : nullptr;
             continue;
         }
+        if (ex.pid == pid) d->peer_in_process = true;
         const int side = r == d->rank - 1 ? 0 : (r == d->rank + 1 ? 1 : -1);
         for (int k = 0; k < DIST_NARR; k++) {
             if (k == ARR_RECV && side < 0) continue;  // only neighbours push particles

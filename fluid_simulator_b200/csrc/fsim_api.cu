@@ -133,18 +133,26 @@ void fold_timings(fsim* h) {
                  us_proj = ms[4] * 1e3, us_ext = ms[5] * 1e3, us_g2p = ms[6] * 1e3;
     FsimTimings& t = h->timings;
     const double f = 0.9;  // slidingAvgFactor, simulator.cpp:52
-    t.simulate_particles = (int64_t)(t.simulate_particles * f + (us_adv - (h->push_timed ? 0.0 : 0.0)) * (1 - f));
-    double us_push = 0;
-    if (h->push_timed) { float pm = 0; cudaEventElapsedTime(&pm, h->ev[9], h->ev[15]); us_push = pm * 1e3; }
+    // with push-apart on, ev[0]..ev[1] spans advect | sort + push-apart (ev[9]..ev[15]) | push-out pass (ev[15]..ev[1]): each goes
+    // to the reference's own key (simulator.cpp:57-68); without it advect and push-out are one kernel, reported as SimulateParticles
+    double us_push = 0, us_pushout = 0, us_sim = us_adv;
+    if (h->push_timed) {
+        float pm = 0, po = 0, pa = 0;
+        cudaEventElapsedTime(&pa, h->ev[0], h->ev[9]);
+        cudaEventElapsedTime(&pm, h->ev[9], h->ev[15]);
+        cudaEventElapsedTime(&po, h->ev[15], h->ev[1]);
+        us_sim = pa * 1e3; us_push = pm * 1e3; us_pushout = po * 1e3;
+    }
+    t.simulate_particles = (int64_t)(t.simulate_particles * f + us_sim * (1 - f));
     t.push_particles_apart = (int64_t)(t.push_particles_apart * f + us_push * (1 - f));
-    t.push_particles_out_of_obstacles = (int64_t)(t.push_particles_out_of_obstacles * f);  // fused into the advect kernel
+    t.push_particles_out_of_obstacles = (int64_t)(t.push_particles_out_of_obstacles * f + us_pushout * (1 - f));
     t.p2g_transfer = (int64_t)(t.p2g_transfer * f + (us_sort + us_p2g) * (1 - f));
     t.incompressibility_prep = (int64_t)(t.incompressibility_prep * f + us_prep * (1 - f));
     t.incompressibility = (int64_t)(t.incompressibility * f + us_proj * (1 - f));
     t.velocity_extrapolation = (int64_t)(t.velocity_extrapolation * f + us_ext * (1 - f));
     t.g2p_transfer = (int64_t)(t.g2p_transfer * f + us_g2p * (1 - f));
     t.incompressibility_it_count = h->solve.iterations;
-    t.last_raw_us[0] = us_adv; t.last_raw_us[1] = us_push; t.last_raw_us[2] = 0; t.last_raw_us[3] = us_p2g;
+    t.last_raw_us[0] = us_sim; t.last_raw_us[1] = us_push; t.last_raw_us[2] = us_pushout; t.last_raw_us[3] = us_p2g;
     t.last_raw_us[4] = us_prep; t.last_raw_us[5] = us_proj; t.last_raw_us[6] = us_ext; t.last_raw_us[7] = us_g2p;
     t.last_sort_us = us_sort;
     float total;
@@ -292,6 +300,7 @@ static int create_impl(const FsimGridDesc* desc, int rank, int nranks, fsim_t** 
     p.transfer_type = FSIM_TRANSFER_FLIP; p.flip_ratio = 0.99f; p.gravity = 150.0f; p.gravity_enabled = 1;
     p.push_apart_enabled = 1; p.pressure_enabled = 1; p.max_iterations = 80; p.pressure_k = 2.0;
     p.average_pressure = 2.0; p.fluid_density = 1.0; p.residual_tolerance = 1e-6;
+    if (nranks > 1) p.push_apart_enabled = 0;  // not available on slab handles: a handle that never calls fsim_set_params must still step
     h->nobs = 0;
     h->np = 0; h->cap = 0; h->cur = 0; h->have_c = false; h->track_ids = true; h->sorted = false; h->binned = false; h->kill_pending = false;
     memset(h->ps, 0, sizeof(h->ps));
@@ -528,6 +537,8 @@ int fsim_set_params(fsim_t* h, const FsimParams* p) {
     if (p->transfer_type < 0 || p->transfer_type > 2) return fsim_fail(h, FSIM_ERR_INVALID, "bad transfer type %d", p->transfer_type);
     if (!(p->fluid_density > 0)) return fsim_fail(h, FSIM_ERR_INVALID, "fluid density must be > 0");
     if (p->solver_type != FSIM_SOLVER_BRIDSON && p->solver_type != FSIM_SOLVER_BASIC) return fsim_fail(h, FSIM_ERR_INVALID, "bad solver type %d", p->solver_type);
+    if (h->dist && p->push_apart_enabled) return fsim_fail(h, FSIM_ERR_INVALID, "push-apart is not available on slab handles");
+    if (h->dist && p->solver_type != FSIM_SOLVER_BRIDSON) return fsim_fail(h, FSIM_ERR_INVALID, "slab handles run the PCG projection only");
     if (p->transfer_type != h->par.transfer_type || p->flip_ratio != h->par.flip_ratio) TRY(flush_g2p(h));  // a pending G2P uses the old blend
     h->par = *p;
     if (p->transfer_type == FSIM_TRANSFER_APIC) TRY(ensure_c(h));
@@ -708,6 +719,16 @@ int fsim_download_particles_f32(fsim_t* h, float* pos, float* vel, float* c, int
 // the spawned set, is identical to the reference's (util/random.h:13-26)
 int fsim_stage_spawn(fsim_t* h, double dt) {
     BIND(h);
+    // slab handles: every rank draws the WHOLE spawn set from libc rand() and keeps its planes' share, which is only the
+    // single-handle sequence when each rank owns a rand() stream of its own, i.e. one process per rank.  Ranks that share a
+    // process would interleave one stream (particles lost or duplicated, colliding ids): refused, not silently wrong.
+    if (h->dist && dist_peer_in_process(h)) {
+        bool any_source = false;
+        for (int k = 0; k < h->nobs; k++) any_source |= h->obs[k].kind == FSIM_OBSTACLE_SOURCE && h->obs[k].spawn_rate * dt + h->obs[k].last_spawn_fraction >= 1.0;
+        if (any_source)
+            return fsim_fail(h, FSIM_ERR_INVALID, "particle spawning on a slab group needs one process per rank (libc rand() is process-global); "
+                                                   "ranks of this group share a process");
+    }
     std::vector<double> fresh;
     for (int k = 0; k < h->nobs; k++) {
         FsimObstacle& ob = h->obs[k];

@@ -447,6 +447,7 @@ int k_project(fsim* h, double dt, int* iterations) {
     a.avg_pressure = h->par.average_pressure; a.pressure_k = h->par.pressure_k;
     a.pressure_enabled = h->par.pressure_enabled;
     a.warm = (h->warm_start && h->pressure_valid) ? (h->warm_extrapolate && h->warm_history >= 2 ? 2 : 1) : 0;
+    if (h->par.max_iterations <= 0) a.warm = 0;  // zero iterations apply p = 0 like the reference, not last step's pressure
     a.p_prev = h->warm_extrapolate ? h->p_prev : nullptr;
     { const char* e = getenv("FSIM_SLAB_CUT"); a.cut_neumann = (e && e[0] == 'n') ? 1 : 0; }
     a.z32 = nullptr;

@@ -10,6 +10,9 @@ __device__ __forceinline__ void pcg_finish_rhs(PcgScalars* sc, PcgHostStatus* st
     sc->fluid_cells = (long long)(cells + 0.5);
     sc->early_out = sumsq < 1e-7;  // bridsonSolverGrid.cpp:254-258
     sc->done = sc->early_out;
+    // incompressibilityMaxIterationCount <= 0: the reference's loop body never runs (bridsonSolverGrid.cpp:267) and p = 0 is
+    // applied; done = 2 keeps the device-side loop from running its first iteration (k_project starts such a solve cold)
+    if (!sc->done && sc->max_it <= 0) sc->done = 2;
     sc->iterations = 0;
     sc->nan_break = 0;
     sc->rmax = 0.0;

@@ -305,7 +305,10 @@ void Simulator::pushParams() {
 
 void Simulator::pushObstacles() {
     std::vector<FsimObstacle> flat;
+    flatIndex.assign(obstacles.size(), -1);
+    size_t oi = 0;
     for (auto& up : obstacles) {
+        const size_t self = oi++;
         const obstacle::Obstacle* o = up.get();
         FsimObstacle f;
         std::memset(&f, 0, sizeof(f));
@@ -320,7 +323,8 @@ void Simulator::pushObstacles() {
             f.kind = FSIM_OBSTACLE_SINK; f.r = k->r;
         } else if (auto* sp = dynamic_cast<const obstacle::SphericalObstacle*>(o)) {
             f.kind = FSIM_OBSTACLE_SPHERE; f.r = sp->r;
-        } else continue;
+        } else continue;  // an Obstacle subclass the device does not know: not flattened, flatIndex stays -1
+        flatIndex[self] = (int)flat.size();
         flat.push_back(f);
     }
     check(fsim_set_obstacles(backend->h, flat.data(), (int)flat.size()), backend->h, "fsim_set_obstacles");
@@ -332,11 +336,10 @@ void Simulator::pullSpawnFractions() {
     FsimObstacle flat[FSIM_MAX_OBSTACLES];
     int n = 0;
     check(fsim_get_obstacles(backend->h, flat, FSIM_MAX_OBSTACLES, &n), backend->h, "fsim_get_obstacles");
-    int i = 0;
-    for (auto& up : obstacles) {
-        if (i >= n) break;
-        if (auto* s = dynamic_cast<obstacle::SphericalParticleSource*>(up.get())) s->lastSpawnFraction = flat[i].last_spawn_fraction;
-        i++;
+    for (size_t i = 0; i < obstacles.size() && i < flatIndex.size(); i++) {
+        const int k = flatIndex[i];  // the slot pushObstacles gave this obstacle (skipped subclasses have none)
+        if (k < 0 || k >= n) continue;
+        if (auto* s = dynamic_cast<obstacle::SphericalParticleSource*>(obstacles[i].get())) s->lastSpawnFraction = flat[k].last_spawn_fraction;
     }
 }
 

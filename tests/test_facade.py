@@ -98,3 +98,54 @@ def test_reference_manager_runs_on_b200_backend():
     assert m, out
     assert int(m[1]) == 30000 and (int(m[2]), int(m[3]), int(m[4])) == (40, 25, 20)
     assert 0.0 < float(m[5]) < 25.0 and float(m[6]) > 0.0  # the fluid fell and moves
+
+
+@pytest.mark.gpu
+def test_facade_reconfiguration_paths_match_oracle(oracle_lib, tmp_path):
+    """setParticleNum (grow and shrink), setParticleR, updateGridParams + setNewMacGrid at another resolution and
+    the restart path, EXECUTED on the GPU through the reference-shaped classes in the order the manager applies them
+    (manager/simulationManager.cpp:176-216; particles/hashedParticles.cpp:132-151, 186-193, 340-353).  Each phase is followed
+    by a simulate(); the oracle is given the same host-side state (tests/cpp/facade_reconfig.cpp dumps it) on a grid built
+    from the same constructor arguments and must reproduce the step: cell flags bit-exact, v2 and particle state to 1e-5."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from fluid_simulator_b200 import abi, scenes
+    from oracle.oracle import OracleSim
+    from util import diag, rel_l2
+    exe = os.path.join(CPP, "build", "facade_reconfig")
+    if not os.path.exists(exe):
+        subprocess.check_call(["bash", os.path.join(CPP, "build_facade.sh")], env=_env())
+    out = subprocess.check_output([exe, str(tmp_path), "20"], text=True, timeout=300)
+    assert "RECONFIG ok" in out, out
+    phases = {}
+    for ln in open(tmp_path / "meta.txt"):
+        f = ln.split()
+        phases[f[0]] = dict(kv.split("=") for kv in f[1:])
+    assert list(phases) == ["grow", "shrink", "radius", "regrid", "restart"]
+    n0 = (20 // 2 - 1) * 18 * 18 * 8
+    assert int(phases["grow"]["np_pre"]) == n0 + 777 and int(phases["shrink"]["np_pre"]) == n0 + 777 - 2000
+    assert phases["regrid"]["grid"] == "25,25,25" and float(phases["radius"]["r"]) == 0.2
+    for name, m in phases.items():
+        dims = tuple(float(x) for x in m["dims"].split(","))
+        gs = tuple(int(x) for x in m["grid"].split(","))
+        pre = np.fromfile(tmp_path / f"{name}_pre.bin").reshape(-1, 15)
+        post = np.fromfile(tmp_path / f"{name}_post.bin").reshape(-1, 15)
+        cells = np.fromfile(tmp_path / f"{name}_grid.bin").reshape(-1, 4)
+        assert pre.shape[0] == int(m["np_pre"]) and post.shape[0] == int(m["np_post"]) == pre.shape[0]
+        o = OracleSim(dims, float(m["res"]), False, float(m["r"]))
+        assert tuple(o.grid_size) == gs
+        o.set_params(scenes.default_params(abi.FLIP, tol=1e-9))
+        # the device stores fp32: the oracle starts from the same rounded state (random fills are fp64 on the host)
+        o.upload_particles(pre.astype(np.float32).astype(np.float64))
+        o.step(0.005)
+        po = o.download_particles()
+        # the device returns particles in cell-binned order (SURVEY §8b "Ownership"): compare as sets through a position sort
+        kg = np.lexsort((post[:, 2].astype(np.float32), post[:, 1].astype(np.float32), post[:, 0].astype(np.float32)))
+        ko = np.lexsort((po[:, 2].astype(np.float32), po[:, 1].astype(np.float32), po[:, 0].astype(np.float32)))
+        res = dict(pos=rel_l2(post[kg, 0:3], po[ko, 0:3]), vel=rel_l2(post[kg, 3:6], po[ko, 3:6]),
+                   type_mismatch=int((cells[:, 0].astype(np.uint8) != o.download_grid(abi.FIELD_TYPE)).sum()),
+                   v2=rel_l2(cells[:, 1:4], o.download_grid(abi.FIELD_V2)))
+        diag(test=f"facade_reconfig/{name}", np=int(pre.shape[0]), grid=list(gs), its=int(m["its"]), **res)
+        assert res["type_mismatch"] == 0, (name, res)
+        assert res["pos"] <= 1e-6 and res["vel"] <= 1e-5 and res["v2"] <= 1e-5, (name, res)
