@@ -145,6 +145,7 @@ struct fsim {
     std::vector<MgLevel*> mg;
     int mg_tail_first;                     // levels >= this run inside the single-cluster tail kernel
     int mg_tail_cluster;                   // CTAs of that cluster (0: not probed yet)
+    int mg_tail_smem;                      // shared-memory-resident tail kernel: -1 not probed, 0 off, 1 on (FSIM_MG_TAIL_SMEM=0: off)
     PcgScalars* scal;                      // device
     PcgScalars* scal_host;                 // pinned (parameter upload)
     PcgScalars* result_host;               // pinned + mapped: the solve's scalars, written by publish_kernel
@@ -156,6 +157,7 @@ struct fsim {
     int pcg_graph_launches;                // kernels per graph launch
     int pcg_graph_class[K_COUNT];          // ... per kernel class
     bool use_graph, warm_start, warm_extrapolate;
+    bool pdl;           // solver kernels are launched as programmatic dependents (launch.cuh; FSIM_PDL=0: off)
     int warm_history;   // consecutive solves whose pressure is available for the warm start
     float* p_prev;      // pressure of the step before the last one (fp32)
     double* partials;                      // reduction partials [3][max_blocks]

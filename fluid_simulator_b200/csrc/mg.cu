@@ -22,6 +22,7 @@
 
 #include "fsim_internal.h"
 #include "reduce.cuh"
+#include "launch.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -91,6 +92,8 @@ __device__ __forceinline__ bool active(const Lv& L, int64_t c) {
 template <bool FINE>
 __global__ void __launch_bounds__(256) mg_first_kernel(Lv L, const double* __restrict__ r64, const PcgScalars* __restrict__ sc,
                                                         float* __restrict__ b, float* __restrict__ xout) {
+    pdl_wait();
+    pdl_trigger();
     int x, y, z; int64_t c;
     if (sc->done) return;
     const double inv_scale = sc->inv_scale;
@@ -109,6 +112,8 @@ __global__ void __launch_bounds__(256) mg_first_kernel(Lv L, const double* __res
 template <bool FINE>
 __global__ void __launch_bounds__(256) mg_jacobi_kernel(Lv L, const PcgScalars* __restrict__ sc, const float* __restrict__ b, const float* __restrict__ xin,
                                                          float* __restrict__ xout, float om) {
+    pdl_wait();
+    pdl_trigger();
     if (sc->done) return;
     int x, y, z; int64_t c;
     if (!cell_of(L, x, y, z, c)) return;
@@ -144,6 +149,8 @@ __device__ __forceinline__ float pre2_value(const Lv& L, const float* __restrict
 }
 __global__ void __launch_bounds__(256) mg_pre2_kernel(Lv L, const PcgScalars* __restrict__ sc, const float* __restrict__ b,
                                                       float* __restrict__ xout) {
+    pdl_wait();
+    pdl_trigger();
     if (sc->done) return;
     int x, y, z; int64_t c;
     if (!cell_of(L, x, y, z, c)) return;
@@ -154,6 +161,8 @@ __global__ void __launch_bounds__(256) mg_pre2_kernel(Lv L, const PcgScalars* __
 template <bool FINE>
 __global__ void __launch_bounds__(256) mg_restrict_kernel(Lv L, Lv C, const PcgScalars* __restrict__ sc, const float* __restrict__ b, const float* __restrict__ xf,
                                                            float* __restrict__ bc) {
+    pdl_wait();
+    pdl_trigger();
     if (sc->done) return;
     int X, Y, Z; int64_t cc;
     if (!cell_of(C, X, Y, Z, cc)) return;
@@ -179,6 +188,8 @@ __global__ void __launch_bounds__(256) mg_restrict_kernel(Lv L, Lv C, const PcgS
 // coarse cell, three shuffles
 __global__ void __launch_bounds__(256) mg_restrict8_kernel(Lv L, Lv C, const PcgScalars* __restrict__ sc, const float* __restrict__ b,
                                                             const float* __restrict__ xf, float* __restrict__ bc, int ncc) {
+    pdl_wait();
+    pdl_trigger();
     if (sc->done) return;
     const int g = blockIdx.x * 256 + threadIdx.x;
     const int cc = g >> 3, sub = g & 7;
@@ -206,6 +217,8 @@ __global__ void __launch_bounds__(256) mg_restrict8_kernel(Lv L, Lv C, const Pcg
 template <bool FINE>
 __global__ void __launch_bounds__(256) mg_prolong_jacobi_kernel(Lv L, Lv C, const PcgScalars* __restrict__ sc, const float* __restrict__ b, const float* __restrict__ xin,
                                                                  const float* __restrict__ ec, float* __restrict__ xout) {
+    pdl_wait();
+    pdl_trigger();
     if (sc->done) return;
     int x, y, z; int64_t c;
     if (!cell_of(L, x, y, z, c)) return;
@@ -292,6 +305,8 @@ __device__ __forceinline__ Stencil4 load_stencil4(const Lv& L, const float* __re
 
 __global__ void __launch_bounds__(256) mg_first4_kernel(Lv L, const double* __restrict__ r64, const PcgScalars* __restrict__ sc,
                                                         float* __restrict__ b, float* __restrict__ xout) {
+    pdl_wait();
+    pdl_trigger();
     int64_t c; unsigned cd[4];
     if (sc->done) return;
     const double inv_scale = sc->inv_scale;
@@ -314,6 +329,8 @@ __global__ void __launch_bounds__(256) mg_first4_kernel(Lv L, const double* __re
 
 __global__ void __launch_bounds__(256) mg_jacobi4_kernel(Lv L, PcgScalars* __restrict__ sc, const float* __restrict__ b, const float* __restrict__ xin,
                                                          float* __restrict__ xout, float om) {
+    pdl_wait();
+    pdl_trigger();
     if (sc->done) return;
     int64_t c; unsigned cd[4];
     if (group_of(L, c, cd) && ((cd[0] | cd[1] | cd[2] | cd[3]) & CODE_ACTIVE)) {
@@ -338,6 +355,8 @@ __global__ void __launch_bounds__(256) mg_jacobi4_kernel(Lv L, PcgScalars* __res
 __global__ void __launch_bounds__(256) mg_jacobi4_dot_kernel(Lv L, PcgScalars* __restrict__ sc, const float* __restrict__ b, const float* __restrict__ xin,
                                                              float* __restrict__ xout, double* partials, unsigned int* counter, float om,
                                                              int ntx, int nty, int ntiles) {
+    pdl_wait();
+    pdl_trigger();
     if (sc->done) return;
     double acc[1] = {0.0};
     const int tx = threadIdx.x & 31, ty = (threadIdx.x >> 5) & 3, tz = threadIdx.x >> 7;
@@ -373,6 +392,8 @@ __global__ void __launch_bounds__(256) mg_update_first4_kernel(Lv L, int64_t nc,
                                                                const float* __restrict__ sv, double* __restrict__ r,
                                                                const double* __restrict__ q, float* __restrict__ b, float* __restrict__ xout,
                                                                double* partials, unsigned int* counter) {
+    pdl_wait();
+    pdl_trigger();
     if (sc->done) return;
     const double alpha = sc->sigma / sc->sq;
     const bool bad = alpha != alpha;  // NaN => the reference breaks before touching p (bridsonSolverGrid.cpp:271-272)
@@ -433,6 +454,8 @@ __global__ void __launch_bounds__(256) mg_update_first4_kernel(Lv L, int64_t nc,
 // one thread = two coarse cells in x = a 4x2x2 block of fine cells
 __global__ void __launch_bounds__(256) mg_restrict4_kernel(Lv L, Lv C, const PcgScalars* __restrict__ sc, const float* __restrict__ b, const float* __restrict__ xf,
                                                            float* __restrict__ bc, int cz0, int cz1) {
+    pdl_wait();
+    pdl_trigger();
     if (sc->done) return;
     const int X = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
     const int Y = blockIdx.y * blockDim.y + threadIdx.y, Z = blockIdx.z * blockDim.z + threadIdx.z + cz0;
@@ -464,6 +487,8 @@ __global__ void __launch_bounds__(256) mg_restrict4_kernel(Lv L, Lv C, const Pcg
 
 __global__ void __launch_bounds__(256) mg_prolong_jacobi4_kernel(Lv L, Lv C, const PcgScalars* __restrict__ sc, const float* __restrict__ b, const float* __restrict__ xin,
                                                                  const float* __restrict__ ec, float* __restrict__ xout) {
+    pdl_wait();
+    pdl_trigger();
     if (sc->done) return;
     int64_t c; unsigned cd[4];
     if (!group_of(L, c, cd)) return;
@@ -504,6 +529,8 @@ __global__ void __launch_bounds__(256) mg_prolong_jacobi4_kernel(Lv L, Lv C, con
 // face; diagonal = # connections from WATER children to non-solid cells outside the aggregate
 __global__ void __launch_bounds__(256) mg_build1_kernel(Lv L, Lv C, float* __restrict__ wx, float* __restrict__ wy,
                                                          float* __restrict__ wz, float* __restrict__ diag) {
+    pdl_wait();
+    pdl_trigger();
     int X, Y, Z; int64_t cc;
     if (!cell_of(C, X, Y, Z, cc)) return;
     float w[3] = {0.f, 0.f, 0.f}, d = 0.f;
@@ -533,6 +560,8 @@ __global__ void __launch_bounds__(256) mg_build1_kernel(Lv L, Lv C, float* __res
 // Galerkin operator of level l+1 from level l: outer face weights add up, inner ones cancel out of the diagonal
 __global__ void __launch_bounds__(256) mg_buildn_kernel(Lv L, Lv C, float* __restrict__ wx, float* __restrict__ wy,
                                                          float* __restrict__ wz, float* __restrict__ diag) {
+    pdl_wait();
+    pdl_trigger();
     int X, Y, Z; int64_t cc;
     if (!cell_of(C, X, Y, Z, cc)) return;
     float w[3] = {0.f, 0.f, 0.f}, d = 0.f;
@@ -567,6 +596,7 @@ constexpr int TAIL_MAX_LEVELS = 8;
 constexpr int TAIL_CLUSTER = 16;     // non-portable cluster size (one GPC); 8 is used when 16 cannot be scheduled
 constexpr int TAIL_CLUSTER_PORTABLE = 8;
 constexpr int TAIL_THREADS = 1024;
+constexpr size_t TAIL_SMEM_MAX = 200 * 1024;  // dynamic shared memory the shared-memory-resident tail kernel may use per CTA
 
 struct TailLevel { Lv L; float *xa, *xb, *b; };
 struct TailArgs {
@@ -703,6 +733,8 @@ __device__ __forceinline__ void tail_cycle(const TailLevel* lv, int n, bool zero
 }
 
 __global__ void __launch_bounds__(TAIL_THREADS, 1) mg_tail_kernel(TailArgs a) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ float xs[2][COARSE_MAX];
     if (a.sc->done) return;  // uniform over the cluster
     cg::cluster_group cluster = cg::this_cluster();
@@ -710,6 +742,265 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) mg_tail_kernel(TailArgs a) {
     const int nt = (int)cluster.num_blocks() * TAIL_THREADS;
     auto bar = [&]() { cluster.sync(); };
     tail_cycle(a.lv, a.n, a.zero_guess != 0, t0, nt, cluster.block_rank() == 0, xs, bar);
+}
+
+// ---- the same sub-cycle with every tail level RESIDENT IN (DISTRIBUTED) SHARED MEMORY -------------------------------------
+// mg_tail_kernel exchanges its iterates through global memory: every phase is at least one dependent L2 round trip plus the
+// store drain in front of the cluster barrier (measured 42 us per call at 256^3, two calls per cycle = the largest single
+// item of the coarse levels).  Here CTA r of the cluster owns a block of z-planes of every level and keeps their operator
+// rows (six face weights + diagonal), right-hand side and both iterates in its shared memory for the whole call; in-plane
+// neighbours are local shared-memory reads, z-neighbours and parent / child cells of other blocks are read (or written)
+// through distributed shared memory (mapa + ld/st.shared::cluster).  A phase then costs a shared-memory round trip instead
+// of an L2 one.  Plane blocks start at even planes, so the eight children of a coarse cell always share an owner; the
+// coarsest level lives in CTA 0.  Same arithmetic, same order of operations as tail_cycle => the same iterates.
+enum { SA_WXM = 0, SA_WXP, SA_WYM, SA_WYP, SA_WZM, SA_WZP, SA_D, SA_B, SA_XA, SA_XB, SA_COUNT };
+
+struct SLevelArg {
+    int gx, gy, gz;
+    int cap;   // cells of the largest block of this level (uniform shared-memory layout across the cluster)
+    int off;   // float offset of the level's arrays in dynamic shared memory
+    const float *wx, *wy, *wz, *diag;
+};
+struct STailArgs {
+    int n;  // levels; the last one is the coarsest (<= COARSE_MAX cells, owned by CTA 0)
+    SLevelArg lv[TAIL_MAX_LEVELS];
+    const float* b_in;   // right-hand side of the first level (global)
+    const float* xa_in;  // its iterate when the visit does not start from zero
+    float* xa_out;       // result
+    const PcgScalars* sc;
+    int zero_guess;
+};
+
+struct SLv {
+    int gx, gy, gz, plane, cap, hz, coarsest, zb, ze;
+    float* base;
+};
+// blocks of plane PAIRS: rank r owns pairs [r*hz/nb, (r+1)*hz/nb), hz = ceil(gz/2)
+__device__ __forceinline__ int s_z0(const SLv& L, int r, int nb) {
+    if (L.coarsest) return r == 0 ? 0 : L.gz;
+    return min(2 * ((r * L.hz) / nb), L.gz);
+}
+__device__ __forceinline__ int s_owner(const SLv& L, int z, int nb) {
+    if (L.coarsest) return 0;
+    return (((z >> 1) + 1) * nb + L.hz - 1) / L.hz - 1;
+}
+__device__ __forceinline__ float* s_arr(const SLv& L, int arr) { return L.base + arr * L.cap; }
+// address of element (plane z, in-plane index j) of array arr in the shared memory of the CTA that owns plane z
+__device__ __forceinline__ float* s_remote(cg::cluster_group& cl, const SLv& L, int arr, int z, int j, int nb) {
+    const int o = s_owner(L, z, nb);
+    float* p = L.base + arr * L.cap + (z - s_z0(L, o, nb)) * L.plane + j;
+    return cl.map_shared_rank(p, o);
+}
+
+// x-, x+, y-, y+, z-, z+ neighbour values of array arr around local cell li = (z - zb) * plane + j (0 where the weight is 0)
+struct Nb6 { float v[6]; };
+__device__ __forceinline__ Nb6 s_nb6(cg::cluster_group& cl, const SLv& L, int arr, int li, int z, int j, const float w[6], int nb) {
+    Nb6 r;
+    const float* a = s_arr(L, arr);
+    r.v[0] = w[0] > 0.f ? a[li - 1] : 0.f;
+    r.v[1] = w[1] > 0.f ? a[li + 1] : 0.f;
+    r.v[2] = w[2] > 0.f ? a[li - L.gx] : 0.f;
+    r.v[3] = w[3] > 0.f ? a[li + L.gx] : 0.f;
+    r.v[4] = w[4] > 0.f ? (z - 1 >= L.zb ? a[li - L.plane] : *s_remote(cl, L, arr, z - 1, j, nb)) : 0.f;
+    r.v[5] = w[5] > 0.f ? (z + 1 < L.ze ? a[li + L.plane] : *s_remote(cl, L, arr, z + 1, j, nb)) : 0.f;
+    return r;
+}
+__device__ __forceinline__ void s_w6(const SLv& L, int li, float w[6]) {
+#pragma unroll
+    for (int k = 0; k < 6; k++) w[k] = s_arr(L, SA_WXM + k)[li];
+}
+// t_row: (diag, sum w x) with the operand order of the global-memory kernels: x+, x-, y+, y-, z+, z-
+__device__ __forceinline__ float s_off(const float w[6], const Nb6& x) {
+    return w[1] * x.v[1] + w[0] * x.v[0] + w[3] * x.v[3] + w[2] * x.v[2] + w[5] * x.v[5] + w[4] * x.v[4];
+}
+
+__device__ void s_jacobi(cg::cluster_group& cl, const SLv& L, int in, int out, float om, int nb) {
+    const int n = (L.ze - L.zb) * L.plane;
+    for (int li = threadIdx.x; li < n; li += TAIL_THREADS) {
+        const int z = L.zb + li / L.plane, j = li % L.plane;
+        float w[6];
+        s_w6(L, li, w);
+        const Nb6 x = s_nb6(cl, L, in, li, z, j, w, nb);
+        const float d = s_arr(L, SA_D)[li], xi = s_arr(L, in)[li];
+        s_arr(L, out)[li] = d > 0.f ? xi + om * (s_arr(L, SA_B)[li] - (d * xi - s_off(w, x))) / d : 0.f;
+    }
+}
+// two pre-smoothing sweeps from a zero guess in one pass (pre2_value)
+__device__ void s_pre2(cg::cluster_group& cl, const SLv& L, int nb) {
+    const int n = (L.ze - L.zb) * L.plane;
+    for (int li = threadIdx.x; li < n; li += TAIL_THREADS) {
+        const int z = L.zb + li / L.plane, j = li % L.plane;
+        float w[6];
+        s_w6(L, li, w);
+        const Nb6 dn = s_nb6(cl, L, SA_D, li, z, j, w, nb), bn = s_nb6(cl, L, SA_B, li, z, j, w, nb);
+        const float d = s_arr(L, SA_D)[li], bb = s_arr(L, SA_B)[li];
+        float off = 0.f;
+#pragma unroll
+        for (int k = 0; k < 6; k++)
+            if (w[k] > 0.f && dn.v[k] > 0.f) off += w[k] * (OM_A * bn.v[k] / dn.v[k]);
+        float v = 0.f;
+        if (d > 0.f) {
+            const float xi = OM_A * bb / d;
+            v = xi + OM_B * (bb - (d * xi - off)) / d;
+        }
+        s_arr(L, SA_XA)[li] = v;
+    }
+}
+// restriction: the eight children of a coarse cell sit in eight neighbouring lanes of the CTA that owns them; the sum goes
+// to the coarse cell's owner
+__device__ void s_restrict(cg::cluster_group& cl, const SLv& L, const SLv& C, int nb) {
+    const int Z0 = L.zb >> 1, Z1 = (L.ze + 1) >> 1;  // coarse planes whose children this CTA owns (blocks start at even planes)
+    const int ncc = (Z1 - Z0) * C.plane;
+    const int n8 = (ncc * 8 + 31) & ~31;  // whole warps take part in the shuffles
+    for (int g = threadIdx.x; g < n8; g += TAIL_THREADS) {
+        const int cc = g >> 3, sub = g & 7;
+        float r = 0.f;
+        int Z = 0, J = 0;
+        if (cc < ncc) {
+            Z = Z0 + cc / C.plane; J = cc % C.plane;
+            const int X = J % C.gx, Y = J / C.gx;
+            const int x = 2 * X + (sub & 1), y = 2 * Y + ((sub >> 1) & 1), z = 2 * Z + (sub >> 2);
+            if (x < L.gx && y < L.gy && z < L.ze) {
+                const int j = y * L.gx + x, li = (z - L.zb) * L.plane + j;
+                const float d = s_arr(L, SA_D)[li];
+                float w[6];
+                s_w6(L, li, w);
+                const Nb6 xn = s_nb6(cl, L, SA_XA, li, z, j, w, nb);
+                if (d > 0.f) r = s_arr(L, SA_B)[li] - (d * s_arr(L, SA_XA)[li] - s_off(w, xn));
+            }
+        }
+        r += __shfl_xor_sync(0xffffffffu, r, 1);
+        r += __shfl_xor_sync(0xffffffffu, r, 2);
+        r += __shfl_xor_sync(0xffffffffu, r, 4);
+        if (sub == 0 && cc < ncc) *s_remote(cl, C, SA_B, Z, J, nb) = r;
+    }
+}
+// prolongation + over-corrected update fused with the first post-smoothing sweep (t_prolong_jacobi): XA -> XB
+__device__ void s_prolong_jacobi(cg::cluster_group& cl, const SLv& L, const SLv& C, int nb) {
+    const int n = (L.ze - L.zb) * L.plane;
+    for (int li = threadIdx.x; li < n; li += TAIL_THREADS) {
+        const int z = L.zb + li / L.plane, j = li % L.plane;
+        const int y = j / L.gx, x = j % L.gx;
+        float w[6];
+        s_w6(L, li, w);
+        const Nb6 xn = s_nb6(cl, L, SA_XA, li, z, j, w, nb);
+        auto ec = [&](int xx, int yy, int zz) -> float { return *s_remote(cl, C, SA_XA, zz >> 1, (yy >> 1) * C.gx + (xx >> 1), nb); };
+        const float d = s_arr(L, SA_D)[li], bb = s_arr(L, SA_B)[li];
+        const float x0 = s_arr(L, SA_XA)[li] + OVER * ec(x, y, z);
+        float off = 0.f;
+        if (w[0] > 0.f) off += w[0] * (xn.v[0] + OVER * ec(x - 1, y, z));
+        if (w[1] > 0.f) off += w[1] * (xn.v[1] + OVER * ec(x + 1, y, z));
+        if (w[2] > 0.f) off += w[2] * (xn.v[2] + OVER * ec(x, y - 1, z));
+        if (w[3] > 0.f) off += w[3] * (xn.v[3] + OVER * ec(x, y + 1, z));
+        if (w[4] > 0.f) off += w[4] * (xn.v[4] + OVER * ec(x, y, z - 1));
+        if (w[5] > 0.f) off += w[5] * (xn.v[5] + OVER * ec(x, y, z + 1));
+        s_arr(L, SA_XB)[li] = d > 0.f ? x0 + OM_B * (bb - (d * x0 - off)) / d : 0.f;
+    }
+}
+
+__global__ void __launch_bounds__(TAIL_THREADS, 1) mg_tail_smem_kernel(const __grid_constant__ STailArgs a) {
+    pdl_wait();
+    pdl_trigger();
+    extern __shared__ float s_dyn[];
+    if (a.sc->done) return;  // uniform over the cluster
+    cg::cluster_group cl = cg::this_cluster();
+    const int rank = (int)cl.block_rank(), nb = (int)cl.num_blocks();
+    __shared__ SLv lv[TAIL_MAX_LEVELS];
+    if (threadIdx.x < a.n) {
+        const int i = threadIdx.x;
+        SLv L;
+        const SLevelArg& A = a.lv[i];
+        L.gx = A.gx; L.gy = A.gy; L.gz = A.gz; L.plane = A.gx * A.gy; L.cap = A.cap; L.hz = (A.gz + 1) >> 1;
+        L.coarsest = i == a.n - 1;
+        L.base = s_dyn + A.off;
+        L.zb = s_z0(L, rank, nb);
+        L.ze = (L.coarsest || rank == nb - 1) ? L.gz : s_z0(L, rank + 1, nb);
+        lv[i] = L;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int i = 0; i < a.n; i++) {
+        const SLv& L = lv[i];
+        const SLevelArg& A = a.lv[i];
+        // operator rows of the planes this CTA owns (one pass over global memory, all loads independent)
+        const int n = (L.ze - L.zb) * L.plane;
+        for (int li = threadIdx.x; li < n; li += TAIL_THREADS) {
+            const int z = L.zb + li / L.plane, j = li % L.plane;
+            const int y = j / L.gx, x = j % L.gx;
+            const int c = z * L.plane + j;
+            s_arr(L, SA_WXM)[li] = x > 0 ? A.wx[c - 1] : 0.f;
+            s_arr(L, SA_WXP)[li] = x + 1 < L.gx ? A.wx[c] : 0.f;
+            s_arr(L, SA_WYM)[li] = y > 0 ? A.wy[c - L.gx] : 0.f;
+            s_arr(L, SA_WYP)[li] = y + 1 < L.gy ? A.wy[c] : 0.f;
+            s_arr(L, SA_WZM)[li] = z > 0 ? A.wz[c - L.plane] : 0.f;
+            s_arr(L, SA_WZP)[li] = z + 1 < L.gz ? A.wz[c] : 0.f;
+            s_arr(L, SA_D)[li] = A.diag[c];
+            if (i == 0) {
+                s_arr(L, SA_B)[li] = a.b_in[c];
+                if (!a.zero_guess) s_arr(L, SA_XA)[li] = a.xa_in[c];
+            }
+        }
+    }
+    cl.sync();
+    const int n = a.n;
+    // down
+    for (int i = 0; i + 1 < n; i++) {
+        if (i == 0 && !a.zero_guess) {
+            s_jacobi(cl, lv[0], SA_XA, SA_XB, OM_A, nb); cl.sync();
+            s_jacobi(cl, lv[0], SA_XB, SA_XA, OM_B, nb); cl.sync();
+        } else {
+            s_pre2(cl, lv[i], nb); cl.sync();
+        }
+        s_restrict(cl, lv[i], lv[i + 1], nb); cl.sync();
+    }
+    // coarsest level: damped Jacobi by CTA 0, one cell per thread, iterates ping-pong between XA and XB
+    if (rank == 0) {
+        const SLv& L = lv[n - 1];
+        const int c = threadIdx.x, nc = L.gz * L.plane;
+        const bool in = c < nc;
+        float d = 0.f, w[6] = {0, 0, 0, 0, 0, 0}, bb = 0.f;
+        int nbi[6] = {0, 0, 0, 0, 0, 0};
+        if (in) {
+            d = s_arr(L, SA_D)[c]; bb = s_arr(L, SA_B)[c];
+            s_w6(L, c, w);
+            nbi[0] = c - 1; nbi[1] = c + 1; nbi[2] = c - L.gx; nbi[3] = c + L.gx; nbi[4] = c - L.plane; nbi[5] = c + L.plane;
+#pragma unroll
+            for (int k = 0; k < 6; k++)
+                if (!(w[k] > 0.f)) { w[k] = 0.f; nbi[k] = c; }
+            if (n != 1 || a.zero_guess) s_arr(L, SA_XA)[c] = 0.f;
+        }
+        __syncthreads();
+        int cur = SA_XA;
+        for (int sw = 0; sw < COARSE_SWEEPS; sw++) {
+            float v = 0.f;
+            if (in && d > 0.f) {
+                const float* xv = s_arr(L, cur);
+                const float off = w[0] * xv[nbi[0]] + w[1] * xv[nbi[1]] + w[2] * xv[nbi[2]] + w[3] * xv[nbi[3]] + w[4] * xv[nbi[4]] + w[5] * xv[nbi[5]];
+                const float xi = xv[c];
+                v = xi + OMEGA * (bb - (d * xi - off)) / d;
+            }
+            const int nxt = cur == SA_XA ? SA_XB : SA_XA;
+            if (in) s_arr(L, nxt)[c] = v;
+            __syncthreads();
+            cur = nxt;
+        }
+        if (in && cur != SA_XA) s_arr(L, SA_XA)[c] = s_arr(L, SA_XB)[c];  // (COARSE_SWEEPS is even: not taken)
+    }
+    cl.sync();
+    // up
+    for (int i = n - 2; i >= 0; i--) {
+        s_prolong_jacobi(cl, lv[i], lv[i + 1], nb); cl.sync();
+        s_jacobi(cl, lv[i], SA_XB, SA_XA, OM_A, nb);
+        if (i > 0) cl.sync();
+    }
+    // result of the first level -> global (only this CTA's threads wrote these entries: a block barrier orders them)
+    __syncthreads();
+    {
+        const SLv& L = lv[0];
+        const int nn = (L.ze - L.zb) * L.plane;
+        for (int li = threadIdx.x; li < nn; li += TAIL_THREADS) a.xa_out[L.zb * L.plane + li] = s_arr(L, SA_XA)[li];
+    }
+    cl.sync();  // no CTA may exit while a peer can still read its shared memory
 }
 
 Lv view(const fsim* h, const MgLevel* m, int level) {
@@ -782,13 +1073,73 @@ int cycle(fsim* h, int l, bool zero_guess, float** result, bool first_done = fal
             if (const char* e = getenv("FSIM_MG_TAIL_CLUSTER")) { const int v = atoi(e); if (v >= 1 && v <= h->mg_tail_cluster) h->mg_tail_cluster = v; }
         }
         const int tail_cluster = h->mg_tail_cluster;
+        // shared-memory-resident variant (mg_tail_smem_kernel) when every level's block fits the CTA's shared memory
+        if (h->mg_tail_smem != 0) {
+            STailArgs sa;
+            sa.n = ta.n; sa.sc = sc; sa.zero_guess = ta.zero_guess;
+            sa.b_in = m->b; sa.xa_in = m->xa; sa.xa_out = m->xa;
+            size_t floats = 0;
+            for (int i = 0; i < sa.n; i++) {
+                MgLevel* t = h->mg[l + i];
+                SLevelArg& A = sa.lv[i];
+                A.gx = t->gx; A.gy = t->gy; A.gz = t->gz; A.wx = t->wx; A.wy = t->wy; A.wz = t->wz; A.diag = t->diag;
+                const int plane = t->gx * t->gy, hz = (t->gz + 1) / 2;
+                int planes = 0;
+                if (i == sa.n - 1) planes = t->gz;  // coarsest: CTA 0 holds all of it
+                else
+                    for (int r = 0; r < tail_cluster; r++) {
+                        const int z0 = std::min(2 * ((r * hz) / tail_cluster), t->gz);
+                        const int z1 = r == tail_cluster - 1 ? t->gz : std::min(2 * (((r + 1) * hz) / tail_cluster), t->gz);
+                        planes = std::max(planes, z1 - z0);
+                    }
+                A.cap = std::max(planes * plane, 1);
+                A.off = (int)floats;
+                floats += (size_t)SA_COUNT * A.cap;
+            }
+            const size_t bytes = floats * sizeof(float);
+            const bool coarse_ok = h->mg[l + sa.n - 1]->nc <= TAIL_THREADS;
+            if (h->mg_tail_smem < 0) {  // first use: opt in to the large dynamic shared memory, make sure the cluster still fits
+                h->mg_tail_smem = 0;
+                if (!(getenv("FSIM_MG_TAIL_SMEM") && getenv("FSIM_MG_TAIL_SMEM")[0] == '0') &&
+                    cudaFuncSetAttribute(mg_tail_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TAIL_SMEM_MAX) == cudaSuccess &&
+                    cudaFuncSetAttribute(mg_tail_smem_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+                    cudaLaunchConfig_t q = {};
+                    q.gridDim = dim3(tail_cluster); q.blockDim = dim3(TAIL_THREADS); q.dynamicSmemBytes = std::min(bytes, TAIL_SMEM_MAX);
+                    cudaLaunchAttribute qa[1];
+                    qa[0].id = cudaLaunchAttributeClusterDimension;
+                    qa[0].val.clusterDim.x = tail_cluster; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+                    q.attrs = qa; q.numAttrs = 1;
+                    int nclusters = 0;
+                    if (cudaOccupancyMaxActiveClusters(&nclusters, mg_tail_smem_kernel, &q) == cudaSuccess && nclusters >= 1) h->mg_tail_smem = 1;
+                }
+                cudaGetLastError();
+            }
+            if (h->mg_tail_smem == 1 && bytes <= TAIL_SMEM_MAX && coarse_ok) {
+                cfg.gridDim = dim3(tail_cluster);
+                cfg.blockDim = dim3(TAIL_THREADS);
+                cfg.dynamicSmemBytes = bytes;
+                cfg.stream = h->stream;
+                cudaLaunchAttribute at[2];
+                at[0].id = cudaLaunchAttributeClusterDimension;
+                at[0].val.clusterDim.x = tail_cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                at[1].val.programmaticStreamSerializationAllowed = 1;
+                cfg.attrs = at; cfg.numAttrs = h->pdl ? 2 : 1;
+                KScope ks(h, K_MG2);
+                FSIM_CUDA(h, cudaLaunchKernelEx(&cfg, mg_tail_smem_kernel, sa));
+                *result = m->xa;
+                return FSIM_OK;
+            }
+        }
         cfg.gridDim = dim3(tail_cluster);
         cfg.blockDim = dim3(TAIL_THREADS);
         cfg.stream = h->stream;
-        cudaLaunchAttribute at[1];
+        cudaLaunchAttribute at[2];
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = tail_cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
+        at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = h->pdl ? 2 : 1;
         KScope ks(h, K_MG2);
         FSIM_CUDA(h, cudaLaunchKernelEx(&cfg, mg_tail_kernel, ta));
         *result = m->xa;
@@ -799,15 +1150,15 @@ int cycle(fsim* h, int l, bool zero_guess, float** result, bool first_done = fal
     float *cur = m->xa, *oth = m->xb;
     if (!fine && zero_guess && PRE == 2) {
         KScope ks(h, kid);
-        mg_pre2_kernel<<<grdL, blk, 0, h->stream>>>(L, sc, m->b, cur);
+        launch_k(h, mg_pre2_kernel, grdL, blk, 0, L, sc, m->b, cur);
     } else {
         std::unique_ptr<KScope> ks(new KScope(h, kid, PRE - ((zero_guess && first_done) ? 1 : 0)));
         for (int s = 0; s < PRE; s++) {
             if (s == 0 && zero_guess && first_done) continue;  // x1 and b were written by the fused CG update
             if (s == 0 && zero_guess) {
-                if (v4) mg_first4_kernel<<<grd4, blk4, 0, h->stream>>>(L, h->r, sc, m->b, cur);
-                else if (fine) mg_first_kernel<true><<<grdL, blk, 0, h->stream>>>(L, h->r, sc, m->b, cur);
-                else mg_first_kernel<false><<<grdL, blk, 0, h->stream>>>(L, nullptr, sc, m->b, cur);
+                if (v4) launch_k(h, mg_first4_kernel, grd4, blk4, 0, L, h->r, sc, m->b, cur);
+                else if (fine) launch_k(h, mg_first_kernel<true>, grdL, blk, 0, L, h->r, sc, m->b, cur);
+                else launch_k(h, mg_first_kernel<false>, grdL, blk, 0, L, nullptr, sc, m->b, cur);
             } else {
                 const float om = s == 0 ? OM_A : OM_B;
                 if (fine && h->hybrid) {  // the neighbours' planes of the iterate (timed as an exchange, not as a sweep)
@@ -816,9 +1167,9 @@ int cycle(fsim* h, int l, bool zero_guess, float** result, bool first_done = fal
                     if (rc) return rc;
                     ks.reset(new KScope(h, kid, 0));
                 }
-                if (v4) mg_jacobi4_kernel<<<grd4, blk4, 0, h->stream>>>(L, h->scal, m->b, cur, oth, om);
-                else if (fine) mg_jacobi_kernel<true><<<grdL, blk, 0, h->stream>>>(L, sc, m->b, cur, oth, om);
-                else mg_jacobi_kernel<false><<<grdL, blk, 0, h->stream>>>(L, sc, m->b, cur, oth, om);
+                if (v4) launch_k(h, mg_jacobi4_kernel, grd4, blk4, 0, L, h->scal, m->b, cur, oth, om);
+                else if (fine) launch_k(h, mg_jacobi_kernel<true>, grdL, blk, 0, L, sc, m->b, cur, oth, om);
+                else launch_k(h, mg_jacobi_kernel<false>, grdL, blk, 0, L, sc, m->b, cur, oth, om);
                 float* t = cur; cur = oth; oth = t;
             }
         }
@@ -829,10 +1180,10 @@ int cycle(fsim* h, int l, bool zero_guess, float** result, bool first_done = fal
     const int cz1 = (fine && h->hybrid && h->g.zown1 < h->g.gz) ? h->g.zown1 / 2 : (1 << 30);
     {
         KScope ks(h, kid);
-        if (v4) mg_restrict4_kernel<<<dim3(div_up(mc->gx, 2 * 32), div_up(mc->gy, 4), div_up(std::min(cz1, mc->gz) - cz0, 2)), blk4, 0, h->stream>>>(L, C, sc, m->b, cur, mc->b, cz0, cz1);
-        else if (fine) mg_restrict_kernel<true><<<grid_of(mc, blk), blk, 0, h->stream>>>(L, C, sc, m->b, cur, mc->b);
-        else if (mc->nc > 100000) mg_restrict_kernel<false><<<grid_of(mc, blk), blk, 0, h->stream>>>(L, C, sc, m->b, cur, mc->b);  // enough threads as it is
-        else mg_restrict8_kernel<<<div_up(mc->nc * 8, 256), 256, 0, h->stream>>>(L, C, sc, m->b, cur, mc->b, (int)mc->nc);
+        if (v4) launch_k(h, mg_restrict4_kernel, dim3(div_up(mc->gx, 2 * 32), div_up(mc->gy, 4), div_up(std::min(cz1, mc->gz) - cz0, 2)), blk4, 0, L, C, sc, m->b, cur, mc->b, cz0, cz1);
+        else if (fine) launch_k(h, mg_restrict_kernel<true>, grid_of(mc, blk), blk, 0, L, C, sc, m->b, cur, mc->b);
+        else if (mc->nc > 100000) launch_k(h, mg_restrict_kernel<false>, grid_of(mc, blk), blk, 0, L, C, sc, m->b, cur, mc->b);  // enough threads as it is
+        else launch_k(h, mg_restrict8_kernel, div_up(mc->nc * 8, 256), 256, 0, L, C, sc, m->b, cur, mc->b, (int)mc->nc);
     }
     // hybrid: every rank restricted the planes it owns; with all ranks' coarse planes gathered, levels >= 1 run replicated
     if (fine && h->hybrid) { int rc = dist_gather_coarse(h, true); if (rc) return rc; }
@@ -847,9 +1198,9 @@ int cycle(fsim* h, int l, bool zero_guess, float** result, bool first_done = fal
     }
     {
         std::unique_ptr<KScope> ks(new KScope(h, kid, POST));
-        if (v4) mg_prolong_jacobi4_kernel<<<grd4, blk4, 0, h->stream>>>(L, C, sc, m->b, cur, mc->xa, oth);
-        else if (fine) mg_prolong_jacobi_kernel<true><<<grdL, blk, 0, h->stream>>>(L, C, sc, m->b, cur, mc->xa, oth);
-        else mg_prolong_jacobi_kernel<false><<<grdL, blk, 0, h->stream>>>(L, C, sc, m->b, cur, mc->xa, oth);
+        if (v4) launch_k(h, mg_prolong_jacobi4_kernel, grd4, blk4, 0, L, C, sc, m->b, cur, mc->xa, oth);
+        else if (fine) launch_k(h, mg_prolong_jacobi_kernel<true>, grdL, blk, 0, L, C, sc, m->b, cur, mc->xa, oth);
+        else launch_k(h, mg_prolong_jacobi_kernel<false>, grdL, blk, 0, L, C, sc, m->b, cur, mc->xa, oth);
         { float* t = cur; cur = oth; oth = t; }
         for (int s = 1; s < POST; s++) {
             const float om = OM_A;  // post-sweeps run the pre-sweep weights in reverse order (B in the fused prolongation sweep, then A)
@@ -861,11 +1212,11 @@ int cycle(fsim* h, int l, bool zero_guess, float** result, bool first_done = fal
             }
             if (v4 && with_dot && s == POST - 1) {
                 const int ntiles = (int)(grd4.x * grd4.y * grd4.z);
-                mg_jacobi4_dot_kernel<<<std::min(ntiles, h->sm_count * 8), 256, 0, h->stream>>>(L, h->scal, m->b, cur, oth, h->partials, h->red_counter, om,
+                launch_k(h, mg_jacobi4_dot_kernel, std::min(ntiles, h->sm_count * 8), 256, 0, L, h->scal, m->b, cur, oth, h->partials, h->red_counter, om,
                                                                                                (int)grd4.x, (int)grd4.y, ntiles);
-            } else if (v4) mg_jacobi4_kernel<<<grd4, blk4, 0, h->stream>>>(L, h->scal, m->b, cur, oth, om);
-            else if (fine) mg_jacobi_kernel<true><<<grdL, blk, 0, h->stream>>>(L, sc, m->b, cur, oth, om);
-            else mg_jacobi_kernel<false><<<grdL, blk, 0, h->stream>>>(L, sc, m->b, cur, oth, om);
+            } else if (v4) launch_k(h, mg_jacobi4_kernel, grd4, blk4, 0, L, h->scal, m->b, cur, oth, om);
+            else if (fine) launch_k(h, mg_jacobi_kernel<true>, grdL, blk, 0, L, sc, m->b, cur, oth, om);
+            else launch_k(h, mg_jacobi_kernel<false>, grdL, blk, 0, L, sc, m->b, cur, oth, om);
             float* t = cur; cur = oth; oth = t;
         }
     }
@@ -928,8 +1279,8 @@ int mg_build(fsim* h) {
         KScope ks(h, K_MG);
         Lv f0 = view(h, f, 0);
         if (h->code_full) f0.code = h->code_full;  // hybrid: the coarse operators are global, h->code only marks this rank's planes
-        if (l == 1) mg_build1_kernel<<<grid_of(c, blk), blk, 0, h->stream>>>(f0, view(h, c, 1), c->wx, c->wy, c->wz, c->diag);
-        else mg_buildn_kernel<<<grid_of(c, blk), blk, 0, h->stream>>>(view(h, f, (int)l - 1), view(h, c, (int)l), c->wx, c->wy, c->wz, c->diag);
+        if (l == 1) launch_k(h, mg_build1_kernel, grid_of(c, blk), blk, 0, f0, view(h, c, 1), c->wx, c->wy, c->wz, c->diag);
+        else launch_k(h, mg_buildn_kernel, grid_of(c, blk), blk, 0, view(h, f, (int)l - 1), view(h, c, (int)l), c->wx, c->wy, c->wz, c->diag);
     }
     FSIM_CHECK_LAUNCH(h);
     return FSIM_OK;
@@ -943,7 +1294,7 @@ int mg_update_first(fsim* h) {
     MgLevel* m = h->mg[0];
     const Lv L = view(h, m, 0);
     KScope ks(h, K_UPDATE);
-    mg_update_first4_kernel<<<div_up(h->g.nc, UF_CHUNK), 256, 0, h->stream>>>(L, h->g.nc, h->scal, h->status_dev, h->p, h->s, h->r, h->q, m->b,
+    launch_k(h, mg_update_first4_kernel, div_up(h->g.nc, UF_CHUNK), 256, 0, L, h->g.nc, h->scal, h->status_dev, h->p, h->s, h->r, h->q, m->b,
                                                                               m->xa, h->partials, h->red_counter);
     FSIM_CHECK_LAUNCH(h);
     return FSIM_OK;

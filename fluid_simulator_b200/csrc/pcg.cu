@@ -18,6 +18,7 @@
 #include "fsim_internal.h"
 #include "reduce.cuh"
 #include "pcg_finish.cuh"
+#include "launch.cuh"
 
 int mg_apply(fsim* h, bool first_done, bool with_dot);  // z = M^-1 r   (mg.cu)
 int mg_update_first(fsim* h);
@@ -128,6 +129,8 @@ __global__ void __launch_bounds__(PT) rhs_kernel(PcgArgs a) {
 
 // warm start: r = rhs - A p for the pressure kept from the previous step; also max |r| (already converged => done)
 __global__ void __launch_bounds__(PT) residual_kernel(PcgArgs a) {
+    pdl_wait();
+    pdl_trigger();
     if (a.sc->done) return;
     double acc[1] = {0.0};
     const double scale = a.sc->scale;
@@ -166,6 +169,8 @@ __device__ __forceinline__ double jacobi_z(double scale, unsigned code, double r
 // first preconditioner application (:262-265): s = z ; sigma = z.r, with z = r / A_ii (diagonal) or the multigrid result
 template <bool JACOBI>
 __global__ void __launch_bounds__(PT) start_kernel(PcgArgs a) {
+    pdl_wait();
+    pdl_trigger();
     if (a.sc->done) return;
     double acc[1] = {0.0};
     FOR_CHUNK(c0, a.g.nc)
@@ -190,6 +195,8 @@ __global__ void __launch_bounds__(PT) start_kernel(PcgArgs a) {
 // q = A s fused with s.q  (applyAMatrix :165-198 + dotProduct :200-214); VEC: 16-byte loads, two cells per thread
 template <bool VEC>
 __global__ void __launch_bounds__(PT) spmv_kernel(PcgArgs a) {
+    pdl_wait();
+    pdl_trigger();
     if (a.sc->done) return;
     double acc[1] = {0.0};
     const int64_t sy = a.g.sy, sz = a.g.sz;
@@ -260,6 +267,8 @@ __global__ void __launch_bounds__(PT) spmv_kernel(PcgArgs a) {
 // same as spmv_kernel<true> with four cells per thread and trip (gx % 4 == 0): 13 independent loads in flight per thread
 // (issuing all neighbour loads unconditionally, in parallel with the code load, was measured slower: +50 % traffic over AIR)
 __global__ void __launch_bounds__(PT, 4) spmv4_kernel(PcgArgs a) {
+    pdl_wait();
+    pdl_trigger();
     if (a.sc->done) return;
     double acc[1] = {0.0};
     const int64_t sy = a.g.sy, sz = a.g.sz;
@@ -306,6 +315,8 @@ __global__ void __launch_bounds__(PT, 4) spmv4_kernel(PcgArgs a) {
 // alpha = sigma / s.q ; p += alpha s ; r -= alpha q ; ||r||_inf ; (JACOBI: z = r / A_ii ; sigma' = z.r)   (:270-284)
 template <bool JACOBI>
 __global__ void __launch_bounds__(PT) update_kernel(PcgArgs a) {
+    pdl_wait();
+    pdl_trigger();
     if (a.sc->done) return;
     const double alpha = a.sc->sigma / a.sc->sq;
     const bool bad = alpha != alpha;  // NaN => the reference breaks before touching p (:271-272)
@@ -339,6 +350,8 @@ __global__ void __launch_bounds__(PT) update_kernel(PcgArgs a) {
 
 // sigma' = z.r for an externally computed z (multigrid)
 __global__ void __launch_bounds__(PT) dot_zr_kernel(PcgArgs a) {
+    pdl_wait();
+    pdl_trigger();
     if (a.sc->done) return;
     double acc[1] = {0.0};
     FOR_CHUNK(c0, a.g.nc)
@@ -354,6 +367,8 @@ __global__ void __launch_bounds__(PT) dot_zr_kernel(PcgArgs a) {
 
 // beta = sigma'/sigma ; s = z + beta s   (:284-289); sigma <- sigma' is published by sigma_kernel afterwards
 __global__ void __launch_bounds__(PT) direction_kernel(PcgArgs a) {
+    pdl_wait();
+    pdl_trigger();
     if (a.sc->done) return;
     const double beta = a.sc->sigma_new / a.sc->sigma;
     FOR_CHUNK(c0, a.g.nc)
@@ -372,24 +387,31 @@ __global__ void publish_kernel(const PcgScalars* sc, PcgScalars* out) {
     __threadfence_system();
 }
 
-// loop condition of the device-side WHILE graph: keep iterating until an update kernel has set the done flag
-__global__ void loop_condition_kernel(cudaGraphConditionalHandle handle, const PcgScalars* sc) {
-    cudaGraphSetConditional(handle, sc->done ? 0u : 1u);
+// closes iteration `it`: sigma <- sigma', it <- it + 1, progress published to the host-mapped status word; inside the
+// device-side WHILE graph (use_handle) the same thread re-arms the loop condition from the done flag -- one 1-thread launch
+// per iteration instead of two (sigma_kernel + loop_condition_kernel)
+__global__ void close_kernel(PcgScalars* sc, PcgHostStatus* status, cudaGraphConditionalHandle handle, int use_handle) {
+    pdl_wait();
+    pdl_trigger();
+    const int done = sc->done;
+    if (!done) {
+        sc->sigma = sc->sigma_new;
+        sc->it = sc->it + 1;
+        status->it_done = sc->it;
+        __threadfence_system();
+    }
+    if (use_handle) cudaGraphSetConditional(handle, done ? 0u : 1u);
 }
 
-// closes iteration `it`: sigma <- sigma', it <- it + 1, progress published to the host-mapped status word
-__global__ void sigma_kernel(PcgScalars* sc, PcgHostStatus* status) {
-    if (sc->done) return;
-    sc->sigma = sc->sigma_new;
-    sc->it = sc->it + 1;
-    status->it_done = sc->it;
-    __threadfence_system();
+// first evaluation of the loop condition (graph root, before the WHILE node)
+__global__ void loop_condition_kernel(cudaGraphConditionalHandle handle, const PcgScalars* sc) {
+    cudaGraphSetConditional(handle, sc->done ? 0u : 1u);
 }
 
 }  // namespace
 
 // one PCG iteration: SpMV -> update -> (multigrid cycle -> z.r | fused diagonal) -> direction -> close
-static int enqueue_iteration(fsim* h, const PcgArgs& a, bool vec, bool use_mg, int nbv) {
+static int enqueue_iteration(fsim* h, const PcgArgs& a, bool vec, bool use_mg, int nbv, cudaGraphConditionalHandle handle = 0, int use_handle = 0) {
     const int mode = h->dist ? 1 : (h->hybrid ? 2 : 0);  // 1: slab-local solve, 2: full-grid context restricted to the owned planes
     auto AR = [&](int kind) { return mode ? dist_allreduce(h, kind, true) : FSIM_OK; };
     // the neighbours' boundary planes of the search direction
@@ -397,9 +419,9 @@ static int enqueue_iteration(fsim* h, const PcgArgs& a, bool vec, bool use_mg, i
     if (mode == 2) { int rc = dist_halo_sym(h, SYM_S, h->s, true); if (rc) return rc; }
     {
         KScope ks(h, K_SPMV);
-        if (vec && a.g.gx % 4 == 0 && a.g.nc % 4 == 0) spmv4_kernel<<<nbv, PT, 0, h->stream>>>(a);
-        else if (vec) spmv_kernel<true><<<nbv, PT, 0, h->stream>>>(a);
-        else spmv_kernel<false><<<nbv, PT, 0, h->stream>>>(a);
+        if (vec && a.g.gx % 4 == 0 && a.g.nc % 4 == 0) launch_k(h, spmv4_kernel, dim3(nbv), dim3(PT), 0, a);
+        else if (vec) launch_k(h, spmv_kernel<true>, dim3(nbv), dim3(PT), 0, a);
+        else launch_k(h, spmv_kernel<false>, dim3(nbv), dim3(PT), 0, a);
     }
     { int rc = AR(AR_SPMV); if (rc) return rc; }
     if (use_mg && mg_can_fuse(h)) {
@@ -410,24 +432,24 @@ static int enqueue_iteration(fsim* h, const PcgArgs& a, bool vec, bool use_mg, i
         if (rc) return rc;
         if (a.z32 != h->mg_z32) return fsim_fail(h, FSIM_ERR_INVALID, "multigrid result buffer moved between cycles");
     } else if (use_mg) {
-        { KScope ks(h, K_UPDATE); update_kernel<false><<<nbv, PT, 0, h->stream>>>(a); }
+        { KScope ks(h, K_UPDATE); launch_k(h, update_kernel<false>, dim3(nbv), dim3(PT), 0, a); }
         int rc = AR(AR_UPDATE);
         if (rc) return rc;
         rc = mg_apply(h, false, false);
         if (rc) return rc;
         if (a.z32 != h->mg_z32) return fsim_fail(h, FSIM_ERR_INVALID, "multigrid result buffer moved between cycles");
-        { KScope ks(h, K_UPDATE); dot_zr_kernel<<<nbv, PT, 0, h->stream>>>(a); }
+        { KScope ks(h, K_UPDATE); launch_k(h, dot_zr_kernel, dim3(nbv), dim3(PT), 0, a); }
         rc = AR(AR_DOTZR);
         if (rc) return rc;
     } else {
-        { KScope ks(h, K_UPDATE); update_kernel<true><<<nbv, PT, 0, h->stream>>>(a); }
+        { KScope ks(h, K_UPDATE); launch_k(h, update_kernel<true>, dim3(nbv), dim3(PT), 0, a); }
         int rc = AR(AR_UPDATE_JACOBI);
         if (rc) return rc;
     }
     {
         KScope ks(h, K_DIRECTION, 2);
-        direction_kernel<<<nbv, PT, 0, h->stream>>>(a);
-        sigma_kernel<<<1, 1, 0, h->stream>>>(h->scal, h->status_dev);
+        launch_k(h, direction_kernel, dim3(nbv), dim3(PT), 0, a);
+        launch_k(h, close_kernel, dim3(1), dim3(1), 0, h->scal, h->status_dev, handle, use_handle);
     }
     return FSIM_OK;
 }
@@ -529,13 +551,12 @@ int k_project(fsim* h, double dt, int* iterations) {
                 memcpy(c0, h->launch_n, sizeof(c0));
                 ok = cudaStreamBeginCaptureToGraph(h->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
                 if (ok) {
-                    const int rc = enqueue_iteration(h, a, vec, use_mg, nbv);
-                    loop_condition_kernel<<<1, 1, 0, h->stream>>>(handle, h->scal);
+                    const int rc = enqueue_iteration(h, a, vec, use_mg, nbv, handle, 1);
                     cudaGraph_t dummy = nullptr;
                     const cudaError_t e = cudaStreamEndCapture(h->stream, &dummy);
                     ok = rc == FSIM_OK && e == cudaSuccess;
                 }
-                h->pcg_graph_launches = (int)(h->launches - l0) + 1;
+                h->pcg_graph_launches = (int)(h->launches - l0);
                 for (int k = 0; k < K_COUNT; k++) { h->pcg_graph_class[k] = (int)(h->launch_n[k] - c0[k]); h->launch_n[k] = c0[k]; }
                 h->launches = l0;  // capture does not execute
             }
