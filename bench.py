@@ -266,6 +266,8 @@ def main():
         local_rank = 0
     red_dev = "cpu" if same_dev else "cuda"
     torch.cuda.set_device(local_rank)
+    from fluid_simulator_b200 import dist as fdist
+    numa = fdist.bind_to_gpu_numa_node(local_rank) if world > 1 else {"bound": False, "why": "single rank"}
     if world > 1:
         # NCCL_DEBUG at VERSION / WARN or above prints on stdout, in front of the JSON line: keep the setting, but send the log to
         # a file per rank (gpurun_out/nccl_<host>_<pid>.log); rank 0 echoes the communicator lines to stderr at the end
@@ -443,7 +445,7 @@ def main():
         el = allmax(time.perf_counter() - t0)
         e2e = {"value": total_particles * k / el, "unit": UNIT, "steps": k,
                "h2d_bytes_per_step": int(__import__("ctypes").sizeof(abi.Params)),
-               "d2h_bytes_per_step": int(np_local * 20),
+               "d2h_bytes_per_step": int(np_local * 20), "numa": numa,
                "what": "per step: fsim_set_params + fsim_set_obstacles + fsim_step + fsim_export_gfx_async into pinned host memory "
                        "(double-buffered: the copy of step k overlaps step k+1; all copies complete inside the timed region)"}
         del gfx
@@ -540,7 +542,7 @@ def main():
             "step_hbm_frac_impl_b_it": step_frac_impl, "b_it_impl": B_IT,
             "stage_us": {k: v for k, v in zip(["advect", "", "", "p2g", "classify", "project", "extrapolate", "g2p"], list(timings.last_raw_us)) if k},
             "sort_us": timings.last_sort_us, "kernel_ms": kernel_ms, "kernel_roofline": per_class, "roofline": roofline, "e2e": e2e, "setup_s": t_gen}
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:  # (the contract asks for it on rank 0 at N = 1 only)
         try:
             r = run_reference(args, args.cpu_grid if args.cpu_grid else 96, args.cpu_steps, args.cpu_warmup)
             line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}

@@ -377,14 +377,14 @@ __global__ void __launch_bounds__(256) mig_recv_kernel(const __grid_constant__ M
         // same key expression as the advect kernels (particles.cu cell_key)
         int ix = (int)((double)x * g.dihx), iy = (int)((double)y * g.dihy), iz = (int)((double)z * g.dihz) - g.zoff;
         ix = min(max(ix, 0), g.gx - 1); iy = min(max(iy, 0), g.gy - 1);
-        if (iz < g.zown0 || iz >= g.zown1) {  // crossed a whole slab in one step: not supported, flagged
+        if (iz < g.zown0 || iz >= g.zown1) {  // crossed a whole slab in one step: not supported, flagged; the particle is dropped
             *(volatile uint32_t*)&c->error = 3u;
             *(volatile uint32_t*)a.err_host = 3u;
-            iz = min(max(iz, g.zown0), g.zown1 - 1);
+            a.rank[d] = 0xFFFFFFFFu;
+            continue;
         }
         const uint32_t k = (uint32_t)((iz * g.gy + iy) * g.gx + ix);
-        a.key[d] = k;
-        a.rank[d] = atomicAdd(&a.cnt[k], 1u);
+        a.rank[d] = atomicAdd(&a.cnt[k], 1u);  // (the reorder recomputes the key from the position it moves)
     }
     if (gtid == 0) {
         c->n_src = (uint32_t)a.np + total;

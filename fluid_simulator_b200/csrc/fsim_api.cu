@@ -363,6 +363,8 @@ static int create_impl(const FsimGridDesc* desc, int rank, int nranks, fsim_t** 
     if (nranks > 1) A(dev_alloc(h, &h->code_mg, g.nc + 8)); else h->code_mg = h->code;
     for (int a = 0; a < 3; a++) { A(dev_alloc(h, &h->u[a], g.nc)); A(dev_alloc(h, &h->u2[a], g.nc)); A(dev_alloc(h, &h->wsum[a], g.nc)); }
     A(dev_alloc(h, &h->dens, g.nc));
+    h->g2p_tma = false;
+    if (!rc) A(g2p_init_tma(h));
     A(dev_alloc(h, &h->p, g.nc)); A(dev_alloc(h, &h->rhs, g.nc)); A(dev_alloc(h, &h->r, g.nc));
     A(dev_alloc(h, &h->s, g.nc)); A(dev_alloc(h, &h->q, g.nc)); A(dev_alloc(h, &h->z, g.nc));
     A(dev_alloc(h, &h->p_prev, g.nc));

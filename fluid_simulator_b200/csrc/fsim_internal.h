@@ -137,6 +137,8 @@ struct fsim {
     float* mg_b0;                          // level-0 multigrid right-hand side (inside hot)
     bool l2_persist;                       // FSIM_L2_PERSIST=0 switches the L2 persistence window on the codes off
     float *u[3], *u2[3], *wsum[3], *dens;  // u: post-P2G v / accumulators; u2: working v2
+    struct alignas(64) TensorMapStorage { unsigned char b[128]; } tmap_u[3], tmap_u2[3];  // CUtensorMap of u / u2 (TMA tile staging of the G2P, g2p.cu)
+    bool g2p_tma;                          // the maps are valid (FSIM_G2P_TMA=0, or a grid whose rows are not 16-byte multiples: scalar staging)
     double *p, *rhs, *r, *q, *z;           // pressure + PCG vectors (fp64)
     float* s;                              // PCG search direction (fp32 storage, see pcg.cu)
     float* mg_z32;                         // result of the last multigrid cycle (fp32, 0 outside WATER)
@@ -259,6 +261,7 @@ int k_project_basic(fsim* h, int* iterations);
 int k_project(fsim* h, double dt, int* iterations);
 int k_extrapolate(fsim* h);
 int k_g2p(fsim* h);
+int g2p_init_tma(fsim* h);
 int k_export_gfx(fsim* h, FsimParticleGfx* dev_out);
 int k_particles_aos_to_soa(fsim* h, const double* dev_aos, int64_t first, int64_t n);
 int k_particles_soa_to_aos(fsim* h, double* dev_aos, int64_t first, int64_t n);

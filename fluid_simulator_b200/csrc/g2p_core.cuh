@@ -8,7 +8,16 @@
 // I/O is coalesced SoA.  FLIP needs sum w*v2 and sum w*(v2 - v): both are linear in the taps, so the tile stores the
 // single combined field (a+b)*v2 - b*v with a = double(1 - flipRatio) (float arithmetic, simulator.cpp:408) and
 // b = double(flipRatio), and one gather gives  v_new = sum w*field + b*v_old  -- half the taps of the reference loop.
+//
+// Tile staging (BASELINE.json north_star: "TMA-staged grid tiles"): one elected thread issues cp.async.bulk.tensor.3d loads
+// of the (36 x 6 x 6)-float box around the tile, one per face-velocity channel, straight from the grid arrays into shared
+// memory; the copy engine clips the box against the grid and zero-fills what lies outside (the halo of border tiles), the
+// CTA waits on one mbarrier.  That replaces ~5 trips per thread through a loop with two integer divisions, six bounds
+// tests and up to six scalar loads each.  FLIP stages v2 and v and combines them in place with a linear pass.  The scalar
+// loop remains for grids whose rows are not 16-byte multiples (the tensor map needs it) and as FSIM_G2P_TMA=0.
 #pragma once
+#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
+
 #include "fsim_internal.h"
 
 namespace g2p {
@@ -16,7 +25,9 @@ namespace g2p {
 constexpr int TX = 32, TY = 4, TZ = 4;
 constexpr int ROWS = TY * TZ;
 constexpr int SX = TX + 2, SY = TY + 2, SZ = TZ + 2;
-constexpr int SN = SX * SY * SZ;
+constexpr int SXP = 36;                       // row pitch of the staged tile: the TMA box is 36 floats wide (144 B = 9 x 16 B)
+constexpr int SN = ((SXP * SY * SZ + 31) / 32) * 32;  // floats per channel, padded so that every channel starts 128-byte aligned
+constexpr uint32_t TILE_BYTES = SXP * SY * SZ * sizeof(float);
 
 struct Args {
     GridDims g;
@@ -27,6 +38,9 @@ struct Args {
     const float *u[3], *u2[3];
     int transfer;   // FSIM_TRANSFER_*
     float ka, kb;   // field = ka*v2 - kb*v ; v_new = gather + kb*v_old   (PIC/APIC: ka = 1, kb = 0)
+    int use_tma;    // the tensor maps below are valid
+    alignas(64) CUtensorMap tm_u2[3];  // u2[ax] / u[ax] as (gx, gy, gz) fp32 tensors, box (SXP, SY, SZ)
+    alignas(64) CUtensorMap tm_u[3];
 };
 
 struct Tap {
@@ -65,8 +79,8 @@ __device__ __forceinline__ void tile_rows(const Args& a, int x0, int y0, int z0,
 // stage the combined face field of the tile + 1-cell halo (zero outside the grid)
 __device__ __forceinline__ void stage_tile(const Args& a, float (*s)[SN], int x0, int y0, int z0, int nthreads) {
     const GridDims& g = a.g;
-    for (int i = threadIdx.x; i < SN; i += nthreads) {
-        const int sx = i % SX, sy = (i / SX) % SY, sz = i / (SX * SY);
+    for (int i = threadIdx.x; i < SXP * SY * SZ; i += nthreads) {
+        const int sx = i % SXP, sy = (i / SXP) % SY, sz = i / (SXP * SY);
         const int gx = x0 - 1 + sx, gy = y0 - 1 + sy, gz = z0 - 1 + sz;
         float v0 = 0.f, v1 = 0.f, v2 = 0.f;
         if (gx >= 0 && gy >= 0 && gz >= 0 && gx < g.gx && gy < g.gy && gz < g.gz) {
@@ -75,6 +89,46 @@ __device__ __forceinline__ void stage_tile(const Args& a, float (*s)[SN], int x0
             if (a.kb != 0.f) { v0 -= a.kb * a.u[0][c]; v1 -= a.kb * a.u[1][c]; v2 -= a.kb * a.u[2][c]; }
         }
         s[0][i] = v0; s[1][i] = v1; s[2][i] = v2;
+    }
+}
+
+// ---- TMA staging ----------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(smem_u32(dst)), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
+}
+// Stages the tile with the copy engine: s <- box of u2 (PIC / APIC) or ka * u2 - kb * u (FLIP; t is scratch for the u box).
+// Called by all threads of the CTA; returns once the staged field is visible to every thread.
+__device__ __forceinline__ void stage_tile_tma(const Args& a, float (*s)[SN], float (*t)[SN], uint64_t* bar, int x0, int y0, int z0, int nthreads) {
+    const bool flip = a.kb != 0.f;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)) : "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the initialised barrier is visible to the async proxy
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(TILE_BYTES * (flip ? 6u : 3u)) : "memory");
+#pragma unroll
+        for (int ax = 0; ax < 3; ax++) {
+            tma_load_3d(s[ax], &a.tm_u2[ax], x0 - 1, y0 - 1, z0 - 1, bar);
+            if (flip) tma_load_3d(t[ax], &a.tm_u[ax], x0 - 1, y0 - 1, z0 - 1, bar);
+        }
+    }
+    __syncthreads();  // the barrier is initialised before anybody polls it
+    uint32_t ok = 0, spins = 0;
+    while (!ok) {
+        if (++spins > (1u << 26)) __trap();  // a copy that never lands (bad tensor map) must not hang the device
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(bar)) : "memory");
+    }
+    if (flip || a.ka != 1.f) {  // combined FLIP field, in place (same expression as the scalar loop: ka * v2 - kb * v)
+        float4* s4 = reinterpret_cast<float4*>(&s[0][0]);
+        const float4* t4 = reinterpret_cast<const float4*>(&t[0][0]);
+        for (int i = threadIdx.x; i < 3 * SN / 4; i += nthreads) {
+            float4 v = s4[i];
+            v.x *= a.ka; v.y *= a.ka; v.z *= a.ka; v.w *= a.ka;
+            if (flip) { const float4 u = t4[i]; v.x -= a.kb * u.x; v.y -= a.kb * u.y; v.z -= a.kb * u.z; v.w -= a.kb * u.w; }
+            s4[i] = v;
+        }
+        __syncthreads();
     }
 }
 
@@ -93,9 +147,9 @@ __device__ __forceinline__ void gather(const Args& a, const float (*s)[SN], int 
         const Tap tx = tap(gxp - (ax == 0 ? 1.f : 0.5f) - ox, SX);
         const Tap ty = tap(gyp - (ax == 1 ? 1.f : 0.5f) - oy, SY);
         const Tap tz = tap(gzp - (ax == 2 ? 1.f : 0.5f) - oz, SZ);
-        const float* f = s[ax] + (tz.i0 * SY + ty.i0) * SX + tx.i0;
-        const float f000 = f[0], f100 = f[1], f010 = f[SX], f110 = f[SX + 1];
-        const float f001 = f[SX * SY], f101 = f[SX * SY + 1], f011 = f[SX * SY + SX], f111 = f[SX * SY + SX + 1];
+        const float* f = s[ax] + (tz.i0 * SY + ty.i0) * SXP + tx.i0;
+        const float f000 = f[0], f100 = f[1], f010 = f[SXP], f110 = f[SXP + 1];
+        const float f001 = f[SXP * SY], f101 = f[SXP * SY + 1], f011 = f[SXP * SY + SXP], f111 = f[SXP * SY + SXP + 1];
         const float wx1 = tx.w1, wx0 = 1.f - wx1, wy1 = ty.w1, wy0 = 1.f - wy1, wz1 = tz.w1, wz0 = 1.f - wz1;
         const float a00 = f000 * wx0 + f100 * wx1, a10 = f010 * wx0 + f110 * wx1;
         const float a01 = f001 * wx0 + f101 * wx1, a11 = f011 * wx0 + f111 * wx1;

@@ -771,9 +771,12 @@ struct STailArgs {
     int zero_guess;
 };
 
+constexpr int STAIL_MAX_PLANES = 64;  // z-planes of a level the owner tables hold (larger levels: global-memory kernel)
 struct SLv {
     int gx, gy, gz, plane, cap, hz, coarsest, zb, ze;
     float* base;
+    const uint8_t* own;   // [gz] cluster rank that owns plane z          (tables in shared memory: the hot loops must not
+    const int16_t* z0;    // [gz] first plane of that rank's block          spend their time in integer divisions)
 };
 // blocks of plane PAIRS: rank r owns pairs [r*hz/nb, (r+1)*hz/nb), hz = ceil(gz/2)
 __device__ __forceinline__ int s_z0(const SLv& L, int r, int nb) {
@@ -786,23 +789,22 @@ __device__ __forceinline__ int s_owner(const SLv& L, int z, int nb) {
 }
 __device__ __forceinline__ float* s_arr(const SLv& L, int arr) { return L.base + arr * L.cap; }
 // address of element (plane z, in-plane index j) of array arr in the shared memory of the CTA that owns plane z
-__device__ __forceinline__ float* s_remote(cg::cluster_group& cl, const SLv& L, int arr, int z, int j, int nb) {
-    const int o = s_owner(L, z, nb);
-    float* p = L.base + arr * L.cap + (z - s_z0(L, o, nb)) * L.plane + j;
-    return cl.map_shared_rank(p, o);
+__device__ __forceinline__ float* s_remote(cg::cluster_group& cl, const SLv& L, int arr, int z, int j) {
+    float* p = L.base + arr * L.cap + (z - (int)L.z0[z]) * L.plane + j;
+    return cl.map_shared_rank(p, (int)L.own[z]);
 }
 
 // x-, x+, y-, y+, z-, z+ neighbour values of array arr around local cell li = (z - zb) * plane + j (0 where the weight is 0)
 struct Nb6 { float v[6]; };
-__device__ __forceinline__ Nb6 s_nb6(cg::cluster_group& cl, const SLv& L, int arr, int li, int z, int j, const float w[6], int nb) {
+__device__ __forceinline__ Nb6 s_nb6(cg::cluster_group& cl, const SLv& L, int arr, int li, int z, int j, const float w[6]) {
     Nb6 r;
     const float* a = s_arr(L, arr);
     r.v[0] = w[0] > 0.f ? a[li - 1] : 0.f;
     r.v[1] = w[1] > 0.f ? a[li + 1] : 0.f;
     r.v[2] = w[2] > 0.f ? a[li - L.gx] : 0.f;
     r.v[3] = w[3] > 0.f ? a[li + L.gx] : 0.f;
-    r.v[4] = w[4] > 0.f ? (z - 1 >= L.zb ? a[li - L.plane] : *s_remote(cl, L, arr, z - 1, j, nb)) : 0.f;
-    r.v[5] = w[5] > 0.f ? (z + 1 < L.ze ? a[li + L.plane] : *s_remote(cl, L, arr, z + 1, j, nb)) : 0.f;
+    r.v[4] = w[4] > 0.f ? (z - 1 >= L.zb ? a[li - L.plane] : *s_remote(cl, L, arr, z - 1, j)) : 0.f;
+    r.v[5] = w[5] > 0.f ? (z + 1 < L.ze ? a[li + L.plane] : *s_remote(cl, L, arr, z + 1, j)) : 0.f;
     return r;
 }
 __device__ __forceinline__ void s_w6(const SLv& L, int li, float w[6]) {
@@ -813,26 +815,26 @@ __device__ __forceinline__ void s_w6(const SLv& L, int li, float w[6]) {
 __device__ __forceinline__ float s_off(const float w[6], const Nb6& x) {
     return w[1] * x.v[1] + w[0] * x.v[0] + w[3] * x.v[3] + w[2] * x.v[2] + w[5] * x.v[5] + w[4] * x.v[4];
 }
+// the cells of this CTA's block: planes outside, in-plane index inside (no division per cell)
+#define S_FOR_CELLS(L, z, j, li)                      \
+    for (int z = (L).zb; z < (L).ze; z++)             \
+        for (int j = threadIdx.x, li = (z - (L).zb) * (L).plane + threadIdx.x; j < (L).plane; j += TAIL_THREADS, li += TAIL_THREADS)
 
-__device__ void s_jacobi(cg::cluster_group& cl, const SLv& L, int in, int out, float om, int nb) {
-    const int n = (L.ze - L.zb) * L.plane;
-    for (int li = threadIdx.x; li < n; li += TAIL_THREADS) {
-        const int z = L.zb + li / L.plane, j = li % L.plane;
+__device__ void s_jacobi(cg::cluster_group& cl, const SLv& L, int in, int out, float om) {
+    S_FOR_CELLS(L, z, j, li) {
         float w[6];
         s_w6(L, li, w);
-        const Nb6 x = s_nb6(cl, L, in, li, z, j, w, nb);
+        const Nb6 x = s_nb6(cl, L, in, li, z, j, w);
         const float d = s_arr(L, SA_D)[li], xi = s_arr(L, in)[li];
         s_arr(L, out)[li] = d > 0.f ? xi + om * (s_arr(L, SA_B)[li] - (d * xi - s_off(w, x))) / d : 0.f;
     }
 }
 // two pre-smoothing sweeps from a zero guess in one pass (pre2_value)
-__device__ void s_pre2(cg::cluster_group& cl, const SLv& L, int nb) {
-    const int n = (L.ze - L.zb) * L.plane;
-    for (int li = threadIdx.x; li < n; li += TAIL_THREADS) {
-        const int z = L.zb + li / L.plane, j = li % L.plane;
+__device__ void s_pre2(cg::cluster_group& cl, const SLv& L) {
+    S_FOR_CELLS(L, z, j, li) {
         float w[6];
         s_w6(L, li, w);
-        const Nb6 dn = s_nb6(cl, L, SA_D, li, z, j, w, nb), bn = s_nb6(cl, L, SA_B, li, z, j, w, nb);
+        const Nb6 dn = s_nb6(cl, L, SA_D, li, z, j, w), bn = s_nb6(cl, L, SA_B, li, z, j, w);
         const float d = s_arr(L, SA_D)[li], bb = s_arr(L, SA_B)[li];
         float off = 0.f;
 #pragma unroll
@@ -848,52 +850,50 @@ __device__ void s_pre2(cg::cluster_group& cl, const SLv& L, int nb) {
 }
 // restriction: the eight children of a coarse cell sit in eight neighbouring lanes of the CTA that owns them; the sum goes
 // to the coarse cell's owner
-__device__ void s_restrict(cg::cluster_group& cl, const SLv& L, const SLv& C, int nb) {
+__device__ void s_restrict(cg::cluster_group& cl, const SLv& L, const SLv& C) {
     const int Z0 = L.zb >> 1, Z1 = (L.ze + 1) >> 1;  // coarse planes whose children this CTA owns (blocks start at even planes)
-    const int ncc = (Z1 - Z0) * C.plane;
-    const int n8 = (ncc * 8 + 31) & ~31;  // whole warps take part in the shuffles
-    for (int g = threadIdx.x; g < n8; g += TAIL_THREADS) {
-        const int cc = g >> 3, sub = g & 7;
-        float r = 0.f;
-        int Z = 0, J = 0;
-        if (cc < ncc) {
-            Z = Z0 + cc / C.plane; J = cc % C.plane;
-            const int X = J % C.gx, Y = J / C.gx;
-            const int x = 2 * X + (sub & 1), y = 2 * Y + ((sub >> 1) & 1), z = 2 * Z + (sub >> 2);
-            if (x < L.gx && y < L.gy && z < L.ze) {
-                const int j = y * L.gx + x, li = (z - L.zb) * L.plane + j;
-                const float d = s_arr(L, SA_D)[li];
-                float w[6];
-                s_w6(L, li, w);
-                const Nb6 xn = s_nb6(cl, L, SA_XA, li, z, j, w, nb);
-                if (d > 0.f) r = s_arr(L, SA_B)[li] - (d * s_arr(L, SA_XA)[li] - s_off(w, xn));
+    const int n8 = (C.plane * 8 + 31) & ~31;         // whole warps take part in the shuffles
+    for (int Z = Z0; Z < Z1; Z++)
+        for (int g = threadIdx.x; g < n8; g += TAIL_THREADS) {
+            const int J = g >> 3, sub = g & 7;
+            float r = 0.f;
+            if (J < C.plane) {
+                const int X = J % C.gx, Y = J / C.gx;
+                const int x = 2 * X + (sub & 1), y = 2 * Y + ((sub >> 1) & 1), z = 2 * Z + (sub >> 2);
+                if (x < L.gx && y < L.gy && z < L.ze) {
+                    const int j = y * L.gx + x, li = (z - L.zb) * L.plane + j;
+                    const float d = s_arr(L, SA_D)[li];
+                    float w[6];
+                    s_w6(L, li, w);
+                    const Nb6 xn = s_nb6(cl, L, SA_XA, li, z, j, w);
+                    if (d > 0.f) r = s_arr(L, SA_B)[li] - (d * s_arr(L, SA_XA)[li] - s_off(w, xn));
+                }
             }
+            r += __shfl_xor_sync(0xffffffffu, r, 1);
+            r += __shfl_xor_sync(0xffffffffu, r, 2);
+            r += __shfl_xor_sync(0xffffffffu, r, 4);
+            if (sub == 0 && J < C.plane) *s_remote(cl, C, SA_B, Z, J) = r;
         }
-        r += __shfl_xor_sync(0xffffffffu, r, 1);
-        r += __shfl_xor_sync(0xffffffffu, r, 2);
-        r += __shfl_xor_sync(0xffffffffu, r, 4);
-        if (sub == 0 && cc < ncc) *s_remote(cl, C, SA_B, Z, J, nb) = r;
-    }
 }
 // prolongation + over-corrected update fused with the first post-smoothing sweep (t_prolong_jacobi): XA -> XB
-__device__ void s_prolong_jacobi(cg::cluster_group& cl, const SLv& L, const SLv& C, int nb) {
-    const int n = (L.ze - L.zb) * L.plane;
-    for (int li = threadIdx.x; li < n; li += TAIL_THREADS) {
-        const int z = L.zb + li / L.plane, j = li % L.plane;
-        const int y = j / L.gx, x = j % L.gx;
+__device__ void s_prolong_jacobi(cg::cluster_group& cl, const SLv& L, const SLv& C) {
+    S_FOR_CELLS(L, z, j, li) {
+        const int y = j / L.gx, x = j - y * L.gx;
         float w[6];
         s_w6(L, li, w);
-        const Nb6 xn = s_nb6(cl, L, SA_XA, li, z, j, w, nb);
-        auto ec = [&](int xx, int yy, int zz) -> float { return *s_remote(cl, C, SA_XA, zz >> 1, (yy >> 1) * C.gx + (xx >> 1), nb); };
+        const Nb6 xn = s_nb6(cl, L, SA_XA, li, z, j, w);
+        // parents: own row (y>>1, z>>1) and the rows of the y / z neighbours
+        const int jp = (y >> 1) * C.gx + (x >> 1);
+        const float* e_own = s_remote(cl, C, SA_XA, z >> 1, 0);
         const float d = s_arr(L, SA_D)[li], bb = s_arr(L, SA_B)[li];
-        const float x0 = s_arr(L, SA_XA)[li] + OVER * ec(x, y, z);
+        const float x0 = s_arr(L, SA_XA)[li] + OVER * e_own[jp];
         float off = 0.f;
-        if (w[0] > 0.f) off += w[0] * (xn.v[0] + OVER * ec(x - 1, y, z));
-        if (w[1] > 0.f) off += w[1] * (xn.v[1] + OVER * ec(x + 1, y, z));
-        if (w[2] > 0.f) off += w[2] * (xn.v[2] + OVER * ec(x, y - 1, z));
-        if (w[3] > 0.f) off += w[3] * (xn.v[3] + OVER * ec(x, y + 1, z));
-        if (w[4] > 0.f) off += w[4] * (xn.v[4] + OVER * ec(x, y, z - 1));
-        if (w[5] > 0.f) off += w[5] * (xn.v[5] + OVER * ec(x, y, z + 1));
+        if (w[0] > 0.f) off += w[0] * (xn.v[0] + OVER * e_own[(y >> 1) * C.gx + ((x - 1) >> 1)]);
+        if (w[1] > 0.f) off += w[1] * (xn.v[1] + OVER * e_own[(y >> 1) * C.gx + ((x + 1) >> 1)]);
+        if (w[2] > 0.f) off += w[2] * (xn.v[2] + OVER * e_own[((y - 1) >> 1) * C.gx + (x >> 1)]);
+        if (w[3] > 0.f) off += w[3] * (xn.v[3] + OVER * e_own[((y + 1) >> 1) * C.gx + (x >> 1)]);
+        if (w[4] > 0.f) off += w[4] * (xn.v[4] + OVER * *s_remote(cl, C, SA_XA, (z - 1) >> 1, jp));
+        if (w[5] > 0.f) off += w[5] * (xn.v[5] + OVER * *s_remote(cl, C, SA_XA, (z + 1) >> 1, jp));
         s_arr(L, SA_XB)[li] = d > 0.f ? x0 + OM_B * (bb - (d * x0 - off)) / d : 0.f;
     }
 }
@@ -906,6 +906,8 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) mg_tail_smem_kernel(const __g
     cg::cluster_group cl = cg::this_cluster();
     const int rank = (int)cl.block_rank(), nb = (int)cl.num_blocks();
     __shared__ SLv lv[TAIL_MAX_LEVELS];
+    __shared__ uint8_t t_own[TAIL_MAX_LEVELS][STAIL_MAX_PLANES];
+    __shared__ int16_t t_z0[TAIL_MAX_LEVELS][STAIL_MAX_PLANES];
     if (threadIdx.x < a.n) {
         const int i = threadIdx.x;
         SLv L;
@@ -915,7 +917,18 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) mg_tail_smem_kernel(const __g
         L.base = s_dyn + A.off;
         L.zb = s_z0(L, rank, nb);
         L.ze = (L.coarsest || rank == nb - 1) ? L.gz : s_z0(L, rank + 1, nb);
+        if (L.coarsest && rank != 0) L.zb = L.ze = L.gz;
+        L.own = t_own[i]; L.z0 = t_z0[i];
         lv[i] = L;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < a.n * STAIL_MAX_PLANES; t += TAIL_THREADS) {  // owner tables: one entry per (level, plane)
+        const int i = t / STAIL_MAX_PLANES, z = t % STAIL_MAX_PLANES;
+        if (z < lv[i].gz) {
+            const int o = s_owner(lv[i], z, nb);
+            t_own[i][z] = (uint8_t)o;
+            t_z0[i][z] = (int16_t)s_z0(lv[i], o, nb);
+        }
     }
     __syncthreads();
 #pragma unroll 1
@@ -923,10 +936,8 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) mg_tail_smem_kernel(const __g
         const SLv& L = lv[i];
         const SLevelArg& A = a.lv[i];
         // operator rows of the planes this CTA owns (one pass over global memory, all loads independent)
-        const int n = (L.ze - L.zb) * L.plane;
-        for (int li = threadIdx.x; li < n; li += TAIL_THREADS) {
-            const int z = L.zb + li / L.plane, j = li % L.plane;
-            const int y = j / L.gx, x = j % L.gx;
+        S_FOR_CELLS(L, z, j, li) {
+            const int y = j / L.gx, x = j - y * L.gx;
             const int c = z * L.plane + j;
             s_arr(L, SA_WXM)[li] = x > 0 ? A.wx[c - 1] : 0.f;
             s_arr(L, SA_WXP)[li] = x + 1 < L.gx ? A.wx[c] : 0.f;
@@ -946,12 +957,12 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) mg_tail_smem_kernel(const __g
     // down
     for (int i = 0; i + 1 < n; i++) {
         if (i == 0 && !a.zero_guess) {
-            s_jacobi(cl, lv[0], SA_XA, SA_XB, OM_A, nb); cl.sync();
-            s_jacobi(cl, lv[0], SA_XB, SA_XA, OM_B, nb); cl.sync();
+            s_jacobi(cl, lv[0], SA_XA, SA_XB, OM_A); cl.sync();
+            s_jacobi(cl, lv[0], SA_XB, SA_XA, OM_B); cl.sync();
         } else {
-            s_pre2(cl, lv[i], nb); cl.sync();
+            s_pre2(cl, lv[i]); cl.sync();
         }
-        s_restrict(cl, lv[i], lv[i + 1], nb); cl.sync();
+        s_restrict(cl, lv[i], lv[i + 1]); cl.sync();
     }
     // coarsest level: damped Jacobi by CTA 0, one cell per thread, iterates ping-pong between XA and XB
     if (rank == 0) {
@@ -989,8 +1000,8 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) mg_tail_smem_kernel(const __g
     cl.sync();
     // up
     for (int i = n - 2; i >= 0; i--) {
-        s_prolong_jacobi(cl, lv[i], lv[i + 1], nb); cl.sync();
-        s_jacobi(cl, lv[i], SA_XB, SA_XA, OM_A, nb);
+        s_prolong_jacobi(cl, lv[i], lv[i + 1]); cl.sync();
+        s_jacobi(cl, lv[i], SA_XB, SA_XA, OM_A);
         if (i > 0) cl.sync();
     }
     // result of the first level -> global (only this CTA's threads wrote these entries: a block barrier orders them)
@@ -1097,7 +1108,8 @@ int cycle(fsim* h, int l, bool zero_guess, float** result, bool first_done = fal
                 floats += (size_t)SA_COUNT * A.cap;
             }
             const size_t bytes = floats * sizeof(float);
-            const bool coarse_ok = h->mg[l + sa.n - 1]->nc <= TAIL_THREADS;
+            bool coarse_ok = h->mg[l + sa.n - 1]->nc <= TAIL_THREADS;
+            for (int i = 0; i < sa.n; i++) coarse_ok = coarse_ok && h->mg[l + i]->gz <= STAIL_MAX_PLANES;
             if (h->mg_tail_smem < 0) {  // first use: opt in to the large dynamic shared memory, make sure the cluster still fits
                 h->mg_tail_smem = 0;
                 if (!(getenv("FSIM_MG_TAIL_SMEM") && getenv("FSIM_MG_TAIL_SMEM")[0] == '0') &&

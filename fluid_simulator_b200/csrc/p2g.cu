@@ -11,6 +11,8 @@
 // (j+dy,k+dz), lanes own distinct x -- no shared-memory atomics (fp32 smem atomicAdd is a CAS loop on
 // sm_100a) and a deterministic summation order inside the tile.  The tile (+1-cell halo) is flushed with
 // one fp32 RED per touched node and channel; only tile-halo nodes are shared between CTAs.
+#include <atomic>
+
 #include "fsim_internal.h"
 
 namespace {
@@ -221,19 +223,43 @@ __device__ __forceinline__ void stage_row(float* const (&dst)[NA], const float* 
     __syncwarp();
 }
 
+// Tile + halo -> global accumulators, one fp32 RED per touched node and channel.  A warp takes whole rows of the shared tile:
+// lane l owns node sx = l + 1 (grid x = x0 + l: the 32 REDs of a row fall into ONE 128-byte line), lanes 0 / 1 also own the two
+// halo nodes sx = 0 and sx = SX - 1.  No per-node index arithmetic (the flat loop it replaces spent two integer divisions and
+// three bounds tests per node; r1 ncu: issue-bound kernel).
 __device__ __forceinline__ void flush_pass(const P2GArgs& a, float* s_val, float* s_w, float* g_val, float* g_w, int x0, int y0, int z0) {
-    for (int i = threadIdx.x; i < SN; i += NTHREADS) {
-        const float w = s_w[i];
-        if (w != 0.f) {
-            const int sx = i % SX, sy = (i / SX) % SY, sz = i / (SX * SY);
-            const int gx = x0 - 1 + sx, gy = y0 - 1 + sy, gz = z0 - 1 + sz;
-            if (gx >= 0 && gy >= 0 && gz >= 0 && gx < a.g.gx && gy < a.g.gy && gz < a.g.gz) {
-                const int64_t c = ((int64_t)gz * a.g.gy + gy) * a.g.gx + gx;
-                atomicAdd(g_w + c, w);
-                if (g_val) atomicAdd(g_val + c, s_val[i]);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int r = warp; r < SY * SZ; r += NTHREADS / 32) {
+        const int sy = r % SY, sz = r / SY;
+        const int gy = y0 - 1 + sy, gz = z0 - 1 + sz;
+        const bool row_ok = gy >= 0 && gy < a.g.gy && gz >= 0 && gz < a.g.gz;  // warp-uniform
+        const int64_t cb = ((int64_t)gz * a.g.gy + gy) * a.g.gx + (x0 - 1);
+        const int rb = r * SX;
+        {
+            const int sx = lane + 1;
+            const float w = s_w[rb + sx];
+            if (w != 0.f) {
+                if (row_ok && x0 - 1 + sx < a.g.gx) {
+                    atomicAdd(g_w + cb + sx, w);
+                    if (g_val) atomicAdd(g_val + cb + sx, s_val[rb + sx]);
+                }
+                s_w[rb + sx] = 0.f;
+                s_val[rb + sx] = 0.f;
             }
-            s_w[i] = 0.f;
-            s_val[i] = 0.f;
+        }
+        if (lane < 2) {
+            const int sx = lane * (SX - 1);
+            const float w = s_w[rb + sx];
+            if (w != 0.f) {
+                const int gx = x0 - 1 + sx;
+                if (row_ok && gx >= 0 && gx < a.g.gx) {
+                    atomicAdd(g_w + cb + sx, w);
+                    if (g_val) atomicAdd(g_val + cb + sx, s_val[rb + sx]);
+                }
+                s_w[rb + sx] = 0.f;
+                s_val[rb + sx] = 0.f;
+            }
         }
     }
     __syncthreads();
@@ -327,12 +353,13 @@ int k_p2g(fsim* h) {
     dim3 grid(div_up(g.gx, TX), div_up(g.gy, TY), div_up(g.gz, TZ));
     {
         // the opt-in shared-memory size is a per-device function attribute: set it once per device, not per launch
-        static bool attr_set[2][64] = {};
+        // (slab groups drive several handles from several host threads: the flags are atomic, setting the attribute twice is harmless)
+        static std::atomic<bool> attr_set[2][64];
         const int dev = h->device & 63;
-        if (!attr_set[a.apic ? 1 : 0][dev]) {
+        if (!attr_set[a.apic ? 1 : 0][dev].load(std::memory_order_acquire)) {
             if (a.apic) FSIM_CUDA(h, cudaFuncSetAttribute(p2g_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STAGED_SMEM));
             else FSIM_CUDA(h, cudaFuncSetAttribute(p2g_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STAGED_SMEM));
-            attr_set[a.apic ? 1 : 0][dev] = true;
+            attr_set[a.apic ? 1 : 0][dev].store(true, std::memory_order_release);
         }
         KScope ks(h, K_P2G);
         if (a.apic) p2g_kernel<true><<<grid, NTHREADS, STAGED_SMEM, h->stream>>>(a);

@@ -227,10 +227,9 @@ __device__ __forceinline__ void bin_particle(const AdvectArgs& a, int64_t i, boo
     uint32_t base = 0;
     if (lane == leader && k != INVALID_KEY) base = atomicAdd(&a.cnt[k], (uint32_t)__popc(peers));
     base = __shfl_sync(0xffffffffu, base, leader);
-    if (live) {
-        a.key[i] = k;
-        a.rank[i] = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
-    }
+    // only the rank travels to the reorder pass: it reads the position anyway and recomputes the key from it (same expression,
+    // same stored fp32 coordinates); particles that leave the set -- sink captures, emigrants -- carry an invalid rank
+    if (live) a.rank[i] = k == INVALID_KEY ? INVALID_KEY : base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
 }
 
 __global__ void __launch_bounds__(256, 4) advect_kernel(const __grid_constant__ AdvectArgs a) {
@@ -261,7 +260,9 @@ constexpr int GA_THREADS = 256;
 // warps more than it minds the spills; prefetching the next particle into registers and a warp-per-row loop were slower.
 __global__ void __launch_bounds__(GA_THREADS, 6) g2p_advect_kernel(const __grid_constant__ g2p::Args ga, const __grid_constant__ AdvectArgs a) {
     using namespace g2p;
-    __shared__ float s[3][SN];
+    __shared__ alignas(128) float s[3][SN];
+    __shared__ alignas(128) float tb[3][SN];  // FLIP: box of v next to the box of v2 (TMA staging)
+    __shared__ alignas(8) uint64_t bar;
     __shared__ uint32_t row_beg[ROWS], row_end[ROWS], row_pre[ROWS + 1];
     const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY, z0 = blockIdx.z * TZ;
     tile_rows(ga, x0, y0, z0, row_beg, row_end);
@@ -274,8 +275,8 @@ __global__ void __launch_bounds__(GA_THREADS, 6) g2p_advect_kernel(const __grid_
     __syncthreads();
     const uint32_t total = row_pre[ROWS];
     if (total == 0) return;  // no particle in the tile
-    stage_tile(ga, s, x0, y0, z0, GA_THREADS);
-    __syncthreads();
+    if (ga.use_tma) stage_tile_tma(ga, s, tb, &bar, x0, y0, z0, GA_THREADS);
+    else { stage_tile(ga, s, x0, y0, z0, GA_THREADS); __syncthreads(); }
     auto one = [&](uint32_t p, bool live) {
         D3 pos = mk(0, 0, 0), v = mk(0, 0, 0);
         bool killed = false;
@@ -335,10 +336,7 @@ __global__ void __launch_bounds__(256) bin_kernel(GridDims g, const float* __res
     uint32_t base = 0;
     if (lane == leader && k != INVALID_KEY) base = atomicAdd(&cnt[k], (uint32_t)__popc(peers));
     base = __shfl_sync(0xffffffffu, base, leader);
-    if (i < n) {
-        key[i] = k;
-        rank[i] = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
-    }
+    if (i < n) rank[i] = k == INVALID_KEY ? INVALID_KEY : base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
 }
 
 // ---- exclusive scan of cnt[nc] -> cell_start[nc+1] -----------------------------------------------------
@@ -431,9 +429,10 @@ struct ReorderArgs {
     const uint32_t* src_id;
     uint32_t* dst_id;
     int nch;
-    const uint32_t *key, *rank, *cell_start;
+    const uint32_t *rank, *cell_start;
     int64_t n;
     const uint32_t* n_dev;  // slab mode: the source count (locals + immigrants) is only known on the device
+    GridDims g;
 };
 
 // All channel loads are issued before the first scattered store (source and destination sets never alias, but the
@@ -442,15 +441,14 @@ template <int NCH>
 __global__ void __launch_bounds__(256) reorder_kernel(ReorderArgs a) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (a.n_dev ? (int64_t)*a.n_dev : a.n)) return;
-    const uint32_t k = __ldg(a.key + i);
     const uint32_t r = __ldg(a.rank + i);
     float v[NCH];
 #pragma unroll
     for (int c = 0; c < NCH; c++) v[c] = __ldg(a.src[c] + i);
     uint32_t id = 0;
     if (a.src_id) id = __ldg(a.src_id + i);
-    if (k == INVALID_KEY) return;
-    const uint32_t d = __ldg(a.cell_start + k) + r;
+    if (r == INVALID_KEY) return;  // captured by a sink / migrated to a neighbour slab
+    const uint32_t d = __ldg(a.cell_start + cell_key(a.g, v[0], v[1], v[2])) + r;
 #pragma unroll
     for (int c = 0; c < NCH; c++) a.dst[c][d] = v[c];
     if (a.src_id) a.dst_id[d] = id;
@@ -597,7 +595,7 @@ ReorderArgs reorder_args(fsim* h) {
     for (int c = 0; c < 15; c++) { a.src[c] = s.ch[c]; a.dst[c] = d.ch[c]; }
     a.src_id = h->track_ids ? h->ps[h->cur].id : nullptr;
     a.dst_id = h->track_ids ? h->ps[h->cur ^ 1].id : nullptr;
-    a.key = h->key; a.rank = h->rank; a.cell_start = h->cell_start; a.n = h->np; a.n_dev = nullptr;
+    a.rank = h->rank; a.cell_start = h->cell_start; a.n = h->np; a.n_dev = nullptr; a.g = h->g;
     return a;
 }
 

@@ -20,7 +20,9 @@ def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     dist.init_process_group("gloo")
     dev = int(os.environ.get("LOCAL_RANK", "0")) % torch.cuda.device_count()
-    sc = scenes.dam_break_3d(16, abi.FLIP, tol=1e-9)
+    sc = scenes.dam_break_3d(int(os.environ.get("FSIM_WORKER_GRID", "16")), abi.FLIP, tol=1e-9)
+    if rank == 0:
+        print(f"slab worker: {world} ranks, devices {[r % torch.cuda.device_count() for r in range(world)]} of {torch.cuda.device_count()}, grid {sc.dims}")
     s = FluidSim(sc.dims, sc.resolution, sc.two_d, sc.particle_radius, device=dev, rank=rank, nranks=world)
     slab.connect_torch(s, dist)
     s.set_params(sc.params)

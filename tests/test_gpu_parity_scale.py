@@ -8,11 +8,11 @@ the COMPILED REFERENCE (oracle/_ref, unmodified sources, OpenMP on the box's hos
   * cfg 4: 3D PIC with source, sink and moving box, 96^3, spawning and despawning on.
 
 Bars (BASELINE.json north_star): cell flags and particle->cell indices bit-exact; grid velocities, pressure and particle
-velocities within 1e-5 relative L2.  Two facts decide what "pressure within 1e-5" can mean at the DEFAULT tolerance: both
-solvers stop at ||r||_inf < 1e-6 with different preconditioners, so their pressures differ by A^-1 (r_a - r_b), which the
-smooth modes of a 128^3 grid (lambda_min ~ 1e-5) amplify.  The test therefore holds the velocities (what the step hands on)
-to 1e-5 at both tolerances and the pressure to 1e-5 at 1e-9 and to PRESSURE_TOL_DEFAULT at 1e-6; measured values are
-written to gpurun_out/parity_diag.jsonl.
+velocities within 1e-5 relative L2 -- at the DEFAULT solver tolerance (1e-6 absolute, two different preconditioners) as
+well as at 1e-9.  Measured on B200 (profiles/r2_parity_scale.md): v2 1.5e-6, pressure 1.2e-6, particle velocities 1.6e-6 at
+128^3 at BOTH tolerances (the difference is fp32 storage, not the stopping rule), the same numbers at 256^3.
+The APIC matrices are finite differences of the velocity field (c[a] = sum grad(w) v2, simulator.cpp:409-415): a relative
+error e in v2 becomes e * |v| / (h |grad v|) in C, a factor ~10 in the sheared test field, so C is held to C_TOL.
 """
 import numpy as np
 import pytest
@@ -24,7 +24,8 @@ from util import diag
 pytestmark = pytest.mark.gpu
 
 TOL = 1e-5                   # relative L2, BASELINE.json north_star
-PRESSURE_TOL_DEFAULT = 1e-4  # pressure at residualTolerance 1e-6 (see the module docstring)
+PRESSURE_TOL_DEFAULT = 1e-5  # pressure at residualTolerance 1e-6: the same bar (measured 1.2e-6)
+C_TOL = 5e-5                 # APIC matrices (velocity gradients; measured 1.6e-5 at 128^3, see the module docstring)
 CELL_ROUNDING_FRACTION = 2e-6  # particles whose fp32-rounded position may land in the neighbouring cell of the fp64 one
 
 
@@ -53,7 +54,7 @@ def check(tag, res, apic=False, pressure_tol=TOL, vel_tol=TOL):
     assert res["vel"] <= vel_tol, f"{tag}: particle velocity rel L2 {res['vel']:.3e} > {vel_tol}"
     assert res["pressure"] <= pressure_tol, f"{tag}: pressure rel L2 {res['pressure']:.3e} > {pressure_tol}"
     if apic:
-        assert res["c"] <= TOL, f"{tag}: APIC matrix rel L2 {res['c']:.3e}"
+        assert res["c"] <= C_TOL, f"{tag}: APIC matrix rel L2 {res['c']:.3e}"
     # gfx export (manager/simulationManager.cpp:218-231): positions are the same fp32 numbers, |v| and density to 1e-5
     assert res["gfx_pos"] <= 1e-6 and res["gfx_speed"] <= TOL and res["gfx_density"] <= TOL, f"{tag}: gfx export {res}"
 
@@ -89,6 +90,8 @@ def test_cfg4_96_pic_source_sink_moving_box_vs_reference(gpu):
     obs = scenes.cfg4_obstacles(n, 7, sc.dt)       # step 7 of the box's sinusoid: it moves, speed = (pos - prevPos) / dt
     obs[1].pos[:] = (0.3 * n, 0.3 * n, 0.5 * n)    # sink inside the dam block so that despawning removes particles
     obs[1].prev_pos[:] = obs[1].pos[:]
-    res = scale_parity.one_step(gpu, sc, obstacles=obs, srand=4242, by_position=True)
+    # particle order: the reference appends the spawned particles and compacts the captured ones away in place (stable,
+    # hashedParticles.cpp:153-172); the device's persistent ids reproduce exactly that order
+    res = scale_parity.one_step(gpu, sc, obstacles=obs, srand=4242)
     assert res["count_ref"] != sc.n_particles, "the scene must add and remove particles"
     check("scale/cfg4_96_pic_source_sink", res, pressure_tol=PRESSURE_TOL_DEFAULT)

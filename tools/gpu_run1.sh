@@ -4,6 +4,7 @@ cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/r2a_smi.txt 2>&1
 nproc > gpurun_out/r2a_host.txt; free -g >> gpurun_out/r2a_host.txt
+timeout 120 tools/_bin/red_probe > gpurun_out/r2a_red_probe.txt 2>&1; cat gpurun_out/r2a_red_probe.txt
 # solver A/B first (seconds each): programmatic dependent launch and the shared-memory-resident multigrid tail, on and off
 for cfg in "1 1" "0 1" "1 0" "0 0"; do set -- $cfg
   echo "== FSIM_PDL=$1 FSIM_MG_TAIL_SMEM=$2" >> gpurun_out/r2a_projection_ab.log
