@@ -11,8 +11,9 @@ using namespace g2p;
 constexpr int NT = 256;
 
 __global__ void __launch_bounds__(NT) g2p_kernel(const __grid_constant__ Args a) {
-    __shared__ alignas(128) float s[3][SN];
-    __shared__ alignas(128) float t[3][SN];  // FLIP: box of v next to the box of v2 (TMA staging)
+    extern __shared__ __align__(128) float g2p_dyn[];  // [3][SN] staged field (+ [3][SN] box of v: TMA staging of a FLIP field)
+    float (*s)[SN] = reinterpret_cast<float (*)[SN]>(g2p_dyn);
+    float (*t)[SN] = reinterpret_cast<float (*)[SN]>(g2p_dyn + 3 * SN);
     __shared__ alignas(8) uint64_t bar;
     __shared__ uint32_t row_beg[ROWS], row_end[ROWS];
     const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY, z0 = blockIdx.z * TZ;
@@ -127,7 +128,7 @@ int k_g2p(fsim* h) {
     int rc = g2p_make_args(h, &a);
     if (rc) return rc;
     dim3 grid(div_up(g.gx, TX), div_up(g.gy, TY), div_up(g.gz, TZ));
-    { KScope ks(h, K_G2P); g2p_kernel<<<grid, NT, 0, h->stream>>>(a); }
+    { KScope ks(h, K_G2P); g2p_kernel<<<grid, NT, g2p::smem_bytes(a), h->stream>>>(a); }
     FSIM_CHECK_LAUNCH(h);
     return FSIM_OK;
 }

@@ -12,7 +12,9 @@
 // Tile staging (BASELINE.json north_star: "TMA-staged grid tiles"): one elected thread issues cp.async.bulk.tensor.3d loads
 // of the (36 x 6 x 6)-float box around the tile, one per face-velocity channel, straight from the grid arrays into shared
 // memory; the copy engine clips the box against the grid and zero-fills what lies outside (the halo of border tiles), the
-// CTA waits on one mbarrier.  That replaces ~5 trips per thread through a loop with two integer divisions, six bounds
+// CTA waits on one mbarrier.  The innermost start coordinate of a tiled TMA load must be 16-byte aligned (tools/tma_probe.cu on
+// B200: x = -1 or 3 faults with "illegal instruction", x = -4 is fine; y and z are free), so the box starts at x0 - 4 and is
+// 40 floats wide: tile node sx lives in box column sx + 3.  That replaces ~5 trips per thread through a loop with two integer divisions, six bounds
 // tests and up to six scalar loads each.  FLIP stages v2 and v and combines them in place with a linear pass.  The scalar
 // loop remains for grids whose rows are not 16-byte multiples (the tensor map needs it) and as FSIM_G2P_TMA=0.
 #pragma once
@@ -25,7 +27,8 @@ namespace g2p {
 constexpr int TX = 32, TY = 4, TZ = 4;
 constexpr int ROWS = TY * TZ;
 constexpr int SX = TX + 2, SY = TY + 2, SZ = TZ + 2;
-constexpr int SXP = 36;                       // row pitch of the staged tile: the TMA box is 36 floats wide (144 B = 9 x 16 B)
+constexpr int SXP = 40;                       // row pitch of the staged tile = width of the TMA box (x0 - 4 .. x0 + 35)
+constexpr int XOFF = 3;                       // box column of tile node sx = 0 (grid x = x0 - 1)
 constexpr int SN = ((SXP * SY * SZ + 31) / 32) * 32;  // floats per channel, padded so that every channel starts 128-byte aligned
 constexpr uint32_t TILE_BYTES = SXP * SY * SZ * sizeof(float);
 
@@ -42,6 +45,9 @@ struct Args {
     alignas(64) CUtensorMap tm_u2[3];  // u2[ax] / u[ax] as (gx, gy, gz) fp32 tensors, box (SXP, SY, SZ)
     alignas(64) CUtensorMap tm_u[3];
 };
+
+// dynamic shared memory of the kernels that stage a tile: one box per channel, two when the copy engine stages a FLIP field
+inline size_t smem_bytes(const Args& a) { return (size_t)((a.use_tma && a.kb != 0.f) ? 6 : 3) * SN * sizeof(float); }
 
 struct Tap {
     int i0;    // local node index of the lower node
@@ -80,7 +86,7 @@ __device__ __forceinline__ void tile_rows(const Args& a, int x0, int y0, int z0,
 __device__ __forceinline__ void stage_tile(const Args& a, float (*s)[SN], int x0, int y0, int z0, int nthreads) {
     const GridDims& g = a.g;
     for (int i = threadIdx.x; i < SXP * SY * SZ; i += nthreads) {
-        const int sx = i % SXP, sy = (i / SXP) % SY, sz = i / (SXP * SY);
+        const int sx = i % SXP - XOFF, sy = (i / SXP) % SY, sz = i / (SXP * SY);
         const int gx = x0 - 1 + sx, gy = y0 - 1 + sy, gz = z0 - 1 + sz;
         float v0 = 0.f, v1 = 0.f, v2 = 0.f;
         if (gx >= 0 && gy >= 0 && gz >= 0 && gx < g.gx && gy < g.gy && gz < g.gz) {
@@ -108,8 +114,8 @@ __device__ __forceinline__ void stage_tile_tma(const Args& a, float (*s)[SN], fl
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(TILE_BYTES * (flip ? 6u : 3u)) : "memory");
 #pragma unroll
         for (int ax = 0; ax < 3; ax++) {
-            tma_load_3d(s[ax], &a.tm_u2[ax], x0 - 1, y0 - 1, z0 - 1, bar);
-            if (flip) tma_load_3d(t[ax], &a.tm_u[ax], x0 - 1, y0 - 1, z0 - 1, bar);
+            tma_load_3d(s[ax], &a.tm_u2[ax], x0 - 1 - XOFF, y0 - 1, z0 - 1, bar);
+            if (flip) tma_load_3d(t[ax], &a.tm_u[ax], x0 - 1 - XOFF, y0 - 1, z0 - 1, bar);
         }
     }
     __syncthreads();  // the barrier is initialised before anybody polls it
@@ -147,7 +153,7 @@ __device__ __forceinline__ void gather(const Args& a, const float (*s)[SN], int 
         const Tap tx = tap(gxp - (ax == 0 ? 1.f : 0.5f) - ox, SX);
         const Tap ty = tap(gyp - (ax == 1 ? 1.f : 0.5f) - oy, SY);
         const Tap tz = tap(gzp - (ax == 2 ? 1.f : 0.5f) - oz, SZ);
-        const float* f = s[ax] + (tz.i0 * SY + ty.i0) * SXP + tx.i0;
+        const float* f = s[ax] + (tz.i0 * SY + ty.i0) * SXP + tx.i0 + XOFF;
         const float f000 = f[0], f100 = f[1], f010 = f[SXP], f110 = f[SXP + 1];
         const float f001 = f[SXP * SY], f101 = f[SXP * SY + 1], f011 = f[SXP * SY + SXP], f111 = f[SXP * SY + SXP + 1];
         const float wx1 = tx.w1, wx0 = 1.f - wx1, wy1 = ty.w1, wy0 = 1.f - wy1, wz1 = tz.w1, wz0 = 1.f - wz1;

@@ -23,6 +23,7 @@
 #include "fsim_internal.h"
 #include "reduce.cuh"
 #include "launch.cuh"
+#include "tile4.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -360,17 +361,27 @@ __global__ void __launch_bounds__(256) mg_jacobi4_dot_kernel(Lv L, PcgScalars* _
     if (sc->done) return;
     double acc[1] = {0.0};
     const int tx = threadIdx.x & 31, ty = (threadIdx.x >> 5) & 3, tz = threadIdx.x >> 7;
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    // the codes of the next tile are requested before this tile's stencil loads: one exposed round trip per tile instead of two
+    auto tile_cell = [&](int t, int64_t& c) -> bool {
         const int bx = t % ntx, by = (t / ntx) % nty, bz = t / (ntx * nty);
         const int x = (bx * 32 + tx) * 4, y = by * 4 + ty, z = bz * 2 + tz;
-        if (x >= L.gx || y >= L.gy || z >= L.gz) continue;
-        const int64_t c = ((int64_t)z * L.gy + y) * L.gx + x;
-        const ushort4 tc = *reinterpret_cast<const ushort4*>(L.code + c);
+        c = ((int64_t)z * L.gy + y) * L.gx + x;
+        return x < L.gx && y < L.gy && z < L.gz;
+    };
+    int64_t c = 0;
+    ushort4 tc = make_ushort4(0, 0, 0, 0);
+    if ((int)blockIdx.x < ntiles && tile_cell(blockIdx.x, c)) tc = *reinterpret_cast<const ushort4*>(L.code + c);
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        int64_t cn = 0;
+        ushort4 tcn = make_ushort4(0, 0, 0, 0);
+        if (t + (int)gridDim.x < ntiles && tile_cell(t + gridDim.x, cn)) tcn = *reinterpret_cast<const ushort4*>(L.code + cn);
         const unsigned cd[4] = {tc.x, tc.y, tc.z, tc.w};
-        if (!((cd[0] | cd[1] | cd[2] | cd[3]) & CODE_ACTIVE)) continue;
+        const int64_t cc = c;
+        tc = tcn; c = cn;
+        if (!((cd[0] | cd[1] | cd[2] | cd[3]) & CODE_ACTIVE)) continue;  // (also every out-of-grid thread: its codes stay 0)
         F4 xo = zero4();
-        const Stencil4 s = load_stencil4(L, xin, c, cd);
-        const F4 bb = ld4(b + c);
+        const Stencil4 s = load_stencil4(L, xin, cc, cd);
+        const F4 bb = ld4(b + cc);
 #pragma unroll
         for (int i = 0; i < 4; i++)
             if (cd[i] & CODE_ACTIVE) {
@@ -379,16 +390,16 @@ __global__ void __launch_bounds__(256) mg_jacobi4_dot_kernel(Lv L, PcgScalars* _
                 xo.v[i] = d > 0.f ? xi + om * (bb.v[i] - (d * xi - off4(s, i, cd[i]))) / d : 0.f;
                 acc[0] += (double)xo.v[i] * (double)bb.v[i];
             }
-        st4(xout + c, xo);
+        st4(xout + cc, xo);
     }
     double out[1];
     if (grid_reduce<1, 0>(acc, partials, counter, out)) sc->sigma_new = out[0] * sc->scale;
 }
 
+constexpr int UF_MIN_BLOCKS = 4;  // 64 registers: four resident CTAs instead of three (ncu r2: 35 % active warps at 68 registers)
 // CG update fused with the first smoothing sweep of the next cycle (level 0, linear chunks of 4-cell groups):
 //   alpha = sigma / s.q ; p += alpha s ; r -= alpha q ; ||r||_inf ; b = r / scale ; x1 = omega b / diag
-constexpr int UF_CHUNK = 8192;
-__global__ void __launch_bounds__(256) mg_update_first4_kernel(Lv L, int64_t nc, PcgScalars* sc, PcgHostStatus* status, double* __restrict__ p,
+__global__ void __launch_bounds__(256, UF_MIN_BLOCKS) mg_update_first4_kernel(Lv L, Tile4 t4, PcgScalars* sc, PcgHostStatus* status, double* __restrict__ p,
                                                                const float* __restrict__ sv, double* __restrict__ r,
                                                                const double* __restrict__ q, float* __restrict__ b, float* __restrict__ xout,
                                                                double* partials, unsigned int* counter) {
@@ -400,10 +411,15 @@ __global__ void __launch_bounds__(256) mg_update_first4_kernel(Lv L, int64_t nc,
     const double inv_scale = sc->inv_scale;
     double acc[1] = {0.0};
     if (!bad) {
-        const int64_t cend = min((int64_t)(blockIdx.x + 1) * UF_CHUNK, nc);
-        for (int64_t c = (int64_t)blockIdx.x * UF_CHUNK + (int64_t)threadIdx.x * 4; c < cend; c += 256 * 4) {
-            const ushort4 t = *reinterpret_cast<const ushort4*>(L.code + c);
+        // 2-D blocks (tile4.cuh); the stencil codes of the next trip are requested before this trip's vector loads
+        int64_t c = 0, cn = 0;
+        ushort4 t = make_ushort4(0, 0, 0, 0);
+        if (tile4_cell(t4, 0, c)) t = *reinterpret_cast<const ushort4*>(L.code + c);
+        for (int trip = 0; trip < T4_TRIPS; trip++, c = cn) {
+            ushort4 tn = make_ushort4(0, 0, 0, 0);
+            if (trip + 1 < T4_TRIPS && tile4_cell(t4, trip + 1, cn)) tn = *reinterpret_cast<const ushort4*>(L.code + cn);
             const unsigned cd[4] = {t.x, t.y, t.z, t.w};
+            t = tn;
             if (!((cd[0] | cd[1] | cd[2] | cd[3]) & CODE_ACTIVE)) continue;
             double pp[4], ss[4], rr[4], qq[4];
             {
@@ -742,6 +758,79 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) mg_tail_kernel(TailArgs a) {
     const int nt = (int)cluster.num_blocks() * TAIL_THREADS;
     auto bar = [&]() { cluster.sync(); };
     tail_cycle(a.lv, a.n, a.zero_guess != 0, t0, nt, cluster.block_rank() == 0, xs, bar);
+}
+
+// ---- tail kernel, second form: only the FIRST tail level is shared by the cluster ------------------------------------------
+// In mg_tail_kernel every phase of every level ends in a cluster barrier with release / acquire semantics: the CTA's stores
+// must have reached L2 before it arrives, the loads after it miss L1 (ncu r2: 54 % of the samples in UCGABAR_WAIT, ~3 us per
+// phase, 9 phases).  The levels below the first one are tiny (16^3 and 8^3 at 256^3): here EVERY CTA keeps its own copy of their
+// operators and iterates in shared memory and runs their whole sub-cycle redundantly with block barriers only.  What is left
+// for the cluster: pre-smoothing and restriction of the first level (its coarse right-hand side is assembled in global memory
+// by all CTAs), and its prolongation + post-smoothing -- 3 cluster barriers instead of 9.  Same functions, same operand order
+// as mg_tail_kernel => the same iterates.
+constexpr size_t TAIL2_SMEM_MAX = 200 * 1024;
+__host__ __device__ inline int tail2_pad(int sz) { return (sz + 1 + 3) & ~3; }  // halo of every local array: covers c +- sz and c +- 1
+
+__global__ void __launch_bounds__(TAIL_THREADS, 1) mg_tail2_kernel(const __grid_constant__ TailArgs a) {
+    pdl_wait();
+    pdl_trigger();
+    extern __shared__ float sm2[];
+    __shared__ float xs[2][COARSE_MAX];
+    __shared__ TailLevel loc[TAIL_MAX_LEVELS];  // levels 1 .. n-1 with every pointer redirected into shared memory
+    if (a.sc->done) return;  // uniform over the cluster
+    cg::cluster_group cluster = cg::this_cluster();
+    const int t0 = (int)cluster.block_rank() * TAIL_THREADS + threadIdx.x;
+    const int nt = (int)cluster.num_blocks() * TAIL_THREADS;
+    const int n = a.n;
+    // local copies of the operators of levels 1 .. n-1 (halo included: the global arrays are padded with zeros, alloc_level)
+    if (threadIdx.x == 0) {
+        size_t off = 0;
+        for (int i = 1; i < n; i++) {
+            const Lv& G = a.lv[i].L;
+            const int nc = G.gx * G.gy * G.gz, pad = tail2_pad(G.sz), stride = nc + 2 * pad;
+            TailLevel T = a.lv[i];
+            float* base = sm2 + off + pad;
+            T.L.wx = base; T.L.wy = base + stride; T.L.wz = base + 2 * stride; T.L.diag = base + 3 * stride;
+            T.b = base + 4 * stride; T.xa = base + 5 * stride; T.xb = base + 6 * stride;
+            loc[i - 1] = T;
+            off += (size_t)7 * stride;
+        }
+    }
+    __syncthreads();
+    for (int i = 1; i < n; i++) {
+        const Lv& G = a.lv[i].L;
+        const TailLevel& T = loc[i - 1];
+        const int nc = G.gx * G.gy * G.gz, pad = tail2_pad(G.sz);
+        float* dst[4] = {const_cast<float*>(T.L.wx), const_cast<float*>(T.L.wy), const_cast<float*>(T.L.wz), const_cast<float*>(T.L.diag)};
+        const float* src[4] = {G.wx, G.wy, G.wz, G.diag};
+        for (int c = (int)threadIdx.x - pad; c < nc + pad; c += TAIL_THREADS) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) dst[k][c] = src[k][c];
+            T.b[c] = 0.f; T.xa[c] = 0.f; T.xb[c] = 0.f;
+        }
+    }
+    // first level: pre-smoothing and restriction by the whole cluster, through global memory
+    const TailLevel& F = a.lv[0];
+    if (!a.zero_guess) {
+        t_jacobi(F.L, F.b, F.xa, F.xb, t0, nt, OM_A); cluster.sync();
+        t_jacobi(F.L, F.b, F.xb, F.xa, t0, nt, OM_B); cluster.sync();
+    } else {
+        t_pre2(F.L, F.b, F.xa, t0, nt); cluster.sync();
+    }
+    t_restrict(F.L, a.lv[1].L, F.b, F.xa, a.lv[1].b, t0, nt); cluster.sync();
+    // every CTA: the coarse right-hand side, then the whole sub-cycle of levels 1 .. n-1 in its own shared memory
+    {
+        const Lv& G = a.lv[1].L;
+        const int nc = G.gx * G.gy * G.gz;
+        for (int c = threadIdx.x; c < nc; c += TAIL_THREADS) loc[0].b[c] = a.lv[1].b[c];
+    }
+    __syncthreads();
+    auto bbar = [&]() { __syncthreads(); };
+    tail_cycle(loc, n - 1, true, (int)threadIdx.x, TAIL_THREADS, true, xs, bbar);
+    __syncthreads();
+    // first level: prolongation + post-smoothing (the coarse correction is this CTA's own copy)
+    t_prolong_jacobi(F.L, loc[0].L, F.b, F.xa, loc[0].xa, F.xb, t0, nt); cluster.sync();
+    t_jacobi(F.L, F.b, F.xb, F.xa, t0, nt, OM_A);
 }
 
 // ---- the same sub-cycle with every tail level RESIDENT IN (DISTRIBUTED) SHARED MEMORY -------------------------------------
@@ -1112,7 +1201,10 @@ int cycle(fsim* h, int l, bool zero_guess, float** result, bool first_done = fal
             for (int i = 0; i < sa.n; i++) coarse_ok = coarse_ok && h->mg[l + i]->gz <= STAIL_MAX_PLANES;
             if (h->mg_tail_smem < 0) {  // first use: opt in to the large dynamic shared memory, make sure the cluster still fits
                 h->mg_tail_smem = 0;
-                if (!(getenv("FSIM_MG_TAIL_SMEM") && getenv("FSIM_MG_TAIL_SMEM")[0] == '0') &&
+                // opt-in (FSIM_MG_TAIL_SMEM=1): measured SLOWER than the global-memory kernel on B200 (60 us vs 33 us per call at
+                // 256^3 under ncu, +0.4 ms per step; profiles/r2_mg_tail_ab.md) -- both spend their time in cluster barriers,
+                // and this one executes 1.8x the instructions (operator rows re-staged on every call, generic loads)
+                if ((getenv("FSIM_MG_TAIL_SMEM") && getenv("FSIM_MG_TAIL_SMEM")[0] == '1') &&
                     cudaFuncSetAttribute(mg_tail_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TAIL_SMEM_MAX) == cudaSuccess &&
                     cudaFuncSetAttribute(mg_tail_smem_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
                     cudaLaunchConfig_t q = {};
@@ -1152,8 +1244,30 @@ int cycle(fsim* h, int l, bool zero_guess, float** result, bool first_done = fal
         at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[1].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = at; cfg.numAttrs = h->pdl ? 2 : 1;
+        // second form (mg_tail2_kernel): the levels below the first one run redundantly in every CTA's shared memory
+        size_t bytes2 = 0;
+        for (int i = 1; i < ta.n; i++) {
+            const MgLevel* t = h->mg[l + i];
+            bytes2 += (size_t)7 * (t->nc + 2 * tail2_pad(t->sz)) * sizeof(float);
+        }
+        if (h->mg_tail2 < 0) {  // first use: opt in to the dynamic shared memory, make sure the cluster can still be scheduled
+            h->mg_tail2 = 0;
+            const char* e = getenv("FSIM_MG_TAIL2");
+            if (!(e && e[0] == '0') && cudaFuncSetAttribute(mg_tail2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TAIL2_SMEM_MAX) == cudaSuccess &&
+                cudaFuncSetAttribute(mg_tail2_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+                cudaLaunchConfig_t q = cfg;
+                q.numAttrs = 1; q.dynamicSmemBytes = TAIL2_SMEM_MAX;
+                int nclusters = 0;
+                if (cudaOccupancyMaxActiveClusters(&nclusters, mg_tail2_kernel, &q) == cudaSuccess && nclusters >= 1) h->mg_tail2 = 1;
+            }
+            cudaGetLastError();
+        }
         KScope ks(h, K_MG2);
-        FSIM_CUDA(h, cudaLaunchKernelEx(&cfg, mg_tail_kernel, ta));
+        if (h->mg_tail2 == 1 && ta.n >= 2 && bytes2 <= TAIL2_SMEM_MAX) {
+            cfg.dynamicSmemBytes = bytes2;
+            FSIM_CUDA(h, cudaLaunchKernelEx(&cfg, mg_tail2_kernel, ta));
+        } else
+            FSIM_CUDA(h, cudaLaunchKernelEx(&cfg, mg_tail_kernel, ta));
         *result = m->xa;
         return FSIM_OK;
     }
@@ -1224,7 +1338,12 @@ int cycle(fsim* h, int l, bool zero_guess, float** result, bool first_done = fal
             }
             if (v4 && with_dot && s == POST - 1) {
                 const int ntiles = (int)(grd4.x * grd4.y * grd4.z);
-                launch_k(h, mg_jacobi4_dot_kernel, std::min(ntiles, h->sm_count * 8), 256, 0, L, h->scal, m->b, cur, oth, h->partials, h->red_counter, om,
+                // persistent CTAs walk the tiles with stride gridDim: the stride must not share a factor with the tile grid's x
+                // extent, or a CTA only ever sees tiles of one x-column -- in a dam-break scene half the CTAs then got nothing but
+                // air tiles and the other half all the work (64 us against 37 us for the same sweep without the dot product)
+                int nper = std::min(ntiles, h->sm_count * 8);
+                while (nper > 1 && (int)grd4.x > 1 && nper % (int)grd4.x == 0) nper--;
+                launch_k(h, mg_jacobi4_dot_kernel, nper, 256, 0, L, h->scal, m->b, cur, oth, h->partials, h->red_counter, om,
                                                                                                (int)grd4.x, (int)grd4.y, ntiles);
             } else if (v4) launch_k(h, mg_jacobi4_kernel, grd4, blk4, 0, L, h->scal, m->b, cur, oth, om);
             else if (fine) launch_k(h, mg_jacobi_kernel<true>, grdL, blk, 0, L, sc, m->b, cur, oth, om);
@@ -1306,8 +1425,9 @@ int mg_update_first(fsim* h) {
     MgLevel* m = h->mg[0];
     const Lv L = view(h, m, 0);
     KScope ks(h, K_UPDATE);
-    launch_k(h, mg_update_first4_kernel, div_up(h->g.nc, UF_CHUNK), 256, 0, L, h->g.nc, h->scal, h->status_dev, h->p, h->s, h->r, h->q, m->b,
-                                                                              m->xa, h->partials, h->red_counter);
+    { const Tile4 t4 = tile4_make(h->g.gx, 0, h->g.nc / h->g.gx);
+    launch_k(h, mg_update_first4_kernel, tile4_blocks(t4), 256, 0, L, t4, h->scal, h->status_dev, h->p, h->s, h->r, h->q, m->b,
+                                                                              m->xa, h->partials, h->red_counter); }
     FSIM_CHECK_LAUNCH(h);
     return FSIM_OK;
 }

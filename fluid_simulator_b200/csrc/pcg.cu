@@ -19,6 +19,7 @@
 #include "reduce.cuh"
 #include "pcg_finish.cuh"
 #include "launch.cuh"
+#include "tile4.cuh"
 
 int mg_apply(fsim* h, bool first_done, bool with_dot);  // z = M^-1 r   (mg.cu)
 int mg_update_first(fsim* h);
@@ -52,6 +53,7 @@ struct PcgArgs {
     int pressure_enabled, warm;
     int cut_neumann;  // slab mode: how code_mg treats a cut link
     int64_t cb, ce;   // cell range of the chunked kernels
+    Tile4 t4;         // the same range as 2-D blocks (tile4.cuh): iteration space of the four-cells-per-thread kernels
 };
 
 // iteration space of the chunked kernels: block b owns cells [b*CHUNK, (b+1)*CHUNK), a thread visits CV cells per trip
@@ -273,40 +275,47 @@ __global__ void __launch_bounds__(PT, 4) spmv4_kernel(PcgArgs a) {
     double acc[1] = {0.0};
     const int64_t sy = a.g.sy, sz = a.g.sz;
     const double scale = a.sc->scale;
-    const int64_t cend = min(a.cb + (int64_t)(blockIdx.x + 1) * CHUNK, a.ce);
-    for (int64_t c = a.cb + (int64_t)blockIdx.x * CHUNK + (int64_t)threadIdx.x * 4; c < cend; c += PT * 4) {
-        const ushort4 t = *reinterpret_cast<const ushort4*>(a.code + c);
-        double sc[4], ym[4] = {0, 0, 0, 0}, yp[4] = {0, 0, 0, 0}, zm[4] = {0, 0, 0, 0}, zp[4] = {0, 0, 0, 0};
-        double xl = 0.0, xr = 0.0;
-        auto ld = [&](double* dst, const float* src) {
-            const float4 u = *reinterpret_cast<const float4*>(src);
-            dst[0] = (double)u.x; dst[1] = (double)u.y; dst[2] = (double)u.z; dst[3] = (double)u.w;
-        };
+    // A thread visits four groups of four cells (tile4.cuh); every trip is two dependent round trips (stencil codes, then the
+    // stencil itself).  The codes of the NEXT trip are requested before this trip's stencil loads.
+    int64_t c = 0, cn = 0;
+    ushort4 t = make_ushort4(0, 0, 0, 0);
+    if (tile4_cell(a.t4, 0, c)) t = *reinterpret_cast<const ushort4*>(a.code + c);
+    for (int trip = 0; trip < T4_TRIPS; trip++, c = cn) {
+        ushort4 tn = make_ushort4(0, 0, 0, 0);
+        if (trip + 1 < T4_TRIPS && tile4_cell(a.t4, trip + 1, cn)) tn = *reinterpret_cast<const ushort4*>(a.code + cn);
         const unsigned cd[4] = {t.x, t.y, t.z, t.w};
         const unsigned any = cd[0] | cd[1] | cd[2] | cd[3];
-        if (!(any & CODE_ACTIVE)) continue;
-        ld(sc, a.s + c);
-        if (any & 4u) ld(ym, a.s + c - sy);
-        if (any & 8u) ld(yp, a.s + c + sy);
-        if (any & 16u) ld(zm, a.s + c - sz);
-        if (any & 32u) ld(zp, a.s + c + sz);
-        xl = (cd[0] & 1u) ? (double)a.s[c - 1] : 0.0; xr = (cd[3] & 2u) ? (double)a.s[c + 4] : 0.0;
-        double q[4] = {0, 0, 0, 0};
+        if (any & CODE_ACTIVE) {
+            double sc[4], ym[4] = {0, 0, 0, 0}, yp[4] = {0, 0, 0, 0}, zm[4] = {0, 0, 0, 0}, zp[4] = {0, 0, 0, 0};
+            double xl = 0.0, xr = 0.0;
+            auto ld = [&](double* dst, const float* src) {
+                const float4 u = *reinterpret_cast<const float4*>(src);
+                dst[0] = (double)u.x; dst[1] = (double)u.y; dst[2] = (double)u.z; dst[3] = (double)u.w;
+            };
+            ld(sc, a.s + c);
+            if (any & 4u) ld(ym, a.s + c - sy);
+            if (any & 8u) ld(yp, a.s + c + sy);
+            if (any & 16u) ld(zm, a.s + c - sz);
+            if (any & 32u) ld(zp, a.s + c + sz);
+            xl = (cd[0] & 1u) ? (double)a.s[c - 1] : 0.0; xr = (cd[3] & 2u) ? (double)a.s[c + 4] : 0.0;
+            double q[4] = {0, 0, 0, 0};
 #pragma unroll
-        for (int i = 0; i < 4; i++)
-            if (cd[i] & CODE_ACTIVE) {
-                double n = 0.0;
-                if (cd[i] & 1u) n += i == 0 ? xl : sc[i - 1];
-                if (cd[i] & 2u) n += i == 3 ? xr : sc[i + 1];
-                if (cd[i] & 4u) n += ym[i];
-                if (cd[i] & 8u) n += yp[i];
-                if (cd[i] & 16u) n += zm[i];
-                if (cd[i] & 32u) n += zp[i];
-                q[i] = scale * ((double)code_ns(cd[i]) * sc[i] - n);
-                acc[0] += sc[i] * q[i];
-            }
-        *reinterpret_cast<double2*>(a.q + c) = make_double2(q[0], q[1]);
-        *reinterpret_cast<double2*>(a.q + c + 2) = make_double2(q[2], q[3]);
+            for (int i = 0; i < 4; i++)
+                if (cd[i] & CODE_ACTIVE) {
+                    double n = 0.0;
+                    if (cd[i] & 1u) n += i == 0 ? xl : sc[i - 1];
+                    if (cd[i] & 2u) n += i == 3 ? xr : sc[i + 1];
+                    if (cd[i] & 4u) n += ym[i];
+                    if (cd[i] & 8u) n += yp[i];
+                    if (cd[i] & 16u) n += zm[i];
+                    if (cd[i] & 32u) n += zp[i];
+                    q[i] = scale * ((double)code_ns(cd[i]) * sc[i] - n);
+                    acc[0] += sc[i] * q[i];
+                }
+            *reinterpret_cast<double2*>(a.q + c) = make_double2(q[0], q[1]);
+            *reinterpret_cast<double2*>(a.q + c + 2) = make_double2(q[2], q[3]);
+        }
+        t = tn;
     }
     double out[1];
     if (grid_reduce<1, 0>(acc, a.partials, a.counter, out)) { if (a.sc->dist) a.sc->loc[0] = out[0]; else a.sc->sq = out[0]; }
@@ -380,6 +389,31 @@ __global__ void __launch_bounds__(PT) direction_kernel(PcgArgs a) {
         a.s[c] = (float)((double)a.s[c] * beta + (a.z32 ? (double)a.z32[c] : a.z[c]));
     }
 }
+// the same update with four cells per trip (gx % 4 == 0, multigrid preconditioner): 16-byte loads, stencil codes of the next
+// trip prefetched (see spmv4_kernel)
+__global__ void __launch_bounds__(PT) direction4_kernel(PcgArgs a) {
+    pdl_wait();
+    pdl_trigger();
+    if (a.sc->done) return;
+    const double beta = a.sc->sigma_new / a.sc->sigma;
+    int64_t c = 0, cn = 0;
+    ushort4 t = make_ushort4(0, 0, 0, 0);
+    if (tile4_cell(a.t4, 0, c)) t = *reinterpret_cast<const ushort4*>(a.code + c);
+    for (int trip = 0; trip < T4_TRIPS; trip++, c = cn) {
+        ushort4 tn = make_ushort4(0, 0, 0, 0);
+        if (trip + 1 < T4_TRIPS && tile4_cell(a.t4, trip + 1, cn)) tn = *reinterpret_cast<const ushort4*>(a.code + cn);
+        const unsigned cd[4] = {t.x, t.y, t.z, t.w};
+        t = tn;
+        if (!((cd[0] | cd[1] | cd[2] | cd[3]) & CODE_ACTIVE)) continue;
+        const float4 sv = *reinterpret_cast<const float4*>(a.s + c), zv = *reinterpret_cast<const float4*>(a.z32 + c);
+        float so[4] = {sv.x, sv.y, sv.z, sv.w};
+        const float zz[4] = {zv.x, zv.y, zv.z, zv.w};
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            if (cd[i] & CODE_ACTIVE) so[i] = (float)((double)so[i] * beta + (double)zz[i]);
+        *reinterpret_cast<float4*>(a.s + c) = make_float4(so[0], so[1], so[2], so[3]);
+    }
+}
 // the host reads the solve's scalars from mapped pinned memory: a D2H memcpy would queue behind whatever bulk copy the
 // application has in flight on the device-to-host copy engine (the async gfx export is 1.3 GB per step at 256^3)
 __global__ void publish_kernel(const PcgScalars* sc, PcgScalars* out) {
@@ -419,7 +453,7 @@ static int enqueue_iteration(fsim* h, const PcgArgs& a, bool vec, bool use_mg, i
     if (mode == 2) { int rc = dist_halo_sym(h, SYM_S, h->s, true); if (rc) return rc; }
     {
         KScope ks(h, K_SPMV);
-        if (vec && a.g.gx % 4 == 0 && a.g.nc % 4 == 0) launch_k(h, spmv4_kernel, dim3(nbv), dim3(PT), 0, a);
+        if (vec && a.g.gx % 4 == 0 && a.g.nc % 4 == 0) launch_k(h, spmv4_kernel, dim3(tile4_blocks(a.t4)), dim3(PT), 0, a);
         else if (vec) launch_k(h, spmv_kernel<true>, dim3(nbv), dim3(PT), 0, a);
         else launch_k(h, spmv_kernel<false>, dim3(nbv), dim3(PT), 0, a);
     }
@@ -448,7 +482,8 @@ static int enqueue_iteration(fsim* h, const PcgArgs& a, bool vec, bool use_mg, i
     }
     {
         KScope ks(h, K_DIRECTION, 2);
-        launch_k(h, direction_kernel, dim3(nbv), dim3(PT), 0, a);
+        if (vec && a.z32 && a.g.gx % 4 == 0 && a.g.nc % 4 == 0 && a.cb % 4 == 0) launch_k(h, direction4_kernel, dim3(tile4_blocks(a.t4)), dim3(PT), 0, a);
+        else launch_k(h, direction_kernel, dim3(nbv), dim3(PT), 0, a);
         launch_k(h, close_kernel, dim3(1), dim3(1), 0, h->scal, h->status_dev, handle, use_handle);
     }
     return FSIM_OK;
@@ -476,6 +511,7 @@ int k_project(fsim* h, double dt, int* iterations) {
     a.cb = h->hybrid ? (int64_t)g.zown0 * g.sz : 0;
     a.ce = h->hybrid ? (int64_t)g.zown1 * g.sz : g.nc;
     const int nbv = div_up(a.ce - a.cb, CHUNK);     // chunked kernels
+    a.t4 = tile4_make(g.gx, a.cb / g.gx, (a.ce - a.cb) / g.gx);
     const bool vec = (g.gx % 2 == 0) && (g.nc % 2 == 0);
     const bool use_mg = mg_enabled(h);
     const int max_it = h->par.max_iterations;
