@@ -232,6 +232,15 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries ONE JSON line and nothing else: libraries that write to fd 1 (NCCL prints its version banner there when
+    # NCCL_DEBUG is set, whatever NCCL_DEBUG_FILE says) are sent to stderr, where the log stays visible
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+    def emit(obj):
+        json_out.write(json.dumps(obj) + "\n")
+        json_out.flush()
 
     if args.impl == "reference":
         if rank != 0:
@@ -250,7 +259,7 @@ def main():
                 "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
                 "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        emit(line)
         return
 
     import torch
@@ -548,7 +557,7 @@ def main():
             line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
         except Exception as ex:  # the baseline is reported, never required for the GPU number
             line["cpu_baseline"] = {"error": str(ex)}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         if os.environ.get("NCCL_DEBUG_FILE"):  # the communicator lines of NCCL's log, for whoever reads this run's stderr
             import glob

@@ -147,7 +147,7 @@ struct fsim {
     std::vector<MgLevel*> mg;
     int mg_tail_first;                     // levels >= this run inside the single-cluster tail kernel
     int mg_tail_cluster;                   // CTAs of that cluster (0: not probed yet)
-    int mg_tail2;                          // tail kernel with block-local coarse levels (mg_tail2_kernel): -1 not probed, 0 off, 1 on (FSIM_MG_TAIL2=0: off)
+    int mg_tail2;                          // tail kernel with block-local coarse levels (mg_tail2_kernel): -1 not probed, 0 off, 1 on (opt-in: FSIM_MG_TAIL2=1; measured slower, see mg.cu)
     int mg_tail_smem;                      // shared-memory-resident tail kernel: -1 not probed, 0 off, 1 on (opt-in: FSIM_MG_TAIL_SMEM=1; measured slower, see mg.cu)
     PcgScalars* scal;                      // device
     PcgScalars* scal_host;                 // pinned (parameter upload)

@@ -104,7 +104,13 @@ int g2p_make_args(fsim* h, g2p::Args* out) {
     for (int c = 0; c < 9; c++) a.c[c] = p.c[c];
     a.cell_start = h->cell_start;
     for (int ax = 0; ax < 3; ax++) { a.u[ax] = h->u[ax]; a.u2[ax] = h->u2[ax]; }
-    a.use_tma = h->g2p_tma ? 1 : 0;
+    // TMA staging by default where ONE box per channel is enough (PIC / APIC).  A FLIP field needs the boxes of v2 AND v: the
+    // second buffer doubles the kernel's shared memory (17 -> 35 KB x 6 CTAs), the carve-out shrinks L1 and the fused
+    // G2P + advect kernel loses more on its particle traffic than the copy engine saves on the tile (B200, 256^3 FLIP:
+    // 1.36 ms against 1.24 ms with the scalar loop; profiles/r2_g2p_tma_ab.md).  FSIM_G2P_TMA=1 forces it on for FLIP too.
+    static const bool force = [] { const char* e = getenv("FSIM_G2P_TMA"); return e && e[0] == '1'; }();
+    const bool flip = h->par.transfer_type == FSIM_TRANSFER_FLIP;
+    a.use_tma = (h->g2p_tma && (!flip || force)) ? 1 : 0;
     if (a.use_tma) {
         static_assert(sizeof(CUtensorMap) == sizeof(h->tmap_u[0]), "tensor map storage");
         for (int ax = 0; ax < 3; ax++) { memcpy(&a.tm_u[ax], &h->tmap_u[ax], sizeof(CUtensorMap)); memcpy(&a.tm_u2[ax], &h->tmap_u2[ax], sizeof(CUtensorMap)); }

@@ -1252,8 +1252,11 @@ int cycle(fsim* h, int l, bool zero_guess, float** result, bool first_done = fal
         }
         if (h->mg_tail2 < 0) {  // first use: opt in to the dynamic shared memory, make sure the cluster can still be scheduled
             h->mg_tail2 = 0;
+            // opt-in (FSIM_MG_TAIL2=1): measured SLOWER on B200 (+15 us per call at 256^3: profiles/r2_mg_tail_ab.md) -- re-staging the
+            // operators of the local levels on every call and running them on one CTA's 1024 threads costs more than the six
+            // cluster barriers it removes
             const char* e = getenv("FSIM_MG_TAIL2");
-            if (!(e && e[0] == '0') && cudaFuncSetAttribute(mg_tail2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TAIL2_SMEM_MAX) == cudaSuccess &&
+            if ((e && e[0] == '1') && cudaFuncSetAttribute(mg_tail2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TAIL2_SMEM_MAX) == cudaSuccess &&
                 cudaFuncSetAttribute(mg_tail2_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
                 cudaLaunchConfig_t q = cfg;
                 q.numAttrs = 1; q.dynamicSmemBytes = TAIL2_SMEM_MAX;
