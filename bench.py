@@ -457,6 +457,21 @@ def main():
                "d2h_bytes_per_step": int(np_local * 20), "numa": numa,
                "what": "per step: fsim_set_params + fsim_set_obstacles + fsim_step + fsim_export_gfx_async into pinned host memory "
                        "(double-buffered: the copy of step k overlaps step k+1; all copies complete inside the timed region)"}
+        # the same loop with the subsampled export (every 8th particle; an option of the ABI, not the manager's contract)
+        sub = 8
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(k):
+            sim.set_params(params)
+            sim.set_obstacles([scenes.cfg3_box(n)] if args.obstacle_box else [])
+            sim.step(DT)
+            sim.export_gfx_strided_async_ptr(gfx[i % 2].data_ptr(), gfx_cap, sub)
+            sim.export_gfx_wait_previous()
+        sim.export_gfx_wait()
+        barrier()
+        el = allmax(time.perf_counter() - t0)
+        e2e["subsampled_export"] = {"value": total_particles * k / el, "unit": UNIT, "stride": sub, "d2h_bytes_per_step": int((np_local + sub - 1) // sub * 20),
+                                    "what": "same loop, fsim_export_gfx_strided_async with every 8th particle (not the headline: the manager's contract is the full export)"}
         del gfx
 
     # ---- per-kernel-class durations: CUDA events around every launch on the launching stream.  The timed steps replay the

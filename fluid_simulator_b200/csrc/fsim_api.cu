@@ -1000,10 +1000,12 @@ int fsim_export_gfx(fsim_t* h, FsimParticleGfx* out, int64_t cap, int64_t* n) {
     return FSIM_OK;
 }
 
-int fsim_export_gfx_async(fsim_t* h, FsimParticleGfx* out, int64_t cap, int64_t* n) {
+static int export_gfx_async_impl(fsim_t* h, FsimParticleGfx* out, int64_t cap, int64_t stride, int64_t* n) {
     BIND_FLUSH(h);
-    if (n) *n = h->np;
-    const int64_t m = std::min(cap, h->np);
+    if (stride < 1) return fsim_fail(h, FSIM_ERR_INVALID, "stride must be >= 1");
+    const int64_t nout = (h->np + stride - 1) / stride;
+    if (n) *n = nout;
+    const int64_t m = std::min(cap, nout);
     if (m <= 0 || !out) return FSIM_OK;
     if (!h->copy_stream) {
         FSIM_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
@@ -1023,7 +1025,7 @@ int fsim_export_gfx_async(fsim_t* h, FsimParticleGfx* out, int64_t cap, int64_t*
         h->gfx_async_cap[k] = h->cap;
         FSIM_CUDA(h, cudaMalloc((void**)&h->gfx_async[k], sizeof(FsimParticleGfx) * (size_t)(h->cap > 0 ? h->cap : 1)));
     }
-    TRY(k_export_gfx(h, h->gfx_async[k]));
+    TRY(k_export_gfx(h, h->gfx_async[k], stride));
     FSIM_CUDA(h, cudaEventRecord(h->gfx_ready[k], h->stream));
     FSIM_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->gfx_ready[k], 0));
     FSIM_CUDA(h, cudaMemcpyAsync(out, h->gfx_async[k], sizeof(FsimParticleGfx) * m, cudaMemcpyDeviceToHost, h->copy_stream));
@@ -1031,6 +1033,9 @@ int fsim_export_gfx_async(fsim_t* h, FsimParticleGfx* out, int64_t cap, int64_t*
     h->gfx_inflight[k] = true;
     return FSIM_OK;
 }
+
+int fsim_export_gfx_async(fsim_t* h, FsimParticleGfx* out, int64_t cap, int64_t* n) { return export_gfx_async_impl(h, out, cap, 1, n); }
+int fsim_export_gfx_strided_async(fsim_t* h, FsimParticleGfx* out, int64_t cap, int64_t stride, int64_t* n) { return export_gfx_async_impl(h, out, cap, stride, n); }
 
 int fsim_export_gfx_wait(fsim_t* h) {
     BIND(h);

@@ -263,7 +263,7 @@ int k_project(fsim* h, double dt, int* iterations);
 int k_extrapolate(fsim* h);
 int k_g2p(fsim* h);
 int g2p_init_tma(fsim* h);
-int k_export_gfx(fsim* h, FsimParticleGfx* dev_out);
+int k_export_gfx(fsim* h, FsimParticleGfx* dev_out, int64_t stride = 1);
 int k_particles_aos_to_soa(fsim* h, const double* dev_aos, int64_t first, int64_t n);
 int k_particles_soa_to_aos(fsim* h, double* dev_aos, int64_t first, int64_t n);
 int k_particles_f32_to_soa(fsim* h, const float* pos, const float* vel, const float* c, int64_t first, int64_t n);

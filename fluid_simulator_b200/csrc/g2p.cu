@@ -35,10 +35,12 @@ __global__ void __launch_bounds__(NT) g2p_kernel(const __grid_constant__ Args a)
 }
 
 // ParticleGfxData: float pos, |v|, density = sum trilinear(cell centre) * avgPNum  (simulationManager.cpp:223-230)
+// (stride > 1: record j describes particle j * stride -- the subsampled export, fsim_export_gfx_strided_async)
 __global__ void __launch_bounds__(256) gfx_kernel(GridDims g, const float* px, const float* py, const float* pz, const float* vx,
-                                                   const float* vy, const float* vz, const float* dens, int64_t n,
+                                                   const float* vy, const float* vz, const float* dens, int64_t n, int64_t stride,
                                                    FsimParticleGfx* out) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t i = j * stride;
     if (i >= n) return;
     const float x = px[i], y = py[i], z = pz[i];
     const float qx = x * g.ihx - 0.5f, qy = y * g.ihy - 0.5f, qz = z * g.ihz - 0.5f - (float)g.zoff;
@@ -60,7 +62,7 @@ __global__ void __launch_bounds__(256) gfx_kernel(GridDims g, const float* px, c
     const float a = vx[i], b = vy[i], c = vz[i];
     o.v = sqrtf(a * a + b * b + c * c);
     o.density = d;
-    out[i] = o;
+    out[j] = o;
 }
 
 }  // namespace
@@ -139,13 +141,14 @@ int k_g2p(fsim* h) {
     return FSIM_OK;
 }
 
-int k_export_gfx(fsim* h, FsimParticleGfx* dev_out) {
+int k_export_gfx(fsim* h, FsimParticleGfx* dev_out, int64_t stride) {
     if (h->np == 0) return FSIM_OK;
+    const int64_t nout = (h->np + stride - 1) / stride;
     ParticleSet& p = h->ps[h->cur];
     {
         KScope ks(h, K_GFX);
-        gfx_kernel<<<div_up(h->np, 256), 256, 0, h->stream>>>(h->g, p.pos[0], p.pos[1], p.pos[2], p.vel[0], p.vel[1], p.vel[2],
-                                                             h->dens, h->np, dev_out);
+        gfx_kernel<<<div_up(nout, 256), 256, 0, h->stream>>>(h->g, p.pos[0], p.pos[1], p.pos[2], p.vel[0], p.vel[1], p.vel[2],
+                                                           h->dens, h->np, stride, dev_out);
     }
     FSIM_CHECK_LAUNCH(h);
     return FSIM_OK;

@@ -299,6 +299,8 @@ __global__ void __launch_bounds__(GA_THREADS, 6) g2p_advect_kernel(const __grid_
         bin_particle(a, p, live, killed, fx, fy, fz);
     };
     {
+        // (Splitting the histogram atomic from the use of its return value -- issue in trip t, rank in trip t + 1, so that the
+        // ~1 us return overlaps the next particle's loads -- measured 1.345 ms against 1.238 ms: the extra live state spills.)
         for (uint32_t base = 0; base < total; base += GA_THREADS) {  // CTA-uniform trip count
             const uint32_t j = base + threadIdx.x;
             const bool live = j < total;

@@ -83,6 +83,7 @@ def load_library():
         "fsim_download_particle_cells": (i32, [vp, vp, i64]),
         "fsim_export_gfx": (i32, [vp, vp, i64, P(i64)]),
         "fsim_export_gfx_async": (i32, [vp, vp, i64, P(i64)]),
+        "fsim_export_gfx_strided_async": (i32, [vp, vp, i64, i64, P(i64)]),
         "fsim_export_gfx_wait": (i32, [vp]),
         "fsim_export_gfx_wait_previous": (i32, [vp]),
         "fsim_get_step_durations": (i32, [vp, P(abi.Timings)]),
@@ -292,6 +293,12 @@ class FluidSim:
         """Enqueues the gfx export; the copy into `ptr` (pinned host memory) overlaps the following steps."""
         n = C.c_int64()
         self._ck(self.L.fsim_export_gfx_async(self.h, ptr, cap, C.byref(n)))
+        return int(n.value)
+
+    def export_gfx_strided_async_ptr(self, ptr, cap, stride):
+        """Every `stride`-th particle only (an option for consumers that draw a subset); returns the record count."""
+        n = C.c_int64()
+        self._ck(self.L.fsim_export_gfx_strided_async(self.h, ptr, cap, int(stride), C.byref(n)))
         return int(n.value)
 
     def export_gfx_wait(self): self._ck(self.L.fsim_export_gfx_wait(self.h))

@@ -190,6 +190,13 @@ def test_gfx_export_matches_oracle_one_step(gpu, oracle_lib):
     a = buf.numpy()[np.argsort(ids, kind="stable")]
     b = o.export_gfx()
     assert rel_l2(a[:, 3], b[:, 3]) <= TOL and rel_l2(a[:, 4], b[:, 4]) <= TOL and rel_l2(a[:, 0:3], b[:, 0:3]) < 1e-6
+    # the subsampled export is every stride-th record of the full one, in the device's order
+    full = g.export_gfx(by_id=False)
+    for stride in (1, 3, 8):
+        n_out = g.export_gfx_strided_async_ptr(buf.data_ptr(), sc.n_particles, stride)
+        g.export_gfx_wait()
+        assert n_out == (sc.n_particles + stride - 1) // stride
+        assert np.array_equal(buf.numpy()[:n_out], full[::stride])
 
 
 def test_long_run_statistics_2d(gpu, oracle_lib):
