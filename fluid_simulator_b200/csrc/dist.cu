@@ -625,6 +625,15 @@ int dist_connect(fsim* h, const FsimDistExport* all, int n) {
             d->peer_bnd[side] = side == 0 ? ex.zown1 - 1 : ex.zown0;
         }
     }
+    if (d->peer_in_process) {
+        // Ranks that share a process spin on each other's flags from kernels of ONE CUDA context: with lazy module loading the
+        // first launch of a kernel waits for the device to go idle, which never happens while a peer's kernel spins -> dead wait
+        // (profiles/r1_concurrency_probe_lazy_loading.txt).  Refuse the connection instead of hanging in the first step.
+        const char* e = getenv("CUDA_MODULE_LOADING");
+        if (!(e && (strcmp(e, "EAGER") == 0 || strcmp(e, "eager") == 0)))
+            return fsim_fail(h, FSIM_ERR_INVALID, "slab ranks that share a process need CUDA_MODULE_LOADING=EAGER in the environment before CUDA is "
+                                                   "initialised (one process per GPU has no such requirement)");
+    }
     d->connected = true;
     return FSIM_OK;
 }

@@ -364,9 +364,9 @@ __global__ void __launch_bounds__(256) mg_jacobi4_dot_kernel(Lv L, PcgScalars* _
     // the codes of the next tile are requested before this tile's stencil loads: one exposed round trip per tile instead of two
     auto tile_cell = [&](int t, int64_t& c) -> bool {
         const int bx = t % ntx, by = (t / ntx) % nty, bz = t / (ntx * nty);
-        const int x = (bx * 32 + tx) * 4, y = by * 4 + ty, z = bz * 2 + tz;
+        const int x = (bx * 32 + tx) * 4, y = by * 4 + ty, z = bz * 2 + tz + L.z0;  // (hybrid slab projection: the owned planes only)
         c = ((int64_t)z * L.gy + y) * L.gx + x;
-        return x < L.gx && y < L.gy && z < L.gz;
+        return x < L.gx && y < L.gy && z < L.z1;
     };
     int64_t c = 0;
     ushort4 tc = make_ushort4(0, 0, 0, 0);
@@ -393,7 +393,10 @@ __global__ void __launch_bounds__(256) mg_jacobi4_dot_kernel(Lv L, PcgScalars* _
         st4(xout + cc, xo);
     }
     double out[1];
-    if (grid_reduce<1, 0>(acc, partials, counter, out)) sc->sigma_new = out[0] * sc->scale;
+    if (grid_reduce<1, 0>(acc, partials, counter, out)) {
+        if (sc->dist) sc->loc[0] = out[0] * sc->scale;  // slab mode: finished by the all-rank reduction (AR_DOTZR)
+        else sc->sigma_new = out[0] * sc->scale;
+    }
 }
 
 constexpr int UF_MIN_BLOCKS = 4;  // 64 registers: four resident CTAs instead of three (ncu r2: 35 % active warps at 68 registers)
@@ -455,15 +458,19 @@ __global__ void __launch_bounds__(256, UF_MIN_BLOCKS) mg_update_first4_kernel(Lv
     }
     double out[1];
     if (grid_reduce<0, 1>(acc, partials, counter, out)) {
-        const int it = sc->it;
-        if (bad) {
-            sc->nan_break = 1; sc->done = 1; sc->iterations = it;
+        if (sc->dist) {
+            sc->loc[2] = out[0];  // slab mode: this rank's max |r|; dist_allreduce_kernel takes the decision (pcg_finish_update)
         } else {
-            sc->rmax = out[0];
-            if (out[0] < sc->tol) { sc->done = 1; sc->iterations = it; }                       // :280-281, 292
-            else if (it + 1 >= sc->max_it) { sc->done = 2; sc->iterations = sc->max_it; }       // iteration cap
+            const int it = sc->it;
+            if (bad) {
+                sc->nan_break = 1; sc->done = 1; sc->iterations = it;
+            } else {
+                sc->rmax = out[0];
+                if (out[0] < sc->tol) { sc->done = 1; sc->iterations = it; }                       // :280-281, 292
+                else if (it + 1 >= sc->max_it) { sc->done = 2; sc->iterations = sc->max_it; }       // iteration cap
+            }
+            if (sc->done) { status->done = sc->done; __threadfence_system(); }
         }
-        if (sc->done) { status->done = sc->done; __threadfence_system(); }
     }
 }
 
@@ -1421,14 +1428,17 @@ int mg_build(fsim* h) {
 }
 
 // the fused paths need the float4 level-0 kernels
-bool mg_can_fuse(const fsim* h) { return h->use_mg && !h->dist && !h->hybrid && !h->mg.empty() && h->mg[0]->gx % 4 == 0 && h->g.nc % 4 == 0; }
+// (hybrid slab projection included: the fused kernels then leave their partial reductions in PcgScalars::loc for the all-rank
+// reduction; the slab-local solve of FSIM_SLAB_SOLVER=distributed keeps the separate kernels)
+bool mg_can_fuse(const fsim* h) { return h->use_mg && !h->dist && !h->mg.empty() && h->mg[0]->gx % 4 == 0 && h->g.nc % 4 == 0; }
 
 // CG update (p, r, ||r||_inf, convergence flags) fused with the first smoothing sweep of the cycle that follows
 int mg_update_first(fsim* h) {
     MgLevel* m = h->mg[0];
     const Lv L = view(h, m, 0);
     KScope ks(h, K_UPDATE);
-    { const Tile4 t4 = tile4_make(h->g.gx, 0, h->g.nc / h->g.gx);
+    { const Tile4 t4 = h->hybrid ? tile4_make(h->g.gx, (int64_t)h->g.zown0 * h->g.gy, (int64_t)(h->g.zown1 - h->g.zown0) * h->g.gy)
+                               : tile4_make(h->g.gx, 0, h->g.nc / h->g.gx);
     launch_k(h, mg_update_first4_kernel, tile4_blocks(t4), 256, 0, L, t4, h->scal, h->status_dev, h->p, h->s, h->r, h->q, m->b,
                                                                               m->xa, h->partials, h->red_counter); }
     FSIM_CHECK_LAUNCH(h);

@@ -462,9 +462,13 @@ static int enqueue_iteration(fsim* h, const PcgArgs& a, bool vec, bool use_mg, i
         // update fused with the cycle's first sweep, z.r fused with its last sweep: 2 passes and 2 launches fewer
         int rc = mg_update_first(h);
         if (rc) return rc;
+        rc = AR(AR_UPDATE);  // (slab modes: max |r| over the ranks + the convergence decision)
+        if (rc) return rc;
         rc = mg_apply(h, true, true);
         if (rc) return rc;
         if (a.z32 != h->mg_z32) return fsim_fail(h, FSIM_ERR_INVALID, "multigrid result buffer moved between cycles");
+        rc = AR(AR_DOTZR);
+        if (rc) return rc;
     } else if (use_mg) {
         { KScope ks(h, K_UPDATE); launch_k(h, update_kernel<false>, dim3(nbv), dim3(PT), 0, a); }
         int rc = AR(AR_UPDATE);

@@ -15,20 +15,23 @@ import pytest
 # and wait for theirs; ("read", a): a kernel that reads my ghost planes of a; ("ar",): all-rank reduction; ("gpush",):
 # all-rank push of the coarse right-hand side (waits for everybody's flags); ("write", a): a kernel that rewrites my owned
 # planes of a (it never touches ghost planes: float4 kernels only store active groups)
-ITERATION = [
-    ("push", "s"), ("read", "s"),            # halo of the search direction, SpMV
-    ("ar",),                                  # s.As
-    ("ar",),                                  # update: ||r||_inf (decision)
-    ("write", "xa"),                          # first sweep (no neighbour reads)
+CYCLE_REST = [                                # the multigrid cycle after its first sweep
     ("push", "xa"), ("read", "xa"), ("write", "xb"),   # pre-sweep 2
     ("push", "xb"), ("read", "xb"),           # restriction
     ("gpush",),                               # coarse right-hand side to every rank; coarse levels replicated
     ("read", "xb"), ("write", "xa"),          # prolongation + sweep (reads the same halo of xb)
-    ("push", "xa"), ("read", "xa"), ("write", "xb"),   # last sweep
+    ("push", "xa"), ("read", "xa"), ("write", "xb"),   # last sweep (fused with z.r)
     ("ar",),                                  # z.r
+]
+ITERATION = [
+    ("push", "s"), ("read", "s"),            # halo of the search direction, SpMV
+    ("ar",),                                  # s.As
+    ("write", "xa"),                          # CG update fused with the cycle's first sweep (no neighbour reads)
+    ("ar",),                                  # ||r||_inf (decision)
+] + CYCLE_REST + [
     ("write", "s"),                           # direction update
 ]
-FIRST_CYCLE = ITERATION[4:17]                 # the cycle before the loop (mg_apply ... start_kernel, AR_START)
+FIRST_CYCLE = [("write", "xa")] + CYCLE_REST  # the cycle before the loop (mg_apply ... start_kernel, AR_START)
 PROGRAM_HEAD = FIRST_CYCLE + [("write", "s")]
 
 
