@@ -371,6 +371,8 @@ def main():
     for _ in range(args.warmup):
         sim.step(DT)
     sim.profile_read(reset=True)  # zero the launch counters
+    if slab_mode:
+        sim.dist_wait_stats(reset=True)
 
     barrier()
     n_before = len(sampler.lines)
@@ -387,6 +389,14 @@ def main():
     n_timed = len(sampler.lines) - n_before
     counts = sim.profile_read(reset=True)
     launches = sum(v[2] for v in counts.values())
+    # time this rank's exchange kernels spent spinning on a peer's flag (device clock, inside the timed region): the part of the
+    # exchange cost that is skew between ranks + NVLink flight, as opposed to this rank's own launches and copies
+    exchange_wait = None
+    if slab_mode:
+        ws = sim.dist_wait_stats(reset=True)
+        exchange_wait = {k: {"ms_per_step_mean_over_ranks": round(allsum(1e3 * v[0]) / world / args.steps, 4),
+                             "ms_per_step_max_over_ranks": round(allmax(1e3 * v[0]) / args.steps, 4),
+                             "waits_per_step": round(allsum(v[1]) / world / args.steps, 2)} for k, v in ws.items()}
     info = sim.solve_info()
     nf = int(info.fluid_cells)
     nf_local = nf // world if slab_mode else nf  # the solve reports the all-rank count
@@ -565,7 +575,7 @@ def main():
             "step_hbm_frac": step_frac, "step_algorithmic_bytes": b_step, "b_it": B_IT_SURVEY,
             "step_hbm_frac_impl_b_it": step_frac_impl, "b_it_impl": B_IT,
             "stage_us": {k: v for k, v in zip(["advect", "", "", "p2g", "classify", "project", "extrapolate", "g2p"], list(timings.last_raw_us)) if k},
-            "sort_us": timings.last_sort_us, "kernel_ms": kernel_ms, "kernel_roofline": per_class, "roofline": roofline, "e2e": e2e, "setup_s": t_gen}
+            "sort_us": timings.last_sort_us, "exchange_wait": exchange_wait, "kernel_ms": kernel_ms, "kernel_roofline": per_class, "roofline": roofline, "e2e": e2e, "setup_s": t_gen}
     if not args.no_cpu_baseline and world == 1:  # (the contract asks for it on rank 0 at N = 1 only)
         try:
             r = run_reference(args, args.cpu_grid if args.cpu_grid else 96, args.cpu_steps, args.cpu_warmup)

@@ -38,6 +38,13 @@ class DistExport(C.Structure):
                 ("z_offset", C.c_int32), ("raw", C.c_uint64 * 24), ("offset", C.c_uint64 * 24), ("ipc", (C.c_uint8 * 64) * 24)]
 
 
+WAIT_CLASSES = ("halo", "push", "gpush", "allreduce", "migrate", "gather")  # FSIM_WAIT_* (include/fsim.h)
+
+
+class DistWaitStats(C.Structure):
+    _fields_ = [("wait_ns", C.c_uint64 * 6), ("waits", C.c_uint64 * 6)]
+
+
 class Params(C.Structure):
     _fields_ = [("transfer_type", C.c_int32), ("flip_ratio", C.c_float), ("gravity", C.c_float),
                 ("gravity_enabled", C.c_int32), ("push_apart_enabled", C.c_int32), ("spawning_enabled", C.c_int32),

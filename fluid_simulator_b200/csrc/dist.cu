@@ -25,6 +25,7 @@
 #include <vector>
 
 #include "fsim_internal.h"
+#include "launch.cuh"
 #include "pcg_finish.cuh"
 
 #define DIST_MAX_RANKS 16
@@ -52,6 +53,9 @@ struct DistComm {
     uint32_t n_src;   // particles the next reorder reads: locals + immigrants
     uint32_t pad0;
     unsigned long long timeout_ns;
+    // time spent spinning in wait_ge and the number of waits, by class (FSIM_WAIT_*, fsim.h): the share of an exchange that is
+    // waiting for the peer (its skew + flight time of the flag) rather than this rank's own launch / copy
+    unsigned long long wait_ns[FSIM_WAIT_CLASSES], waits[FSIM_WAIT_CLASSES];
 };
 
 struct DistState {
@@ -117,6 +121,10 @@ __device__ bool wait_ge(const uint32_t* flag, uint32_t ep, DistComm* c, uint32_t
         }
         __nanosleep(64);
     }
+    const uint32_t w = where >> 4;
+    const int cls = w >= 0x30u ? FSIM_WAIT_ALLREDUCE : (w == 8u ? FSIM_WAIT_PUSH : (w == 7u ? FSIM_WAIT_GPUSH : (w == 4u ? FSIM_WAIT_MIGRATE : (w >= 5u ? FSIM_WAIT_GATHER : FSIM_WAIT_HALO))));
+    atomicAdd(&c->wait_ns[cls], now_ns() - t0);
+    atomicAdd(&c->waits[cls], 1ull);
     return true;
 }
 
@@ -191,6 +199,10 @@ struct PushArgs {
 };
 
 __global__ void __launch_bounds__(256) push_kernel(const __grid_constant__ PushArgs a) {
+    // launched as a programmatic dependent (launch.cuh): resident while the producer of the planes drains.  It never triggers
+    // ITS dependents early: a grid parked behind a kernel that spins on another rank's flag could starve that rank of CTA
+    // slots when several ranks share one device
+    pdl_wait();
     if (a.sc && a.sc->done) return;
     DistComm* c = a.comm;
     const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, gsz = (size_t)gridDim.x * blockDim.x;
@@ -254,6 +266,7 @@ struct ArArgs {
 };
 
 __global__ void __launch_bounds__(32) allreduce_kernel(const __grid_constant__ ArArgs a) {
+    pdl_wait();  // (see push_kernel)
     if (a.check_done && a.sc->done) return;
     DistComm* c = a.comm;
     const int lane = threadIdx.x;
@@ -495,6 +508,18 @@ void dist_rank(const fsim* h, int* rank, int* nranks) { if (h->dist) { *rank = h
 
 bool dist_peer_in_process(const fsim* h) { return h->dist && h->dist->peer_in_process; }
 
+int dist_wait_stats(fsim* h, FsimDistWaitStats* out, int reset) {
+    DistState* d = dist_of(h);
+    if (!d) return fsim_fail(h, FSIM_ERR_INVALID, "not a slab handle (fsim_create_slab with nranks > 1)");
+    FSIM_CUDA(h, cudaStreamSynchronize(h->stream));
+    unsigned long long buf[2 * FSIM_WAIT_CLASSES];
+    char* base = (char*)d->comm + offsetof(DistComm, wait_ns);
+    FSIM_CUDA(h, cudaMemcpy(buf, base, sizeof(buf), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < FSIM_WAIT_CLASSES; k++) { out->wait_ns[k] = buf[k]; out->waits[k] = buf[FSIM_WAIT_CLASSES + k]; }
+    if (reset) FSIM_CUDA(h, cudaMemset(base, 0, sizeof(buf)));
+    return FSIM_OK;
+}
+
 int dist_check(fsim* h) { return (h->dist && h->dist->connected) ? check_err(h) : FSIM_OK; }
 
 // the slab geometry of rank r of n over gzg global planes
@@ -717,7 +742,7 @@ int dist_allreduce(fsim* h, int kind, bool in_pcg_loop) {
     for (int r = 0; r < d->nranks; r++) a.all[r] = d->all_comm[r];
     a.err_host = d->err_dev; a.sc = h->scal; a.status = h->status_dev;
     a.rank = d->rank; a.nranks = d->nranks; a.kind = kind; a.check_done = in_pcg_loop ? 1 : 0;
-    { KScope ks(h, K_ALLREDUCE); allreduce_kernel<<<1, 32, 0, h->stream>>>(a); }
+    { KScope ks(h, K_ALLREDUCE); launch_k(h, allreduce_kernel, dim3(1), dim3(32), 0, a); }
     FSIM_CHECK_LAUNCH(h);
     return FSIM_OK;
 }
@@ -800,7 +825,7 @@ static int halo_sym_push(fsim* hs, DistState* d, int arr, size_t es) {
         bytes += c.bytes;
     }
     const int blocks = (int)std::min<size_t>(128, std::max<size_t>(2, bytes / (16 * 256 * 2)));
-    { KScope ks(hs, K_HALO); push_kernel<<<blocks, 256, 0, hs->stream>>>(a); }
+    { KScope ks(hs, K_HALO); launch_k(hs, push_kernel, dim3(blocks), dim3(256), 0, a); }
     FSIM_CHECK_LAUNCH(hs);
     return FSIM_OK;
 }
@@ -873,7 +898,7 @@ int dist_gather_coarse(fsim* hs, bool in_pcg_loop) {
         }
         int pblocks = (int)std::min<size_t>((size_t)hs->sm_count * 2, std::max<size_t>(2, pbytes / (16 * 256 * 4)));
         if (const char* e = getenv("FSIM_DIST_GATHER_BLOCKS")) pblocks = std::max(1, std::min(pblocks, atoi(e)));
-        { KScope ks(hs, K_HALO); push_kernel<<<pblocks, 256, 0, hs->stream>>>(p); }
+        { KScope ks(hs, K_HALO); launch_k(hs, push_kernel, dim3(pblocks), dim3(256), 0, p); }
         FSIM_CHECK_LAUNCH(hs);
         return FSIM_OK;
     }

@@ -492,6 +492,13 @@ int fsim_dist_connect(fsim_t* h, const FsimDistExport* all, int n) {
     return dist_connect(h, all, n);
 }
 
+int fsim_dist_wait_stats(fsim_t* h, FsimDistWaitStats* out, int reset) {
+    BIND(h);
+    if (!out) return fsim_fail(h, FSIM_ERR_INVALID, "null stats");
+    memset(out, 0, sizeof(*out));
+    return dist_wait_stats(h, out, reset);
+}
+
 int fsim_destroy(fsim_t* h) {
     if (!h) return FSIM_OK;
     cudaSetDevice(h->device);

@@ -297,6 +297,7 @@ int dist_export(fsim* h, FsimDistExport* out);
 int dist_connect(fsim* h, const FsimDistExport* all, int n);
 void dist_rank(const fsim* h, int* rank, int* nranks);
 bool dist_peer_in_process(const fsim* h);  // another rank of the group lives in this process
+int dist_wait_stats(fsim* h, FsimDistWaitStats* out, int reset);
 int dist_check(fsim* h);  // FSIM_ERR_COMM once an exchange timed out / a migration list overflowed
 int fsim_ensure_capacity(fsim* h, int64_t n);  // fsim_api.cu
 MigDev* dist_mig_dev(const fsim* h);

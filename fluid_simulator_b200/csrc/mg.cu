@@ -1324,7 +1324,10 @@ int cycle(fsim* h, int l, bool zero_guess, float** result, bool first_done = fal
     // hybrid: every rank restricted the planes it owns; with all ranks' coarse planes gathered, levels >= 1 run replicated
     if (fine && h->hybrid) { int rc = dist_gather_coarse(h, true); if (rc) return rc; }
     float* ec = nullptr;
-    const int visits = (l + 1 >= W_FIRST && l + 1 <= W_LAST && l + 1 < (int)h->mg.size() - 1) ? 2 : 1;
+    // experiment switches (default: the constants above): FSIM_MG_W_FIRST / FSIM_MG_W_LAST move the doubly visited levels
+    static const int w_first = getenv("FSIM_MG_W_FIRST") ? atoi(getenv("FSIM_MG_W_FIRST")) : W_FIRST;
+    static const int w_last = getenv("FSIM_MG_W_LAST") ? atoi(getenv("FSIM_MG_W_LAST")) : W_LAST;
+    const int visits = (l + 1 >= w_first && l + 1 <= w_last && l + 1 < (int)h->mg.size() - 1) ? 2 : 1;
     for (int v = 0; v < visits; v++) {
         int rc = cycle(h, l + 1, v == 0, &ec);
         if (rc) return rc;

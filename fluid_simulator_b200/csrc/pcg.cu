@@ -98,6 +98,10 @@ __global__ void __launch_bounds__(PT) rhs_kernel(PcgArgs a) {
         }
         a.code[c] = (uint16_t)code;
         if (a.code_full) a.code_full[c] = (uint16_t)full;
+        // hybrid slab projection: of the planes of other ranks only the codes are needed (the replicated coarse operators); their
+        // CG vectors are never read -- kernels walk the owned planes, ghost planes are filled by the exchanges (p before the
+        // warm-start residual and before the pressure is applied, s every iteration)
+        if (a.code_full && !owned) goto reduce;
         if (a.code_mg) {
             // the preconditioner is block-local: a link into a ghost plane is cut, either leaving the neighbour on the diagonal
             // (Dirichlet: the exact diagonal block of A) or dropping it from the diagonal as well (Neumann: A = M + a positive
@@ -122,6 +126,7 @@ __global__ void __launch_bounds__(PT) rhs_kernel(PcgArgs a) {
             a.p[c] = (code & CODE_ACTIVE) ? guess : 0.0;
         }
     }
+reduce:
     double out[2];
     if (grid_reduce<2, 0>(acc, a.partials, a.counter, out)) {
         if (a.sc->dist) { a.sc->loc[0] = out[0]; a.sc->loc[3] = out[1]; a.sc->done = 0; }

@@ -52,6 +52,7 @@ def load_library():
         "fsim_get_slab_info": (i32, [vp, P(abi.SlabInfo)]),
         "fsim_dist_export": (i32, [vp, P(abi.DistExport)]),
         "fsim_dist_connect": (i32, [vp, P(abi.DistExport), i32]),
+        "fsim_dist_wait_stats": (i32, [vp, P(abi.DistWaitStats), i32]),
         "fsim_slab_partition": (i32, [i32, i32, i32, P(abi.SlabInfo)]),
         "fsim_upload_particle_ids": (i32, [vp, vp, i64]),
         "fsim_set_params": (i32, [vp, P(abi.Params)]),
@@ -164,6 +165,12 @@ class FluidSim:
     def dist_connect(self, exports):
         arr = (abi.DistExport * len(exports))(*exports)
         self._ck(self.L.fsim_dist_connect(self.h, arr, len(exports)))
+
+    def dist_wait_stats(self, reset=False):
+        """{class: (seconds spent waiting on peers' flags, number of waits)} since connect / the last reset (fsim_dist_wait_stats)"""
+        st = abi.DistWaitStats()
+        self._ck(self.L.fsim_dist_wait_stats(self.h, C.byref(st), 1 if reset else 0))
+        return {k: (st.wait_ns[i] * 1e-9, int(st.waits[i])) for i, k in enumerate(abi.WAIT_CLASSES)}
 
     def upload_particle_ids(self, ids):
         a = np.ascontiguousarray(ids, dtype=np.uint32)

@@ -221,6 +221,15 @@ FSIM_API int fsim_create_slab(const FsimGridDesc* desc, int rank, int nranks, fs
 FSIM_API int fsim_get_slab_info(const fsim_t* h, FsimSlabInfo* out);
 FSIM_API int fsim_dist_export(fsim_t* h, FsimDistExport* out);
 FSIM_API int fsim_dist_connect(fsim_t* h, const FsimDistExport* all, int n);
+/* Diagnostics of the exchange kernels (csrc/dist.cu): device time rank-local threads spent spinning on a peer's flag, and the
+ * number of such waits, per class, accumulated since the handle was connected (or since the last call with reset != 0).
+ * A profiler cannot serialise kernels that wait for another process, so this is the evidence for where an exchange's time goes. */
+enum { FSIM_WAIT_HALO = 0, FSIM_WAIT_PUSH = 1, FSIM_WAIT_GPUSH = 2, FSIM_WAIT_ALLREDUCE = 3, FSIM_WAIT_MIGRATE = 4, FSIM_WAIT_GATHER = 5, FSIM_WAIT_CLASSES = 6 };
+typedef struct FsimDistWaitStats {
+    uint64_t wait_ns[FSIM_WAIT_CLASSES];
+    uint64_t waits[FSIM_WAIT_CLASSES];
+} FsimDistWaitStats;
+FSIM_API int fsim_dist_wait_stats(fsim_t* h, FsimDistWaitStats* out, int reset);
 /* pure host arithmetic of the partition (usable without a GPU): the planes rank `rank` of `nranks` owns and stores */
 FSIM_API int fsim_slab_partition(int global_gz, int rank, int nranks, FsimSlabInfo* out);
 

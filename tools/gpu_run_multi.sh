@@ -26,6 +26,7 @@ try:
     print("N=${N}", round(d["ms_per_step"], 3), "ms/step", d["config"]["pcg_iterations_mean"], "its; checks", d["checks"]["ok"], d["checks"].get("slab_verify"))
     print("   e2e", d["e2e"]["value"] if d.get("e2e") else None, d["e2e"].get("numa") if d.get("e2e") else None)
     print("   ", {k: v["ms_per_step"] for k, v in d["kernel_ms"].items()})
+    print("   exchange_wait", d.get("exchange_wait"))
 except Exception as e:
     print("bench failed", e)
 PY
