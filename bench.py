@@ -396,7 +396,8 @@ def main():
         ws = sim.dist_wait_stats(reset=True)
         exchange_wait = {k: {"ms_per_step_mean_over_ranks": round(allsum(1e3 * v[0]) / world / args.steps, 4),
                              "ms_per_step_max_over_ranks": round(allmax(1e3 * v[0]) / args.steps, 4),
-                             "waits_per_step": round(allsum(v[1]) / world / args.steps, 2)} for k, v in ws.items()}
+                             "kernels_per_step": round(allsum(v[1]) / world / args.steps, 2),
+                             "in_kernel_ms_per_step_mean_over_ranks": round(allsum(1e3 * v[2]) / world / args.steps, 4)} for k, v in ws.items()}
     info = sim.solve_info()
     nf = int(info.fluid_cells)
     nf_local = nf // world if slab_mode else nf  # the solve reports the all-rank count

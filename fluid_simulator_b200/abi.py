@@ -38,11 +38,11 @@ class DistExport(C.Structure):
                 ("z_offset", C.c_int32), ("raw", C.c_uint64 * 24), ("offset", C.c_uint64 * 24), ("ipc", (C.c_uint8 * 64) * 24)]
 
 
-WAIT_CLASSES = ("halo", "push", "gpush", "allreduce", "migrate", "gather")  # FSIM_WAIT_* (include/fsim.h)
+WAIT_CLASSES = ("halo", "push", "gpush", "allreduce", "migrate", "gather", "fused")  # FSIM_WAIT_* (include/fsim.h)
 
 
 class DistWaitStats(C.Structure):
-    _fields_ = [("wait_ns", C.c_uint64 * 6), ("waits", C.c_uint64 * 6)]
+    _fields_ = [("wait_ns", C.c_uint64 * 7), ("waits", C.c_uint64 * 7), ("kernel_ns", C.c_uint64 * 7)]
 
 
 class Params(C.Structure):

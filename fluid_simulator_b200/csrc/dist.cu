@@ -25,6 +25,7 @@
 #include <vector>
 
 #include "fsim_internal.h"
+#include "fexch.cuh"
 #include "launch.cuh"
 #include "pcg_finish.cuh"
 
@@ -47,7 +48,9 @@ struct DistComm {
     uint32_t arrive_all[DIST_MAX_RANKS], done_all[DIST_MAX_RANKS];  // all-rank handshake of the solver-input gather
     uint32_t push_flag[2];                 // "your ghost plane holds my boundary plane of exchange #epoch" (push halos of the PCG loop)
     uint32_t gpush_flag[DIST_MAX_RANKS];   // the same for the all-rank push of the coarse right-hand side
+    uint32_t fx_cnt[3][2];                 // fused exchanges (fexch.cuh): arrivals [array: s, xa, xb][from the lower / upper neighbour]
     // local
+    uint32_t fx_exp[3][2];                 // ... and how many this rank expects by now
     uint32_t halo_epoch, ar_epoch, mig_ep, blocks_done, mig_blocks_done, gather_epoch, gather_blocks_done, push_epoch, push_blocks_done, gpush_epoch, gpush_blocks_done, pad1;
     uint32_t error;   // 1 wait timed out, 2 emigrant list full, 3 immigrant outside the owned planes
     uint32_t n_src;   // particles the next reorder reads: locals + immigrants
@@ -55,7 +58,7 @@ struct DistComm {
     unsigned long long timeout_ns;
     // time spent spinning in wait_ge and the number of waits, by class (FSIM_WAIT_*, fsim.h): the share of an exchange that is
     // waiting for the peer (its skew + flight time of the flag) rather than this rank's own launch / copy
-    unsigned long long wait_ns[FSIM_WAIT_CLASSES], waits[FSIM_WAIT_CLASSES];
+    unsigned long long wait_ns[FSIM_WAIT_CLASSES], waits[FSIM_WAIT_CLASSES], kern_ns[FSIM_WAIT_CLASSES];
 };
 
 struct DistState {
@@ -121,11 +124,14 @@ __device__ bool wait_ge(const uint32_t* flag, uint32_t ep, DistComm* c, uint32_t
         }
         __nanosleep(64);
     }
-    const uint32_t w = where >> 4;
-    const int cls = w >= 0x30u ? FSIM_WAIT_ALLREDUCE : (w == 8u ? FSIM_WAIT_PUSH : (w == 7u ? FSIM_WAIT_GPUSH : (w == 4u ? FSIM_WAIT_MIGRATE : (w >= 5u ? FSIM_WAIT_GATHER : FSIM_WAIT_HALO))));
+    return true;
+}
+
+// elapsed waiting time of ONE designated thread per kernel (block 0 / the last block; waits of the other blocks and of the
+// other lanes run concurrently with it), so that the sums are time on this rank's stream
+__device__ __forceinline__ void wait_account(DistComm* c, int cls, unsigned long long t0) {
     atomicAdd(&c->wait_ns[cls], now_ns() - t0);
     atomicAdd(&c->waits[cls], 1ull);
-    return true;
 }
 
 struct HaloCopy { void* dst; const void* src; uint32_t bytes; int side; };
@@ -150,8 +156,10 @@ __global__ void __launch_bounds__(256) halo_kernel(const __grid_constant__ HaloA
             for (int side = 0; side < 2; side++)
                 if (a.peer[side]) st_release_sys(&a.peer[side]->arrive[1 - side], ep);
         }
+        const unsigned long long t0 = now_ns();
         for (int side = 0; side < 2; side++)
             if (a.peer[side]) wait_ge(&c->arrive[side], ep, c, a.err_host, 0x10u + side);
+        if (blockIdx.x == 0) wait_account(c, FSIM_WAIT_HALO, t0);
     }
     __syncthreads();
     const uint32_t ep = ep_s;
@@ -175,8 +183,10 @@ __global__ void __launch_bounds__(256) halo_kernel(const __grid_constant__ HaloA
             __threadfence_system();
             for (int side = 0; side < 2; side++)
                 if (a.peer[side]) st_release_sys(&a.peer[side]->done[1 - side], ep);
+            const unsigned long long t0 = now_ns();
             for (int side = 0; side < 2; side++)
                 if (a.peer[side]) wait_ge(&c->done[side], ep, c, a.err_host, 0x20u + side);
+            wait_account(c, FSIM_WAIT_HALO, t0);
             c->halo_epoch = ep;
             __threadfence();
         }
@@ -204,6 +214,7 @@ __global__ void __launch_bounds__(256) push_kernel(const __grid_constant__ PushA
     // slots when several ranks share one device
     pdl_wait();
     if (a.sc && a.sc->done) return;
+    const unsigned long long t_in = now_ns();
     DistComm* c = a.comm;
     const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, gsz = (size_t)gridDim.x * blockDim.x;
     for (int k = 0; k < a.ncopy; k++) {
@@ -224,6 +235,7 @@ __global__ void __launch_bounds__(256) push_kernel(const __grid_constant__ PushA
     __syncthreads();
     if (!last_s) return;
     const uint32_t ep = *(volatile uint32_t*)my_epoch + 1u;
+    const unsigned long long t0 = now_ns();
     if (threadIdx.x < a.npeer && a.peer[threadIdx.x] && !(a.all_ranks && (int)threadIdx.x == a.self)) {
         const int r = threadIdx.x;
         __threadfence_system();
@@ -236,6 +248,10 @@ __global__ void __launch_bounds__(256) push_kernel(const __grid_constant__ PushA
         }
     }
     __syncthreads();
+    if (threadIdx.x == 0) {
+        wait_account(c, a.all_ranks ? FSIM_WAIT_GPUSH : FSIM_WAIT_PUSH, t0);
+        atomicAdd(&c->kern_ns[a.all_ranks ? FSIM_WAIT_GPUSH : FSIM_WAIT_PUSH], now_ns() - t_in);  // entry of the last block -> exit
+    }
     if (threadIdx.x == 0) { *my_count = 0; *my_epoch = ep; __threadfence(); }
 }
 
@@ -268,11 +284,13 @@ struct ArArgs {
 __global__ void __launch_bounds__(32) allreduce_kernel(const __grid_constant__ ArArgs a) {
     pdl_wait();  // (see push_kernel)
     if (a.check_done && a.sc->done) return;
+    const unsigned long long t_in = now_ns();
     DistComm* c = a.comm;
     const int lane = threadIdx.x;
     const uint32_t ep = *(volatile uint32_t*)&c->ar_epoch + 1u;
     const int par = ep & 1u;
     __shared__ double sv[DIST_MAX_RANKS][4];
+    const unsigned long long t0 = now_ns();
     if (lane < a.nranks) {
         DistSlot* s = &a.all[lane]->slot[par][a.rank];
         volatile double* v = s->v;
@@ -286,6 +304,7 @@ __global__ void __launch_bounds__(32) allreduce_kernel(const __grid_constant__ A
     }
     __syncwarp();
     if (lane == 0) {
+        wait_account(c, FSIM_WAIT_ALLREDUCE, t0);  // (slot stores to every rank + the wait for theirs)
         double s0 = 0.0, s1 = 0.0, mx = 0.0, s3 = 0.0;
         for (int r = 0; r < a.nranks; r++) { s0 += sv[r][0]; s1 += sv[r][1]; mx = fmax(mx, sv[r][2]); s3 += sv[r][3]; }
         PcgScalars* sc = a.sc;
@@ -301,6 +320,7 @@ __global__ void __launch_bounds__(32) allreduce_kernel(const __grid_constant__ A
         sc->loc[0] = sc->loc[1] = sc->loc[2] = sc->loc[3] = 0.0;
         c->ar_epoch = ep;
         __threadfence();
+        atomicAdd(&c->kern_ns[FSIM_WAIT_ALLREDUCE], now_ns() - t_in);
     }
 }
 
@@ -367,8 +387,10 @@ __global__ void __launch_bounds__(256) mig_recv_kernel(const __grid_constant__ M
     DistComm* c = a.comm;
     if (threadIdx.x == 0) {
         const uint32_t ep = c->mig_ep;  // advanced by this step's mig_send_kernel
+        const unsigned long long t0 = now_ns();
         for (int side = 0; side < 2; side++)
             if (a.has[side]) wait_ge(&c->mig_epoch[side], ep, c, a.err_host, 0x40u + side);
+        if (blockIdx.x == 0) wait_account(c, FSIM_WAIT_MIGRATE, t0);
     }
     __syncthreads();
     const uint32_t n0 = a.has[0] ? *(volatile uint32_t*)&c->mig_count[0] : 0u, n1 = a.has[1] ? *(volatile uint32_t*)&c->mig_count[1] : 0u;
@@ -426,12 +448,14 @@ __global__ void __launch_bounds__(256) gather_kernel(const __grid_constant__ Gat
     if (threadIdx.x == 0) ep_s = *(volatile uint32_t*)&c->gather_epoch + 1u;
     __syncthreads();
     const uint32_t ep = ep_s;
+    const unsigned long long t0 = now_ns();
     if (threadIdx.x < a.nranks && threadIdx.x != a.rank) {
         const int r = threadIdx.x;
         if (blockIdx.x == 0) { __threadfence_system(); st_release_sys(&a.all[r]->arrive_all[a.rank], ep); }
         wait_ge(&c->arrive_all[r], ep, c, a.err_host, 0x50u + r);
     }
     __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x == 0) wait_account(c, FSIM_WAIT_GATHER, t0);
     const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, gsz = (size_t)gridDim.x * blockDim.x;
     for (int k = 0; k < a.ncopy; k++) {
         const GatherCopy& cp = a.cp[k];
@@ -457,6 +481,7 @@ __global__ void __launch_bounds__(256) gather_kernel(const __grid_constant__ Gat
     }
     __syncthreads();
     if (last_s) {  // last block: nobody may overwrite its planes before every rank has read them
+        const unsigned long long t0_done = now_ns();
         if (threadIdx.x < a.nranks && threadIdx.x != a.rank) {
             const int r = threadIdx.x;
             __threadfence_system();
@@ -464,7 +489,7 @@ __global__ void __launch_bounds__(256) gather_kernel(const __grid_constant__ Gat
             wait_ge(&c->done_all[r], ep, c, a.err_host, 0x60u + r);
         }
         __syncthreads();
-        if (threadIdx.x == 0) { c->gather_blocks_done = 0; c->gather_epoch = ep; __threadfence(); }
+        if (threadIdx.x == 0) { wait_account(c, FSIM_WAIT_GATHER, t0_done); c->gather_blocks_done = 0; c->gather_epoch = ep; __threadfence(); }
     }
 }
 
@@ -512,10 +537,10 @@ int dist_wait_stats(fsim* h, FsimDistWaitStats* out, int reset) {
     DistState* d = dist_of(h);
     if (!d) return fsim_fail(h, FSIM_ERR_INVALID, "not a slab handle (fsim_create_slab with nranks > 1)");
     FSIM_CUDA(h, cudaStreamSynchronize(h->stream));
-    unsigned long long buf[2 * FSIM_WAIT_CLASSES];
+    unsigned long long buf[3 * FSIM_WAIT_CLASSES];
     char* base = (char*)d->comm + offsetof(DistComm, wait_ns);
     FSIM_CUDA(h, cudaMemcpy(buf, base, sizeof(buf), cudaMemcpyDeviceToHost));
-    for (int k = 0; k < FSIM_WAIT_CLASSES; k++) { out->wait_ns[k] = buf[k]; out->waits[k] = buf[FSIM_WAIT_CLASSES + k]; }
+    for (int k = 0; k < FSIM_WAIT_CLASSES; k++) { out->wait_ns[k] = buf[k]; out->waits[k] = buf[FSIM_WAIT_CLASSES + k]; out->kernel_ns[k] = buf[2 * FSIM_WAIT_CLASSES + k]; }
     if (reset) FSIM_CUDA(h, cudaMemset(base, 0, sizeof(buf)));
     return FSIM_OK;
 }
@@ -828,6 +853,47 @@ static int halo_sym_push(fsim* hs, DistState* d, int arr, size_t es) {
     { KScope ks(hs, K_HALO); launch_k(hs, push_kernel, dim3(blocks), dim3(256), 0, a); }
     FSIM_CHECK_LAUNCH(hs);
     return FSIM_OK;
+}
+
+// fused form of the in-loop exchange of one level-0 array (fexch.cuh): arguments for the kernels that write it (FxPush) and
+// for those that read its ghost planes (FxWait).  false: not available (then both are inert and dist_halo_sym does the job)
+static bool fused_enabled() { const char* e = getenv("FSIM_SLAB_FUSED"); return !(e && e[0] == '0'); }
+
+bool dist_fx(fsim* hs, int which, const void* ptr, FxPush* p, FxWait* w) {
+    memset(p, 0, sizeof(*p));
+    memset(w, 0, sizeof(*w));
+    DistState* d = dist_of(hs);
+    if (!d || !d->connected || !hs->hybrid || !push_enabled() || !fused_enabled()) return false;
+    if (hs->g.gx % 4 != 0 || hs->g.gy % 32 != 0 || (d->own_hi - d->own_lo) % 2 != 0 || d->own_hi - d->own_lo < 2) return false;
+    int arr = -1, ix = -1;
+    if (which == SYM_S) { arr = ARR_HS_S; ix = 0; }
+    if (which == SYM_X) {
+        const void* xa = (char*)d->local_arr[ARR_HS_XA] + d->local_off[ARR_HS_XA];
+        const void* xb = (char*)d->local_arr[ARR_HS_XB] + d->local_off[ARR_HS_XB];
+        if (ptr == xa) { arr = ARR_HS_XA; ix = 1; }
+        if (ptr == xb) { arr = ARR_HS_XB; ix = 2; }
+    }
+    if (arr < 0) return false;
+    for (int side = 0; side < 2; side++)
+        if (d->peer_comm[side] && !d->peer_arr[side][arr]) return false;
+    p->my_exp = &d->comm->fx_exp[ix][0];
+    w->cnt = &d->comm->fx_cnt[ix][0];
+    w->exp = &d->comm->fx_exp[ix][0];
+    w->error = &d->comm->error;
+    w->err_host = d->err_dev;
+    w->stat = &d->comm->wait_ns[FSIM_WAIT_FUSED];
+    w->stat_n = &d->comm->waits[FSIM_WAIT_FUSED];
+    const char* e = getenv("FSIM_DIST_TIMEOUT_MS");
+    w->timeout_ns = (unsigned long long)(e ? atoll(e) : 20000) * 1000000ull;
+    p->zb[0] = w->zb[0] = d->own_lo;
+    p->zb[1] = w->zb[1] = d->own_hi - 1;
+    for (int side = 0; side < 2; side++) {
+        if (!d->peer_comm[side]) continue;
+        p->peer[side] = (float*)d->peer_arr[side][arr];
+        p->peer_cnt[side] = &d->peer_comm[side]->fx_cnt[ix][1 - side];  // I am the upper neighbour of my lower neighbour
+        w->has[side] = 1;
+    }
+    return true;
 }
 
 int dist_halo_sym(fsim* hs, int which, const void* ptr, bool in_pcg_loop) {

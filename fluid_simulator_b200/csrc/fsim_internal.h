@@ -145,6 +145,7 @@ struct fsim {
     bool use_mg;                           // multigrid (default) or diagonal preconditioner (FSIM_PRECOND=jacobi)
     double mg_inv_scale;                   // 1 / (dt / (rho h^2)): the hierarchy works on the integer-weight Laplacian
     std::vector<MgLevel*> mg;
+    bool fx_on;                            // hybrid slab projection: in-loop exchanges fused into the solver kernels (fexch.cuh)
     int mg_tail_first;                     // levels >= this run inside the single-cluster tail kernel
     int mg_tail_cluster;                   // CTAs of that cluster (0: not probed yet)
     int mg_tail2;                          // tail kernel with block-local coarse levels (mg_tail2_kernel): -1 not probed, 0 off, 1 on (opt-in: FSIM_MG_TAIL2=1; measured slower, see mg.cu)
@@ -298,6 +299,9 @@ int dist_connect(fsim* h, const FsimDistExport* all, int n);
 void dist_rank(const fsim* h, int* rank, int* nranks);
 bool dist_peer_in_process(const fsim* h);  // another rank of the group lives in this process
 int dist_wait_stats(fsim* h, FsimDistWaitStats* out, int reset);
+struct FxPush;
+struct FxWait;
+bool dist_fx(fsim* hs, int which, const void* ptr, FxPush* p, FxWait* w);  // fused in-loop exchange of a level-0 array (fexch.cuh)
 int dist_check(fsim* h);  // FSIM_ERR_COMM once an exchange timed out / a migration list overflowed
 int fsim_ensure_capacity(fsim* h, int64_t n);  // fsim_api.cu
 MigDev* dist_mig_dev(const fsim* h);

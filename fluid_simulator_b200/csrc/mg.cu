@@ -22,6 +22,7 @@
 
 #include "fsim_internal.h"
 #include "reduce.cuh"
+#include "fexch.cuh"
 #include "launch.cuh"
 #include "tile4.cuh"
 
@@ -282,15 +283,41 @@ __device__ __forceinline__ float off4(const Stencil4& s, int i, unsigned cd) {
     if (cd & 32u) o += s.zp.v[i];
     return o;
 }
-__device__ __forceinline__ bool group_of(const Lv& L, int64_t& c, unsigned cd[4]) {
+// z index of the CTA: blockIdx.z rotated by zrot (fused slab exchanges visit the boundary planes first or last)
+__device__ __forceinline__ int zblock_of(int zrot) {
+    int zb = blockIdx.z + zrot;
+    if (zb >= (int)gridDim.z) zb -= gridDim.z;
+    return zb;
+}
+__device__ __forceinline__ bool group_of(const Lv& L, int64_t& c, unsigned cd[4], int zblk) {
     const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y, z = blockIdx.z * blockDim.z + threadIdx.z + L.z0;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y, z = zblk * blockDim.z + threadIdx.z + L.z0;
     if (x >= L.gx || y >= L.gy || z >= L.z1) return false;
     c = ((int64_t)z * L.gy + y) * L.gx + x;
     const ushort4 t = *reinterpret_cast<const ushort4*>(L.code + c);
     cd[0] = t.x; cd[1] = t.y; cd[2] = t.z; cd[3] = t.w;
     return true;
 }
+// fused exchanges in the kernels whose CTAs cover `planes` planes from plane zlo on (fexch.cuh).  All threads of the CTA call these.
+__device__ __forceinline__ void fx_wait_planes(const FxWait& w, int zlo, int planes) {
+    if (!(w.has[0] | w.has[1])) return;
+#pragma unroll
+    for (int side = 0; side < 2; side++)
+        if (w.has[side] && w.zb[side] >= zlo && w.zb[side] < zlo + planes) fx_wait(w, side);
+}
+__device__ __forceinline__ void fx_signal_planes(const FxPush& f, int zlo, int planes) {
+    if (!(f.peer[0] || f.peer[1])) return;
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0 && threadIdx.y == 0 && threadIdx.z == 0) fx_expect(f);
+#pragma unroll
+    for (int side = 0; side < 2; side++)
+        if (f.peer[side] && f.zb[side] >= zlo && f.zb[side] < zlo + planes) fx_signal(f, side);
+}
+// the neighbour's array when plane z is one of my boundary planes and a neighbour reads it
+__device__ __forceinline__ float* fx_peer_of(const FxPush& f, int z) {
+    const int side = fx_side(f.zb, z);
+    return side >= 0 ? f.peer[side] : nullptr;
+}
+
 __device__ __forceinline__ Stencil4 load_stencil4(const Lv& L, const float* __restrict__ x, int64_t c, const unsigned cd[4]) {
     Stencil4 s;
     const unsigned any = cd[0] | cd[1] | cd[2] | cd[3];
@@ -305,15 +332,15 @@ __device__ __forceinline__ Stencil4 load_stencil4(const Lv& L, const float* __re
 }
 
 __global__ void __launch_bounds__(256) mg_first4_kernel(Lv L, const double* __restrict__ r64, const PcgScalars* __restrict__ sc,
-                                                        float* __restrict__ b, float* __restrict__ xout) {
+                                                        float* __restrict__ b, float* __restrict__ xout, FxPush fp, int zrot) {
     pdl_wait();
     pdl_trigger();
     int64_t c; unsigned cd[4];
     if (sc->done) return;
     const double inv_scale = sc->inv_scale;
-    if (!group_of(L, c, cd)) return;
-    F4 bb = zero4(), xo = zero4();
-    if ((cd[0] | cd[1] | cd[2] | cd[3]) & CODE_ACTIVE) {
+    const int zblk = zblock_of(zrot);
+    if (group_of(L, c, cd, zblk) && ((cd[0] | cd[1] | cd[2] | cd[3]) & CODE_ACTIVE)) {
+        F4 bb = zero4(), xo = zero4();
         const double2 r0 = *reinterpret_cast<const double2*>(r64 + c), r1 = *reinterpret_cast<const double2*>(r64 + c + 2);
         const double rr[4] = {r0.x, r0.y, r1.x, r1.y};
 #pragma unroll
@@ -325,16 +352,20 @@ __global__ void __launch_bounds__(256) mg_first4_kernel(Lv L, const double* __re
             }
         st4(b + c, bb);     // groups without WATER cells are never read (every consumer checks the code) => not written
         st4(xout + c, xo);
+        if (float* peer = fx_peer_of(fp, zblk * 2 + (int)threadIdx.z + L.z0)) st4(peer + c, xo);
     }
+    fx_signal_planes(fp, zblk * 2 + L.z0, 2);
 }
 
 __global__ void __launch_bounds__(256) mg_jacobi4_kernel(Lv L, PcgScalars* __restrict__ sc, const float* __restrict__ b, const float* __restrict__ xin,
-                                                         float* __restrict__ xout, float om) {
+                                                         float* __restrict__ xout, float om, FxWait fw, FxPush fp, int zrot) {
     pdl_wait();
     pdl_trigger();
     if (sc->done) return;
+    const int zblk = zblock_of(zrot);
+    fx_wait_planes(fw, zblk * 2 + L.z0, 2);  // (hybrid slab projection: the neighbours' boundary planes of xin)
     int64_t c; unsigned cd[4];
-    if (group_of(L, c, cd) && ((cd[0] | cd[1] | cd[2] | cd[3]) & CODE_ACTIVE)) {
+    if (group_of(L, c, cd, zblk) && ((cd[0] | cd[1] | cd[2] | cd[3]) & CODE_ACTIVE)) {
         F4 xo = zero4();
         const Stencil4 s = load_stencil4(L, xin, c, cd);
         const F4 bb = ld4(b + c);
@@ -346,7 +377,9 @@ __global__ void __launch_bounds__(256) mg_jacobi4_kernel(Lv L, PcgScalars* __res
                 xo.v[i] = d > 0.f ? xi + om * (bb.v[i] - (d * xi - off4(s, i, cd[i]))) / d : 0.f;
             }
         st4(xout + c, xo);
+        if (float* peer = fx_peer_of(fp, zblk * 2 + (int)threadIdx.z + L.z0)) st4(peer + c, xo);
     }
+    fx_signal_planes(fp, zblk * 2 + L.z0, 2);
 }
 
 // The last sweep of the cycle also accumulates sigma' = z.r = scale * z.b (fp64 accumulation; saves a pass over z and r.
@@ -355,14 +388,17 @@ __global__ void __launch_bounds__(256) mg_jacobi4_kernel(Lv L, PcgScalars* __res
 // partials instead of 16 K -- with one CTA per tile its fence + arrival atomic per CTA cost 30 us on top of the 37 us sweep.
 __global__ void __launch_bounds__(256) mg_jacobi4_dot_kernel(Lv L, PcgScalars* __restrict__ sc, const float* __restrict__ b, const float* __restrict__ xin,
                                                              float* __restrict__ xout, double* partials, unsigned int* counter, float om,
-                                                             int ntx, int nty, int ntiles) {
+                                                             int ntx, int nty, int ntiles, FxWait fw, int trot) {
     pdl_wait();
     pdl_trigger();
     if (sc->done) return;
     double acc[1] = {0.0};
     const int tx = threadIdx.x & 31, ty = (threadIdx.x >> 5) & 3, tz = threadIdx.x >> 7;
+    // tile index -> tile, rotated by trot tiles (fused slab exchanges: the layers next to the ghost planes come last)
+    auto rot = [&](int t) -> int { const int u = t + trot; return u >= ntiles ? u - ntiles : u; };
     // the codes of the next tile are requested before this tile's stencil loads: one exposed round trip per tile instead of two
     auto tile_cell = [&](int t, int64_t& c) -> bool {
+        t = rot(t);
         const int bx = t % ntx, by = (t / ntx) % nty, bz = t / (ntx * nty);
         const int x = (bx * 32 + tx) * 4, y = by * 4 + ty, z = bz * 2 + tz + L.z0;  // (hybrid slab projection: the owned planes only)
         c = ((int64_t)z * L.gy + y) * L.gx + x;
@@ -378,6 +414,7 @@ __global__ void __launch_bounds__(256) mg_jacobi4_dot_kernel(Lv L, PcgScalars* _
         const unsigned cd[4] = {tc.x, tc.y, tc.z, tc.w};
         const int64_t cc = c;
         tc = tcn; c = cn;
+        if (fw.has[0] | fw.has[1]) fx_wait_planes(fw, (rot(t) / (ntx * nty)) * 2 + L.z0, 2);  // (CTA-uniform; a satisfied wait returns at once)
         if (!((cd[0] | cd[1] | cd[2] | cd[3]) & CODE_ACTIVE)) continue;  // (also every out-of-grid thread: its codes stay 0)
         F4 xo = zero4();
         const Stencil4 s = load_stencil4(L, xin, cc, cd);
@@ -405,10 +442,18 @@ constexpr int UF_MIN_BLOCKS = 4;  // 64 registers: four resident CTAs instead of
 __global__ void __launch_bounds__(256, UF_MIN_BLOCKS) mg_update_first4_kernel(Lv L, Tile4 t4, PcgScalars* sc, PcgHostStatus* status, double* __restrict__ p,
                                                                const float* __restrict__ sv, double* __restrict__ r,
                                                                const double* __restrict__ q, float* __restrict__ b, float* __restrict__ xout,
-                                                               double* partials, unsigned int* counter) {
+                                                               double* partials, unsigned int* counter, FxPush fp) {
     pdl_wait();
     pdl_trigger();
     if (sc->done) return;
+    // fused exchange of the first iterate: a CTA on a boundary plane stores its groups into the neighbour's ghost plane too
+    float* xpeer = nullptr;
+    int side = -1;
+    if (fp.peer[0] || fp.peer[1]) {
+        side = fx_side(fp.zb, tile4_plane(t4));
+        if (side >= 0) xpeer = fp.peer[side];
+        if (blockIdx.x == 0 && threadIdx.x == 0) fx_expect(fp);
+    }
     const double alpha = sc->sigma / sc->sq;
     const bool bad = alpha != alpha;  // NaN => the reference breaks before touching p (bridsonSolverGrid.cpp:271-272)
     const double inv_scale = sc->inv_scale;
@@ -454,8 +499,10 @@ __global__ void __launch_bounds__(256, UF_MIN_BLOCKS) mg_update_first4_kernel(Lv
             }
             st4(b + c, bb);
             st4(xout + c, xo);
+            if (xpeer) st4(xpeer + c, xo);
         }
     }
+    if (xpeer) fx_signal(fp, side);
     double out[1];
     if (grid_reduce<0, 1>(acc, partials, counter, out)) {
         if (sc->dist) {
@@ -476,12 +523,14 @@ __global__ void __launch_bounds__(256, UF_MIN_BLOCKS) mg_update_first4_kernel(Lv
 
 // one thread = two coarse cells in x = a 4x2x2 block of fine cells
 __global__ void __launch_bounds__(256) mg_restrict4_kernel(Lv L, Lv C, const PcgScalars* __restrict__ sc, const float* __restrict__ b, const float* __restrict__ xf,
-                                                           float* __restrict__ bc, int cz0, int cz1) {
+                                                           float* __restrict__ bc, int cz0, int cz1, FxWait fw, int zrot) {
     pdl_wait();
     pdl_trigger();
     if (sc->done) return;
+    const int zblk = zblock_of(zrot);
+    fx_wait_planes(fw, 2 * (zblk * 2 + cz0), 4);  // the CTA's two coarse planes have their children in four fine planes
     const int X = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
-    const int Y = blockIdx.y * blockDim.y + threadIdx.y, Z = blockIdx.z * blockDim.z + threadIdx.z + cz0;
+    const int Y = blockIdx.y * blockDim.y + threadIdx.y, Z = zblk * blockDim.z + threadIdx.z + cz0;
     if (X >= C.gx || Y >= C.gy || Z >= C.gz) return;
     if (Z >= cz1) return;  // hybrid: only the coarse planes [cz0, cz1) whose children this rank owns; the others are written by their owners (pushed over NVLink)
     float s0 = 0.f, s1 = 0.f;
@@ -509,17 +558,18 @@ __global__ void __launch_bounds__(256) mg_restrict4_kernel(Lv L, Lv C, const Pcg
 }
 
 __global__ void __launch_bounds__(256) mg_prolong_jacobi4_kernel(Lv L, Lv C, const PcgScalars* __restrict__ sc, const float* __restrict__ b, const float* __restrict__ xin,
-                                                                 const float* __restrict__ ec, float* __restrict__ xout) {
+                                                                 const float* __restrict__ ec, float* __restrict__ xout, FxPush fp, int zrot) {
     pdl_wait();
     pdl_trigger();
     if (sc->done) return;
     int64_t c; unsigned cd[4];
-    if (!group_of(L, c, cd)) return;
+    const int zblk = zblock_of(zrot);
+    const bool in = group_of(L, c, cd, zblk);
     F4 xo = zero4();
-    const unsigned any = cd[0] | cd[1] | cd[2] | cd[3];
+    const unsigned any = in ? (cd[0] | cd[1] | cd[2] | cd[3]) : 0u;
     if (any & CODE_ACTIVE) {
         const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-        const int y = blockIdx.y * blockDim.y + threadIdx.y, z = blockIdx.z * blockDim.z + threadIdx.z + L.z0;
+        const int y = blockIdx.y * blockDim.y + threadIdx.y, z = zblk * blockDim.z + threadIdx.z + L.z0;
         Stencil4 s = load_stencil4(L, xin, c, cd);
         // coarse corrections: the group's parents are (X0, X0+1) in row (y>>1, z>>1); neighbours use their own rows
         const int X0 = x >> 1;
@@ -545,7 +595,9 @@ __global__ void __launch_bounds__(256) mg_prolong_jacobi4_kernel(Lv L, Lv C, con
                 xo.v[i] = d > 0.f ? xi + OM_B * (bb.v[i] - (d * xi - off4(s, i, cd[i]))) / d : 0.f;
             }
         st4(xout + c, xo);
+        if (float* peer = fx_peer_of(fp, z)) st4(peer + c, xo);
     }
+    fx_signal_planes(fp, zblk * 2 + L.z0, 2);
 }
 
 // Galerkin operator of level 1 from the stencil codes: face weight = # WATER-WATER fine connections across the coarse
@@ -1284,6 +1336,24 @@ int cycle(fsim* h, int l, bool zero_guess, float** result, bool first_done = fal
     MgLevel* mc = h->mg[l + 1];
     const Lv C = view(h, mc, l + 1);
     float *cur = m->xa, *oth = m->xb;
+    // hybrid slab projection with fused exchanges (fexch.cuh): the kernel that writes an iterate stores its boundary planes into
+    // the neighbours' ghost planes, the kernel that reads it waits for theirs -- no exchange kernels between the sweeps
+    const bool fx = fine && h->hybrid && h->fx_on && v4;
+    const int zrot_first = fx ? (int)grd4.z - 1 : 0;  // producers: the CTAs of the top boundary plane first, then the bottom one, ...
+    FxPush no_push; FxWait no_wait;
+    memset(&no_push, 0, sizeof(no_push));
+    memset(&no_wait, 0, sizeof(no_wait));
+    int fx_rc = FSIM_OK;
+    auto push_of = [&](const float* arr) -> FxPush {
+        FxPush p = no_push; FxWait w;
+        if (fx) { if (!dist_fx(h, SYM_X, arr, &p, &w)) fx_rc = FSIM_ERR_COMM; p.nblk[0] = p.nblk[1] = grd4.x * grd4.y; }
+        return p;
+    };
+    auto wait_of = [&](const float* arr) -> FxWait {
+        FxPush p; FxWait w = no_wait;
+        if (fx && !dist_fx(h, SYM_X, arr, &p, &w)) fx_rc = FSIM_ERR_COMM;
+        return w;
+    };
     if (!fine && zero_guess && PRE == 2) {
         KScope ks(h, kid);
         launch_k(h, mg_pre2_kernel, grdL, blk, 0, L, sc, m->b, cur);
@@ -1292,31 +1362,35 @@ int cycle(fsim* h, int l, bool zero_guess, float** result, bool first_done = fal
         for (int s = 0; s < PRE; s++) {
             if (s == 0 && zero_guess && first_done) continue;  // x1 and b were written by the fused CG update
             if (s == 0 && zero_guess) {
-                if (v4) launch_k(h, mg_first4_kernel, grd4, blk4, 0, L, h->r, sc, m->b, cur);
+                if (v4) launch_k(h, mg_first4_kernel, grd4, blk4, 0, L, h->r, sc, m->b, cur, push_of(cur), zrot_first);
                 else if (fine) launch_k(h, mg_first_kernel<true>, grdL, blk, 0, L, h->r, sc, m->b, cur);
                 else launch_k(h, mg_first_kernel<false>, grdL, blk, 0, L, nullptr, sc, m->b, cur);
             } else {
                 const float om = s == 0 ? OM_A : OM_B;
-                if (fine && h->hybrid) {  // the neighbours' planes of the iterate (timed as an exchange, not as a sweep)
+                if (fine && h->hybrid && !fx) {  // the neighbours' planes of the iterate (timed as an exchange, not as a sweep)
                     ks.reset();
                     int rc = dist_halo_sym(h, SYM_X, cur, true);
                     if (rc) return rc;
                     ks.reset(new KScope(h, kid, 0));
                 }
-                if (v4) launch_k(h, mg_jacobi4_kernel, grd4, blk4, 0, L, h->scal, m->b, cur, oth, om);
+                if (v4) launch_k(h, mg_jacobi4_kernel, grd4, blk4, 0, L, h->scal, m->b, cur, oth, om, wait_of(cur), push_of(oth), zrot_first);
                 else if (fine) launch_k(h, mg_jacobi_kernel<true>, grdL, blk, 0, L, sc, m->b, cur, oth, om);
                 else launch_k(h, mg_jacobi_kernel<false>, grdL, blk, 0, L, sc, m->b, cur, oth, om);
                 float* t = cur; cur = oth; oth = t;
             }
         }
     }
-    if (fine && h->hybrid) { int rc = dist_halo_sym(h, SYM_X, cur, true); if (rc) return rc; }
+    if (fine && h->hybrid && !fx) { int rc = dist_halo_sym(h, SYM_X, cur, true); if (rc) return rc; }
     // hybrid: the coarse planes whose children this rank owns (slab boundaries are even); otherwise all of them
     const int cz0 = (fine && h->hybrid) ? h->g.zown0 / 2 : 0;
     const int cz1 = (fine && h->hybrid && h->g.zown1 < h->g.gz) ? h->g.zown1 / 2 : (1 << 30);
     {
         KScope ks(h, kid);
-        if (v4) launch_k(h, mg_restrict4_kernel, dim3(div_up(mc->gx, 2 * 32), div_up(mc->gy, 4), div_up(std::min(cz1, mc->gz) - cz0, 2)), blk4, 0, L, C, sc, m->b, cur, mc->b, cz0, cz1);
+        if (v4) {
+            const dim3 grdR(div_up(mc->gx, 2 * 32), div_up(mc->gy, 4), div_up(std::min(cz1, mc->gz) - cz0, 2));
+            // (consumer of the iterate's ghost planes: the layers next to them come last)
+            launch_k(h, mg_restrict4_kernel, grdR, blk4, 0, L, C, sc, m->b, cur, mc->b, cz0, cz1, wait_of(cur), (fx && grdR.z > 1) ? 1 : 0);
+        }
         else if (fine) launch_k(h, mg_restrict_kernel<true>, grid_of(mc, blk), blk, 0, L, C, sc, m->b, cur, mc->b);
         else if (mc->nc > 100000) launch_k(h, mg_restrict_kernel<false>, grid_of(mc, blk), blk, 0, L, C, sc, m->b, cur, mc->b);  // enough threads as it is
         else launch_k(h, mg_restrict8_kernel, div_up(mc->nc * 8, 256), 256, 0, L, C, sc, m->b, cur, mc->b, (int)mc->nc);
@@ -1337,13 +1411,13 @@ int cycle(fsim* h, int l, bool zero_guess, float** result, bool first_done = fal
     }
     {
         std::unique_ptr<KScope> ks(new KScope(h, kid, POST));
-        if (v4) launch_k(h, mg_prolong_jacobi4_kernel, grd4, blk4, 0, L, C, sc, m->b, cur, mc->xa, oth);
+        if (v4) launch_k(h, mg_prolong_jacobi4_kernel, grd4, blk4, 0, L, C, sc, m->b, cur, mc->xa, oth, push_of(oth), zrot_first);
         else if (fine) launch_k(h, mg_prolong_jacobi_kernel<true>, grdL, blk, 0, L, C, sc, m->b, cur, mc->xa, oth);
         else launch_k(h, mg_prolong_jacobi_kernel<false>, grdL, blk, 0, L, C, sc, m->b, cur, mc->xa, oth);
         { float* t = cur; cur = oth; oth = t; }
         for (int s = 1; s < POST; s++) {
             const float om = OM_A;  // post-sweeps run the pre-sweep weights in reverse order (B in the fused prolongation sweep, then A)
-            if (fine && h->hybrid) {
+            if (fine && h->hybrid && !fx) {
                 ks.reset();
                 int rc = dist_halo_sym(h, SYM_X, cur, true);
                 if (rc) return rc;
@@ -1356,15 +1430,17 @@ int cycle(fsim* h, int l, bool zero_guess, float** result, bool first_done = fal
                 // air tiles and the other half all the work (64 us against 37 us for the same sweep without the dot product)
                 int nper = std::min(ntiles, h->sm_count * 8);
                 while (nper > 1 && (int)grd4.x > 1 && nper % (int)grd4.x == 0) nper--;
+                const int layer = (int)(grd4.x * grd4.y);
                 launch_k(h, mg_jacobi4_dot_kernel, nper, 256, 0, L, h->scal, m->b, cur, oth, h->partials, h->red_counter, om,
-                                                                                               (int)grd4.x, (int)grd4.y, ntiles);
-            } else if (v4) launch_k(h, mg_jacobi4_kernel, grd4, blk4, 0, L, h->scal, m->b, cur, oth, om);
+                                                                                               (int)grd4.x, (int)grd4.y, ntiles, wait_of(cur), (fx && ntiles > layer) ? layer : 0);
+            } else if (v4) launch_k(h, mg_jacobi4_kernel, grd4, blk4, 0, L, h->scal, m->b, cur, oth, om, wait_of(cur), no_push, 0);
             else if (fine) launch_k(h, mg_jacobi_kernel<true>, grdL, blk, 0, L, sc, m->b, cur, oth, om);
             else launch_k(h, mg_jacobi_kernel<false>, grdL, blk, 0, L, sc, m->b, cur, oth, om);
             float* t = cur; cur = oth; oth = t;
         }
     }
     *result = cur;
+    if (fx_rc) return fsim_fail(h, FSIM_ERR_COMM, "fused slab exchange: a level-0 multigrid array is not published to the neighbours");
     return FSIM_OK;
 }
 
@@ -1440,10 +1516,17 @@ int mg_update_first(fsim* h) {
     MgLevel* m = h->mg[0];
     const Lv L = view(h, m, 0);
     KScope ks(h, K_UPDATE);
-    { const Tile4 t4 = h->hybrid ? tile4_make(h->g.gx, (int64_t)h->g.zown0 * h->g.gy, (int64_t)(h->g.zown1 - h->g.zown0) * h->g.gy)
-                               : tile4_make(h->g.gx, 0, h->g.nc / h->g.gx);
+    { Tile4 t4 = h->hybrid ? tile4_make(h->g.gx, (int64_t)h->g.zown0 * h->g.gy, (int64_t)(h->g.zown1 - h->g.zown0) * h->g.gy, h->g.gy)
+                         : tile4_make(h->g.gx, 0, h->g.nc / h->g.gx, h->g.gy);
+    FxPush fp; FxWait fw;
+    memset(&fp, 0, sizeof(fp));
+    if (h->hybrid && h->fx_on) {  // fused exchange of the first iterate (fexch.cuh): boundary planes first
+        if (!dist_fx(h, SYM_X, m->xa, &fp, &fw)) return fsim_fail(h, FSIM_ERR_COMM, "fused slab exchange: the multigrid iterate is not published to the neighbours");
+        t4 = tile4_boundary_first(t4);
+        fp.nblk[0] = fp.nblk[1] = (uint32_t)(t4.nbx * (h->g.gy / T4_ROWS));
+    }
     launch_k(h, mg_update_first4_kernel, tile4_blocks(t4), 256, 0, L, t4, h->scal, h->status_dev, h->p, h->s, h->r, h->q, m->b,
-                                                                              m->xa, h->partials, h->red_counter); }
+                                                                              m->xa, h->partials, h->red_counter, fp); }
     FSIM_CHECK_LAUNCH(h);
     return FSIM_OK;
 }

@@ -18,6 +18,7 @@
 #include "fsim_internal.h"
 #include "reduce.cuh"
 #include "pcg_finish.cuh"
+#include "fexch.cuh"
 #include "launch.cuh"
 #include "tile4.cuh"
 
@@ -54,6 +55,11 @@ struct PcgArgs {
     int cut_neumann;  // slab mode: how code_mg treats a cut link
     int64_t cb, ce;   // cell range of the chunked kernels
     Tile4 t4;         // the same range as 2-D blocks (tile4.cuh): iteration space of the four-cells-per-thread kernels
+    // hybrid slab projection with fused exchanges (fexch.cuh): direction4 stores the boundary planes of s into the neighbours'
+    // ghost planes (t4p: boundary planes first), spmv4's boundary CTAs wait for the neighbours' (t4: boundary planes last)
+    Tile4 t4p;
+    FxPush fxs;
+    FxWait fws;
 };
 
 // iteration space of the chunked kernels: block b owns cells [b*CHUNK, (b+1)*CHUNK), a thread visits CV cells per trip
@@ -277,6 +283,10 @@ __global__ void __launch_bounds__(PT, 4) spmv4_kernel(PcgArgs a) {
     pdl_wait();
     pdl_trigger();
     if (a.sc->done) return;
+    if (a.fws.has[0] | a.fws.has[1]) {  // fused exchange of s: a CTA on a boundary plane reads the neighbour's plane
+        const int side = fx_side(a.fws.zb, tile4_plane(a.t4));
+        if (side >= 0 && a.fws.has[side]) fx_wait(a.fws, side);
+    }
     double acc[1] = {0.0};
     const int64_t sy = a.g.sy, sz = a.g.sz;
     const double scale = a.sc->scale;
@@ -401,12 +411,20 @@ __global__ void __launch_bounds__(PT) direction4_kernel(PcgArgs a) {
     pdl_trigger();
     if (a.sc->done) return;
     const double beta = a.sc->sigma_new / a.sc->sigma;
+    // fused exchange: a CTA on a boundary plane stores its groups into the neighbour's ghost plane as well, then signals
+    float* speer = nullptr;
+    int side = -1;
+    if (a.fxs.peer[0] || a.fxs.peer[1]) {
+        side = fx_side(a.fxs.zb, tile4_plane(a.t4p));
+        if (side >= 0) speer = a.fxs.peer[side];
+        if (blockIdx.x == 0 && threadIdx.x == 0) fx_expect(a.fxs);
+    }
     int64_t c = 0, cn = 0;
     ushort4 t = make_ushort4(0, 0, 0, 0);
-    if (tile4_cell(a.t4, 0, c)) t = *reinterpret_cast<const ushort4*>(a.code + c);
+    if (tile4_cell(a.t4p, 0, c)) t = *reinterpret_cast<const ushort4*>(a.code + c);
     for (int trip = 0; trip < T4_TRIPS; trip++, c = cn) {
         ushort4 tn = make_ushort4(0, 0, 0, 0);
-        if (trip + 1 < T4_TRIPS && tile4_cell(a.t4, trip + 1, cn)) tn = *reinterpret_cast<const ushort4*>(a.code + cn);
+        if (trip + 1 < T4_TRIPS && tile4_cell(a.t4p, trip + 1, cn)) tn = *reinterpret_cast<const ushort4*>(a.code + cn);
         const unsigned cd[4] = {t.x, t.y, t.z, t.w};
         t = tn;
         if (!((cd[0] | cd[1] | cd[2] | cd[3]) & CODE_ACTIVE)) continue;
@@ -417,7 +435,9 @@ __global__ void __launch_bounds__(PT) direction4_kernel(PcgArgs a) {
         for (int i = 0; i < 4; i++)
             if (cd[i] & CODE_ACTIVE) so[i] = (float)((double)so[i] * beta + (double)zz[i]);
         *reinterpret_cast<float4*>(a.s + c) = make_float4(so[0], so[1], so[2], so[3]);
+        if (speer) *reinterpret_cast<float4*>(speer + c) = make_float4(so[0], so[1], so[2], so[3]);
     }
+    if (speer) fx_signal(a.fxs, side);
 }
 // the host reads the solve's scalars from mapped pinned memory: a D2H memcpy would queue behind whatever bulk copy the
 // application has in flight on the device-to-host copy engine (the async gfx export is 1.3 GB per step at 256^3)
@@ -455,7 +475,7 @@ static int enqueue_iteration(fsim* h, const PcgArgs& a, bool vec, bool use_mg, i
     auto AR = [&](int kind) { return mode ? dist_allreduce(h, kind, true) : FSIM_OK; };
     // the neighbours' boundary planes of the search direction
     if (mode == 1) { int rc = dist_halo(h, HALO_S, true); if (rc) return rc; }
-    if (mode == 2) { int rc = dist_halo_sym(h, SYM_S, h->s, true); if (rc) return rc; }
+    if (mode == 2 && !h->fx_on) { int rc = dist_halo_sym(h, SYM_S, h->s, true); if (rc) return rc; }  // (fused: direction4 -> spmv4)
     {
         KScope ks(h, K_SPMV);
         if (vec && a.g.gx % 4 == 0 && a.g.nc % 4 == 0) launch_k(h, spmv4_kernel, dim3(tile4_blocks(a.t4)), dim3(PT), 0, a);
@@ -491,7 +511,7 @@ static int enqueue_iteration(fsim* h, const PcgArgs& a, bool vec, bool use_mg, i
     }
     {
         KScope ks(h, K_DIRECTION, 2);
-        if (vec && a.z32 && a.g.gx % 4 == 0 && a.g.nc % 4 == 0 && a.cb % 4 == 0) launch_k(h, direction4_kernel, dim3(tile4_blocks(a.t4)), dim3(PT), 0, a);
+        if (vec && a.z32 && a.g.gx % 4 == 0 && a.g.nc % 4 == 0 && a.cb % 4 == 0) launch_k(h, direction4_kernel, dim3(tile4_blocks(a.t4p)), dim3(PT), 0, a);
         else launch_k(h, direction_kernel, dim3(nbv), dim3(PT), 0, a);
         launch_k(h, close_kernel, dim3(1), dim3(1), 0, h->scal, h->status_dev, handle, use_handle);
     }
@@ -520,9 +540,20 @@ int k_project(fsim* h, double dt, int* iterations) {
     a.cb = h->hybrid ? (int64_t)g.zown0 * g.sz : 0;
     a.ce = h->hybrid ? (int64_t)g.zown1 * g.sz : g.nc;
     const int nbv = div_up(a.ce - a.cb, CHUNK);     // chunked kernels
-    a.t4 = tile4_make(g.gx, a.cb / g.gx, (a.ce - a.cb) / g.gx);
+    a.t4 = tile4_make(g.gx, a.cb / g.gx, (a.ce - a.cb) / g.gx, g.gy);
+    a.t4p = a.t4;
     const bool vec = (g.gx % 2 == 0) && (g.nc % 2 == 0);
     const bool use_mg = mg_enabled(h);
+    // hybrid slab projection: the in-loop exchanges ride inside the solver kernels when the whole four-cells-per-thread chain runs
+    h->fx_on = false;
+    memset(&a.fxs, 0, sizeof(a.fxs));
+    memset(&a.fws, 0, sizeof(a.fws));
+    if (h->hybrid && use_mg && mg_can_fuse(h) && vec && g.gx % 4 == 0 && g.nc % 4 == 0 && a.cb % 4 == 0 && dist_fx(h, SYM_S, h->s, &a.fxs, &a.fws)) {
+        h->fx_on = true;
+        a.t4p = tile4_boundary_first(a.t4);
+        a.t4 = tile4_boundary_last(a.t4);
+        a.fxs.nblk[0] = a.fxs.nblk[1] = (uint32_t)(a.t4.nbx * (g.gy / T4_ROWS));
+    }
     const int max_it = h->par.max_iterations;
 
     // solve parameters live on the device: the captured iteration graph stays valid when dt / tolerance change
@@ -560,6 +591,8 @@ int k_project(fsim* h, double dt, int* iterations) {
         start_kernel<true><<<nbv, PT, 0, h->stream>>>(a);
     }
     if (dist) { int rc = dist_allreduce(h, AR_START, true); if (rc) return rc; }
+    // fused exchanges: the first search direction comes from start_kernel, which has no fused store -- one stand-alone push
+    if (h->fx_on) { int rc = dist_halo_sym(h, SYM_S, h->s, true); if (rc) return rc; }
     FSIM_CHECK_LAUNCH(h);
 
     // The whole PCG loop runs on the device: a CUDA graph whose body (one iteration, captured once -- every argument is a

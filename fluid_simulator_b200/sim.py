@@ -167,10 +167,11 @@ class FluidSim:
         self._ck(self.L.fsim_dist_connect(self.h, arr, len(exports)))
 
     def dist_wait_stats(self, reset=False):
-        """{class: (seconds spent waiting on peers' flags, number of waits)} since connect / the last reset (fsim_dist_wait_stats)"""
+        """{class: (seconds one thread per kernel spent waiting on peers' flags, number of such kernels, seconds inside the
+        signalling block of the push / all-reduce kernels)} since connect / the last reset (fsim_dist_wait_stats)"""
         st = abi.DistWaitStats()
         self._ck(self.L.fsim_dist_wait_stats(self.h, C.byref(st), 1 if reset else 0))
-        return {k: (st.wait_ns[i] * 1e-9, int(st.waits[i])) for i, k in enumerate(abi.WAIT_CLASSES)}
+        return {k: (st.wait_ns[i] * 1e-9, int(st.waits[i]), st.kernel_ns[i] * 1e-9) for i, k in enumerate(abi.WAIT_CLASSES)}
 
     def upload_particle_ids(self, ids):
         a = np.ascontiguousarray(ids, dtype=np.uint32)

@@ -224,10 +224,13 @@ FSIM_API int fsim_dist_connect(fsim_t* h, const FsimDistExport* all, int n);
 /* Diagnostics of the exchange kernels (csrc/dist.cu): device time rank-local threads spent spinning on a peer's flag, and the
  * number of such waits, per class, accumulated since the handle was connected (or since the last call with reset != 0).
  * A profiler cannot serialise kernels that wait for another process, so this is the evidence for where an exchange's time goes. */
-enum { FSIM_WAIT_HALO = 0, FSIM_WAIT_PUSH = 1, FSIM_WAIT_GPUSH = 2, FSIM_WAIT_ALLREDUCE = 3, FSIM_WAIT_MIGRATE = 4, FSIM_WAIT_GATHER = 5, FSIM_WAIT_CLASSES = 6 };
+enum { FSIM_WAIT_HALO = 0, FSIM_WAIT_PUSH = 1, FSIM_WAIT_GPUSH = 2, FSIM_WAIT_ALLREDUCE = 3, FSIM_WAIT_MIGRATE = 4, FSIM_WAIT_GATHER = 5,
+       FSIM_WAIT_FUSED = 6 /* waits inside the solver kernels (csrc/fexch.cuh): SUM over the waiting CTAs of a launch, `waits` counts CTAs */,
+       FSIM_WAIT_CLASSES = 7 };
 typedef struct FsimDistWaitStats {
-    uint64_t wait_ns[FSIM_WAIT_CLASSES];
-    uint64_t waits[FSIM_WAIT_CLASSES];
+    uint64_t wait_ns[FSIM_WAIT_CLASSES];   /* elapsed waiting of one designated thread per kernel */
+    uint64_t waits[FSIM_WAIT_CLASSES];     /* number of kernels that waited */
+    uint64_t kernel_ns[FSIM_WAIT_CLASSES]; /* push / gpush / allreduce: entry of the signalling block to its exit (copy + fences + wait) */
 } FsimDistWaitStats;
 FSIM_API int fsim_dist_wait_stats(fsim_t* h, FsimDistWaitStats* out, int reset);
 /* pure host arithmetic of the partition (usable without a GPU): the planes rank `rank` of `nranks` owns and stores */

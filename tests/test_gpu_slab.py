@@ -245,7 +245,7 @@ def test_one_process_per_gpu_on_real_gpus():
         pytest.skip("needs >= 2 GPUs")
     import socket
     n = min(torch.cuda.device_count(), 8)
-    env = dict(os.environ, FSIM_DIST_TIMEOUT_MS="60000", FSIM_WORKER_GRID="48")
+    env = dict(os.environ, FSIM_DIST_TIMEOUT_MS="60000", FSIM_WORKER_GRID="64")
     with socket.socket() as sk:
         sk.bind(("127.0.0.1", 0))
         port = sk.getsockname()[1]

@@ -135,6 +135,122 @@ def test_model_detects_a_race_when_nothing_orders_the_ranks():
     assert found
 
 
+# ---- fused exchanges (csrc/fexch.cuh): the producer kernel stores its boundary planes into the neighbours' ghost planes and
+# adds to their arrival counters without waiting for anything; the consumer kernel's boundary CTAs wait until the arrivals
+# match the number of producer launches this rank has done itself for that array ------------------------------------------------
+# ("wpush", a): producer of a (local write + remote stores + signal); ("read", a): consumer (waits, then reads the ghosts);
+# ("push", "s"): the one stand-alone push per solve (start_kernel has no fused store)
+FUSED_CYCLE_REST = [
+    ("read", "xa"), ("wpush", "xb"),          # pre-sweep 2 (mg_jacobi4_kernel: waits for xa, pushes xb)
+    ("read", "xb"),                           # restriction
+    ("gpush",),
+    ("read", "xb"), ("wpush", "xa"),          # prolongation + sweep
+    ("read", "xa"), ("write", "xb"),          # last sweep (fused with z.r inside the loop)
+    ("ar",),                                  # z.r / AR_START
+]
+FUSED_HEAD = [("wpush", "xa")] + FUSED_CYCLE_REST + [("write", "s"), ("push", "s")]
+FUSED_ITERATION = [
+    ("read", "s"), ("ar",),                   # SpMV (waits for s), s.As
+    ("wpush", "xa"), ("ar",),                 # CG update + first sweep (pushes xa), ||r||_inf
+] + FUSED_CYCLE_REST + [
+    ("wpush", "s"),                           # direction update (pushes s)
+]
+
+
+def simulate_fused(nranks, iterations, seed, drop_barriers=False, reads_wait=True):
+    rng = random.Random(seed)
+    prog = FUSED_HEAD + FUSED_ITERATION * iterations
+    if drop_barriers:
+        prog = [op for op in prog if op[0] not in ("ar", "gpush")]
+    reads_per_push = {}
+    for i, op in enumerate(prog):
+        if op[0] in ("push", "wpush"):
+            n = 0
+            for nxt in prog[i + 1:]:
+                if nxt[0] in ("push", "wpush") and nxt[1] == op[1]:
+                    break
+                if nxt == ("read", op[1]):
+                    n += 1
+            assert reads_per_push.setdefault(op[1], n) == n or i + 40 > len(prog)  # (the tail of the program may be cut short)
+    pc = [0] * nranks
+    ghost, pushed, arrived = {}, {}, {}
+    barrier_count = [0] * nranks
+    phase = ["start"] * nranks
+
+    def sides(r):  # (neighbour, the ghost side of the neighbour that I write, my ghost side that it writes)
+        return [(nb, s_theirs, s_mine) for nb, s_theirs, s_mine in ((r - 1, 1, 0), (r + 1, 0, 1)) if 0 <= nb < nranks]
+
+    steps = 0
+    while any(pc[r] < len(prog) for r in range(nranks)):
+        steps += 1
+        assert steps < 10_000_000
+        r = rng.randrange(nranks)
+        if pc[r] >= len(prog):
+            continue
+        op = prog[pc[r]]
+        if op[0] in ("wpush", "push"):
+            a = op[1]
+            if phase[r] == "start":
+                k = pushed.get((r, a), 0) + 1
+                for nb, s_theirs, _ in sides(r):
+                    g = ghost.setdefault((nb, a, s_theirs), {"ver": 0, "readers_left": 0})
+                    assert g["readers_left"] == 0, f"rank {r} overwrites ghost {a} of rank {nb} before it was read (exchange {k})"
+                    g["ver"], g["readers_left"] = k, reads_per_push[a]
+                    arrived[(nb, a, s_theirs)] = k
+                pushed[(r, a)] = k
+                if op[0] == "wpush":
+                    pc[r] += 1          # fire and forget
+                else:
+                    phase[r] = "wait"   # the stand-alone push_kernel also waits for the neighbours' flags
+            elif all(arrived.get((r, a, s_mine), 0) >= pushed[(r, a)] for _, _, s_mine in sides(r)):
+                phase[r] = "start"
+                pc[r] += 1
+        elif op[0] == "read":
+            a = op[1]
+            k = pushed[(r, a)]  # expectation = my own number of producer launches for this array
+            if reads_wait and not all(arrived.get((r, a, s_mine), 0) >= k for _, _, s_mine in sides(r)):
+                continue        # the boundary CTAs spin
+            for _, _, s_mine in sides(r):
+                g = ghost.setdefault((r, a, s_mine), {"ver": 0, "readers_left": 0})
+                assert g["ver"] == k, f"rank {r} reads exchange {g['ver']} of {a}, expected {k}"
+                g["readers_left"] -= 1
+            pc[r] += 1
+        elif op[0] in ("ar", "gpush"):
+            if phase[r] == "start":
+                barrier_count[r] += 1
+                phase[r] = "wait"
+            elif all(barrier_count[q] >= barrier_count[r] for q in range(nranks)):
+                phase[r] = "start"
+                pc[r] += 1
+        else:
+            pc[r] += 1
+    return steps
+
+
+@pytest.mark.parametrize("nranks", [2, 3, 8])
+def test_fused_schedule_never_overwrites_unread_ghosts(nranks):
+    for seed in range(60):
+        simulate_fused(nranks, iterations=6, seed=seed)
+
+
+def test_fused_schedule_is_ordered_by_its_data_dependencies_alone():
+    """Every producer of an array sits behind a consumer wait whose matching neighbour store comes after the neighbour's last
+    read of the old contents, so the schedule stays race-free even with the reductions removed."""
+    for seed in range(60):
+        simulate_fused(3, iterations=6, seed=seed, drop_barriers=True)
+
+
+def test_fused_model_detects_a_consumer_that_does_not_wait():
+    found = False
+    for seed in range(200):
+        try:
+            simulate_fused(3, iterations=6, seed=seed, reads_wait=False)
+        except AssertionError:
+            found = True
+            break
+    assert found
+
+
 # ---- allreduce_kernel: slot[parity][source rank] on every rank, double-buffered by the parity of the epoch -----------------
 def simulate_allreduce(nranks, rounds, seed, nbuf=2):
     """Every rank: for ep = 1..rounds: store (value(rank, ep), ep) into slot[ep % nbuf][rank] of EVERY rank (one store at a

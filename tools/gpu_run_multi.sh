@@ -8,13 +8,13 @@ nvidia-smi topo -m > gpurun_out/r2m_n${N}_topo.txt 2>&1
 if [ "$SKIP_TESTS" != "1" ]; then ( time timeout 900 python -m pytest tests/test_gpu_slab.py -q -k "real_gpus or two_processes" -s ) > gpurun_out/r2m_n${N}_slabtest.log 2>&1; fi
 grep -E "passed|failed|slab worker|rel L2|SLAB_WORKER" gpurun_out/r2m_n${N}_slabtest.log | tail -8
 PORT=29512
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((PORT+7)) tools/pcie_probe_ranks.py > gpurun_out/r2m_n${N}_pcie.json 2> gpurun_out/r2m_n${N}_pcie.err; cut -c1-600 gpurun_out/r2m_n${N}_pcie.json
-PYTHONFAULTHANDLER=1 timeout 900 python -u -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $PORT bench.py --gpus $N --steps 10 --warmup 5 \
+[ "$SKIP_PCIE" = "1" ] || timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((PORT+7)) tools/pcie_probe_ranks.py > gpurun_out/r2m_n${N}_pcie.json 2> gpurun_out/r2m_n${N}_pcie.err; cut -c1-600 gpurun_out/r2m_n${N}_pcie.json
+PYTHONFAULTHANDLER=1 timeout 900 python -u -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $PORT bench.py --gpus $N --steps 20 --warmup 5 \
     > gpurun_out/r2m_n${N}_bench.json 2> gpurun_out/r2m_n${N}_bench.err
 echo "bench rc=$?"
 tail -c 1500 gpurun_out/r2m_n${N}_bench.err
 if [ ! -s gpurun_out/r2m_n${N}_bench.json ]; then
-  PYTHONFAULTHANDLER=1 timeout 900 python -u -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((PORT+1)) bench.py --gpus $N --steps 10 --warmup 5 --no-verify \
+  PYTHONFAULTHANDLER=1 timeout 900 python -u -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((PORT+1)) bench.py --gpus $N --steps 20 --warmup 5 --no-verify \
       > gpurun_out/r2m_n${N}_bench.json 2> gpurun_out/r2m_n${N}_bench_noverify.err
   echo "bench (no verify) rc=$?"
   tail -c 1500 gpurun_out/r2m_n${N}_bench_noverify.err
