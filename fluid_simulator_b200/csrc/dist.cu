@@ -134,7 +134,9 @@ __device__ __forceinline__ void wait_account(DistComm* c, int cls, unsigned long
     atomicAdd(&c->waits[cls], 1ull);
 }
 
-struct HaloCopy { void* dst; const void* src; uint32_t bytes; int side; };
+// mask >= 0: a plane of floats of which only the cells with (x + y) & 1 == mask are copied (row length gx): the red-black sweeps of
+// the BasicMacGrid solver on slabs, where each rank owns the updates of one colour of a shared face plane
+struct HaloCopy { void* dst; const void* src; uint32_t bytes; int side; int mask, gx; };
 struct HaloArgs {
     DistComm* comm;
     DistComm* peer[2];
@@ -167,7 +169,13 @@ __global__ void __launch_bounds__(256) halo_kernel(const __grid_constant__ HaloA
     for (int k = 0; k < a.ncopy; k++) {
         const HaloCopy& cp = a.cp[k];
         if (!a.peer[cp.side]) continue;
-        if ((((size_t)cp.dst | (size_t)cp.src | (size_t)cp.bytes) & 15) == 0) {
+        if (cp.mask >= 0) {
+            const size_t n = cp.bytes >> 2;
+            for (size_t i = gtid; i < n; i += gsz) {
+                const int x = (int)(i % cp.gx), y = (int)(i / cp.gx);
+                if (((x + y) & 1) == cp.mask) reinterpret_cast<float*>(cp.dst)[i] = reinterpret_cast<const volatile float*>(cp.src)[i];
+            }
+        } else if ((((size_t)cp.dst | (size_t)cp.src | (size_t)cp.bytes) & 15) == 0) {
             const size_t n = cp.bytes >> 4;
             for (size_t i = gtid; i < n; i += gsz) reinterpret_cast<uint4*>(cp.dst)[i] = ld_peer_u4(reinterpret_cast<const uint4*>(cp.src) + i);
         } else {
@@ -707,6 +715,7 @@ int dist_halo(fsim* h, int what, bool in_pcg_loop) {
             c.src = (const char*)d->peer_arr[side][arr] + (size_t)d->peer_bnd[side] * plane * es;
             c.bytes = (uint32_t)(plane * es);
             c.side = side;
+            c.mask = -1;
         }
     };
     size_t bytes = 0;
@@ -727,7 +736,30 @@ int dist_halo(fsim* h, int what, bool in_pcg_loop) {
                         c.src = (const float*)d->peer_arr[side][chan[ch]] + (size_t)(which == 0 ? d->peer_ghost[side] : d->peer_bnd[side]) * plane;
                         c.bytes = (uint32_t)(plane * sizeof(float));
                         c.side = side;
+                        c.mask = -1;
                     }
+            }
+            break;
+        }
+        case HALO_BASIC_ODD: case HALO_BASIC_EVEN: {
+            // BasicMacGrid sweep of one colour (grid.cu basic_sor_kernel) just ran on the owned planes.  The z faces between two
+            // slabs live in the lower rank's top plane: cells of this colour there were updated by their owner, the others by the
+            // upper rank's cells through their -z face (its ghost plane).  Each rank takes the half the other one wrote.
+            const int colour = what == HALO_BASIC_ODD ? 1 : 0;
+            const int zg_lo = g.zoff + g.zown0 - 1, zg_hi = g.zoff + g.zown1;  // global planes of my ghost planes
+            if (d->peer_comm[0]) {  // my ghost plane below <- the lower rank's top plane: the cells it owns and swept (x + y + zg_lo of this colour)
+                HaloCopy& c = a.cp[a.ncopy++];
+                c.dst = (float*)d->local_arr[ARR_U2 + 2] + (size_t)my_ghost[0] * plane;
+                c.src = (const float*)d->peer_arr[0][ARR_U2 + 2] + (size_t)d->peer_bnd[0] * plane;
+                c.bytes = (uint32_t)(plane * sizeof(float)); c.side = 0; c.gx = g.gx;
+                c.mask = colour ^ (zg_lo & 1);
+            }
+            if (d->peer_comm[1]) {  // my top plane <- the upper rank's ghost plane: the faces its cells of this colour (plane zg_hi) pushed on
+                HaloCopy& c = a.cp[a.ncopy++];
+                c.dst = (float*)d->local_arr[ARR_U2 + 2] + (size_t)my_bnd[1] * plane;
+                c.src = (const float*)d->peer_arr[1][ARR_U2 + 2] + (size_t)d->peer_ghost[1] * plane;
+                c.bytes = (uint32_t)(plane * sizeof(float)); c.side = 1; c.gx = g.gx;
+                c.mask = colour ^ (zg_hi & 1);
             }
             break;
         }
@@ -924,6 +956,7 @@ int dist_halo_sym(fsim* hs, int which, const void* ptr, bool in_pcg_loop) {
         c.src = (const char*)d->peer_arr[side][arr] + (size_t)zpl[side] * plane * es;
         c.bytes = (uint32_t)(plane * es);
         c.side = side;
+        c.mask = -1;
     }
     size_t bytes = 0;
     for (int k = 0; k < a.ncopy; k++) bytes += a.cp[k].bytes;

@@ -548,7 +548,6 @@ int fsim_set_params(fsim_t* h, const FsimParams* p) {
     if (!(p->fluid_density > 0)) return fsim_fail(h, FSIM_ERR_INVALID, "fluid density must be > 0");
     if (p->solver_type != FSIM_SOLVER_BRIDSON && p->solver_type != FSIM_SOLVER_BASIC) return fsim_fail(h, FSIM_ERR_INVALID, "bad solver type %d", p->solver_type);
     if (h->dist && p->push_apart_enabled) return fsim_fail(h, FSIM_ERR_INVALID, "push-apart is not available on slab handles");
-    if (h->dist && p->solver_type != FSIM_SOLVER_BRIDSON) return fsim_fail(h, FSIM_ERR_INVALID, "slab handles run the PCG projection only");
     if (p->transfer_type != h->par.transfer_type || p->flip_ratio != h->par.flip_ratio) TRY(flush_g2p(h));  // a pending G2P uses the old blend
     h->par = *p;
     if (p->transfer_type == FSIM_TRANSFER_APIC) TRY(ensure_c(h));
@@ -826,6 +825,12 @@ int fsim_stage_g2p(fsim_t* h) { BIND_FLUSH(h); TRY(ensure_sorted(h)); return k_g
 static int project_slab(fsim* h, double dt, int* its_out) {
     int its_local = 0;
     if (!its_out) its_out = &its_local;
+    if (h->par.solver_type == FSIM_SOLVER_BASIC) {
+        // BasicMacGrid::solveIncompressibility (basicMacGrid.cpp:15-102) works on the velocities in place: red-black sweeps over the
+        // owned planes, the shared z faces exchanged after every colour (dist.cu HALO_BASIC_*)
+        TRY(k_project(h, dt, its_out));
+        return FSIM_OK;
+    }
     if (h->solver) {
         // replicated projection: gather every rank's planes of the solver inputs, solve the whole system here, keep our planes
         fsim* hs = h->solver;
@@ -857,7 +862,6 @@ static int project_slab(fsim* h, double dt, int* its_out) {
 static int step_slab(fsim* h, double dt, int* pcg_iterations) {
     TRY(dist_check(h));
     if (h->par.push_apart_enabled) return fsim_fail(h, FSIM_ERR_INVALID, "push-apart is not available on slab handles");
-    if (h->par.solver_type != FSIM_SOLVER_BRIDSON) return fsim_fail(h, FSIM_ERR_INVALID, "slab handles run the PCG projection only");
     fold_timings(h);
     const int64_t l0 = h->launches;
     FSIM_CUDA(h, cudaEventRecord(h->ev[0], h->stream));

@@ -279,7 +279,7 @@ void mg_free(fsim* h);
 
 // ---- z-slab decomposition over peer memory (dist.cu) ----------------------------------------------------
 enum { AR_RHS = 0, AR_RESIDUAL, AR_START, AR_SPMV, AR_UPDATE, AR_UPDATE_JACOBI, AR_DOTZR };
-enum { HALO_P2G = 0, HALO_P, HALO_S, HALO_U2, HALO_U2_FLAGS };
+enum { HALO_P2G = 0, HALO_P, HALO_S, HALO_U2, HALO_U2_FLAGS, HALO_BASIC_ODD, HALO_BASIC_EVEN };
 int dist_halo(fsim* h, int what, bool in_pcg_loop);      // ghost-plane exchange with both z-neighbours (pull over peer memory)
 int dist_allreduce(fsim* h, int kind, bool in_pcg_loop);  // finishes a PCG reduction across the ranks
 int dist_migrate(fsim* h);

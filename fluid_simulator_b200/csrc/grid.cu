@@ -279,8 +279,9 @@ __global__ void __launch_bounds__(256) basic_sor_kernel(BasicArgs a) {
     int x, y, z;
     int64_t c;
     if (!cell_xyz(g, x, y, z, c)) return;
-    if (((x + y + z) & 1) != a.parity) return;
-    if (x < 1 || y < 1 || z < 1 || x >= g.gx - 1 || y >= g.gy - 1 || z >= g.gz - 1) return;  // (single-GPU only)
+    const int zg = z + g.zoff;  // (slab handles: global plane; they sweep the planes they own)
+    if (((x + y + zg) & 1) != a.parity) return;
+    if (x < 1 || y < 1 || zg < 1 || x >= g.gx - 1 || y >= g.gy - 1 || zg >= g.gzg - 1 || z < g.zown0 || z >= g.zown1) return;
     if ((a.flags[c] & FL_TYPE_MASK) != FSIM_CELL_WATER) return;
     const int s1 = (a.flags[c + g.sz] & FL_TYPE_MASK) != FSIM_CELL_SOLID, s2 = (a.flags[c - g.sz] & FL_TYPE_MASK) != FSIM_CELL_SOLID;
     const int s3 = (a.flags[c + g.sy] & FL_TYPE_MASK) != FSIM_CELL_SOLID, s4 = (a.flags[c - g.sy] & FL_TYPE_MASK) != FSIM_CELL_SOLID;
@@ -407,8 +408,9 @@ int k_project_basic(fsim* h, int* iterations) {
     for (int it = 0; it < n; it++)
         for (int colour = 1; colour >= 0; colour--) {  // odd cells first (z starts at 1 + (x+y)%2), then even
             a.parity = colour;
-            KScope ks(h, K_APPLY);
-            basic_sor_kernel<<<cell_grid(h->g), cell_block(), 0, h->stream>>>(a);
+            { KScope ks(h, K_APPLY); basic_sor_kernel<<<cell_grid(h->g), cell_block(), 0, h->stream>>>(a); }
+            // slab handles: a cell updates the z face it shares with the neighbouring slab; hand over the half each side wrote
+            if (h->dist) { int rc = dist_halo(h, colour ? HALO_BASIC_ODD : HALO_BASIC_EVEN, false); if (rc) return rc; }
         }
     FSIM_CHECK_LAUNCH(h);
     h->solve.iterations = n; h->solve.early_out = 0; h->solve.rhs_sumsq = 0; h->solve.residual_max = 0; h->solve.fluid_cells = 0;

@@ -89,6 +89,20 @@ def test_slab_matches_single_flip(gpu, nranks, solver, monkeypatch):
 
 
 @pytest.mark.parametrize("nranks", [2, 3])
+def test_slab_basic_solver(gpu, nranks):
+    """BasicMacGrid's red-black Gauss-Seidel (basicMacGrid.cpp:15-102) on slab handles: every colour sweeps the owned planes and
+    the z faces shared by two slabs change hands after it -- the same sweep-for-sweep arithmetic as the single handle."""
+    sc = scenes.dam_break_3d(24, abi.PIC, ny=20, nz=26, solver_type=abi.SOLVER_BASIC, max_iterations=25)
+    one, grp = make_pair(gpu, sc, nranks)
+    for st in range(3):
+        i1, ig = one.step(sc.dt), grp.step(sc.dt)
+        assert i1 == ig == 25
+        compare(f"slab_basic_n{nranks}_step{st}", one, grp)
+    grp.close()
+    one.close()
+
+
+@pytest.mark.parametrize("nranks", [2, 3])
 def test_slab_apic_obstacles(gpu, nranks):
     """APIC with a box and a moving sphere that straddle slab boundaries (obstacle rasterisation uses global planes)."""
     n = 24
