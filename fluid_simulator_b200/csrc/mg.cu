@@ -313,10 +313,7 @@ __device__ __forceinline__ void fx_signal_planes(const FxPush& f, int zlo, int p
         if (f.peer[side] && f.zb[side] >= zlo && f.zb[side] < zlo + planes) fx_signal(f, side);
 }
 // the neighbour's array when plane z is one of my boundary planes and a neighbour reads it
-__device__ __forceinline__ float* fx_peer_of(const FxPush& f, int z) {
-    const int side = fx_side(f.zb, z);
-    return side >= 0 ? f.peer[side] : nullptr;
-}
+__device__ __forceinline__ float* fx_peer_of(const FxPush& f, int z) { return fx_peer(f, fx_side(f.zb, z)); }
 
 __device__ __forceinline__ Stencil4 load_stencil4(const Lv& L, const float* __restrict__ x, int64_t c, const unsigned cd[4]) {
     Stencil4 s;
@@ -451,7 +448,7 @@ __global__ void __launch_bounds__(256, UF_MIN_BLOCKS) mg_update_first4_kernel(Lv
     int side = -1;
     if (fp.peer[0] || fp.peer[1]) {
         side = fx_side(fp.zb, tile4_plane(t4));
-        if (side >= 0) xpeer = fp.peer[side];
+        xpeer = fx_peer(fp, side);
         if (blockIdx.x == 0 && threadIdx.x == 0) fx_expect(fp);
     }
     const double alpha = sc->sigma / sc->sq;
@@ -598,6 +595,172 @@ __global__ void __launch_bounds__(256) mg_prolong_jacobi4_kernel(Lv L, Lv C, con
         if (float* peer = fx_peer_of(fp, z)) st4(peer + c, xo);
     }
     fx_signal_planes(fp, zblk * 2 + L.z0, 2);
+}
+
+// ---- stored-operator levels, four consecutive x cells per thread (gx % 4 == 0, level 1 of a 256^3 grid = 2 M cells) -----------
+// One cell per thread these sweeps are ~7 waves of threads that each wait for one L2 round trip; with four cells per thread
+// the same loads are in flight from a quarter of the threads (16-byte loads of the iterate, the right-hand side and the four
+// weight arrays).  Per cell the arithmetic and its order are those of row<false> / pre2_value / mg_prolong_jacobi_kernel<false>.
+struct Row4 {  // weights of four consecutive cells: w[0..5] = to x-1, x+1, y-1, y+1, z-1, z+1
+    F4 d, xp, ym, yp, zm, zp;
+    float xm0;  // weight of cell 0 towards x-1 (cells 1..3: xp of their left neighbour)
+};
+__device__ __forceinline__ Row4 load_row4(const Lv& L, int64_t c) {
+    Row4 r;
+    r.d = ld4(L.diag + c);
+    r.xp = ld4(L.wx + c); r.xm0 = L.wx[c - 1];
+    r.yp = ld4(L.wy + c); r.ym = ld4(L.wy + c - L.sy);
+    r.zp = ld4(L.wz + c); r.zm = ld4(L.wz + c - L.sz);
+    return r;
+}
+__device__ __forceinline__ bool group4_of(const Lv& L, int& x, int& y, int& z, int64_t& c) {
+    x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    y = blockIdx.y * blockDim.y + threadIdx.y;
+    z = blockIdx.z * blockDim.z + threadIdx.z;
+    c = ((int64_t)z * L.gy + y) * L.gx + x;
+    return x < L.gx && y < L.gy && z < L.gz;
+}
+__device__ __forceinline__ Stencil4 load_stencil4_all(const Lv& L, const float* __restrict__ x, int64_t c) {
+    Stencil4 s;
+    s.c = ld4(x + c);
+    s.ym = ld4(x + c - L.sy); s.yp = ld4(x + c + L.sy);
+    s.zm = ld4(x + c - L.sz); s.zp = ld4(x + c + L.sz);
+    s.xl = x[c - 1]; s.xr = x[c + 4];
+    return s;
+}
+// sum of w_nbr * x_nbr of cell i, in the order of row<false>
+__device__ __forceinline__ float offc4(const Row4& r, const Stencil4& s, int i) {
+    const float xr = i == 3 ? s.xr : s.c.v[i + 1], xl = i == 0 ? s.xl : s.c.v[i - 1];
+    const float wl = i == 0 ? r.xm0 : r.xp.v[i - 1];
+    return r.xp.v[i] * xr + wl * xl + r.yp.v[i] * s.yp.v[i] + r.ym.v[i] * s.ym.v[i] + r.zp.v[i] * s.zp.v[i] + r.zm.v[i] * s.zm.v[i];
+}
+
+__global__ void __launch_bounds__(256) mg_jacobic4_kernel(Lv L, const PcgScalars* __restrict__ sc, const float* __restrict__ b, const float* __restrict__ xin,
+                                                          float* __restrict__ xout, float om) {
+    pdl_wait();
+    pdl_trigger();
+    if (sc->done) return;
+    int x, y, z; int64_t c;
+    if (!group4_of(L, x, y, z, c)) return;
+    const Row4 r = load_row4(L, c);
+    F4 xo = zero4();
+    if (r.d.v[0] > 0.f || r.d.v[1] > 0.f || r.d.v[2] > 0.f || r.d.v[3] > 0.f) {
+        const Stencil4 s = load_stencil4_all(L, xin, c);
+        const F4 bb = ld4(b + c);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const float d = r.d.v[i], xi = s.c.v[i];
+            if (d > 0.f) xo.v[i] = xi + om * (bb.v[i] - (d * xi - offc4(r, s, i))) / d;
+        }
+    }
+    st4(xout + c, xo);
+}
+
+__global__ void __launch_bounds__(256) mg_pre2c4_kernel(Lv L, const PcgScalars* __restrict__ sc, const float* __restrict__ b, float* __restrict__ xout) {
+    pdl_wait();
+    pdl_trigger();
+    if (sc->done) return;
+    int x, y, z; int64_t c;
+    if (!group4_of(L, x, y, z, c)) return;
+    const Row4 r = load_row4(L, c);
+    F4 xo = zero4();
+    if (r.d.v[0] > 0.f || r.d.v[1] > 0.f || r.d.v[2] > 0.f || r.d.v[3] > 0.f) {
+        const Stencil4 dn = load_stencil4_all(L, L.diag, c), bn = load_stencil4_all(L, b, c);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const float d = r.d.v[i], bb = bn.c.v[i];
+            if (!(d > 0.f)) continue;
+            // pre2_value: neighbours in the order x-1, x+1, y-1, y+1, z-1, z+1
+            const float w[6] = {i == 0 ? r.xm0 : r.xp.v[i - 1], r.xp.v[i], r.ym.v[i], r.yp.v[i], r.zm.v[i], r.zp.v[i]};
+            const float dk[6] = {i == 0 ? dn.xl : dn.c.v[i - 1], i == 3 ? dn.xr : dn.c.v[i + 1], dn.ym.v[i], dn.yp.v[i], dn.zm.v[i], dn.zp.v[i]};
+            const float bk[6] = {i == 0 ? bn.xl : bn.c.v[i - 1], i == 3 ? bn.xr : bn.c.v[i + 1], bn.ym.v[i], bn.yp.v[i], bn.zm.v[i], bn.zp.v[i]};
+            float off = 0.f;
+#pragma unroll
+            for (int k = 0; k < 6; k++)
+                if (w[k] > 0.f && dk[k] > 0.f) off += w[k] * (OM_A * bk[k] / dk[k]);
+            const float xi = OM_A * bb / d;
+            xo.v[i] = xi + OM_B * (bb - (d * xi - off)) / d;
+        }
+    }
+    st4(xout + c, xo);
+}
+
+// restriction from a stored-operator level: one thread = two coarse cells in x = a 4x2x2 block of fine cells
+__global__ void __launch_bounds__(256) mg_restrictc4_kernel(Lv L, Lv C, const PcgScalars* __restrict__ sc, const float* __restrict__ b, const float* __restrict__ xf,
+                                                            float* __restrict__ bc) {
+    pdl_wait();
+    pdl_trigger();
+    if (sc->done) return;
+    const int X = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
+    const int Y = blockIdx.y * blockDim.y + threadIdx.y, Z = blockIdx.z * blockDim.z + threadIdx.z;
+    if (X >= C.gx || Y >= C.gy || Z >= C.gz) return;
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 2; k++)
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const int y = 2 * Y + j, z = 2 * Z + k;
+            if (y >= L.gy || z >= L.gz) continue;
+            const int64_t c = ((int64_t)z * L.gy + y) * L.gx + 2 * X;
+            const Row4 r = load_row4(L, c);
+            if (!(r.d.v[0] > 0.f || r.d.v[1] > 0.f || r.d.v[2] > 0.f || r.d.v[3] > 0.f)) continue;
+            const Stencil4 s = load_stencil4_all(L, xf, c);
+            const F4 bb = ld4(b + c);
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                if (r.d.v[i] > 0.f) {
+                    const float res = bb.v[i] - (r.d.v[i] * s.c.v[i] - offc4(r, s, i));
+                    if (i < 2) s0 += res; else s1 += res;
+                }
+        }
+    *reinterpret_cast<float2*>(bc + ((int64_t)Z * C.gy + Y) * C.gx + X) = make_float2(s0, s1);
+}
+
+__global__ void __launch_bounds__(256) mg_prolong_jacobic4_kernel(Lv L, Lv C, const PcgScalars* __restrict__ sc, const float* __restrict__ b, const float* __restrict__ xin,
+                                                                  const float* __restrict__ ec, float* __restrict__ xout) {
+    pdl_wait();
+    pdl_trigger();
+    if (sc->done) return;
+    int x, y, z; int64_t c;
+    if (!group4_of(L, x, y, z, c)) return;
+    const Row4 r = load_row4(L, c);
+    F4 xo = zero4();
+    if (r.d.v[0] > 0.f || r.d.v[1] > 0.f || r.d.v[2] > 0.f || r.d.v[3] > 0.f) {
+        Stencil4 s = load_stencil4_all(L, xin, c);
+        // coarse corrections: the group's parents are (X0, X0+1) in row (y>>1, z>>1); the neighbour rows use their own parents
+        // (rows outside the grid carry zero weights; their parent row index is clamped to stay inside the padded array)
+        const int X0 = x >> 1;
+        auto prow = [&](int yy, int zz) -> const float* {
+            const int py = min(max(yy, 0), L.gy - 1) >> 1, pz = min(max(zz, 0), L.gz - 1) >> 1;
+            return ec + ((int64_t)pz * C.gy + py) * C.gx;
+        };
+        auto add2 = [&](F4& v, const float* row) {
+            const float2 e = *reinterpret_cast<const float2*>(row + X0);
+            v.v[0] += OVER * e.x; v.v[1] += OVER * e.x; v.v[2] += OVER * e.y; v.v[3] += OVER * e.y;
+        };
+        const float* r0 = prow(y, z);
+        add2(s.c, r0);
+        add2(s.ym, prow(y - 1, z)); add2(s.yp, prow(y + 1, z));
+        add2(s.zm, prow(y, z - 1)); add2(s.zp, prow(y, z + 1));
+        s.xl += OVER * r0[X0 - 1];   // (x = 0: the element before the row, finite, multiplied by a zero weight below)
+        s.xr += OVER * r0[X0 + 2];
+        const F4 bb = ld4(b + c);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const float d = r.d.v[i];
+            if (!(d > 0.f)) continue;
+            // mg_prolong_jacobi_kernel<false>: conditional adds in the order x-1, x+1, y-1, y+1, z-1, z+1
+            const float w[6] = {i == 0 ? r.xm0 : r.xp.v[i - 1], r.xp.v[i], r.ym.v[i], r.yp.v[i], r.zm.v[i], r.zp.v[i]};
+            const float xn[6] = {i == 0 ? s.xl : s.c.v[i - 1], i == 3 ? s.xr : s.c.v[i + 1], s.ym.v[i], s.yp.v[i], s.zm.v[i], s.zp.v[i]};
+            float off = 0.f;
+#pragma unroll
+            for (int k = 0; k < 6; k++)
+                if (w[k] > 0.f) off += w[k] * xn[k];
+            const float xi = s.c.v[i];
+            xo.v[i] = xi + OM_B * (bb.v[i] - (d * xi - off)) / d;
+        }
+    }
+    st4(xout + c, xo);
 }
 
 // Galerkin operator of level 1 from the stencil codes: face weight = # WATER-WATER fine connections across the coarse
@@ -1338,6 +1501,11 @@ int cycle(fsim* h, int l, bool zero_guess, float** result, bool first_done = fal
     float *cur = m->xa, *oth = m->xb;
     // hybrid slab projection with fused exchanges (fexch.cuh): the kernel that writes an iterate stores its boundary planes into
     // the neighbours' ghost planes, the kernel that reads it waits for theirs -- no exchange kernels between the sweeps
+    // stored-operator levels with >= 1 M cells (level 1 of a 256^3 grid): four cells per thread (mg_*c4_kernel).  Measured at 256^3: level 1
+    // 0.65 -> 0.53 ms/step, whole step -0.09 ms; also on level 2 (262 k cells) +0.06 ms -- there the launch is the cost, not the waves
+    const int64_t c4_min = getenv("FSIM_MG_C4_MIN") ? atoll(getenv("FSIM_MG_C4_MIN")) : 1000000;
+    const bool c4 = !fine && m->gx % 4 == 0 && m->pad % 4 == 0 && m->nc >= c4_min;
+    const dim3 grdC4(div_up(m->gx, 4 * 32), div_up(m->gy, 4), div_up(m->gz, 2));
     const bool fx = fine && h->hybrid && h->fx_on && v4;
     const int zrot_first = fx ? (int)grd4.z - 1 : 0;  // producers: the CTAs of the top boundary plane first, then the bottom one, ...
     FxPush no_push; FxWait no_wait;
@@ -1356,7 +1524,8 @@ int cycle(fsim* h, int l, bool zero_guess, float** result, bool first_done = fal
     };
     if (!fine && zero_guess && PRE == 2) {
         KScope ks(h, kid);
-        launch_k(h, mg_pre2_kernel, grdL, blk, 0, L, sc, m->b, cur);
+        if (c4) launch_k(h, mg_pre2c4_kernel, grdC4, blk4, 0, L, sc, m->b, cur);
+        else launch_k(h, mg_pre2_kernel, grdL, blk, 0, L, sc, m->b, cur);
     } else {
         std::unique_ptr<KScope> ks(new KScope(h, kid, PRE - ((zero_guess && first_done) ? 1 : 0)));
         for (int s = 0; s < PRE; s++) {
@@ -1375,6 +1544,7 @@ int cycle(fsim* h, int l, bool zero_guess, float** result, bool first_done = fal
                 }
                 if (v4) launch_k(h, mg_jacobi4_kernel, grd4, blk4, 0, L, h->scal, m->b, cur, oth, om, wait_of(cur), push_of(oth), zrot_first);
                 else if (fine) launch_k(h, mg_jacobi_kernel<true>, grdL, blk, 0, L, sc, m->b, cur, oth, om);
+                else if (c4) launch_k(h, mg_jacobic4_kernel, grdC4, blk4, 0, L, sc, m->b, cur, oth, om);
                 else launch_k(h, mg_jacobi_kernel<false>, grdL, blk, 0, L, sc, m->b, cur, oth, om);
                 float* t = cur; cur = oth; oth = t;
             }
@@ -1392,6 +1562,8 @@ int cycle(fsim* h, int l, bool zero_guess, float** result, bool first_done = fal
             launch_k(h, mg_restrict4_kernel, grdR, blk4, 0, L, C, sc, m->b, cur, mc->b, cz0, cz1, wait_of(cur), (fx && grdR.z > 1) ? 1 : 0);
         }
         else if (fine) launch_k(h, mg_restrict_kernel<true>, grid_of(mc, blk), blk, 0, L, C, sc, m->b, cur, mc->b);
+        else if (c4 && mc->gx % 2 == 0 && mc->pad % 2 == 0)
+            launch_k(h, mg_restrictc4_kernel, dim3(div_up(mc->gx, 2 * 32), div_up(mc->gy, 4), div_up(mc->gz, 2)), blk4, 0, L, C, sc, m->b, cur, mc->b);
         else if (mc->nc > 100000) launch_k(h, mg_restrict_kernel<false>, grid_of(mc, blk), blk, 0, L, C, sc, m->b, cur, mc->b);  // enough threads as it is
         else launch_k(h, mg_restrict8_kernel, div_up(mc->nc * 8, 256), 256, 0, L, C, sc, m->b, cur, mc->b, (int)mc->nc);
     }
@@ -1413,6 +1585,7 @@ int cycle(fsim* h, int l, bool zero_guess, float** result, bool first_done = fal
         std::unique_ptr<KScope> ks(new KScope(h, kid, POST));
         if (v4) launch_k(h, mg_prolong_jacobi4_kernel, grd4, blk4, 0, L, C, sc, m->b, cur, mc->xa, oth, push_of(oth), zrot_first);
         else if (fine) launch_k(h, mg_prolong_jacobi_kernel<true>, grdL, blk, 0, L, C, sc, m->b, cur, mc->xa, oth);
+        else if (c4 && mc->gx % 2 == 0 && mc->pad % 2 == 0) launch_k(h, mg_prolong_jacobic4_kernel, grdC4, blk4, 0, L, C, sc, m->b, cur, mc->xa, oth);
         else launch_k(h, mg_prolong_jacobi_kernel<false>, grdL, blk, 0, L, C, sc, m->b, cur, mc->xa, oth);
         { float* t = cur; cur = oth; oth = t; }
         for (int s = 1; s < POST; s++) {
@@ -1435,6 +1608,7 @@ int cycle(fsim* h, int l, bool zero_guess, float** result, bool first_done = fal
                                                                                                (int)grd4.x, (int)grd4.y, ntiles, wait_of(cur), (fx && ntiles > layer) ? layer : 0);
             } else if (v4) launch_k(h, mg_jacobi4_kernel, grd4, blk4, 0, L, h->scal, m->b, cur, oth, om, wait_of(cur), no_push, 0);
             else if (fine) launch_k(h, mg_jacobi_kernel<true>, grdL, blk, 0, L, sc, m->b, cur, oth, om);
+            else if (c4) launch_k(h, mg_jacobic4_kernel, grdC4, blk4, 0, L, sc, m->b, cur, oth, om);
             else launch_k(h, mg_jacobi_kernel<false>, grdL, blk, 0, L, sc, m->b, cur, oth, om);
             float* t = cur; cur = oth; oth = t;
         }

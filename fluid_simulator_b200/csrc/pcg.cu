@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(PT, 4) spmv4_kernel(PcgArgs a) {
     if (a.sc->done) return;
     if (a.fws.has[0] | a.fws.has[1]) {  // fused exchange of s: a CTA on a boundary plane reads the neighbour's plane
         const int side = fx_side(a.fws.zb, tile4_plane(a.t4));
-        if (side >= 0 && a.fws.has[side]) fx_wait(a.fws, side);
+        if (fx_has(a.fws, side)) fx_wait(a.fws, side);
     }
     double acc[1] = {0.0};
     const int64_t sy = a.g.sy, sz = a.g.sz;
@@ -416,7 +416,7 @@ __global__ void __launch_bounds__(PT) direction4_kernel(PcgArgs a) {
     int side = -1;
     if (a.fxs.peer[0] || a.fxs.peer[1]) {
         side = fx_side(a.fxs.zb, tile4_plane(a.t4p));
-        if (side >= 0) speer = a.fxs.peer[side];
+        speer = fx_peer(a.fxs, side);
         if (blockIdx.x == 0 && threadIdx.x == 0) fx_expect(a.fxs);
     }
     int64_t c = 0, cn = 0;

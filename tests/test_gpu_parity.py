@@ -273,6 +273,36 @@ def test_projection_only_cfg5(gpu, oracle_lib):
     assert res["pressure"] < TOL and res["v2"] < TOL
 
 
+@pytest.mark.parametrize("n", [48, 40])
+def test_coarse_levels_four_cells_per_thread(gpu, oracle_lib, n, monkeypatch):
+    """The stored-operator multigrid levels with four cells per thread (mg_*c4_kernel, mg.cu; by default only levels with
+    >= 1 M cells, i.e. level 1 of a 256^3 grid): forced on for every level whose row length allows it, the cold cfg-5 solve
+    takes the same number of iterations as with the one-cell-per-thread kernels and lands on the same pressure / the oracle's."""
+    from oracle.oracle import OracleSim
+    p = scenes.default_params(pressure_enabled=False, tol=1e-9)
+    types = scenes.hydrostatic_types(n)
+    out = {}
+    for mode, cmin in (("scalar", str(1 << 40)), ("c4", "1")):
+        monkeypatch.setenv("FSIM_MG_C4_MIN", cmin)
+        monkeypatch.setenv("FSIM_NO_WARM_START", "1")
+        g = gpu((n, n, n), 1.0, False, 0.25)
+        g.set_params(p)
+        g.upload_grid(abi.FIELD_TYPE, types)
+        g.post_p2g_update(-39.24 * 0.005)
+        out[mode] = (g.stage_project(0.005), g.download_grid(abi.FIELD_PRESSURE), g.download_grid(abi.FIELD_V2))
+        g.close()
+    o = OracleSim((n, n, n), 1.0, False, 0.25)
+    o.set_params(p)
+    o.upload_grid(abi.FIELD_TYPE, types)
+    o.post_p2g_update(-39.24 * 0.005)
+    o.stage_project(0.005)
+    res = dict(its_scalar=out["scalar"][0], its_c4=out["c4"][0], c4_vs_scalar=rel_l2(out["c4"][1], out["scalar"][1]),
+               pressure=rel_l2(out["c4"][1], o.download_grid(abi.FIELD_PRESSURE)), v2=rel_l2(out["c4"][2], o.download_grid(abi.FIELD_V2)))
+    diag(test=f"coarse_c4/{n}", **res)
+    assert res["its_c4"] == res["its_scalar"] and res["c4_vs_scalar"] < 1e-7
+    assert res["pressure"] < TOL and res["v2"] < TOL
+
+
 def test_properties_at_scale(gpu):
     """Size-independent properties at BASELINE's single-GPU size (cfg 2: 128^3, ~8 M particles), where the CPU oracle
     would take minutes: partition of unity (sum of face weights = particle count per axis), particle count
