@@ -472,16 +472,19 @@ def main():
         sub = 8
         barrier()
         t0 = time.perf_counter()
+        lap, laps, sub_its = t0, [], []
         for i in range(k):
             sim.set_params(params)
             sim.set_obstacles([scenes.cfg3_box(n)] if args.obstacle_box else [])
-            sim.step(DT)
+            sub_its.append(sim.step(DT))
             sim.export_gfx_strided_async_ptr(gfx[i % 2].data_ptr(), gfx_cap, sub)
             sim.export_gfx_wait_previous()
+            laps.append(round(1e3 * (time.perf_counter() - lap), 2)); lap = time.perf_counter()
         sim.export_gfx_wait()
         barrier()
         el = allmax(time.perf_counter() - t0)
         e2e["subsampled_export"] = {"value": total_particles * k / el, "unit": UNIT, "stride": sub, "d2h_bytes_per_step": int((np_local + sub - 1) // sub * 20),
+                                    "host_ms_per_iteration": laps, "pcg_iterations": sub_its,
                                     "what": "same loop, fsim_export_gfx_strided_async with every 8th particle (not the headline: the manager's contract is the full export)"}
         del gfx
 

@@ -40,6 +40,10 @@ def main(path, traffic):
         rank = 0 if h.startswith("smsp__average_warps_issue_stalled") and "per_issue_active" in h else (1 if "pcsamp" in h else 2)
         if reason not in stall_cols or rank < stall_cols[reason][0]:
             stall_cols[reason] = (rank, h)
+    # one unit for all reasons: the per-issue-active ratios when the report has them (the pc-sampling columns are raw sample
+    # counts and name some reasons in the plural, e.g. "no_instructions": mixing them in would dwarf every ratio)
+    best = min((rk for rk, _ in stall_cols.values()), default=2)
+    stall_cols = {k: v for k, v in stall_cols.items() if v[0] == best}
     for r in rows[2:]:
         name = r[idx["Kernel Name"]].split("(")[0][-48:]
 
