@@ -303,8 +303,7 @@ __global__ void __launch_bounds__(32) allreduce_kernel(const __grid_constant__ A
         DistSlot* s = &a.all[lane]->slot[par][a.rank];
         volatile double* v = s->v;
         v[0] = a.sc->loc[0]; v[1] = a.sc->loc[1]; v[2] = a.sc->loc[2]; v[3] = a.sc->loc[3];
-        __threadfence_system();
-        st_release_sys(&s->epoch, ep);
+        st_release_sys(&s->epoch, ep);  // (orders this lane's four stores before the epoch: no separate fence.sys)
         DistSlot* m = &c->slot[par][lane];
         wait_ge(&m->epoch, ep, c, a.err_host, 0x300u + (a.kind << 4) + lane);
         volatile double* w = m->v;
