@@ -49,8 +49,10 @@ struct DistComm {
     uint32_t push_flag[2];                 // "your ghost plane holds my boundary plane of exchange #epoch" (push halos of the PCG loop)
     uint32_t gpush_flag[DIST_MAX_RANKS];   // the same for the all-rank push of the coarse right-hand side
     uint32_t fx_cnt[3][2];                 // fused exchanges (fexch.cuh): arrivals [array: s, xa, xb][from the lower / upper neighbour]
+    uint32_t gx_cnt;                       // fused all-rank push of the level-1 right-hand side: arrivals from all other ranks
     // local
     uint32_t fx_exp[3][2];                 // ... and how many this rank expects by now
+    uint32_t gx_exp;
     uint32_t halo_epoch, ar_epoch, mig_ep, blocks_done, mig_blocks_done, gather_epoch, gather_blocks_done, push_epoch, push_blocks_done, gpush_epoch, gpush_blocks_done, pad1;
     uint32_t error;   // 1 wait timed out, 2 emigrant list full, 3 immigrant outside the owned planes
     uint32_t n_src;   // particles the next reorder reads: locals + immigrants
@@ -82,6 +84,7 @@ struct DistState {
     int all_zown0[DIST_MAX_RANKS], all_zown1[DIST_MAX_RANKS], all_zoff[DIST_MAX_RANKS];
     bool connected, nsrc_valid;
     bool peer_in_process;  // some other rank of the group lives in this process (they would share libc's rand() stream)
+    FxAllTable* gx_table;  // device copy of the peer table of the fused all-rank push (built on first use)
     std::vector<void*> ipc_opened;
 };
 
@@ -538,7 +541,7 @@ const uint32_t* dist_nsrc_dev(fsim* h) {
 
 void dist_rank(const fsim* h, int* rank, int* nranks) { if (h->dist) { *rank = h->dist->rank; *nranks = h->dist->nranks; } }
 
-bool dist_peer_in_process(const fsim* h) { return h->dist && h->dist->peer_in_process; }
+bool dist_peer_in_process(const fsim* h) { const DistState* d = dist_of(h); return d && d->peer_in_process; }
 
 int dist_wait_stats(fsim* h, FsimDistWaitStats* out, int reset) {
     DistState* d = dist_of(h);
@@ -600,6 +603,7 @@ int dist_init(fsim* h, int rank, int nranks, int own_lo, int own_hi) {
 }
 
 void dist_free(fsim* h) {
+    if (h->dist && h->dist->gx_table) { cudaFree(h->dist->gx_table); h->dist->gx_table = nullptr; }
     DistState* d = h->dist;
     if (!d) return;
     for (void* p : d->ipc_opened) cudaIpcCloseMemHandle(p);
@@ -690,6 +694,24 @@ int dist_connect(fsim* h, const FsimDistExport* all, int n) {
         if (!(e && (strcmp(e, "EAGER") == 0 || strcmp(e, "eager") == 0)))
             return fsim_fail(h, FSIM_ERR_INVALID, "slab ranks that share a process need CUDA_MODULE_LOADING=EAGER in the environment before CUDA is "
                                                    "initialised (one process per GPU has no such requirement)");
+    }
+    // peer table of the fused all-rank push (fexch.cuh); allocated here, not in the solve: a cudaMalloc may synchronise the device
+    if (h->solver && n <= 16) {
+        FxAllTable t;
+        memset(&t, 0, sizeof(t));
+        bool ok = true;
+        for (int r = 0; r < n && ok; r++) {
+            if (r == d->rank) continue;
+            if (!d->all_arr[r][ARR_HS_B1] || !d->all_comm[r]) { ok = false; break; }
+            t.peer[t.n] = (float*)d->all_arr[r][ARR_HS_B1];
+            t.peer_cnt[t.n] = &d->all_comm[r]->gx_cnt;
+            t.n++;
+        }
+        if (ok && t.n > 0) {
+            if (d->gx_table) { cudaFree(d->gx_table); d->gx_table = nullptr; }
+            FSIM_CUDA(h, cudaMalloc((void**)&d->gx_table, sizeof(t)));
+            FSIM_CUDA(h, cudaMemcpy(d->gx_table, &t, sizeof(t), cudaMemcpyHostToDevice));
+        }
     }
     d->connected = true;
     return FSIM_OK;
@@ -924,6 +946,36 @@ bool dist_fx(fsim* hs, int which, const void* ptr, FxPush* p, FxWait* w) {
         p->peer_cnt[side] = &d->peer_comm[side]->fx_cnt[ix][1 - side];  // I am the upper neighbour of my lower neighbour
         w->has[side] = 1;
     }
+    return true;
+}
+
+// fused form of dist_gather_coarse (fexch.cuh, all-rank form): arguments for mg_restrict4_kernel (producer) and for the first
+// level-1 kernel (consumer).  (cgx, cgy, cgz): the level-1 grid -- the producer's launch geometry on every rank follows from it
+bool dist_gx(fsim* hs, int cgx, int cgy, int cgz, FxAllPush* p, FxWait* w) {
+    memset(p, 0, sizeof(*p));
+    memset(w, 0, sizeof(*w));
+    DistState* d = dist_of(hs);
+    if (!d || !d->connected || !hs->hybrid || !push_enabled() || !fused_enabled()) return false;
+    // measured (256^3, one box each, --steps 20): 8 GPUs 4.051 -> 3.994 ms/step, 2 GPUs 6.45 -> 6.48 -- the same bytes leave through
+    // the restriction's stores instead of a copy kernel; it pays once several peers are written in parallel.  Default: on from 4
+    // ranks (FSIM_SLAB_FUSED_GATHER=1 / =0 force it)
+    { const char* e = getenv("FSIM_SLAB_FUSED_GATHER"); if (e ? e[0] == '0' : d->nranks < 4) return false; }
+    if (d->nranks > 16 || cgx % 2 != 0 || d->local_off[ARR_HS_B1] % 8 != 0) return false;
+    if (!d->gx_table) return false;  // built by dist_connect
+    uint32_t add = 0;
+    for (int r = 0; r < d->nranks; r++) {
+        if (r == d->rank) continue;
+        const int lo = d->all_zoff[r] + d->all_zown0[r], hi = d->all_zoff[r] + d->all_zown1[r];
+        const int clo = lo / 2, chi = r == d->nranks - 1 ? cgz : hi / 2;  // (as in dist_gather_coarse / the launch in mg.cu cycle())
+        add += (uint32_t)(((cgx + 63) / 64) * ((cgy + 3) / 4) * ((chi - clo + 1) / 2));
+    }
+    p->tab = d->gx_table; p->my_exp = &d->comm->gx_exp; p->add = add;
+    w->cnt = &d->comm->gx_cnt; w->exp = &d->comm->gx_exp;
+    w->error = &d->comm->error; w->err_host = d->err_dev;
+    w->stat = &d->comm->wait_ns[FSIM_WAIT_FUSED]; w->stat_n = &d->comm->waits[FSIM_WAIT_FUSED];
+    const char* e = getenv("FSIM_DIST_TIMEOUT_MS");
+    w->timeout_ns = (unsigned long long)(e ? atoll(e) : 20000) * 1000000ull;
+    w->has[0] = 1;
     return true;
 }
 

@@ -43,6 +43,22 @@ struct FxWait {
     int zb[2];
 };
 
+// All-rank form (the level-1 right-hand side after the restriction: every rank owns some coarse planes, every rank needs all of
+// them): the producer stores its results into every other rank's array as well and each of its CTAs adds 1 to ONE counter on
+// every rank; a consumer CTA waits until the counter holds the CTAs of all other ranks' producer launches so far.
+// The peer tables live in device memory (not in the parameter struct: a run-time index into a parameter array costs a
+// local-memory copy of the struct per thread).
+struct FxAllTable {
+    float* peer[16];         // the other ranks' arrays (same indexing), n entries
+    uint32_t* peer_cnt[16];  // their arrival counters
+    int n;
+};
+struct FxAllPush {
+    const FxAllTable* tab;   // nullptr: not in use
+    uint32_t* my_exp;        // local expectation
+    uint32_t add;            // CTAs of all OTHER ranks' launches of the same kernel (they differ with the planes a rank owns)
+};
+
 #ifdef __CUDACC__
 __device__ __forceinline__ unsigned long long fx_now_ns() {
     unsigned long long t;
@@ -72,6 +88,22 @@ __device__ __forceinline__ void fx_signal(const FxPush& f, int side) {
         uint32_t* cnt = side == 0 ? f.peer_cnt[0] : f.peer_cnt[1];
         asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(cnt), "r"(1u) : "memory");
     }
+}
+
+// all threads of a producer CTA of the all-rank form, after their stores (fx_all_store)
+__device__ __forceinline__ void fx_all_signal(const FxAllPush& f) {
+    if (!f.tab) return;
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0 && threadIdx.y == 0 && threadIdx.z == 0) *f.my_exp += f.add;
+    __syncthreads();
+    const int t = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
+    if (t < f.tab->n) {  // lane r signals rank r: its release orders the CTA's stores (barrier above) before the count
+        asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(f.tab->peer_cnt[t]), "r"(1u) : "memory");
+    }
+}
+__device__ __forceinline__ void fx_all_store2(const FxAllPush& f, int64_t idx, float2 v) {
+    if (!f.tab) return;
+    const int n = f.tab->n;
+    for (int r = 0; r < n; r++) *reinterpret_cast<float2*>(f.tab->peer[r] + idx) = v;
 }
 
 // all threads of a CTA that is about to read ghost plane `side`

@@ -150,10 +150,11 @@ __device__ __forceinline__ float pre2_value(const Lv& L, const float* __restrict
     return xi + OM_B * (bb - (d * xi - off)) / d;
 }
 __global__ void __launch_bounds__(256) mg_pre2_kernel(Lv L, const PcgScalars* __restrict__ sc, const float* __restrict__ b,
-                                                      float* __restrict__ xout) {
+                                                      float* __restrict__ xout, FxWait gw) {
     pdl_wait();
     pdl_trigger();
     if (sc->done) return;
+    if (gw.has[0]) fx_wait(gw, 0);  // (hybrid slab projection, fused all-rank push: every rank's planes of b have arrived)
     int x, y, z; int64_t c;
     if (!cell_of(L, x, y, z, c)) return;
     xout[c] = pre2_value(L, b, c);
@@ -520,7 +521,7 @@ __global__ void __launch_bounds__(256, UF_MIN_BLOCKS) mg_update_first4_kernel(Lv
 
 // one thread = two coarse cells in x = a 4x2x2 block of fine cells
 __global__ void __launch_bounds__(256) mg_restrict4_kernel(Lv L, Lv C, const PcgScalars* __restrict__ sc, const float* __restrict__ b, const float* __restrict__ xf,
-                                                           float* __restrict__ bc, int cz0, int cz1, FxWait fw, int zrot) {
+                                                           float* __restrict__ bc, int cz0, int cz1, FxWait fw, int zrot, FxAllPush gp) {
     pdl_wait();
     pdl_trigger();
     if (sc->done) return;
@@ -528,30 +529,34 @@ __global__ void __launch_bounds__(256) mg_restrict4_kernel(Lv L, Lv C, const Pcg
     fx_wait_planes(fw, 2 * (zblk * 2 + cz0), 4);  // the CTA's two coarse planes have their children in four fine planes
     const int X = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
     const int Y = blockIdx.y * blockDim.y + threadIdx.y, Z = zblk * blockDim.z + threadIdx.z + cz0;
-    if (X >= C.gx || Y >= C.gy || Z >= C.gz) return;
-    if (Z >= cz1) return;  // hybrid: only the coarse planes [cz0, cz1) whose children this rank owns; the others are written by their owners (pushed over NVLink)
-    float s0 = 0.f, s1 = 0.f;
+    // hybrid: only the coarse planes [cz0, cz1) whose children this rank owns; the others are written by their owners
+    if (X < C.gx && Y < C.gy && Z < C.gz && Z < cz1) {
+        float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-    for (int k = 0; k < 2; k++)
+        for (int k = 0; k < 2; k++)
 #pragma unroll
-        for (int j = 0; j < 2; j++) {
-            const int y = 2 * Y + j, z = 2 * Z + k;
-            if (y >= L.gy || z >= L.gz) continue;
-            const int64_t c = ((int64_t)z * L.gy + y) * L.gx + 2 * X;
-            const ushort4 t = *reinterpret_cast<const ushort4*>(L.code + c);
-            const unsigned cd[4] = {t.x, t.y, t.z, t.w};
-            if (!((cd[0] | cd[1] | cd[2] | cd[3]) & CODE_ACTIVE)) continue;
-            const Stencil4 s = load_stencil4(L, xf, c, cd);
-            const F4 bb = ld4(b + c);
+            for (int j = 0; j < 2; j++) {
+                const int y = 2 * Y + j, z = 2 * Z + k;
+                if (y >= L.gy || z >= L.gz) continue;
+                const int64_t c = ((int64_t)z * L.gy + y) * L.gx + 2 * X;
+                const ushort4 t = *reinterpret_cast<const ushort4*>(L.code + c);
+                const unsigned cd[4] = {t.x, t.y, t.z, t.w};
+                if (!((cd[0] | cd[1] | cd[2] | cd[3]) & CODE_ACTIVE)) continue;
+                const Stencil4 s = load_stencil4(L, xf, c, cd);
+                const F4 bb = ld4(b + c);
 #pragma unroll
-            for (int i = 0; i < 4; i++)
-                if (cd[i] & CODE_ACTIVE) {
-                    const float d = (float)((cd[i] >> 6) & 7u);
-                    const float res = bb.v[i] - (d * s.c.v[i] - off4(s, i, cd[i]));
-                    if (i < 2) s0 += res; else s1 += res;
-                }
-        }
-    *reinterpret_cast<float2*>(bc + ((int64_t)Z * C.gy + Y) * C.gx + X) = make_float2(s0, s1);
+                for (int i = 0; i < 4; i++)
+                    if (cd[i] & CODE_ACTIVE) {
+                        const float d = (float)((cd[i] >> 6) & 7u);
+                        const float res = bb.v[i] - (d * s.c.v[i] - off4(s, i, cd[i]));
+                        if (i < 2) s0 += res; else s1 += res;
+                    }
+            }
+        const int64_t idx = ((int64_t)Z * C.gy + Y) * C.gx + X;
+        *reinterpret_cast<float2*>(bc + idx) = make_float2(s0, s1);
+        fx_all_store2(gp, idx, make_float2(s0, s1));  // (fused all-rank push: the same two cells in every other rank's array)
+    }
+    fx_all_signal(gp);
 }
 
 __global__ void __launch_bounds__(256) mg_prolong_jacobi4_kernel(Lv L, Lv C, const PcgScalars* __restrict__ sc, const float* __restrict__ b, const float* __restrict__ xin,
@@ -656,10 +661,12 @@ __global__ void __launch_bounds__(256) mg_jacobic4_kernel(Lv L, const PcgScalars
     st4(xout + c, xo);
 }
 
-__global__ void __launch_bounds__(256) mg_pre2c4_kernel(Lv L, const PcgScalars* __restrict__ sc, const float* __restrict__ b, float* __restrict__ xout) {
+__global__ void __launch_bounds__(256) mg_pre2c4_kernel(Lv L, const PcgScalars* __restrict__ sc, const float* __restrict__ b, float* __restrict__ xout,
+                                                        FxWait gw) {
     pdl_wait();
     pdl_trigger();
     if (sc->done) return;
+    if (gw.has[0]) fx_wait(gw, 0);  // (see mg_pre2_kernel)
     int x, y, z; int64_t c;
     if (!group4_of(L, x, y, z, c)) return;
     const Row4 r = load_row4(L, c);
@@ -842,6 +849,7 @@ struct TailArgs {
     TailLevel lv[TAIL_MAX_LEVELS];
     const PcgScalars* sc;
     int zero_guess;
+    FxWait gw;  // hybrid slab projection with the fused all-rank push, tail starting at level 1: wait for every rank's planes of b
 };
 
 __device__ __forceinline__ float t_row(const Lv& L, int c, const float* x, float* offsum) {
@@ -975,6 +983,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) mg_tail_kernel(TailArgs a) {
     pdl_trigger();
     __shared__ float xs[2][COARSE_MAX];
     if (a.sc->done) return;  // uniform over the cluster
+    if (a.gw.has[0]) fx_wait(a.gw, 0);
     cg::cluster_group cluster = cg::this_cluster();
     const int t0 = (int)cluster.block_rank() * TAIL_THREADS + threadIdx.x;
     const int nt = (int)cluster.num_blocks() * TAIL_THREADS;
@@ -1377,6 +1386,11 @@ int cycle(fsim* h, int l, bool zero_guess, float** result, bool first_done = fal
         }
         ta.sc = sc;
         ta.zero_guess = zero_guess ? 1 : 0;
+        memset(&ta.gw, 0, sizeof(ta.gw));
+        if (l == 1 && zero_guess && h->hybrid && h->gx_on) {  // its right-hand side arrives through the fused all-rank push
+            FxAllPush gp;
+            if (!dist_gx(h, m->gx, m->gy, m->gz, &gp, &ta.gw)) return fsim_fail(h, FSIM_ERR_COMM, "fused all-rank push: peer table unavailable");
+        }
         cudaLaunchConfig_t cfg = {};
         if (h->mg_tail_cluster == 0) {  // first use: can a 16-CTA cluster of 1024-thread CTAs be co-scheduled on this device?
             h->mg_tail_cluster = TAIL_CLUSTER_PORTABLE;
@@ -1524,8 +1538,14 @@ int cycle(fsim* h, int l, bool zero_guess, float** result, bool first_done = fal
     };
     if (!fine && zero_guess && PRE == 2) {
         KScope ks(h, kid);
-        if (c4) launch_k(h, mg_pre2c4_kernel, grdC4, blk4, 0, L, sc, m->b, cur);
-        else launch_k(h, mg_pre2_kernel, grdL, blk, 0, L, sc, m->b, cur);
+        FxWait gw;
+        memset(&gw, 0, sizeof(gw));
+        if (l == 1 && h->hybrid && h->gx_on) {  // the right-hand side arrives through the fused all-rank push
+            FxAllPush gp;
+            if (!dist_gx(h, m->gx, m->gy, m->gz, &gp, &gw)) return fsim_fail(h, FSIM_ERR_COMM, "fused all-rank push: peer table unavailable");
+        }
+        if (c4) launch_k(h, mg_pre2c4_kernel, grdC4, blk4, 0, L, sc, m->b, cur, gw);
+        else launch_k(h, mg_pre2_kernel, grdL, blk, 0, L, sc, m->b, cur, gw);
     } else {
         std::unique_ptr<KScope> ks(new KScope(h, kid, PRE - ((zero_guess && first_done) ? 1 : 0)));
         for (int s = 0; s < PRE; s++) {
@@ -1559,7 +1579,15 @@ int cycle(fsim* h, int l, bool zero_guess, float** result, bool first_done = fal
         if (v4) {
             const dim3 grdR(div_up(mc->gx, 2 * 32), div_up(mc->gy, 4), div_up(std::min(cz1, mc->gz) - cz0, 2));
             // (consumer of the iterate's ghost planes: the layers next to them come last)
-            launch_k(h, mg_restrict4_kernel, grdR, blk4, 0, L, C, sc, m->b, cur, mc->b, cz0, cz1, wait_of(cur), (fx && grdR.z > 1) ? 1 : 0);
+            // fused all-rank push of the coarse right-hand side (fexch.cuh): needs the default tail kernel when the tail starts at level 1
+            FxAllPush gp;
+            FxWait gw_unused;
+            memset(&gp, 0, sizeof(gp));
+            // (ranks sharing one process and device -- the test harness -- keep the gather kernel when the consumer is a full-grid
+            // kernel: all of its CTAs spin on the counter and could starve the other ranks' producers of CTA slots)
+            h->gx_on = fx && (h->mg_tail_first == 1 || !dist_peer_in_process(h)) && (h->mg_tail_first > 1 || (h->mg_tail_smem != 1 && h->mg_tail2 != 1 && !(getenv("FSIM_MG_TAIL_SMEM") || getenv("FSIM_MG_TAIL2")))) &&
+                       (PRE == 2) && dist_gx(h, mc->gx, mc->gy, mc->gz, &gp, &gw_unused);
+            launch_k(h, mg_restrict4_kernel, grdR, blk4, 0, L, C, sc, m->b, cur, mc->b, cz0, cz1, wait_of(cur), (fx && grdR.z > 1) ? 1 : 0, gp);
         }
         else if (fine) launch_k(h, mg_restrict_kernel<true>, grid_of(mc, blk), blk, 0, L, C, sc, m->b, cur, mc->b);
         else if (c4 && mc->gx % 2 == 0 && mc->pad % 2 == 0)
@@ -1568,7 +1596,7 @@ int cycle(fsim* h, int l, bool zero_guess, float** result, bool first_done = fal
         else launch_k(h, mg_restrict8_kernel, div_up(mc->nc * 8, 256), 256, 0, L, C, sc, m->b, cur, mc->b, (int)mc->nc);
     }
     // hybrid: every rank restricted the planes it owns; with all ranks' coarse planes gathered, levels >= 1 run replicated
-    if (fine && h->hybrid) { int rc = dist_gather_coarse(h, true); if (rc) return rc; }
+    if (fine && h->hybrid && !(v4 && h->gx_on)) { int rc = dist_gather_coarse(h, true); if (rc) return rc; }
     float* ec = nullptr;
     // experiment switches (default: the constants above): FSIM_MG_W_FIRST / FSIM_MG_W_LAST move the doubly visited levels
     static const int w_first = getenv("FSIM_MG_W_FIRST") ? atoi(getenv("FSIM_MG_W_FIRST")) : W_FIRST;

@@ -142,8 +142,10 @@ def test_model_detects_a_race_when_nothing_orders_the_ranks():
 # ("push", "s"): the one stand-alone push per solve (start_kernel has no fused store)
 FUSED_CYCLE_REST = [
     ("read", "xa"), ("wpush", "xb"),          # pre-sweep 2 (mg_jacobi4_kernel: waits for xa, pushes xb)
-    ("read", "xb"),                           # restriction
-    ("gpush",),
+    ("read", "xb"),                           # restriction ...
+    ("gstore",),                              # ... whose CTAs store the coarse right-hand side into every rank's array and count there
+    ("gwait",),                               # first level-1 kernel: waits until every other rank's restriction has counted
+    ("gdone",),                               # last level-1 kernel that reads the coarse right-hand side (replicated coarse levels)
     ("read", "xb"), ("wpush", "xa"),          # prolongation + sweep
     ("read", "xa"), ("write", "xb"),          # last sweep (fused with z.r inside the loop)
     ("ar",),                                  # z.r / AR_START
@@ -161,7 +163,7 @@ def simulate_fused(nranks, iterations, seed, drop_barriers=False, reads_wait=Tru
     rng = random.Random(seed)
     prog = FUSED_HEAD + FUSED_ITERATION * iterations
     if drop_barriers:
-        prog = [op for op in prog if op[0] not in ("ar", "gpush")]
+        prog = [op for op in prog if op[0] not in ("ar", "gstore", "gwait", "gdone")]
     reads_per_push = {}
     for i, op in enumerate(prog):
         if op[0] in ("push", "wpush"):
@@ -175,6 +177,7 @@ def simulate_fused(nranks, iterations, seed, drop_barriers=False, reads_wait=Tru
     pc = [0] * nranks
     ghost, pushed, arrived = {}, {}, {}
     barrier_count = [0] * nranks
+    gcount, gread = [0] * nranks, [0] * nranks  # all-rank push: exchanges stored by each rank / consumed by each rank
     phase = ["start"] * nranks
 
     def sides(r):  # (neighbour, the ghost side of the neighbour that I write, my ghost side that it writes)
@@ -215,13 +218,25 @@ def simulate_fused(nranks, iterations, seed, drop_barriers=False, reads_wait=Tru
                 assert g["ver"] == k, f"rank {r} reads exchange {g['ver']} of {a}, expected {k}"
                 g["readers_left"] -= 1
             pc[r] += 1
-        elif op[0] in ("ar", "gpush"):
+        elif op[0] == "ar":
             if phase[r] == "start":
                 barrier_count[r] += 1
                 phase[r] = "wait"
             elif all(barrier_count[q] >= barrier_count[r] for q in range(nranks)):
                 phase[r] = "start"
                 pc[r] += 1
+        elif op[0] == "gstore":   # fire and forget: remote stores into every rank's coarse array + one count per rank
+            gcount[r] += 1
+            for q in range(nranks):
+                if q != r:
+                    assert gread[q] >= gcount[r] - 1, f"rank {r} overwrites the coarse right-hand side of rank {q} before it was read"
+            pc[r] += 1
+        elif op[0] == "gwait":    # consumer of the coarse right-hand side: needs every other rank's stores of this exchange
+            if all(gcount[q] >= gcount[r] for q in range(nranks)):
+                pc[r] += 1
+        elif op[0] == "gdone":
+            gread[r] = gcount[r]
+            pc[r] += 1
         else:
             pc[r] += 1
     return steps
