@@ -35,7 +35,8 @@
 
 enum { ARR_U = 0, ARR_U2 = 3, ARR_W = 6, ARR_DENS = 9, ARR_CNT = 10, ARR_FLAGS = 11, ARR_P = 12, ARR_S = 13, ARR_COMM = 14, ARR_RECV = 15,
        // arrays of the full-grid solver context (hybrid projection): same global plane index on every rank
-       ARR_HS_S = 16, ARR_HS_P = 17, ARR_HS_XA = 18, ARR_HS_XB = 19, ARR_HS_B1 = 20 };
+       ARR_HS_S = 16, ARR_HS_P = 17, ARR_HS_XA = 18, ARR_HS_XB = 19, ARR_HS_B1 = 20,
+       ARR_PA = 21 };  // push-apart: positions of the particles in my two boundary planes, staged for the neighbours
 
 struct DistSlot { double v[4]; uint32_t epoch; uint32_t pad[7]; };
 
@@ -85,6 +86,11 @@ struct DistState {
     bool connected, nsrc_valid;
     bool peer_in_process;  // some other rank of the group lives in this process (they would share libc's rand() stream)
     FxAllTable* gx_table;  // device copy of the peer table of the fused all-rank push (built on first use)
+    // push-apart across slabs (pushParticlesApart, hashedParticles.cpp:64-107): per side one block of words
+    //   [0] particle count | [1 .. sz+1] per-cell starts of the plane (relative) | x[pa_capa] | y[pa_capa] | z[pa_capa]
+    // pa_stage: my boundary planes (read by the neighbours), pa_ghost: the neighbours' boundary planes (pulled)
+    uint32_t *pa_stage, *pa_ghost;
+    int64_t pa_capa, pa_head, pa_words;  // particles per plane (multiple of 4), header words (multiple of 4), words per side
     std::vector<void*> ipc_opened;
 };
 
@@ -139,7 +145,8 @@ __device__ __forceinline__ void wait_account(DistComm* c, int cls, unsigned long
 
 // mask >= 0: a plane of floats of which only the cells with (x + y) & 1 == mask are copied (row length gx): the red-black sweeps of
 // the BasicMacGrid solver on slabs, where each rank owns the updates of one colour of a shared face plane
-struct HaloCopy { void* dst; const void* src; uint32_t bytes; int side; int mask, gx; };
+// limit != nullptr: copy only the first round_up(*limit, 4) 4-byte elements (a count that lives in the neighbour's memory)
+struct HaloCopy { void* dst; const void* src; uint32_t bytes; int side; int mask, gx; const uint32_t* limit; };
 struct HaloArgs {
     DistComm* comm;
     DistComm* peer[2];
@@ -179,7 +186,8 @@ __global__ void __launch_bounds__(256) halo_kernel(const __grid_constant__ HaloA
                 if (((x + y) & 1) == cp.mask) reinterpret_cast<float*>(cp.dst)[i] = reinterpret_cast<const volatile float*>(cp.src)[i];
             }
         } else if ((((size_t)cp.dst | (size_t)cp.src | (size_t)cp.bytes) & 15) == 0) {
-            const size_t n = cp.bytes >> 4;
+            size_t n = cp.bytes >> 4;
+            if (cp.limit) n = min(n, (size_t)((*(const volatile uint32_t*)cp.limit + 3u) >> 2));
             for (size_t i = gtid; i < n; i += gsz) reinterpret_cast<uint4*>(cp.dst)[i] = ld_peer_u4(reinterpret_cast<const uint4*>(cp.src) + i);
         } else {
             for (size_t i = gtid; i < cp.bytes; i += gsz) reinterpret_cast<uint8_t*>(cp.dst)[i] = reinterpret_cast<const volatile uint8_t*>(cp.src)[i];
@@ -595,9 +603,15 @@ int dist_init(fsim* h, int rank, int nranks, int own_lo, int own_hi) {
     FSIM_CUDA(h, cudaStreamSynchronize(h->stream));
     if ((rc = dalloc(h, &d->recv, (size_t)2 * (DIST_NCH + 1) * d->mig_cap))) return rc;
     if ((rc = dalloc(h, &d->stage, (size_t)2 * 2 * 7 * g.sz))) return rc;
+    d->pa_capa = ((std::max<int64_t>(4096, (int64_t)g.sz * 16) + 3) / 4) * 4;
+    d->pa_head = (((int64_t)g.sz + 2 + 3) / 4) * 4;
+    d->pa_words = d->pa_head + 3 * d->pa_capa;
+    if ((rc = dalloc(h, &d->pa_stage, (size_t)2 * d->pa_words))) return rc;
+    if ((rc = dalloc(h, &d->pa_ghost, (size_t)2 * d->pa_words))) return rc;
     for (int a = 0; a < 3; a++) { d->local_arr[ARR_U + a] = h->u[a]; d->local_arr[ARR_U2 + a] = h->u2[a]; d->local_arr[ARR_W + a] = h->wsum[a]; }
     d->local_arr[ARR_DENS] = h->dens; d->local_arr[ARR_CNT] = h->cnt; d->local_arr[ARR_FLAGS] = h->flags;
     d->local_arr[ARR_P] = h->p; d->local_arr[ARR_S] = h->s; d->local_arr[ARR_COMM] = d->comm; d->local_arr[ARR_RECV] = d->recv;
+    d->local_arr[ARR_PA] = d->pa_stage;
     d->all_comm[rank] = d->comm;
     return FSIM_OK;
 }
@@ -607,6 +621,7 @@ void dist_free(fsim* h) {
     DistState* d = h->dist;
     if (!d) return;
     for (void* p : d->ipc_opened) cudaIpcCloseMemHandle(p);
+    cudaFree(d->pa_stage); cudaFree(d->pa_ghost);
     cudaFree(d->comm); cudaFree(d->mig); cudaFree(d->mig_idx[0]); cudaFree(d->mig_idx[1]); cudaFree(d->recv); cudaFree(d->stage);
     if (d->err_host) cudaFreeHost(d->err_host);
     delete d;
@@ -809,6 +824,85 @@ int dist_halo(fsim* h, int what, bool in_pcg_loop) {
     }
     FSIM_CHECK_LAUNCH(h);
     return FSIM_OK;
+}
+
+// ---- push-apart across slabs: the neighbour search of a particle in a boundary plane reaches into the neighbour's boundary
+// plane (search radius one cell).  After the sort the particles of a plane are one contiguous run, so each rank stages the
+// positions + per-cell starts of its two boundary planes and pulls the neighbours' (two-sided handshake, halo_kernel).
+struct PaPackArgs {
+    const float *px, *py, *pz;
+    const uint32_t* cell_start;
+    uint32_t* out[2];       // stage block per side
+    int64_t cell0[2];       // first cell of my boundary plane on that side
+    int has[2];
+    int sz;
+    uint32_t capa, head;
+};
+__global__ void __launch_bounds__(256) pa_pack_kernel(const __grid_constant__ PaPackArgs a) {
+    const int side = blockIdx.y;
+    if (side == 0 ? !a.has[0] : !a.has[1]) return;
+    uint32_t* out = side == 0 ? a.out[0] : a.out[1];
+    const int64_t c0 = side == 0 ? a.cell0[0] : a.cell0[1];
+    const uint32_t base = a.cell_start[c0], end = a.cell_start[c0 + a.sz];
+    const uint32_t n = min(end - base, a.capa);  // (a plane denser than 16 particles per cell on average is truncated)
+    const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, gsz = (size_t)gridDim.x * blockDim.x;
+    if (gtid == 0) out[0] = n;
+    for (size_t i = gtid; i <= (size_t)a.sz; i += gsz) out[1 + i] = min(a.cell_start[c0 + i] - base, n);
+    float* x = reinterpret_cast<float*>(out + a.head);
+    float *y = x + a.capa, *z = y + a.capa;
+    for (size_t i = gtid; i < n; i += gsz) { x[i] = a.px[base + i]; y[i] = a.py[base + i]; z[i] = a.pz[base + i]; }
+}
+
+int dist_push_apart_ghosts(fsim* h) {
+    DistState* d = h->dist;
+    if (!d || !d->connected) return fsim_fail(h, FSIM_ERR_COMM, "slab handle is not connected to its neighbours (fsim_dist_connect)");
+    const GridDims& g = h->g;
+    const ParticleSet& p = h->ps[h->cur];
+    PaPackArgs k;
+    memset(&k, 0, sizeof(k));
+    k.px = p.pos[0]; k.py = p.pos[1]; k.pz = p.pos[2]; k.cell_start = h->cell_start;
+    k.sz = g.sz; k.capa = (uint32_t)d->pa_capa; k.head = (uint32_t)d->pa_head;
+    const int bnd[2] = {g.zown0, g.zown1 - 1};
+    HaloArgs a;
+    memset(&a, 0, sizeof(a));
+    a.comm = d->comm; a.peer[0] = d->peer_comm[0]; a.peer[1] = d->peer_comm[1]; a.err_host = d->err_dev;
+    for (int side = 0; side < 2; side++) {
+        k.has[side] = d->peer_comm[side] != nullptr;
+        k.out[side] = d->pa_stage + (size_t)side * d->pa_words;
+        k.cell0[side] = (int64_t)bnd[side] * g.sz;
+        if (!d->peer_comm[side]) continue;
+        if (!d->peer_arr[side][ARR_PA]) return fsim_fail(h, FSIM_ERR_COMM, "neighbour did not publish its push-apart staging buffer");
+        // the neighbour's block that faces me: its side 1 - side
+        const uint32_t* src = (const uint32_t*)d->peer_arr[side][ARR_PA] + (size_t)(1 - side) * d->pa_words;
+        uint32_t* dst = d->pa_ghost + (size_t)side * d->pa_words;
+        HaloCopy& c0 = a.cp[a.ncopy++];
+        c0.dst = dst; c0.src = src; c0.bytes = (uint32_t)(d->pa_head * 4); c0.side = side; c0.mask = -1;
+        for (int ax = 0; ax < 3; ax++) {
+            HaloCopy& c = a.cp[a.ncopy++];
+            c.dst = dst + d->pa_head + (size_t)ax * d->pa_capa;
+            c.src = src + d->pa_head + (size_t)ax * d->pa_capa;
+            c.bytes = (uint32_t)(d->pa_capa * 4); c.side = side; c.mask = -1;
+            c.limit = src;  // word 0 of the neighbour's block: its particle count
+        }
+    }
+    {
+        KScope ks(h, K_HALO, 2);
+        if (h->np > 0) pa_pack_kernel<<<dim3(64, 2), 256, 0, h->stream>>>(k);
+        else FSIM_CUDA(h, cudaMemsetAsync(d->pa_stage, 0, sizeof(uint32_t) * 2 * d->pa_words, h->stream));  // an empty slab: counts and starts 0
+        halo_kernel<<<64, 256, 0, h->stream>>>(a);
+    }
+    FSIM_CHECK_LAUNCH(h);
+    return FSIM_OK;
+}
+
+// the pulled block of neighbour `side` (nullptr: no neighbour): per-cell starts of its boundary plane and the positions
+bool dist_pa_ghost(const fsim* h, int side, const uint32_t** starts, const float** x, const float** y, const float** z) {
+    const DistState* d = h->dist;
+    if (!d || !d->peer_comm[side]) return false;
+    const uint32_t* blk = d->pa_ghost + (size_t)side * d->pa_words;
+    *starts = blk + 1;
+    *x = reinterpret_cast<const float*>(blk + d->pa_head); *y = *x + d->pa_capa; *z = *y + d->pa_capa;
+    return true;
 }
 
 int dist_allreduce(fsim* h, int kind, bool in_pcg_loop) {

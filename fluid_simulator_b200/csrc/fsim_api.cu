@@ -300,7 +300,7 @@ static int create_impl(const FsimGridDesc* desc, int rank, int nranks, fsim_t** 
     p.transfer_type = FSIM_TRANSFER_FLIP; p.flip_ratio = 0.99f; p.gravity = 150.0f; p.gravity_enabled = 1;
     p.push_apart_enabled = 1; p.pressure_enabled = 1; p.max_iterations = 80; p.pressure_k = 2.0;
     p.average_pressure = 2.0; p.fluid_density = 1.0; p.residual_tolerance = 1e-6;
-    if (nranks > 1) p.push_apart_enabled = 0;  // not available on slab handles: a handle that never calls fsim_set_params must still step
+    if (nranks > 1) p.push_apart_enabled = 0;  // (slab handles: off unless asked for -- it costs a second migration per step)
     h->nobs = 0;
     h->np = 0; h->cap = 0; h->cur = 0; h->have_c = false; h->track_ids = true; h->sorted = false; h->binned = false; h->kill_pending = false;
     memset(h->ps, 0, sizeof(h->ps));
@@ -547,7 +547,6 @@ int fsim_set_params(fsim_t* h, const FsimParams* p) {
     if (p->transfer_type < 0 || p->transfer_type > 2) return fsim_fail(h, FSIM_ERR_INVALID, "bad transfer type %d", p->transfer_type);
     if (!(p->fluid_density > 0)) return fsim_fail(h, FSIM_ERR_INVALID, "fluid density must be > 0");
     if (p->solver_type != FSIM_SOLVER_BRIDSON && p->solver_type != FSIM_SOLVER_BASIC) return fsim_fail(h, FSIM_ERR_INVALID, "bad solver type %d", p->solver_type);
-    if (h->dist && p->push_apart_enabled) return fsim_fail(h, FSIM_ERR_INVALID, "push-apart is not available on slab handles");
     if (p->transfer_type != h->par.transfer_type || p->flip_ratio != h->par.flip_ratio) TRY(flush_g2p(h));  // a pending G2P uses the old blend
     h->par = *p;
     if (p->transfer_type == FSIM_TRANSFER_APIC) TRY(ensure_c(h));
@@ -861,7 +860,6 @@ static int project_slab(fsim* h, double dt, int* its_out) {
 // the same step on one z-slab of the grid (dist.cu): collective over the ranks
 static int step_slab(fsim* h, double dt, int* pcg_iterations) {
     TRY(dist_check(h));
-    if (h->par.push_apart_enabled) return fsim_fail(h, FSIM_ERR_INVALID, "push-apart is not available on slab handles");
     fold_timings(h);
     const int64_t l0 = h->launches;
     FSIM_CUDA(h, cudaEventRecord(h->ev[0], h->stream));
@@ -869,9 +867,22 @@ static int step_slab(fsim* h, double dt, int* pcg_iterations) {
     TRY(ensure_capacity(h, h->np));  // room for this step's immigrants; must happen before the advect kernel bins
     const bool fuse = h->g2p_pending && h->sorted && h->np > 0;
     if (!fuse) TRY(flush_g2p(h));
-    TRY(k_advect(h, dt, true, true, h->par.stop_particles != 0, /*do_bin=*/true, fuse));
-    if (h->np > 0 && !h->binned) return fsim_fail(h, FSIM_ERR_INVALID, "slab step: particles were not binned");
     h->push_timed = false;
+    if (h->par.push_apart_enabled) {
+        // simulate() order (simulator.cpp:57-74): advect -> push apart -> push out of obstacles -> stop.  On slabs the advected
+        // particles change owner first, the pair search then also sees the neighbours' boundary planes, and whatever the two
+        // position passes moved across a slab boundary migrates a second time
+        TRY(k_advect(h, dt, true, false, false, /*do_bin=*/true, fuse));
+        TRY(dist_migrate(h));
+        TRY(k_sort(h));
+        TRY(ensure_capacity(h, h->np));
+        TRY(dist_push_apart_ghosts(h));
+        TRY(k_push_apart(h));
+        TRY(k_advect(h, dt, false, true, h->par.stop_particles != 0, /*do_bin=*/true, false));
+    } else {
+        TRY(k_advect(h, dt, true, true, h->par.stop_particles != 0, /*do_bin=*/true, fuse));
+    }
+    if (h->np > 0 && !h->binned) return fsim_fail(h, FSIM_ERR_INVALID, "slab step: particles were not binned");
     TRY(dist_migrate(h));  // emigrants -> neighbours; immigrants appended behind the locals and binned
     FSIM_CUDA(h, cudaEventRecord(h->ev[1], h->stream));
     TRY(k_sort(h));        // also reads the new particle count back

@@ -284,6 +284,8 @@ enum { HALO_P2G = 0, HALO_P, HALO_S, HALO_U2, HALO_U2_FLAGS, HALO_BASIC_ODD, HAL
 int dist_halo(fsim* h, int what, bool in_pcg_loop);      // ghost-plane exchange with both z-neighbours (pull over peer memory)
 int dist_allreduce(fsim* h, int kind, bool in_pcg_loop);  // finishes a PCG reduction across the ranks
 int dist_migrate(fsim* h);
+int dist_push_apart_ghosts(fsim* h);  // stage my boundary planes' particle positions, pull the neighbours' (push-apart on slabs)
+bool dist_pa_ghost(const fsim* h, int side, const uint32_t** starts, const float** x, const float** y, const float** z);
 int dist_gather_solver_inputs(fsim* h);
 // hybrid projection (solver context hs of a slab handle): arrays live at global plane indices on every rank
 enum { SYM_S = 0, SYM_P, SYM_X };

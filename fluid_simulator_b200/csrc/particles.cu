@@ -491,7 +491,25 @@ struct PushApartArgs {
     float lo[3], hi[3];
     int zconst;
     float zval;
+    // slab handles: the neighbours' boundary planes (dist.cu dist_push_apart_ghosts) stand in for the two ghost planes, whose
+    // cells hold no local particles; [0] below the owned planes, [1] above.  gs: per-cell starts of that plane.  nullptr: none
+    const uint32_t* gs[2];
+    const float *gx[2], *gy[2], *gz[2];
 };
+
+// neighbours of (x, y, z) among the particles [jb, je) of one x-run; `self`: index to skip (or ~0u)
+__device__ __forceinline__ void push_apart_run(const float* __restrict__ px, const float* __restrict__ py, const float* __restrict__ pz, uint32_t jb, uint32_t je,
+                                               uint32_t self, float x, float y, float z, float d, float d2, float& dx, float& dy, float& dz) {
+    for (uint32_t j = jb; j < je; j++) {
+        if (j == self) continue;
+        const float ex = x - px[j], ey = y - py[j], ez = z - pz[j];
+        const float r2 = ex * ex + ey * ey + ez * ez;
+        if (r2 > d2 || r2 < 1e-8f) continue;  // hashedParticles.cpp:88-89
+        const float dist = sqrtf(r2);
+        const float t = (d - dist) / dist * 0.5f;
+        dx += ex * t; dy += ey * t; dz += ez * t;
+    }
+}
 
 __global__ void __launch_bounds__(256) push_apart_kernel(PushApartArgs a) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -502,20 +520,20 @@ __global__ void __launch_bounds__(256) push_apart_kernel(PushApartArgs a) {
               cz = min(max((int)((double)z * g.dihz) - g.zoff, 0), g.gz - 1);
     float dx = 0.f, dy = 0.f, dz = 0.f;
     const int x0 = max(cx - a.R, 0), x1 = min(cx + a.R, g.gx - 1);
-    for (int zz = max(cz - a.R, 0); zz <= min(cz + a.R, g.gz - 1); zz++)
+    for (int zz = max(cz - a.R, 0); zz <= min(cz + a.R, g.gz - 1); zz++) {
+        const bool lower = zz < g.zown0 && a.gs[0] != nullptr, upper = zz >= g.zown1 && a.gs[1] != nullptr;  // a neighbour's plane
         for (int yy = max(cy - a.R, 0); yy <= min(cy + a.R, g.gy - 1); yy++) {
-            const int64_t row = ((int64_t)zz * g.gy + yy) * g.gx;
-            const uint32_t jb = a.cell_start[row + x0], je = a.cell_start[row + x1 + 1];
-            for (uint32_t j = jb; j < je; j++) {
-                if (j == (uint32_t)i) continue;
-                const float ex = x - a.px[j], ey = y - a.py[j], ez = z - a.pz[j];
-                const float r2 = ex * ex + ey * ey + ez * ez;
-                if (r2 > a.d2 || r2 < 1e-8f) continue;  // hashedParticles.cpp:88-89
-                const float dist = sqrtf(r2);
-                const float t = (a.d - dist) / dist * 0.5f;
-                dx += ex * t; dy += ey * t; dz += ez * t;
+            if (lower || upper) {
+                const uint32_t* gs = lower ? a.gs[0] : a.gs[1];
+                const int row = yy * g.gx;
+                push_apart_run(lower ? a.gx[0] : a.gx[1], lower ? a.gy[0] : a.gy[1], lower ? a.gz[0] : a.gz[1], gs[row + x0], gs[row + x1 + 1], 0xFFFFFFFFu,
+                               x, y, z, a.d, a.d2, dx, dy, dz);
+            } else {
+                const int64_t row = ((int64_t)zz * g.gy + yy) * g.gx;
+                push_apart_run(a.px, a.py, a.pz, a.cell_start[row + x0], a.cell_start[row + x1 + 1], (uint32_t)i, x, y, z, a.d, a.d2, dx, dy, dz);
             }
         }
+    }
     float nx = x + dx, ny = y + dy, nz = z + dz;
     nx = fminf(fmaxf(nx, a.lo[0]), a.hi[0]);
     ny = fminf(fmaxf(ny, a.lo[1]), a.hi[1]);
@@ -725,6 +743,11 @@ int k_push_apart(fsim* h) {  // requires cell-binned particles (k_sort)
         a.hi[k] = (float)(h->info.dimensions[k] - (h->info.cell_d[k] + r * 1.01));
     }
     a.zconst = h->zconst; a.zval = (float)h->zval;
+    for (int side = 0; side < 2; side++) {
+        a.gs[side] = nullptr; a.gx[side] = a.gy[side] = a.gz[side] = nullptr;
+        if (h->dist) dist_pa_ghost(h, side, &a.gs[side], &a.gx[side], &a.gy[side], &a.gz[side]);
+    }
+    if (h->dist && a.R > 1) return fsim_fail(h, FSIM_ERR_INVALID, "push-apart on slab handles needs 2 * particle radius <= cell size (one ghost plane)");
     { KScope ks(h, K_PUSH); push_apart_kernel<<<div_up(h->np, 256), 256, 0, h->stream>>>(a); }
     FSIM_CHECK_LAUNCH(h);
     for (int k = 0; k < 3; k++) std::swap(p.pos[k], o.pos[k]);  // velocities, C and ids stay where they are

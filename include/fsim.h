@@ -210,9 +210,10 @@ FSIM_API int fsim_get_grid_info(const fsim_t* h, FsimGridInfo* out);
  * Particles uploaded to a rank must lie in the planes it owns (trunc(pos.z * cellDInv.z) in [own_lo, own_hi)).
  * Life cycle: every rank creates its handle -> fsim_dist_export -> the caller gathers all exports (any transport) ->
  * fsim_dist_connect -> a barrier of the caller -> fsim_step on all ranks (collective: same dt, params and obstacles on
- * every rank, one host thread or process per rank) -> a barrier -> fsim_destroy.  Push-apart is not available on slab
- * handles (fsim_set_params rejects it); the BasicMacGrid solver (basicMacGrid.cpp:15-102) sweeps the owned planes and hands
- * the shared z faces over after every colour; spawning (spawnParticles, simulator.cpp:106-125) needs one process per rank
+ * every rank, one host thread or process per rank) -> a barrier -> fsim_destroy.  Push-apart (hashedParticles.cpp:64-107) runs
+ * on slab handles when 2 * particleRadius <= cell size (the pair search reads the neighbours' boundary planes; off by default
+ * there: it costs a second particle migration per step); the BasicMacGrid solver (basicMacGrid.cpp:15-102) sweeps the owned
+ * planes and hands the shared z faces over after every colour; spawning (spawnParticles, simulator.cpp:106-125) needs one process per rank
  * with libc rand() seeded identically on all of them (every rank draws the whole spawn set and keeps its planes' share).  A peer that stops answering makes the step fail with
  * FSIM_ERR_COMM after FSIM_DIST_TIMEOUT_MS (default 20000).  The projection (bridsonSolverGrid.cpp:244-293) runs as
  * FSIM_SLAB_SOLVER=hybrid (default: CG vectors and the fine multigrid level on the owned planes, coarse levels

@@ -89,6 +89,55 @@ def test_slab_matches_single_flip(gpu, nranks, solver, monkeypatch):
 
 
 @pytest.mark.parametrize("nranks", [2, 3])
+def test_slab_push_apart(gpu, nranks):
+    """pushParticlesApart (hashedParticles.cpp:64-107) on slab handles: the pair search of a particle next to a slab boundary
+    sees the neighbour's boundary plane (staged positions pulled over peer memory), and particles the pass moves across the
+    boundary migrate a second time.  The device pass is the Jacobi form (all displacements from the positions at its start), so
+    the slab group reproduces the single handle particle for particle."""
+    sc = scenes.dam_break_3d(24, abi.FLIP, ny=20, nz=26, tol=1e-9, push_apart_enabled=True)
+    # a dense start: 8 jittered particles per cell overlap their neighbours (2 r = 0.5), so the pass moves most of them
+    one, grp = make_pair(gpu, sc, nranks)
+    moved = 0.0
+    for st in range(3):
+        before = one.download_particles()[:, 0:3].copy()
+        one.step(sc.dt)
+        grp.step(sc.dt)
+        compare(f"slab_push_apart_n{nranks}_step{st}", one, grp)
+        moved = max(moved, float(np.abs(one.download_particles()[:, 0:3] - before).max()))
+    assert moved > 0.05, "the scene must actually push particles apart"
+    assert sum(grp.particle_counts()) == sc.n_particles
+    grp.close()
+    one.close()
+
+
+def test_slab_push_apart_with_migration(gpu):
+    """Push-apart on 3 slabs while the water runs along z: particles change owner after the advection AND after the pair
+    separation / obstacle push-out (two migrations per step); nothing is lost or duplicated and the run stays on top of the
+    single handle (exactly at first, statistically once the two fp summation orders have drifted apart)."""
+    sc = z_flow_scene(24, abi.FLIP, gravity=-9.81 * 40, push_apart_enabled=True)
+    sc.dt = 0.01
+    one, grp = make_pair(gpu, sc, 3)
+    c0 = grp.particle_counts()
+    for st in range(30):
+        one.step(sc.dt)
+        grp.step(sc.dt)
+        if st == 4:
+            pa, pb = grp.download_particles(), one.download_particles()
+            assert rel_l2(pa[:, 0:3], pb[:, 0:3]) <= 1e-5 and rel_l2(pa[:, 3:6], pb[:, 3:6]) <= 1e-4
+    pa, pb = grp.download_particles(), one.download_particles()
+    c1 = grp.particle_counts()
+    k1, k2 = 0.5 * (pa[:, 3:6] ** 2).sum(), 0.5 * (pb[:, 3:6] ** 2).sum()
+    diag(test="slab_push_apart_migration", counts0=c0, counts1=c1, ke_slab=k1, ke_single=k2, pos_rel=rel_l2(pa[:, 0:3], pb[:, 0:3]))
+    assert sum(c1) == sc.n_particles and c1 != c0, f"counts {c0} -> {c1}"
+    assert abs(k1 - k2) <= 0.02 * k2
+    assert np.all(np.abs(pa[:, 0:3].mean(0) - pb[:, 0:3].mean(0)) <= 0.01 * sc.dims[0])
+    ids = np.sort(np.concatenate([s.download_particle_ids() for s in grp.sims]))
+    assert np.array_equal(ids, np.arange(sc.n_particles, dtype=np.uint32)), "ids are not a permutation"
+    grp.close()
+    one.close()
+
+
+@pytest.mark.parametrize("nranks", [2, 3])
 def test_slab_basic_solver(gpu, nranks):
     """BasicMacGrid's red-black Gauss-Seidel (basicMacGrid.cpp:15-102) on slab handles: every colour sweeps the owned planes and
     the z faces shared by two slabs change hands after it -- the same sweep-for-sweep arithmetic as the single handle."""
