@@ -54,6 +54,7 @@ struct PcgArgs {
     int pressure_enabled, warm;
     int cut_neumann;  // slab mode: how code_mg treats a cut link
     int64_t cb, ce;   // cell range of the chunked kernels
+    int64_t rc0, rc1; // cell range rhs_kernel visits (hybrid: the owned planes; the other planes only need codes, codes_full4_kernel)
     Tile4 t4;         // the same range as 2-D blocks (tile4.cuh): iteration space of the four-cells-per-thread kernels
     // hybrid slab projection with fused exchanges (fexch.cuh): direction4 stores the boundary planes of s into the neighbours'
     // ghost planes (t4p: boundary planes first), spmv4's boundary CTAs wait for the neighbours' (t4: boundary planes last)
@@ -76,8 +77,8 @@ __device__ __forceinline__ int code_ns(unsigned c) { return (c >> 6) & 7; }
 // calculateRHS (:79-89) + p = 0, r = rhs + sum(rhs^2) (:254-258) + stencil codes; one thread per cell
 __global__ void __launch_bounds__(PT) rhs_kernel(PcgArgs a) {
     double acc[2] = {0.0, 0.0};
-    const int64_t c = (int64_t)blockIdx.x * PT + threadIdx.x;
-    if (c < a.g.nc) {
+    const int64_t c = a.rc0 + (int64_t)blockIdx.x * PT + threadIdx.x;
+    if (c < a.rc1) {
         double rhs = 0.0;
         unsigned code = 0;
         const int zc = (int)c / a.g.sz;
@@ -138,6 +139,44 @@ reduce:
         if (a.sc->dist) { a.sc->loc[0] = out[0]; a.sc->loc[3] = out[1]; a.sc->done = 0; }
         else pcg_finish_rhs(a.sc, a.status, out[0], out[1]);
     }
+}
+
+// Hybrid slab projection: the replicated coarse operators need the stencil codes of EVERY plane, the right-hand side only
+// exists on the owned ones.  The planes of the other ranks get their codes here, four cells per thread (flags as 4-byte
+// loads; x neighbours of the inner cells from registers): 14.7 M cells at N = 8 in ~30 us where rhs_kernel, one cell per
+// thread with seven byte loads each, took 190 us over the whole grid.
+__global__ void __launch_bounds__(256) codes_full4_kernel(GridDims g, const uint8_t* __restrict__ flags, uint16_t* __restrict__ code_full, int nplanes) {
+    const int x = (blockIdx.x * 32 + (threadIdx.x & 31)) * 4;
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const int pz = blockIdx.z;  // index among the planes this rank does not own: below the slab first, then above it
+    if (x >= g.gx || y >= g.gy || pz >= nplanes) return;
+    const int z = pz < g.zown0 ? pz : pz + (g.zown1 - g.zown0);
+    const int64_t c = ((int64_t)z * g.gy + y) * g.gx + x;
+    const uchar4 f4 = *reinterpret_cast<const uchar4*>(flags + c);
+    const unsigned t[4] = {f4.x & FL_TYPE_MASK, f4.y & FL_TYPE_MASK, f4.z & FL_TYPE_MASK, f4.w & FL_TYPE_MASK};
+    unsigned out[4] = {0, 0, 0, 0};
+    if (t[0] == FSIM_CELL_WATER || t[1] == FSIM_CELL_WATER || t[2] == FSIM_CELL_WATER || t[3] == FSIM_CELL_WATER) {
+        // a WATER cell is interior (border shell), so the rows y +- 1, z +- 1 of this group exist
+        const uchar4 ym = *reinterpret_cast<const uchar4*>(flags + c - g.sy), yp = *reinterpret_cast<const uchar4*>(flags + c + g.sy);
+        const uchar4 zm = *reinterpret_cast<const uchar4*>(flags + c - g.sz), zp = *reinterpret_cast<const uchar4*>(flags + c + g.sz);
+        const unsigned xl = t[0] == FSIM_CELL_WATER ? (flags[c - 1] & FL_TYPE_MASK) : (unsigned)FSIM_CELL_SOLID;
+        const unsigned xr = t[3] == FSIM_CELL_WATER ? (flags[c + 4] & FL_TYPE_MASK) : (unsigned)FSIM_CELL_SOLID;
+        const unsigned ymv[4] = {ym.x, ym.y, ym.z, ym.w}, ypv[4] = {yp.x, yp.y, yp.z, yp.w}, zmv[4] = {zm.x, zm.y, zm.z, zm.w}, zpv[4] = {zp.x, zp.y, zp.z, zp.w};
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            if (t[i] != FSIM_CELL_WATER) continue;
+            // the same neighbour order as rhs_kernel: -x, +x, -y, +y, -z, +z
+            const unsigned nb[6] = {i == 0 ? xl : t[i - 1], i == 3 ? xr : t[i + 1], ymv[i] & FL_TYPE_MASK, ypv[i] & FL_TYPE_MASK, zmv[i] & FL_TYPE_MASK, zpv[i] & FL_TYPE_MASK};
+            unsigned wm = 0, ns = 0;
+#pragma unroll
+            for (int k = 0; k < 6; k++) {
+                ns += (nb[k] != FSIM_CELL_SOLID);
+                wm |= (nb[k] == FSIM_CELL_WATER) ? (1u << k) : 0u;
+            }
+            out[i] = CODE_ACTIVE | (ns << 6) | wm;
+        }
+    }
+    *reinterpret_cast<ushort4*>(code_full + c) = make_ushort4((unsigned short)out[0], (unsigned short)out[1], (unsigned short)out[2], (unsigned short)out[3]);
 }
 
 // warm start: r = rhs - A p for the pressure kept from the previous step; also max |r| (already converged => done)
@@ -570,7 +609,16 @@ int k_project(fsim* h, double dt, int* iterations) {
 
     const int mode = h->dist ? 1 : (h->hybrid ? 2 : 0);
     const bool dist = mode != 0;
-    { KScope ks(h, K_RHS); rhs_kernel<<<div_up(g.nc, PT), PT, 0, h->stream>>>(a); }  // one cell per thread (a chunked loop was 25 % slower)
+    a.rc0 = 0; a.rc1 = g.nc;
+    {
+        // hybrid slab projection: the owned planes get everything, the planes of the other ranks their stencil codes only
+        const int nother = g.gz - (g.zown1 - g.zown0);
+        const bool split = h->hybrid && h->code_full && g.gx % 4 == 0;
+        if (split) { a.rc0 = a.cb; a.rc1 = a.ce; }
+        KScope ks(h, K_RHS, (split && nother > 0) ? 2 : 1);
+        if (split && nother > 0) codes_full4_kernel<<<dim3(div_up(g.gx, 128), div_up(g.gy, 8), nother), 256, 0, h->stream>>>(g, h->flags, h->code_full, nother);
+        rhs_kernel<<<div_up(a.rc1 - a.rc0, PT), PT, 0, h->stream>>>(a);  // one cell per thread (a chunked loop was 25 % slower)
+    }
     if (dist) { int rc = dist_allreduce(h, AR_RHS, false); if (rc) return rc; }
     if (a.warm) {
         // the initial guess of the neighbours' boundary planes
