@@ -5,7 +5,7 @@ compiled reference (oracle/refsim.py), which deliberately reuses the same POD st
 """
 import ctypes as C
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_COMM = 0, 1, 2, 3, 4
 PIC, FLIP, APIC = 0, 1, 2

@@ -41,7 +41,9 @@ extern "C" {
 #define FSIM_API
 #endif
 
-#define FSIM_ABI_VERSION 3
+/* 4: + fsim_export_gfx_strided_async, fsim_dist_wait_stats; FsimDistExport carries one more array (push-apart staging);
+ *    push-apart and FSIM_SOLVER_BASIC accepted on slab handles (all additive for single-handle callers) */
+#define FSIM_ABI_VERSION 4
 
 /* status codes */
 #define FSIM_OK 0
