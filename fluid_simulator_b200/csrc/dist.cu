@@ -25,11 +25,11 @@
 #include <vector>
 
 #include "fsim_internal.h"
+#include "dist_dev.cuh"
 #include "fexch.cuh"
 #include "launch.cuh"
 #include "pcg_finish.cuh"
 
-#define DIST_MAX_RANKS 16
 #define DIST_NARR 24
 #define DIST_NCH 15  // particle channels of the widest (APIC) layout
 
@@ -38,31 +38,7 @@ enum { ARR_U = 0, ARR_U2 = 3, ARR_W = 6, ARR_DENS = 9, ARR_CNT = 10, ARR_FLAGS =
        ARR_HS_S = 16, ARR_HS_P = 17, ARR_HS_XA = 18, ARR_HS_XB = 19, ARR_HS_B1 = 20,
        ARR_PA = 21 };  // push-apart: positions of the particles in my two boundary planes, staged for the neighbours
 
-struct DistSlot { double v[4]; uint32_t epoch; uint32_t pad[7]; };
-
-struct DistComm {
-    // written by the z-neighbours ([0]: by the lower one, [1]: by the upper one)
-    uint32_t arrive[2], done[2];
-    uint32_t mig_epoch[2], mig_count[2];
-    // written by every rank: slot[parity][source rank]
-    DistSlot slot[2][DIST_MAX_RANKS];
-    uint32_t arrive_all[DIST_MAX_RANKS], done_all[DIST_MAX_RANKS];  // all-rank handshake of the solver-input gather
-    uint32_t push_flag[2];                 // "your ghost plane holds my boundary plane of exchange #epoch" (push halos of the PCG loop)
-    uint32_t gpush_flag[DIST_MAX_RANKS];   // the same for the all-rank push of the coarse right-hand side
-    uint32_t fx_cnt[3][2];                 // fused exchanges (fexch.cuh): arrivals [array: s, xa, xb][from the lower / upper neighbour]
-    uint32_t gx_cnt;                       // fused all-rank push of the level-1 right-hand side: arrivals from all other ranks
-    // local
-    uint32_t fx_exp[3][2];                 // ... and how many this rank expects by now
-    uint32_t gx_exp;
-    uint32_t halo_epoch, ar_epoch, mig_ep, blocks_done, mig_blocks_done, gather_epoch, gather_blocks_done, push_epoch, push_blocks_done, gpush_epoch, gpush_blocks_done, pad1;
-    uint32_t error;   // 1 wait timed out, 2 emigrant list full, 3 immigrant outside the owned planes
-    uint32_t n_src;   // particles the next reorder reads: locals + immigrants
-    uint32_t pad0;
-    unsigned long long timeout_ns;
-    // time spent spinning in wait_ge and the number of waits, by class (FSIM_WAIT_*, fsim.h): the share of an exchange that is
-    // waiting for the peer (its skew + flight time of the flag) rather than this rank's own launch / copy
-    unsigned long long wait_ns[FSIM_WAIT_CLASSES], waits[FSIM_WAIT_CLASSES], kern_ns[FSIM_WAIT_CLASSES];
-};
+static bool fused_enabled();
 
 struct DistState {
     int rank, nranks;
@@ -86,6 +62,7 @@ struct DistState {
     bool connected, nsrc_valid;
     bool peer_in_process;  // some other rank of the group lives in this process (they would share libc's rand() stream)
     FxAllTable* gx_table;  // device copy of the peer table of the fused all-rank push (built on first use)
+    ArDev* ar_table;       // device copy of the rank table of the fused all-rank reduction (dist_dev.cuh ar_warp)
     // push-apart across slabs (pushParticlesApart, hashedParticles.cpp:64-107): per side one block of words
     //   [0] particle count | [1 .. sz+1] per-cell starts of the plane (relative) | x[pa_capa] | y[pa_capa] | z[pa_capa]
     // pa_stage: my boundary planes (read by the neighbours), pa_ghost: the neighbours' boundary planes (pulled)
@@ -95,53 +72,6 @@ struct DistState {
 };
 
 namespace {
-
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint4 ld_peer_u4(const void* p) {  // never served from a stale L1 line
-    uint4 v;
-    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ unsigned long long now_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    return t;
-}
-
-// spin until *flag >= ep (epochs only grow); bounded: on time-out the error word is set and every later wait returns at once
-// (err_host[1..3] record which wait gave up: 1 halo arrive, 2 halo done, 3 all-rank reduction, 4 migration; the epoch; the flag)
-__device__ bool wait_ge(const uint32_t* flag, uint32_t ep, DistComm* c, uint32_t* err_host, uint32_t where) {
-    if (*(volatile uint32_t*)&c->error == 1u) return false;
-    const unsigned long long t0 = now_ns();
-    while ((int32_t)(ld_acquire_sys(flag) - ep) < 0) {
-        if (now_ns() - t0 > c->timeout_ns) {
-            if (atomicCAS(&c->error, 0u, 1u) == 0u) {
-                volatile uint32_t* eh = err_host;
-                eh[1] = where; eh[2] = ep; eh[3] = ld_acquire_sys(flag);
-                eh[0] = 1u;
-            }
-            *(volatile uint32_t*)&c->error = 1u;
-            __threadfence_system();
-            return false;
-        }
-        __nanosleep(64);
-    }
-    return true;
-}
-
-// elapsed waiting time of ONE designated thread per kernel (block 0 / the last block; waits of the other blocks and of the
-// other lanes run concurrently with it), so that the sums are time on this rank's stream
-__device__ __forceinline__ void wait_account(DistComm* c, int cls, unsigned long long t0) {
-    atomicAdd(&c->wait_ns[cls], now_ns() - t0);
-    atomicAdd(&c->waits[cls], 1ull);
-}
 
 // mask >= 0: a plane of floats of which only the cells with (x + y) & 1 == mask are copied (row length gx): the red-black sweeps of
 // the BasicMacGrid solver on slabs, where each rank owns the updates of one colour of a shared face plane
@@ -618,6 +548,7 @@ int dist_init(fsim* h, int rank, int nranks, int own_lo, int own_hi) {
 
 void dist_free(fsim* h) {
     if (h->dist && h->dist->gx_table) { cudaFree(h->dist->gx_table); h->dist->gx_table = nullptr; }
+    if (h->dist && h->dist->ar_table) { cudaFree(h->dist->ar_table); h->dist->ar_table = nullptr; }
     DistState* d = h->dist;
     if (!d) return;
     for (void* p : d->ipc_opened) cudaIpcCloseMemHandle(p);
@@ -728,8 +659,26 @@ int dist_connect(fsim* h, const FsimDistExport* all, int n) {
             FSIM_CUDA(h, cudaMemcpy(d->gx_table, &t, sizeof(t), cudaMemcpyHostToDevice));
         }
     }
+    if (h->solver) {  // rank table of the all-rank reduction fused into the reducing kernels
+        ArDev t;
+        memset(&t, 0, sizeof(t));
+        t.comm = d->comm; t.err_host = d->err_dev; t.rank = d->rank; t.nranks = n;
+        for (int r = 0; r < n; r++) t.all[r] = d->all_comm[r];
+        if (d->ar_table) { cudaFree(d->ar_table); d->ar_table = nullptr; }
+        FSIM_CUDA(h, cudaMalloc((void**)&d->ar_table, sizeof(t)));
+        FSIM_CUDA(h, cudaMemcpy(d->ar_table, &t, sizeof(t), cudaMemcpyHostToDevice));
+    }
     d->connected = true;
     return FSIM_OK;
+}
+
+// the rank table for ar_warp, or nullptr when the reductions stay kernels of their own (FSIM_SLAB_FUSED_AR=0, FSIM_SLAB_FUSED=0)
+const ArDev* dist_ar_dev(const fsim* hs) {
+    const DistState* d = dist_of(hs);
+    if (!d || !d->connected || !hs->hybrid || !fused_enabled()) return nullptr;
+    const char* e = getenv("FSIM_SLAB_FUSED_AR");
+    if (e && e[0] == '0') return nullptr;
+    return d->ar_table;
 }
 
 int dist_halo(fsim* h, int what, bool in_pcg_loop) {

@@ -320,7 +320,7 @@ static int create_impl(const FsimGridDesc* desc, int rank, int nranks, fsim_t** 
     { const char* e = getenv("FSIM_NO_WARM_START"); h->warm_start = !(e && e[0] == '1'); }
     { const char* e = getenv("FSIM_PDL"); h->pdl = !(e && e[0] == '0'); }
     { const char* e = getenv("FSIM_WARM_EXTRAPOLATE"); h->warm_extrapolate = !(e && e[0] == '0'); }
-    h->warm_history = 0; h->p_prev = nullptr; h->mg_tail_cluster = 0; h->mg_tail_smem = -1; h->mg_tail2 = -1; h->fx_on = false; h->gx_on = false;
+    h->warm_history = 0; h->p_prev = nullptr; h->mg_tail_cluster = 0; h->mg_tail_smem = -1; h->mg_tail2 = -1; h->fx_on = false; h->gx_on = false; h->ar_dev = nullptr;
     h->status_host = nullptr; h->status_dev = nullptr;
     h->dist = nullptr; h->code_mg = nullptr; h->solver = nullptr; h->stream_shared = false; h->skip_apply = false;
     h->parent = nullptr; h->hybrid = 0; h->code_full = nullptr; h->slab_spawn_id = 0x80000000u;

@@ -147,6 +147,7 @@ struct fsim {
     std::vector<MgLevel*> mg;
     bool fx_on;                            // hybrid slab projection: in-loop exchanges fused into the solver kernels (fexch.cuh)
     bool gx_on;                            // ... including the all-rank push of the level-1 right-hand side
+    const struct ArDev* ar_dev;            // ... and the all-rank reductions (rank table for ar_warp, dist_dev.cuh); nullptr: allreduce_kernel
     int mg_tail_first;                     // levels >= this run inside the single-cluster tail kernel
     int mg_tail_cluster;                   // CTAs of that cluster (0: not probed yet)
     int mg_tail2;                          // tail kernel with block-local coarse levels (mg_tail2_kernel): -1 not probed, 0 off, 1 on (opt-in: FSIM_MG_TAIL2=1; measured slower, see mg.cu)
@@ -304,6 +305,8 @@ bool dist_peer_in_process(const fsim* h);  // another rank of the group lives in
 int dist_wait_stats(fsim* h, FsimDistWaitStats* out, int reset);
 struct FxPush;
 struct FxWait;
+struct ArDev;
+const ArDev* dist_ar_dev(const fsim* hs);  // rank table of the all-rank reduction fused into the reducing kernels (dist_dev.cuh), or nullptr
 struct FxAllPush;
 bool dist_gx(fsim* hs, int cgx, int cgy, int cgz, FxAllPush* p, FxWait* w);  // fused all-rank push of the level-1 right-hand side
 bool dist_fx(fsim* hs, int which, const void* ptr, FxPush* p, FxWait* w);  // fused in-loop exchange of a level-0 array (fexch.cuh)

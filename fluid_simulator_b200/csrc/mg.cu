@@ -22,6 +22,7 @@
 
 #include "fsim_internal.h"
 #include "reduce.cuh"
+#include "dist_dev.cuh"
 #include "fexch.cuh"
 #include "launch.cuh"
 #include "tile4.cuh"
@@ -386,7 +387,7 @@ __global__ void __launch_bounds__(256) mg_jacobi4_kernel(Lv L, PcgScalars* __res
 // partials instead of 16 K -- with one CTA per tile its fence + arrival atomic per CTA cost 30 us on top of the 37 us sweep.
 __global__ void __launch_bounds__(256) mg_jacobi4_dot_kernel(Lv L, PcgScalars* __restrict__ sc, const float* __restrict__ b, const float* __restrict__ xin,
                                                              float* __restrict__ xout, double* partials, unsigned int* counter, float om,
-                                                             int ntx, int nty, int ntiles, FxWait fw, int trot) {
+                                                             int ntx, int nty, int ntiles, FxWait fw, int trot, const ArDev* ar) {
     pdl_wait();
     pdl_trigger();
     if (sc->done) return;
@@ -427,8 +428,12 @@ __global__ void __launch_bounds__(256) mg_jacobi4_dot_kernel(Lv L, PcgScalars* _
             }
         st4(xout + cc, xo);
     }
-    double out[1];
-    if (grid_reduce<1, 0>(acc, partials, counter, out)) {
+    double out[1] = {0.0};
+    const int fr = grid_reduce_w<1, 0>(acc, partials, counter, out);
+    if (fr && ar) {  // slab mode, fused reduction (dist_dev.cuh): sigma' = the all-rank sum
+        const double m[4] = {out[0] * sc->scale, 0.0, 0.0, 0.0};
+        ar_warp(ar, sc, nullptr, AR_DOTZR, m);
+    } else if (fr == 2) {
         if (sc->dist) sc->loc[0] = out[0] * sc->scale;  // slab mode: finished by the all-rank reduction (AR_DOTZR)
         else sc->sigma_new = out[0] * sc->scale;
     }
@@ -440,7 +445,7 @@ constexpr int UF_MIN_BLOCKS = 4;  // 64 registers: four resident CTAs instead of
 __global__ void __launch_bounds__(256, UF_MIN_BLOCKS) mg_update_first4_kernel(Lv L, Tile4 t4, PcgScalars* sc, PcgHostStatus* status, double* __restrict__ p,
                                                                const float* __restrict__ sv, double* __restrict__ r,
                                                                const double* __restrict__ q, float* __restrict__ b, float* __restrict__ xout,
-                                                               double* partials, unsigned int* counter, FxPush fp) {
+                                                               double* partials, unsigned int* counter, FxPush fp, const ArDev* ar) {
     pdl_wait();
     pdl_trigger();
     if (sc->done) return;
@@ -501,8 +506,12 @@ __global__ void __launch_bounds__(256, UF_MIN_BLOCKS) mg_update_first4_kernel(Lv
         }
     }
     if (xpeer) fx_signal(fp, side);
-    double out[1];
-    if (grid_reduce<0, 1>(acc, partials, counter, out)) {
+    double out[1] = {0.0};
+    const int fr = grid_reduce_w<0, 1>(acc, partials, counter, out);
+    if (fr && ar) {  // slab mode, fused reduction (dist_dev.cuh): max |r| over all ranks + the convergence decision
+        const double m[4] = {0.0, 0.0, out[0], 0.0};
+        ar_warp(ar, sc, status, AR_UPDATE, m);
+    } else if (fr == 2) {
         if (sc->dist) {
             sc->loc[2] = out[0];  // slab mode: this rank's max |r|; dist_allreduce_kernel takes the decision (pcg_finish_update)
         } else {
@@ -1633,7 +1642,7 @@ int cycle(fsim* h, int l, bool zero_guess, float** result, bool first_done = fal
                 while (nper > 1 && (int)grd4.x > 1 && nper % (int)grd4.x == 0) nper--;
                 const int layer = (int)(grd4.x * grd4.y);
                 launch_k(h, mg_jacobi4_dot_kernel, nper, 256, 0, L, h->scal, m->b, cur, oth, h->partials, h->red_counter, om,
-                                                                                               (int)grd4.x, (int)grd4.y, ntiles, wait_of(cur), (fx && ntiles > layer) ? layer : 0);
+                                                                                               (int)grd4.x, (int)grd4.y, ntiles, wait_of(cur), (fx && ntiles > layer) ? layer : 0, h->ar_dev);
             } else if (v4) launch_k(h, mg_jacobi4_kernel, grd4, blk4, 0, L, h->scal, m->b, cur, oth, om, wait_of(cur), no_push, 0);
             else if (fine) launch_k(h, mg_jacobi_kernel<true>, grdL, blk, 0, L, sc, m->b, cur, oth, om);
             else if (c4) launch_k(h, mg_jacobic4_kernel, grdC4, blk4, 0, L, sc, m->b, cur, oth, om);
@@ -1728,7 +1737,7 @@ int mg_update_first(fsim* h) {
         fp.nblk[0] = fp.nblk[1] = (uint32_t)(t4.nbx * (h->g.gy / T4_ROWS));
     }
     launch_k(h, mg_update_first4_kernel, tile4_blocks(t4), 256, 0, L, t4, h->scal, h->status_dev, h->p, h->s, h->r, h->q, m->b,
-                                                                              m->xa, h->partials, h->red_counter, fp); }
+                                                                              m->xa, h->partials, h->red_counter, fp, h->ar_dev); }
     FSIM_CHECK_LAUNCH(h);
     return FSIM_OK;
 }

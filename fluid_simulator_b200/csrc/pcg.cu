@@ -18,6 +18,7 @@
 #include "fsim_internal.h"
 #include "reduce.cuh"
 #include "pcg_finish.cuh"
+#include "dist_dev.cuh"
 #include "fexch.cuh"
 #include "launch.cuh"
 #include "tile4.cuh"
@@ -61,6 +62,7 @@ struct PcgArgs {
     Tile4 t4p;
     FxPush fxs;
     FxWait fws;
+    const ArDev* ar;  // all-rank reductions finished inside the reducing kernels (dist_dev.cuh ar_warp); nullptr: allreduce_kernel
 };
 
 // iteration space of the chunked kernels: block b owns cells [b*CHUNK, (b+1)*CHUNK), a thread visits CV cells per trip
@@ -371,8 +373,12 @@ __global__ void __launch_bounds__(PT, 4) spmv4_kernel(PcgArgs a) {
         }
         t = tn;
     }
-    double out[1];
-    if (grid_reduce<1, 0>(acc, a.partials, a.counter, out)) { if (a.sc->dist) a.sc->loc[0] = out[0]; else a.sc->sq = out[0]; }
+    double out[1] = {0.0};
+    const int fr = grid_reduce_w<1, 0>(acc, a.partials, a.counter, out);
+    if (fr && a.ar) {  // slab mode, fused reduction: warp 0 of the last CTA exchanges the partial sums with all ranks
+        const double m[4] = {out[0], 0.0, 0.0, 0.0};
+        ar_warp(a.ar, a.sc, a.status, AR_SPMV, m);
+    } else if (fr == 2) { if (a.sc->dist) a.sc->loc[0] = out[0]; else a.sc->sq = out[0]; }
 }
 
 // alpha = sigma / s.q ; p += alpha s ; r -= alpha q ; ||r||_inf ; (JACOBI: z = r / A_ii ; sigma' = z.r)   (:270-284)
@@ -511,7 +517,8 @@ __global__ void loop_condition_kernel(cudaGraphConditionalHandle handle, const P
 // one PCG iteration: SpMV -> update -> (multigrid cycle -> z.r | fused diagonal) -> direction -> close
 static int enqueue_iteration(fsim* h, const PcgArgs& a, bool vec, bool use_mg, int nbv, cudaGraphConditionalHandle handle = 0, int use_handle = 0) {
     const int mode = h->dist ? 1 : (h->hybrid ? 2 : 0);  // 1: slab-local solve, 2: full-grid context restricted to the owned planes
-    auto AR = [&](int kind) { return mode ? dist_allreduce(h, kind, true) : FSIM_OK; };
+    // (the three reductions of the fused four-cells-per-thread chain are finished inside the reducing kernels when a.ar is set)
+    auto AR = [&](int kind) { return (mode && !(a.ar && (kind == AR_SPMV || kind == AR_UPDATE || kind == AR_DOTZR))) ? dist_allreduce(h, kind, true) : FSIM_OK; };
     // the neighbours' boundary planes of the search direction
     if (mode == 1) { int rc = dist_halo(h, HALO_S, true); if (rc) return rc; }
     if (mode == 2 && !h->fx_on) { int rc = dist_halo_sym(h, SYM_S, h->s, true); if (rc) return rc; }  // (fused: direction4 -> spmv4)
@@ -593,6 +600,8 @@ int k_project(fsim* h, double dt, int* iterations) {
         a.t4 = tile4_boundary_last(a.t4);
         a.fxs.nblk[0] = a.fxs.nblk[1] = (uint32_t)(a.t4.nbx * (g.gy / T4_ROWS));
     }
+    a.ar = h->fx_on ? dist_ar_dev(h) : nullptr;
+    h->ar_dev = a.ar;
     const int max_it = h->par.max_iterations;
 
     // solve parameters live on the device: the captured iteration graph stays valid when dt / tolerance change

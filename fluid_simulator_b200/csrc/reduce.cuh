@@ -22,9 +22,11 @@ __device__ __forceinline__ double warp_max(double v) {
 // partials: [(NS+NM)][nblocks + ngroups] doubles; counters: [1 + ngroups] unsigned, zero-initialised, self-resetting.
 constexpr unsigned RED_GROUP = 32;
 
+// grid_reduce_w: the same, returning 2 in that thread, 1 in the other lanes of its warp (warp 0 of the last CTA; a
+// warp-collective epilogue such as the fused all-rank reduction of the slab mode follows) and 0 everywhere else.
 template <int NS, int NM>
-__device__ __forceinline__ bool grid_reduce(double* vals, double* partials, unsigned int* counters, double* out,
-                                            unsigned bid = blockIdx.x, unsigned nblocks = gridDim.x) {
+__device__ __forceinline__ int grid_reduce_w(double* vals, double* partials, unsigned int* counters, double* out,
+                                             unsigned bid = blockIdx.x, unsigned nblocks = gridDim.x) {
     constexpr int PT = RED_THREADS;
     constexpr int NV = NS + NM;
     __shared__ double sh[NV][PT / 32];
@@ -52,7 +54,7 @@ __device__ __forceinline__ bool grid_reduce(double* vals, double* partials, unsi
         role = (atomicInc(counters + 1 + grp, gsize - 1) == gsize - 1) ? 1 : 0;  // wraps to 0 => self-resetting
     }
     __syncthreads();
-    if (role == 0) return false;
+    if (role == 0) return 0;
     __threadfence();
     // last block of the group: fold the group's block partials in block order (one warp is plenty for <= 32 values)
     if (w == 0) {
@@ -69,7 +71,7 @@ __device__ __forceinline__ bool grid_reduce(double* vals, double* partials, unsi
         }
     }
     __syncthreads();
-    if (role != 2) return false;
+    if (role != 2) return 0;
     __threadfence();
     double tot[NV];
 #pragma unroll
@@ -95,7 +97,12 @@ __device__ __forceinline__ bool grid_reduce(double* vals, double* partials, unsi
             for (int i = 1; i < PT / 32; i++) v = k < NS ? v + sh[k][i] : fmax(v, sh[k][i]);
             out[k] = v;
         }
-        return true;
+        return 2;
     }
-    return false;
+    return w == 0 ? 1 : 0;
+}
+template <int NS, int NM>
+__device__ __forceinline__ bool grid_reduce(double* vals, double* partials, unsigned int* counters, double* out,
+                                            unsigned bid = blockIdx.x, unsigned nblocks = gridDim.x) {
+    return grid_reduce_w<NS, NM>(vals, partials, counters, out, bid, nblocks) == 2;
 }
