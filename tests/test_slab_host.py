@@ -63,12 +63,12 @@ def test_stitch_takes_each_plane_from_its_owner():
 
 
 def test_slab_struct_sizes_match_header():
-    src = '#include <stdio.h>\n#include "fsim.h"\nint main(){printf("%zu %zu\\n",sizeof(FsimSlabInfo),sizeof(FsimDistExport));return 0;}'
+    src = '#include <stdio.h>\n#include "fsim.h"\nint main(){printf("%zu %zu %zu %d\\n",sizeof(FsimSlabInfo),sizeof(FsimDistExport),sizeof(FsimDistWaitStats),FSIM_WAIT_CLASSES);return 0;}'
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "t.c"), "w").write(src)
         subprocess.check_call(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "t.c"), "-o", os.path.join(d, "t")])
         sizes = [int(x) for x in subprocess.check_output([os.path.join(d, "t")]).split()]
-    assert sizes == [C.sizeof(abi.SlabInfo), C.sizeof(abi.DistExport)]
+    assert sizes == [C.sizeof(abi.SlabInfo), C.sizeof(abi.DistExport), C.sizeof(abi.DistWaitStats), len(abi.WAIT_CLASSES)]
 
 
 def _free_port():
